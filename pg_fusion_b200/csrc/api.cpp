@@ -1,0 +1,694 @@
+// extern "C" surface of libpgf_b200.so: context, host-side layout, scan ingest and the
+// Bloom lifecycle.  Kernels live in the .cu files.
+#include <cstring>
+
+#include "context.hpp"
+#include "layout.hpp"
+
+using namespace pgf;
+
+namespace {
+
+Scan* find_scan(pgf_ctx* ctx, uint64_t id) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->scans.find(id);
+  return it == ctx->scans.end() ? nullptr : it->second.get();
+}
+
+bool host_ptr_is_pinned(const void* p) {
+  cudaPointerAttributes a{};
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+pgf_status scan_reserve(pgf_ctx* ctx, Scan& s, uint64_t want_pages) {
+  if (want_pages <= s.cap_pages) return PGF_OK;
+  uint64_t cap = s.cap_pages ? s.cap_pages : 64;
+  while (cap < want_pages) cap *= 2;
+  uint8_t* fresh = nullptr;
+  cudaError_t e = cudaMalloc(&fresh, cap * uint64_t(ctx->page_size));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %llu pages of HBM for scan %llu",
+                     (unsigned long long)cap, (unsigned long long)s.id);
+  }
+  if (s.npages) {
+    // order the move after every copy already queued for this scan
+    CU(ctx, cudaMemcpyAsync(fresh, s.d_pages, s.npages * uint64_t(ctx->page_size), cudaMemcpyDeviceToDevice,
+                            ctx->copy_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  }
+  if (s.d_pages) CU(ctx, cudaFree(s.d_pages));
+  s.d_pages = fresh;
+  s.cap_pages = cap;
+  return PGF_OK;
+}
+
+// Host part of the import checks + descriptor-table entry for one page.
+pgf_status scan_admit_page(pgf_ctx* ctx, Scan& s, const uint8_t* page, uint32_t len) {
+  if (len < kPageHeaderLen || len > ctx->page_size)
+    return ctx->fail(PGF_ERR_IMPORT_PAGE_HEADER_INVALID, "page length %u outside [20, %u]", len, ctx->page_size);
+  uint16_t kind, flags;
+  uint32_t payload_len;
+  if (pgf_status st = decode_page_header(page, &kind, &flags, &payload_len))
+    return ctx->fail(st, "scan %llu page %llu: bad transfer page header", (unsigned long long)s.id,
+                     (unsigned long long)s.npages);
+  if (uint64_t(payload_len) + kPageHeaderLen > len)
+    return ctx->fail(PGF_ERR_LAYOUT_BLOCK_SLICE_TOO_SMALL, "payload_len %u exceeds page length %u", payload_len, len);
+  const uint8_t* block = page + kPageHeaderLen;
+  if (pgf_status st = check_block_structure(kind, flags, block, payload_len, s.schema.data(),
+                                            uint32_t(s.schema.size())))
+    return ctx->fail(st, "scan %llu page %llu rejected by import checks (status %d)", (unsigned long long)s.id,
+                     (unsigned long long)s.npages, int(st));
+  BlockHeader h;
+  std::memcpy(&h, block, sizeof h);
+  // layout class = distinct max_rows (offsets are a pure function of schema and max_rows)
+  uint32_t cls = 0;
+  for (; cls < s.h_classes.size(); ++cls)
+    if (s.h_classes[cls].max_rows == h.max_rows) break;
+  if (cls == s.h_classes.size()) {
+    if (cls >= 65535) return ctx->fail(PGF_ERR_UNSUPPORTED_DATA, "too many distinct page shapes in one scan");
+    LayoutClass lc{};
+    lc.max_rows = h.max_rows;
+    lc.pool_base = h.pool_base + kPageHeaderLen;
+    for (uint32_t c = 0; c < h.col_count; ++c) {
+      ColumnDesc d;
+      std::memcpy(&d, block + sizeof(BlockHeader) + size_t(c) * sizeof(ColumnDesc), sizeof d);
+      lc.values_off[c] = d.values_off + kPageHeaderLen;
+      lc.validity_off[c] = d.validity_off + kPageHeaderLen;
+    }
+    s.h_classes.push_back(lc);
+  }
+  PageDesc pd{};
+  pd.row_count = h.row_count;
+  pd.layout_class = uint16_t(cls);
+  pd.row_base = s.rows;
+  for (uint32_t c = 0; c < h.col_count; ++c) {
+    ColumnDesc d;
+    std::memcpy(&d, block + sizeof(BlockHeader) + size_t(c) * sizeof(ColumnDesc), sizeof d);
+    if (d.null_count) pd.null_mask |= uint16_t(1u << c);
+  }
+  s.h_descs.push_back(pd);
+  s.rows += h.row_count;
+  if (h.row_count > s.max_page_rows) s.max_page_rows = h.row_count;
+  s.descs_dirty = true;
+  return PGF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+pgf_status pgf_device_count(int32_t* count_out) {
+  if (!count_out) return PGF_ERR_INVALID_ARGUMENT;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    n = 0;
+  }
+  *count_out = n;
+  return PGF_OK;
+}
+
+pgf_status pgf_ctx_create(const pgf_config* config, pgf_ctx** ctx_out) {
+  if (!ctx_out) return PGF_ERR_INVALID_ARGUMENT;
+  *ctx_out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return PGF_ERR_NO_DEVICE;  // there is deliberately no CPU fallback
+  }
+  pgf_config cfg{};
+  if (config) cfg = *config;
+  if (cfg.device < 0 || cfg.device >= n) return PGF_ERR_INVALID_ARGUMENT;
+  auto* ctx = new (std::nothrow) pgf_ctx();
+  if (!ctx) return PGF_ERR_OUT_OF_MEMORY;
+  ctx->device = cfg.device;
+  ctx->page_size = cfg.page_size ? cfg.page_size : 65536u;
+  ctx->staging_pages = cfg.staging_pages ? cfg.staging_pages : 512u;
+  auto bail = [&](pgf_status st) {
+    pgf_ctx_destroy(ctx);
+    return st;
+  };
+  if (ctx->page_size % 16 != 0 || ctx->page_size < 1024 || ctx->page_size > (1u << 20)) return bail(PGF_ERR_INVALID_ARGUMENT);
+  if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(PGF_ERR_CUDA);
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return bail(PGF_ERR_CUDA);
+  if (prop.major < 10) return bail(PGF_ERR_NO_DEVICE);  // kernels are built for sm_100a only
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PGF_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PGF_ERR_CUDA);
+  if (cudaEventCreate(&ctx->ev_a) != cudaSuccess || cudaEventCreate(&ctx->ev_b) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess)
+    return bail(PGF_ERR_CUDA);
+  for (int i = 0; i < 2; ++i)
+    if (cudaEventCreateWithFlags(&ctx->staging_ev[i], cudaEventDisableTiming) != cudaSuccess) return bail(PGF_ERR_CUDA);
+  if (cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
+  if (cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
+  if (cudaMalloc(&ctx->d_flags, 64 * sizeof(uint32_t)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
+  if (cudaMallocHost(&ctx->h_flags, 64 * sizeof(uint32_t)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
+  *ctx_out = ctx;
+  return PGF_OK;
+}
+
+void pgf_ctx_destroy(pgf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->scans) {
+    if (kv.second->d_pages) cudaFree(kv.second->d_pages);
+    if (kv.second->d_descs) cudaFree(kv.second->d_descs);
+    if (kv.second->d_classes) cudaFree(kv.second->d_classes);
+  }
+  for (auto& kv : ctx->blooms)
+    if (kv.second.d_words) cudaFree(kv.second.d_words);
+  for (auto& kv : ctx->joins)
+    if (kv.second.d_slots) cudaFree(kv.second.d_slots);
+  for (void* p : ctx->registered) cudaHostUnregister(p);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->staging[i]) cudaFreeHost(ctx->staging[i]);
+    if (ctx->staging_ev[i]) cudaEventDestroy(ctx->staging_ev[i]);
+  }
+  if (ctx->d_counters) cudaFree(ctx->d_counters);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->d_flags) cudaFree(ctx->d_flags);
+  if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+  if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+  if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->compute_stream) cudaStreamDestroy(ctx->compute_stream);
+  cudaGetLastError();
+  delete ctx;
+}
+
+const char* pgf_last_error(const pgf_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+pgf_status pgf_ctx_register_host_region(pgf_ctx* ctx, void* base, size_t len) {
+  if (!ctx || !base || !len) return PGF_ERR_INVALID_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaHostRegister(base, len, cudaHostRegisterPortable));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->registered.push_back(base);
+  return PGF_OK;
+}
+
+pgf_status pgf_ctx_unregister_host_region(pgf_ctx* ctx, void* base) {
+  if (!ctx || !base) return PGF_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  for (size_t i = 0; i < ctx->registered.size(); ++i)
+    if (ctx->registered[i] == base) {
+      CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+      CU(ctx, cudaHostUnregister(base));
+      ctx->registered.erase(ctx->registered.begin() + long(i));
+      return PGF_OK;
+    }
+  return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "host region %p was not registered", base);
+}
+
+pgf_status pgf_ctx_synchronize(pgf_ctx* ctx) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  return PGF_OK;
+}
+
+void* pgf_ctx_compute_stream(pgf_ctx* ctx) { return ctx ? (void*)ctx->compute_stream : nullptr; }
+
+/* ---- host-side layout ---- */
+pgf_status pgf_layout_plan_new(const pgf_column_spec* specs, uint32_t ncols, uint32_t max_rows,
+                               uint32_t block_size, pgf_layout_plan* plan_out) {
+  if ((!specs && ncols) || !plan_out) return PGF_ERR_INVALID_ARGUMENT;
+  return plan_layout(specs, ncols, max_rows, block_size, plan_out);
+}
+pgf_status pgf_layout_fixed_row_cap(const pgf_column_spec* specs, uint32_t ncols, uint32_t block_size,
+                                    uint32_t* cap_out) {
+  if ((!specs && ncols) || !cap_out) return PGF_ERR_INVALID_ARGUMENT;
+  return fixed_row_cap(specs, ncols, block_size, cap_out);
+}
+pgf_status pgf_block_validate(const uint8_t* block, size_t len) {
+  if (!block) return PGF_ERR_INVALID_ARGUMENT;
+  return validate_block(block, len);
+}
+pgf_status pgf_block_import_check(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
+                                  const pgf_column_spec* schema, uint32_t ncols) {
+  if (!block || (!schema && ncols)) return PGF_ERR_INVALID_ARGUMENT;
+  return check_block_full(kind, flags, block, len, schema, ncols);
+}
+pgf_status pgf_block_init(uint8_t* block, size_t len, const pgf_layout_plan* plan) {
+  if (!block || !plan) return PGF_ERR_INVALID_ARGUMENT;
+  return init_block(block, len, *plan);
+}
+pgf_status pgf_block_write_column(uint8_t* block, size_t len, uint32_t col, uint32_t nrows, const void* values,
+                                  const uint8_t* validity) {
+  if (!block || (!values && nrows)) return PGF_ERR_INVALID_ARGUMENT;
+  return write_column(block, len, col, nrows, values, validity);
+}
+pgf_status pgf_block_set_row_count(uint8_t* block, size_t len, uint32_t nrows) {
+  if (!block) return PGF_ERR_INVALID_ARGUMENT;
+  return set_row_count(block, len, nrows);
+}
+pgf_status pgf_page_header_encode(uint16_t kind, uint16_t flags, uint32_t payload_len, uint8_t out[20]) {
+  if (!out) return PGF_ERR_INVALID_ARGUMENT;
+  encode_page_header(kind, flags, payload_len, out);
+  return PGF_OK;
+}
+pgf_status pgf_page_header_decode(const uint8_t in[20], uint16_t* kind, uint16_t* flags, uint32_t* payload_len) {
+  if (!in || !kind || !flags || !payload_len) return PGF_ERR_INVALID_ARGUMENT;
+  return decode_page_header(in, kind, flags, payload_len);
+}
+
+/* ---- scans ---- */
+pgf_status pgf_scan_declare(pgf_ctx* ctx, uint64_t scan_id, const pgf_column_spec* schema, uint32_t ncols,
+                            uint64_t expected_pages) {
+  if (!ctx || (!schema && ncols)) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  if (ncols > PGF_MAX_COLS) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "scan has %u columns; at most %u are staged", ncols, PGF_MAX_COLS);
+  for (uint32_t c = 0; c < ncols; ++c)
+    if (!known_type(schema[c].type_tag)) return ctx->fail(PGF_ERR_LAYOUT_INVALID_TYPE_TAG, "column %u has unknown type tag %u", c, schema[c].type_tag);
+  CU(ctx, cudaSetDevice(ctx->device));
+  auto s = std::make_unique<Scan>();
+  s->id = scan_id;
+  s->schema.assign(schema, schema + ncols);
+  if (expected_pages) PGF_TRY(scan_reserve(ctx, *s, expected_pages));
+  std::lock_guard<std::mutex> g(ctx->mu);
+  if (ctx->scans.count(scan_id)) {
+    if (s->d_pages) cudaFree(s->d_pages);
+    return ctx->fail(PGF_ERR_STATE, "scan %llu already declared", (unsigned long long)scan_id);
+  }
+  ctx->scans[scan_id] = std::move(s);
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_push_pages(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pages, uint64_t npages,
+                               uint64_t stride) {
+  if (!ctx || (!pages && npages)) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  Scan* sp = find_scan(ctx, scan_id);
+  if (!sp) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  Scan& s = *sp;
+  std::lock_guard<std::mutex> g(s.mu);
+  if (s.finished) return ctx->fail(PGF_ERR_STATE, "scan %llu already finished", (unsigned long long)scan_id);
+  if (npages == 0) return PGF_OK;
+  if (stride < kPageHeaderLen) return PGF_ERR_INVALID_ARGUMENT;
+  CU(ctx, cudaSetDevice(ctx->device));
+  PGF_TRY(scan_reserve(ctx, s, s.npages + npages));
+  const uint32_t len = uint32_t(stride < ctx->page_size ? stride : ctx->page_size);
+  const uint64_t first = s.npages;
+  for (uint64_t p = 0; p < npages; ++p) {
+    pgf_status st = scan_admit_page(ctx, s, pages + p * stride, len);
+    if (st) {  // roll back the pages admitted by this call
+      s.h_descs.resize(first);
+      s.rows = first ? s.h_descs.back().row_base + s.h_descs.back().row_count : 0;
+      s.npages = first;
+      return st;
+    }
+    s.npages++;
+  }
+  uint8_t* dst = s.d_pages + first * uint64_t(ctx->page_size);
+  if (host_ptr_is_pinned(pages)) {
+    // caller-owned pinned (or registered shared-memory) pages: DMA straight from them
+    if (stride == ctx->page_size)
+      CU(ctx, cudaMemcpyAsync(dst, pages, npages * stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+    else
+      CU(ctx, cudaMemcpy2DAsync(dst, ctx->page_size, pages, stride, len, npages, cudaMemcpyHostToDevice, ctx->copy_stream));
+    s.pending_async += npages;
+    return PGF_OK;
+  }
+  // pageable memory: bounce through the pinned staging chunks (double buffered)
+  std::lock_guard<std::mutex> gs(ctx->mu);
+  const uint64_t chunk = ctx->staging_pages;
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->staging[i]) {
+      cudaError_t e = cudaMallocHost(&ctx->staging[i], chunk * uint64_t(ctx->page_size));
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate pinned staging");
+      }
+    }
+  for (uint64_t p0 = 0; p0 < npages; p0 += chunk) {
+    const uint64_t n = npages - p0 < chunk ? npages - p0 : chunk;
+    const int b = ctx->staging_next;
+    ctx->staging_next ^= 1;
+    CU(ctx, cudaEventSynchronize(ctx->staging_ev[b]));
+    if (stride == ctx->page_size) {
+      std::memcpy(ctx->staging[b], pages + p0 * stride, n * stride);
+    } else {
+      for (uint64_t p = 0; p < n; ++p)
+        std::memcpy(ctx->staging[b] + p * ctx->page_size, pages + (p0 + p) * stride, len);
+    }
+    CU(ctx, cudaMemcpyAsync(dst + p0 * ctx->page_size, ctx->staging[b], n * uint64_t(ctx->page_size),
+                            cudaMemcpyHostToDevice, ctx->copy_stream));
+    CU(ctx, cudaEventRecord(ctx->staging_ev[b], ctx->copy_stream));
+  }
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_push_page(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* page, uint32_t len) {
+  if (!ctx || !page) return PGF_ERR_INVALID_ARGUMENT;
+  return pgf_scan_push_pages(ctx, scan_id, page, 1, len);
+}
+
+pgf_status pgf_scan_finish(pgf_ctx* ctx, uint64_t scan_id) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  Scan* sp = find_scan(ctx, scan_id);
+  if (!sp) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  Scan& s = *sp;
+  std::lock_guard<std::mutex> g(s.mu);
+  if (s.finished) return PGF_OK;
+  CU(ctx, cudaSetDevice(ctx->device));
+  PGF_TRY(scan_sync_descs(ctx, s));
+  // compute stream waits for the H2D copies; then the row-level import checks run on device
+  CU(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+  CU(ctx, cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copy, 0));
+  PGF_TRY(scan_device_validate(ctx, s));
+  s.pending_async = 0;
+  s.finished = true;
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_get_info(pgf_ctx* ctx, uint64_t scan_id, pgf_scan_info* out) {
+  if (!ctx || !out) return PGF_ERR_INVALID_ARGUMENT;
+  Scan* s = find_scan(ctx, scan_id);
+  if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  out->pages = s->npages;
+  out->rows = s->rows;
+  out->bytes = s->npages * uint64_t(ctx->page_size);
+  out->ncols = uint32_t(s->schema.size());
+  out->finished = s->finished;
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_reset(pgf_ctx* ctx, uint64_t scan_id) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  Scan* s = find_scan(ctx, scan_id);
+  if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  std::lock_guard<std::mutex> g(s->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  s->npages = 0;
+  s->rows = 0;
+  s->finished = false;
+  s->h_descs.clear();
+  s->h_classes.clear();
+  s->max_page_rows = 0;
+  s->descs_dirty = true;
+  s->pending_async = 0;
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_release(pgf_ctx* ctx, uint64_t scan_id) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  auto it = ctx->scans.find(scan_id);
+  if (it == ctx->scans.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
+  cudaStreamSynchronize(ctx->compute_stream);
+  if (it->second->d_pages) cudaFree(it->second->d_pages);
+  if (it->second->d_descs) cudaFree(it->second->d_descs);
+  if (it->second->d_classes) cudaFree(it->second->d_classes);
+  ctx->scans.erase(it);
+  return PGF_OK;
+}
+
+pgf_status pgf_scan_read_pages(pgf_ctx* ctx, uint64_t scan_id, uint64_t first_page, uint64_t npages, uint8_t* out) {
+  if (!ctx || (!out && npages)) return PGF_ERR_INVALID_ARGUMENT;
+  Scan* s = find_scan(ctx, scan_id);
+  if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  if (first_page + npages > s->npages) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "page range out of bounds");
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  CU(ctx, cudaMemcpy(out, s->d_pages + first_page * uint64_t(ctx->page_size), npages * uint64_t(ctx->page_size),
+                     cudaMemcpyDeviceToHost));
+  return PGF_OK;
+}
+
+/* ---- Bloom parameters and lifecycle (host state machine; bits live in HBM) ---- */
+pgf_status pgf_bloom_params_new(uint64_t bit_count, uint64_t hash_count, uint64_t seed, pgf_bloom_params* out) {
+  if (!out) return PGF_ERR_INVALID_ARGUMENT;
+  if (bit_count == 0) return PGF_ERR_BLOOM_ZERO_BIT_COUNT;    // bloom.rs:30-32
+  if (hash_count == 0) return PGF_ERR_BLOOM_ZERO_HASH_COUNT;  // bloom.rs:33-35
+  if (bit_count > UINT64_MAX - 63) return PGF_ERR_BLOOM_TOO_MANY_BITS;
+  out->bit_count = bit_count;
+  out->word_count = (bit_count + 63) / 64;
+  out->hash_count = hash_count;
+  out->seed = seed;
+  return PGF_OK;
+}
+
+}  // extern "C"
+
+#include <cmath>
+
+extern "C" {
+
+pgf_status pgf_bloom_params_for_expected_items(uint64_t expected_items, double fpr, uint64_t seed,
+                                               pgf_bloom_params* out) {
+  if (!out) return PGF_ERR_INVALID_ARGUMENT;
+  if (expected_items == 0) return PGF_ERR_BLOOM_ZERO_EXPECTED_ITEMS;
+  if (!std::isfinite(fpr) || fpr <= 0.0 || fpr >= 1.0) return PGF_ERR_BLOOM_INVALID_FPR;
+  const double n = double(expected_items);
+  const double ln2 = 0.693147180559945309417232121458176568;
+  const double bits = std::ceil(-(n * std::log(fpr)) / (ln2 * ln2));  // bloom.rs:70
+  if (bits > 18446744073709551615.0) return PGF_ERR_BLOOM_TOO_MANY_BITS;
+  const uint64_t bit_count = uint64_t(bits);
+  double k = std::round((double(bit_count) / n) * ln2);  // bloom.rs:75
+  if (k < 1.0) k = 1.0;
+  return pgf_bloom_params_new(bit_count, uint64_t(k), seed, out);
+}
+
+static BloomSlot* find_bloom(pgf_ctx* ctx, uint64_t id) {
+  auto it = ctx->blooms.find(id);
+  return it == ctx->blooms.end() ? nullptr : &it->second;
+}
+
+#define BLOOM_OR_FAIL(ctx, id, var)                                                          \
+  if (!(ctx)) return PGF_ERR_INVALID_ARGUMENT;                                               \
+  if ((ctx)->sticky) return (ctx)->sticky;                                                   \
+  BloomSlot* var = find_bloom((ctx), (id));                                                  \
+  if (!var) return (ctx)->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown bloom filter %llu", (unsigned long long)(id));
+
+pgf_status pgf_bloom_create(pgf_ctx* ctx, const pgf_bloom_params* params, uint64_t* bloom_out) {
+  if (!ctx || !params || !bloom_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  pgf_bloom_params p{};
+  PGF_TRY(pgf_bloom_params_new(params->bit_count, params->hash_count, params->seed, &p));
+  if (p.word_count != params->word_count) return ctx->fail(PGF_ERR_BLOOM_INSUFFICIENT_WORDS, "word_count %llu does not match bit_count", (unsigned long long)params->word_count);
+  CU(ctx, cudaSetDevice(ctx->device));
+  BloomSlot b;
+  b.params = p;
+  cudaError_t e = cudaMalloc(&b.d_words, p.word_count * 8);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %llu Bloom words", (unsigned long long)p.word_count);
+  }
+  CU(ctx, cudaMemsetAsync(b.d_words, 0, p.word_count * 8, ctx->compute_stream));
+  PGF_TRY(bloom_make_dev(p, b.d_words, &b.dev));
+  const uint64_t id = ctx->next_handle++;
+  ctx->blooms[id] = b;
+  *bloom_out = id;
+  return PGF_OK;
+}
+
+pgf_status pgf_bloom_destroy(pgf_ctx* ctx, uint64_t bloom) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->compute_stream);
+  cudaFree(b->d_words);
+  ctx->blooms.erase(bloom);
+  return PGF_OK;
+}
+
+pgf_status pgf_bloom_snapshot(pgf_ctx* ctx, uint64_t bloom, uint64_t* generation, int32_t* state) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (generation) *generation = b->lifecycle >> 2;  // shared.rs:411-416
+  if (state) *state = int32_t(b->lifecycle & 3);
+  return PGF_OK;
+}
+
+pgf_status pgf_bloom_begin_build(pgf_ctx* ctx, uint64_t bloom, uint64_t* generation_out) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  const uint64_t gen = b->lifecycle >> 2;
+  const int state = int(b->lifecycle & 3);
+  if (state == PGF_RF_BUILDING || state == PGF_RF_READY)  // shared.rs:165-169
+    return ctx->fail(PGF_ERR_LIFECYCLE_BUSY, "runtime filter slot is busy: generation %llu state %d", (unsigned long long)gen, state);
+  if (gen + 1 > (UINT64_MAX >> 2))                        // shared.rs:171-180
+    return ctx->fail(PGF_ERR_LIFECYCLE_GENERATION_EXHAUSTED, "runtime filter generation %llu cannot advance", (unsigned long long)gen);
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemsetAsync(b->d_words, 0, b->params.word_count * 8, ctx->compute_stream));  // bloom.clear()
+  b->lifecycle = ((gen + 1) << 2) | PGF_RF_BUILDING;
+  if (generation_out) *generation_out = gen + 1;
+  return PGF_OK;
+}
+
+static pgf_status bloom_transition(pgf_ctx* ctx, BloomSlot* b, int from, int to) {
+  const uint64_t gen = b->lifecycle >> 2;
+  if (int(b->lifecycle & 3) != from)  // shared.rs:377-397 / 244-260
+    return ctx->fail(PGF_ERR_LIFECYCLE_INVALID_TRANSITION, "invalid runtime filter transition: expected state %d, observed generation %llu state %d",
+                     from, (unsigned long long)gen, int(b->lifecycle & 3));
+  b->lifecycle = (gen << 2) | uint64_t(to);
+  return PGF_OK;
+}
+
+pgf_status pgf_bloom_publish_ready(pgf_ctx* ctx, uint64_t bloom) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  // all inserts were queued on the compute stream; Ready is observable once they are done
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  return bloom_transition(ctx, b, PGF_RF_BUILDING, PGF_RF_READY);
+}
+pgf_status pgf_bloom_disable_build(pgf_ctx* ctx, uint64_t bloom) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  return bloom_transition(ctx, b, PGF_RF_BUILDING, PGF_RF_DISABLED);
+}
+pgf_status pgf_bloom_retire_ready(pgf_ctx* ctx, uint64_t bloom) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  return bloom_transition(ctx, b, PGF_RF_READY, PGF_RF_DISABLED);
+}
+
+pgf_status pgf_bloom_insert_keys(pgf_ctx* ctx, uint64_t bloom, const void* keys, int32_t key_width,
+                                 const uint8_t* validity, uint64_t n, uint64_t* rows_inserted) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if ((!keys && n) || (key_width != 2 && key_width != 4 && key_width != 8)) return PGF_ERR_INVALID_ARGUMENT;
+  if (int(b->lifecycle & 3) != PGF_RF_BUILDING)  // pool.rs:480-494 re-checks Building per key
+    return ctx->fail(PGF_ERR_LIFECYCLE_INVALID_TRANSITION, "insert into a filter that is not Building");
+  return bloom_insert_host_keys(ctx, *b, keys, key_width, validity, n, rows_inserted);
+}
+
+pgf_status pgf_bloom_insert_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t scan_id, uint32_t col, uint64_t* rows_inserted) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (int(b->lifecycle & 3) != PGF_RF_BUILDING)
+    return ctx->fail(PGF_ERR_LIFECYCLE_INVALID_TRANSITION, "insert into a filter that is not Building");
+  Scan* s = find_scan(ctx, scan_id);
+  if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  if (!s->finished) return ctx->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)scan_id);
+  return bloom_insert_scan(ctx, *b, *s, col, rows_inserted);
+}
+
+pgf_status pgf_bloom_read_words(pgf_ctx* ctx, uint64_t bloom, uint64_t* words_out, uint64_t nwords) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (!words_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (nwords < b->params.word_count)  // BloomAttachError::InsufficientWords, bloom.rs:168-173
+    return ctx->fail(PGF_ERR_BLOOM_INSUFFICIENT_WORDS, "bloom filter storage has %llu words, but %llu are required",
+                     (unsigned long long)nwords, (unsigned long long)b->params.word_count);
+  CU(ctx, cudaSetDevice(ctx->device));
+  CU(ctx, cudaMemcpyAsync(words_out, b->d_words, b->params.word_count * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  return PGF_OK;
+}
+
+pgf_status pgf_bloom_or_words(pgf_ctx* ctx, uint64_t bloom, const uint64_t* words, uint64_t nwords) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (!words) return PGF_ERR_INVALID_ARGUMENT;
+  if (nwords < b->params.word_count)
+    return ctx->fail(PGF_ERR_BLOOM_INSUFFICIENT_WORDS, "bloom filter storage has %llu words, but %llu are required",
+                     (unsigned long long)nwords, (unsigned long long)b->params.word_count);
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint64_t* tmp = nullptr;
+  CU(ctx, cudaMalloc(&tmp, b->params.word_count * 8));
+  cudaError_t e = cudaMemcpyAsync(tmp, words, b->params.word_count * 8, cudaMemcpyHostToDevice, ctx->compute_stream);
+  pgf_status st = e == cudaSuccess ? bloom_or_device(ctx, *b, tmp, b->params.word_count, 1)
+                                   : ctx->cuda_fail(e, "cudaMemcpyAsync", __FILE__, __LINE__);
+  cudaStreamSynchronize(ctx->compute_stream);
+  cudaFree(tmp);
+  return st;
+}
+
+void* pgf_bloom_device_words(pgf_ctx* ctx, uint64_t bloom) {
+  if (!ctx) return nullptr;
+  BloomSlot* b = find_bloom(ctx, bloom);
+  return b ? b->d_words : nullptr;
+}
+
+pgf_status pgf_bloom_or_device_words(pgf_ctx* ctx, uint64_t bloom, const void* dev_words, uint64_t nwords,
+                                     uint32_t narrays) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (!dev_words || nwords != b->params.word_count) return PGF_ERR_INVALID_ARGUMENT;
+  return bloom_or_device(ctx, *b, dev_words, nwords, narrays);
+}
+
+pgf_status pgf_bloom_probe_keys(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_generation, const void* keys,
+                                int32_t key_width, const uint8_t* validity, uint64_t n, uint8_t* decisions_out,
+                                pgf_probe_stats* stats) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if ((!keys && n) || (!decisions_out && n) || (key_width != 2 && key_width != 4 && key_width != 8)) return PGF_ERR_INVALID_ARGUMENT;
+  // decision_for_hash: only a Ready filter of the expected generation may reject (shared.rs:350-361)
+  const bool ready = (b->lifecycle >> 2) == expected_generation && int(b->lifecycle & 3) == PGF_RF_READY;
+  return bloom_probe_host_keys(ctx, *b, ready, keys, key_width, validity, n, decisions_out, stats);
+}
+
+pgf_status pgf_bloom_probe_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_generation, uint64_t scan_id,
+                                uint32_t col, uint8_t* decisions_out, pgf_probe_stats* stats) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  Scan* s = find_scan(ctx, scan_id);
+  if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
+  if (!s->finished) return ctx->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)scan_id);
+  const bool ready = (b->lifecycle >> 2) == expected_generation && int(b->lifecycle & 3) == PGF_RF_READY;
+  return bloom_probe_scan(ctx, *b, ready, *s, col, decisions_out, stats);
+}
+
+/* ---- pipelines ---- */
+pgf_status pgf_pipeline_check(pgf_ctx* ctx, const pgf_pipeline* plan) {
+  if (!ctx || !plan) return PGF_ERR_INVALID_ARGUMENT;
+  return pipeline_run(ctx, plan, true, nullptr, 0, nullptr, false, nullptr);
+}
+pgf_status pgf_pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, pgf_result** result_out) {
+  if (!ctx || !plan || !result_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return pipeline_run(ctx, plan, false, nullptr, 0, nullptr, false, result_out);
+}
+pgf_status pgf_pipeline_run_partial(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out,
+                                    uint64_t state_capacity_bytes, uint64_t* state_bytes_out, pgf_result** stats_out) {
+  if (!ctx || !plan || !dev_state_out || !state_bytes_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return pipeline_run(ctx, plan, false, dev_state_out, state_capacity_bytes, state_bytes_out, true, stats_out);
+}
+pgf_status pgf_pipeline_merge_partials(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states,
+                                       uint64_t state_stride_bytes, uint32_t nstates, pgf_result** result_out) {
+  if (!ctx || !plan || !dev_states || !result_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return pipeline_merge(ctx, plan, dev_states, state_stride_bytes, nstates, result_out);
+}
+pgf_status pgf_partial_state_bytes(const pgf_pipeline* plan, uint64_t max_groups, uint64_t* bytes_out) {
+  if (!plan || !bytes_out) return PGF_ERR_INVALID_ARGUMENT;
+  // [count][max_groups x (key words, null mask, accumulators (<= 2 words each), counts)]
+  const uint64_t entry = kKeyWords + 1 + uint64_t(plan->nexprs) * 2 + plan->nexprs + 1;
+  *bytes_out = (1 + (max_groups ? max_groups : 1) * entry) * 8;
+  return PGF_OK;
+}
+void pgf_result_free(pgf_result* r) {
+  if (!r) return;
+  delete[] r->keys;
+  delete[] r->aggs;
+  delete r;
+}
+pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  auto it = ctx->joins.find(join_table);
+  if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)join_table);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->compute_stream);
+  cudaFree(it->second.d_slots);
+  ctx->joins.erase(it);
+  return PGF_OK;
+}
+
+pgf_status pgf_gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec) {
+  if (!ctx || !spec) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return gen_scan(ctx, scan_id, spec);
+}
+pgf_status pgf_gen_schema(int32_t table, pgf_column_spec* schema_out, uint32_t* ncols_out) {
+  if (!schema_out || !ncols_out) return PGF_ERR_INVALID_ARGUMENT;
+  return gen_schema(table, schema_out, ncols_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// Library context: device resources, scans (HBM-resident page sets), Bloom filter slots
+// and join tables.  All CUDA calls go through CU() so errors become sticky status codes
+// instead of aborting the host process.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pgf_b200.h"
+#include "device_types.cuh"
+
+struct pgf_ctx;
+
+namespace pgf {
+
+struct Scan {
+  uint64_t id = 0;
+  std::vector<pgf_column_spec> schema;
+  uint8_t* d_pages = nullptr;
+  uint64_t cap_pages = 0;
+  uint64_t npages = 0;
+  uint64_t rows = 0;
+  bool finished = false;
+  bool descs_dirty = true;
+  std::vector<PageDesc> h_descs;
+  std::vector<LayoutClass> h_classes;
+  PageDesc* d_descs = nullptr;
+  uint64_t d_descs_cap = 0;
+  LayoutClass* d_classes = nullptr;
+  uint64_t d_classes_cap = 0;
+  uint32_t max_page_rows = 0;   // largest row_count of any page
+  uint64_t pending_async = 0;   // async copies in flight from caller-owned pinned pages
+  std::mutex mu;                // serialises producers of this scan
+};
+
+struct BloomSlot {
+  pgf_bloom_params params{};
+  uint64_t* d_words = nullptr;
+  uint64_t lifecycle = 0;  // (generation << 2) | state, runtime_filter/src/shared.rs:7-9
+  DevBloom dev{};
+};
+
+struct JoinTable {
+  uint4* d_slots = nullptr;
+  uint32_t capacity = 0;
+  uint32_t slot_u4 = 1;
+  uint64_t rows = 0;
+  int32_t key_type = 0;
+  uint32_t npayload = 0;
+  int32_t payload_type[4] = {0, 0, 0, 0};
+  uint16_t payload_word[4] = {0, 0, 0, 0};
+};
+
+}  // namespace pgf
+
+struct pgf_ctx {
+  int device = 0;
+  uint32_t page_size = 65536;
+  uint32_t staging_pages = 512;
+  int sm_count = 148;
+  cudaStream_t copy_stream = nullptr;
+  cudaStream_t compute_stream = nullptr;
+  cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_copy = nullptr;
+  // pinned staging (two chunks of staging_pages pages) for pageable caller memory
+  uint8_t* staging[2] = {nullptr, nullptr};
+  cudaEvent_t staging_ev[2] = {nullptr, nullptr};
+  int staging_next = 0;
+  pgf::Counters* d_counters = nullptr;
+  pgf::Counters* h_counters = nullptr;  // pinned
+  uint32_t* d_flags = nullptr;          // [0] group-table overflow, [1] table used, [2..] scratch
+  uint32_t* h_flags = nullptr;          // pinned
+  std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;
+  std::map<uint64_t, pgf::BloomSlot> blooms;
+  std::map<uint64_t, pgf::JoinTable> joins;
+  uint64_t next_handle = 1;
+  std::vector<void*> registered;
+  std::mutex mu;
+  std::string last_error;
+  pgf_status sticky = PGF_OK;
+
+  pgf_status fail(pgf_status st, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error = buf;
+    return st;
+  }
+  pgf_status cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    sticky = PGF_ERR_CUDA;
+    return fail(PGF_ERR_CUDA, "CUDA error %d (%s) in %s at %s:%d", int(e), cudaGetErrorString(e), what, file, line);
+  }
+};
+
+#define CU(ctx, call)                                                          \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define PGF_TRY(expr)                   \
+  do {                                  \
+    pgf_status st__ = (expr);           \
+    if (st__ != PGF_OK) return st__;    \
+  } while (0)
+
+namespace pgf {
+// internal entry points implemented in the .cu files
+pgf_status scan_sync_descs(pgf_ctx* ctx, Scan& s);
+pgf_status scan_device_validate(pgf_ctx* ctx, Scan& s);
+pgf_status bloom_make_dev(const pgf_bloom_params& p, uint64_t* d_words, DevBloom* out);
+pgf_status bloom_insert_host_keys(pgf_ctx* ctx, BloomSlot& b, const void* keys, int32_t key_width,
+                                  const uint8_t* validity, uint64_t n, uint64_t* inserted);
+pgf_status bloom_insert_scan(pgf_ctx* ctx, BloomSlot& b, Scan& s, uint32_t col, uint64_t* inserted);
+pgf_status bloom_probe_host_keys(pgf_ctx* ctx, BloomSlot& b, bool ready, const void* keys,
+                                 int32_t key_width, const uint8_t* validity, uint64_t n,
+                                 uint8_t* decisions, pgf_probe_stats* stats);
+pgf_status bloom_probe_scan(pgf_ctx* ctx, BloomSlot& b, bool ready, Scan& s, uint32_t col,
+                            uint8_t* decisions, pgf_probe_stats* stats);
+pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, uint64_t nwords,
+                           uint32_t narrays);
+pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
+                        uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out);
+pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states,
+                          uint64_t stride, uint32_t nstates, pgf_result** out);
+pgf_status gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec);
+pgf_status gen_schema(int32_t table, pgf_column_spec* schema, uint32_t* ncols);
+}  // namespace pgf

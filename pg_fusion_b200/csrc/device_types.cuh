@@ -1,0 +1,157 @@
+// POD types shared between the host planner and the sm_100a kernels.
+#pragma once
+#include <cstdint>
+
+namespace pgf {
+
+constexpr uint32_t kMaxStageCols = 16;  // == PGF_MAX_COLS
+constexpr uint32_t kKeyWords = 4;       // group key: up to 4 x u64 (32 bytes)
+constexpr uint32_t kMaxExprs = 8;
+constexpr uint32_t kMaxTerms = 8;
+constexpr uint32_t kMaxJoins = 2;
+constexpr uint32_t kMaxBlooms = 2;
+constexpr uint32_t kRegGroups = 4;      // groups pre-aggregated in registers per CTA
+
+// ---- HBM data layout of a scan ------------------------------------------------------
+// pages: npages x page_size bytes, each the verbatim shared-memory page (20-byte transfer
+// header + arrow_layout block), so every column buffer is 16-byte aligned physically.
+struct PageDesc {        // 16 bytes per page, built and validated at ingest
+  uint32_t row_count;
+  uint16_t layout_class; // index into LayoutClass[] (pages with equal max_rows share one)
+  uint16_t null_mask;    // bit c set: column c has null_count > 0 in this page
+  uint64_t row_base;     // global row number of the page's first row
+};
+struct LayoutClass {     // byte offsets from the start of the PAGE (block offset + 20)
+  uint32_t max_rows;
+  uint32_t pool_base;
+  uint32_t values_off[kMaxStageCols];
+  uint32_t validity_off[kMaxStageCols];
+};
+
+// ---- Bloom filter parameters on the device -----------------------------------------
+struct DevBloom {
+  uint64_t* words;
+  uint64_t bit_count;
+  uint64_t seed;
+  uint64_t m_lo, m_hi;   // ceil(2^128 / bit_count) for the exact 64-bit fastmod
+  uint32_t hash_count;
+  uint32_t pow2;         // bit_count is a power of two: use mask
+};
+
+// ---- pipeline plan -----------------------------------------------------------------
+enum : uint8_t { SRC_PAGE = 0 };  // 1.. = payload of join (src - 1)
+enum : uint8_t { CLS_F64 = 0, CLS_I64 = 1, CLS_I128 = 2 };
+
+struct DevStageCol {
+  uint16_t page_col;     // column index in the page
+  uint16_t width;        // bytes per row
+  uint32_t smem_off;     // offset of the column tile inside a stage
+  uint32_t valid_off;    // offset of the validity-bitmap tile inside a stage (nullable only)
+  uint16_t nullable;
+  uint16_t type;
+};
+
+struct DevRef {          // where a value comes from
+  uint8_t src;           // SRC_PAGE or join index + 1
+  uint8_t type;          // PGF_T_*
+  uint16_t idx;          // SRC_PAGE: stage column slot; else: first u32 word in the payload
+};
+
+struct DevTerm {
+  DevRef ref;
+  uint32_t cmp;          // PGF_CMP_*
+  int64_t k0;            // literal as an order-preserving (signed hi, unsigned lo) key
+  uint64_t k1;
+};
+
+struct DevFactor {
+  DevRef ref;
+  uint32_t kind;         // PGF_FACTOR_*
+  double cf;             // constant (CLS_F64)
+  int64_t ci_lo, ci_hi;  // constant (CLS_I64 / CLS_I128)
+};
+struct DevExpr {
+  uint32_t nfactors;
+  uint32_t pad;
+  DevFactor f[3];
+};
+
+struct DevKeyPart {
+  DevRef ref;
+  uint16_t word;         // first key word
+  uint16_t nwords;       // 1 or 2
+};
+
+struct DevJoin {
+  const uint4* slots;    // slot_u4 x uint4 per slot: {key lo, key hi, occupied, pay0} [, pay1..4]
+  uint32_t mask;         // capacity - 1
+  uint32_t slot_u4;      // 1 (16-byte slot) or 2 (32-byte slot)
+  DevRef key;
+};
+
+struct DevBloomProbe {
+  DevBloom bloom;
+  DevRef key;
+};
+
+// Global group table (open addressing, linear probing).  state: 0 empty, 1 locked, 2 ready;
+// bits 8.. hold the key null mask.
+struct GroupTable {
+  uint32_t* state;
+  uint64_t* keys;        // capacity x kKeyWords
+  uint64_t* acc;         // capacity x nexprs x acc_words (f64 bits / i64 / i128 lo,hi)
+  uint64_t* cnt;         // capacity x (nexprs + 1): per-expr non-null counts, then row count
+  uint32_t mask;
+  uint32_t acc_words;    // 1 or 2
+  uint32_t* overflow;    // set to 1 when the table is full
+  uint32_t* used;        // number of occupied slots
+};
+
+struct JoinBuild {
+  uint4* slots;
+  uint32_t mask;
+  uint32_t slot_u4;
+  DevRef key;
+  uint32_t npayload;
+  DevRef payload[4];
+  uint16_t payload_word[4];   // first u32 payload word of each payload column
+  uint16_t payload_nwords[4];
+};
+
+struct Counters {        // RuntimeFilter*/Worker* style metrics, filled by the kernel
+  unsigned long long rows_in, rows_bloom, rows_filtered, rows_out, bloom_rows, bad_rows;
+};
+
+enum : uint32_t { SINK_AGG = 1, SINK_JOIN_BUILD = 2, SINK_COUNT = 3 };
+
+struct DevPlan {
+  const uint8_t* pages;
+  const PageDesc* descs;
+  const LayoutClass* classes;
+  uint64_t page_stride;
+  uint32_t npages, tiles_per_page, tile_rows, nitems;
+  uint32_t stage_bytes, nstage_cols;
+  uint32_t used_null_mask;  // page columns whose validity matters to this plan
+  uint32_t view_mask;       // page columns read as views (must be inline)
+  DevStageCol scol[kMaxStageCols];
+
+  uint32_t nbloom, nterms, njoins, sink;
+  DevBloomProbe bloom[kMaxBlooms];
+  DevTerm terms[kMaxTerms];
+  DevJoin joins[kMaxJoins];
+
+  // SINK_AGG
+  uint32_t nkeys, nkeywords, nexprs, acc_cls;
+  DevKeyPart keys[4];
+  DevExpr exprs[kMaxExprs];
+  GroupTable table;
+  // SINK_JOIN_BUILD
+  JoinBuild build;
+  DevBloom build_bloom;
+  uint32_t has_build_bloom;
+  uint32_t pad;
+
+  Counters* counters;
+};
+
+}  // namespace pgf

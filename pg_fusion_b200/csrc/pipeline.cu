@@ -1,0 +1,743 @@
+// Host side of the fused pipelines: lowering of the C-ABI plan (pgf_pipeline) into the
+// device plan, eligibility rules, launch, and extraction of AggregateExec results.
+#include <algorithm>
+#include <cstring>
+
+#include "context.hpp"
+#include "layout.hpp"
+#include "pipeline_kernel.cuh"
+
+namespace pgf {
+
+// implemented in pipeline_inst_*.cu (explicit instantiations split for parallel builds)
+cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t nj, const DevPlan& plan,
+                            uint32_t grid, size_t smem, cudaStream_t stream);
+
+namespace {
+
+// ---- device helpers for the group table ------------------------------------------------
+__global__ void table_init_nogroup_kernel(GroupTable t) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    t.state[0] = 2u;  // the single output row of an aggregate without GROUP BY always exists
+    *t.used = 1u;
+  }
+}
+
+// Partial-state entry: [kKeyWords key][1 null mask][nexprs * acc_words acc][nexprs + 1 counts]
+__host__ __device__ inline uint32_t entry_words(uint32_t nexprs, uint32_t acc_words) {
+  return kKeyWords + 1 + nexprs * acc_words + nexprs + 1;
+}
+
+__global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, uint64_t* out, uint64_t max_entries,
+                                     unsigned long long* count) {
+  const uint32_t ew = entry_words(nexprs, t.acc_words);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i <= t.mask; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint32_t s = t.state[i];
+    if ((s & 3u) != 2u) continue;
+    const unsigned long long pos = atomicAdd(count, 1ull);
+    if (pos >= max_entries) continue;
+    uint64_t* e = out + 1 + pos * ew;
+    for (uint32_t w = 0; w < kKeyWords; ++w) e[w] = t.keys[i * kKeyWords + w];
+    e[kKeyWords] = s >> 8;
+    for (uint32_t w = 0; w < nexprs * t.acc_words; ++w) e[kKeyWords + 1 + w] = t.acc[i * nexprs * t.acc_words + w];
+    for (uint32_t w = 0; w <= nexprs; ++w) e[kKeyWords + 1 + nexprs * t.acc_words + w] = t.cnt[i * (nexprs + 1) + w];
+  }
+}
+
+__global__ void finish_count_kernel(uint64_t* out, const unsigned long long* count) { out[0] = *count; }
+
+// Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
+// rank order, so Float64 sums are added in a fixed order on every rank.
+template <uint32_t ACC>
+__global__ void table_merge_kernel(GroupTable t, uint32_t nexprs, uint32_t nkeywords, const uint64_t* state) {
+  using Ops = AccOps<ACC>;
+  const uint64_t n = state[0];
+  const uint32_t ew = entry_words(nexprs, t.acc_words);
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint64_t* e = state + 1 + i * ew;
+    const int64_t slot = nkeywords ? group_slot(t, e, nkeywords, uint32_t(e[kKeyWords])) : 0;
+    if (slot < 0) continue;
+    for (uint32_t x = 0; x < nexprs; ++x) {
+      typename Ops::T v;
+      memcpy(&v, e + kKeyWords + 1 + x * t.acc_words, sizeof v);
+      Ops::atomic_add(t.acc + (uint64_t(slot) * nexprs + x) * t.acc_words, v);
+    }
+    for (uint32_t x = 0; x <= nexprs; ++x)
+      atomicAdd(reinterpret_cast<unsigned long long*>(t.cnt + uint64_t(slot) * (nexprs + 1) + x),
+                (unsigned long long)e[kKeyWords + 1 + nexprs * t.acc_words + x]);
+  }
+}
+
+// ---- lowering ----------------------------------------------------------------------
+struct Lowered {
+  DevPlan dev{};
+  Scan* scan = nullptr;
+  uint32_t acc_cls = CLS_F64;
+  bool grouped = false;
+  uint32_t nj = 0;
+  size_t smem = 0;
+  int32_t key_types[4] = {0, 0, 0, 0};
+  JoinTable build_table{};
+  uint64_t table_capacity = 0;
+};
+
+struct DevAlloc {  // frees on scope exit unless released
+  std::vector<void*> ptrs;
+  ~DevAlloc() { for (void* p : ptrs) cudaFree(p); }
+  template <class T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T) ? count * sizeof(T) : 1);
+    if (e == cudaSuccess) { ptrs.push_back(p); *out = static_cast<T*>(p); }
+    return e;
+  }
+  void release(void* p) { ptrs.erase(std::remove(ptrs.begin(), ptrs.end(), p), ptrs.end()); }
+};
+
+bool is_int_type(int t) { return t == PGF_T_INT16 || t == PGF_T_INT32 || t == PGF_T_INT64; }
+uint32_t type_u32_words(int t) {
+  switch (t) {
+    case PGF_T_INT16: case PGF_T_INT32: case PGF_T_FLOAT32: return 1;
+    case PGF_T_INT64: case PGF_T_FLOAT64: return 2;
+    case PGF_T_UTF8VIEW: case PGF_T_BINARYVIEW: case PGF_T_DECIMAL128: case PGF_T_UUID: return 4;
+    default: return 0;
+  }
+}
+
+class Lowering {
+ public:
+  Lowering(pgf_ctx* ctx, const pgf_pipeline* plan) : ctx_(ctx), plan_(plan) {}
+
+  pgf_status run(Lowered* out) {
+    L_ = out;
+    auto it = ctx_->scans.find(plan_->scan_id);
+    if (it == ctx_->scans.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)plan_->scan_id);
+    Scan& s = *it->second;
+    if (!s.finished) return ctx_->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)plan_->scan_id);
+    L_->scan = &s;
+    DevPlan& D = L_->dev;
+    if (plan_->nbloom > kMaxBlooms || plan_->nterms > kMaxTerms || plan_->njoins > kMaxJoins ||
+        plan_->nkeys > 4 || plan_->nexprs > kMaxExprs || plan_->naggs > PGF_MAX_AGGS || plan_->npayload > PGF_MAX_PAYLOAD)
+      return not_eligible("plan exceeds the fixed operator limits");
+    if (plan_->njoins > 1) return not_eligible("at most one HashJoinExec probe per pipeline in this build");
+
+    // joins first: payload refs need the tables
+    for (uint32_t j = 0; j < plan_->njoins; ++j) {
+      auto jt = ctx_->joins.find(plan_->joins[j].join_table);
+      if (jt == ctx_->joins.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)plan_->joins[j].join_table);
+      jtables_[j] = &jt->second;
+    }
+    for (uint32_t j = 0; j < plan_->njoins; ++j) {
+      DevJoin& dj = D.joins[j];
+      dj.slots = jtables_[j]->d_slots;
+      dj.mask = jtables_[j]->capacity - 1;
+      dj.slot_u4 = jtables_[j]->slot_u4;
+      PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key));
+      if (!is_int_type(dj.key.type)) return not_eligible("join keys must be Int16/Int32/Int64");
+    }
+    D.njoins = plan_->njoins;
+    L_->nj = plan_->njoins;
+
+    for (uint32_t b = 0; b < plan_->nbloom; ++b) {
+      auto bt = ctx_->blooms.find(plan_->bloom[b].bloom);
+      if (bt == ctx_->blooms.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown bloom filter %llu", (unsigned long long)plan_->bloom[b].bloom);
+      // Only a Ready filter of the expected generation may reject rows; anything else is
+      // PassUnfiltered (runtime_filter/src/shared.rs:350-361), i.e. the probe is dropped.
+      const BloomSlot& bs = bt->second;
+      if ((bs.lifecycle >> 2) != plan_->bloom[b].expected_generation || int(bs.lifecycle & 3) != PGF_RF_READY) continue;
+      DevBloomProbe& bp = D.bloom[D.nbloom];
+      bp.bloom = bs.dev;
+      PGF_TRY(lower_ref(plan_->bloom[b].key, 0, &bp.key));
+      if (bp.key.src != SRC_PAGE) return not_eligible("Bloom probe keys must be scan columns");
+      if (!is_int_type(bp.key.type)) return not_eligible("runtime filter keys must be Int16/Int32/Int64");
+      D.nbloom++;
+    }
+
+    for (uint32_t t = 0; t < plan_->nterms; ++t) {
+      DevTerm& dt = D.terms[t];
+      PGF_TRY(lower_ref(plan_->terms[t].col, plan_->njoins, &dt.ref));
+      if (plan_->terms[t].col.source != 0) return not_eligible("predicates are evaluated on scan columns");
+      if (plan_->terms[t].cmp < PGF_CMP_LT || plan_->terms[t].cmp > PGF_CMP_NE) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad comparison operator");
+      dt.cmp = uint32_t(plan_->terms[t].cmp);
+      PGF_TRY(literal_key(plan_->terms[t].lit, dt.ref.type, &dt.k0, &dt.k1));
+    }
+    D.nterms = plan_->nterms;
+
+    switch (plan_->sink) {
+      case PGF_SINK_AGGREGATE: PGF_TRY(lower_aggregate()); break;
+      case PGF_SINK_JOIN_BUILD: PGF_TRY(lower_join_build()); break;
+      case PGF_SINK_COUNT: D.sink = SINK_COUNT; break;
+      default: return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "unknown sink %d", plan_->sink);
+    }
+    return layout_stage(s);
+  }
+
+ private:
+  pgf_status not_eligible(const char* why) { return ctx_->fail(PGF_ERR_NOT_ELIGIBLE, "pipeline not eligible for the GPU path: %s", why); }
+
+  // Resolve a column reference; scan columns get a stage slot.
+  pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out) {
+    Scan& s = *L_->scan;
+    DevPlan& D = L_->dev;
+    if (r.source == 0) {
+      if (r.col < 0 || size_t(r.col) >= s.schema.size()) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "column %d out of range", r.col);
+      const int type = s.schema[r.col].type_tag;
+      if (row_width(type) == 0 || type == PGF_T_UUID) return not_eligible("Boolean / Uuid columns are not evaluated on the GPU path");
+      uint32_t slot = 0;
+      for (; slot < D.nstage_cols; ++slot)
+        if (D.scol[slot].page_col == r.col) break;
+      if (slot == D.nstage_cols) {
+        DevStageCol& sc = D.scol[D.nstage_cols++];
+        sc.page_col = uint16_t(r.col);
+        sc.width = uint16_t(row_width(type));
+        sc.nullable = s.schema[r.col].nullable;
+        sc.type = uint16_t(type);
+        if (sc.nullable) D.used_null_mask |= 1u << r.col;
+        if (is_view(type)) D.view_mask |= 1u << r.col;
+      }
+      out->src = SRC_PAGE;
+      out->type = uint8_t(type);
+      out->idx = uint16_t(slot);
+      return PGF_OK;
+    }
+    const uint32_t j = uint32_t(r.source - 1);
+    if (r.source < 0 || j >= joins_visible) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "column source %d is not visible here", r.source);
+    const JoinTable& jt = *jtables_[j];
+    if (r.col < 0 || uint32_t(r.col) >= jt.npayload) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "join payload %d out of range", r.col);
+    out->src = uint8_t(j + 1);
+    out->type = uint8_t(jt.payload_type[r.col]);
+    out->idx = uint16_t(jt.payload_word[r.col] | (uint32_t(r.col) << 8));
+    return PGF_OK;
+  }
+
+  // Literal -> order-preserving key, matching raw_to_key on the device.
+  pgf_status literal_key(const pgf_literal& lit, int col_type, int64_t* k0, uint64_t* k1) {
+    *k1 = 0;
+    switch (col_type) {
+      case PGF_T_INT16: case PGF_T_INT32: case PGF_T_INT64:
+        if (lit.type_tag != PGF_T_INT64 && lit.type_tag != PGF_T_INT32 && lit.type_tag != PGF_T_INT16)
+          return not_eligible("integer column compared with a non-integer literal");
+        *k0 = lit.i64;
+        return PGF_OK;
+      case PGF_T_FLOAT64: {
+        double d;
+        if (lit.type_tag == PGF_T_FLOAT64) d = lit.f64;
+        else if (lit.type_tag == PGF_T_INT64) d = double(lit.i64);
+        else return not_eligible("Float64 column compared with an unsupported literal");
+        int64_t b;
+        std::memcpy(&b, &d, 8);
+        b ^= int64_t(uint64_t(b >> 63) >> 1);  // IEEE totalOrder key
+        *k0 = b;
+        return PGF_OK;
+      }
+      case PGF_T_DECIMAL128:
+        if (lit.type_tag != PGF_T_DECIMAL128) return not_eligible("Decimal128 column compared with a non-decimal literal");
+        *k0 = lit.hi;
+        *k1 = uint64_t(lit.i64);
+        return PGF_OK;
+      case PGF_T_UTF8VIEW: case PGF_T_BINARYVIEW: {
+        if (lit.type_tag != PGF_T_UTF8VIEW && lit.type_tag != PGF_T_BINARYVIEW) return not_eligible("string column compared with a non-string literal");
+        if (lit.slen < 0 || lit.slen > 12) return not_eligible("string literals longer than 12 bytes need the out-of-line view path");
+        uint8_t pad[12] = {0};
+        std::memcpy(pad, lit.str, size_t(lit.slen));
+        uint64_t hi = 0;
+        for (int i = 0; i < 8; ++i) hi = (hi << 8) | pad[i];
+        uint32_t lo = 0;
+        for (int i = 8; i < 12; ++i) lo = (lo << 8) | pad[i];
+        *k0 = int64_t(hi ^ 0x8000000000000000ull);
+        *k1 = (uint64_t(lo) << 32) | uint32_t(lit.slen);
+        return PGF_OK;
+      }
+      default:
+        return not_eligible("predicate on a column type the GPU path does not compare");
+    }
+  }
+
+  pgf_status lower_aggregate() {
+    DevPlan& D = L_->dev;
+    D.sink = SINK_AGG;
+    if (plan_->naggs == 0 && plan_->nkeys == 0) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "aggregate without keys or aggregates");
+    // accumulator class: all expressions of one pipeline share it
+    int cls = -1;
+    for (uint32_t e = 0; e < plan_->nexprs; ++e) {
+      const pgf_value_expr& x = plan_->exprs[e];
+      if (x.nfactors < 1 || x.nfactors > 3) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "expression %u has %u factors", e, x.nfactors);
+      DevExpr& dx = D.exprs[e];
+      dx.nfactors = x.nfactors;
+      int ecls = -1;
+      bool all_i64 = true;
+      for (uint32_t f = 0; f < x.nfactors; ++f) {
+        DevFactor& df = dx.f[f];
+        PGF_TRY(lower_ref(x.factors[f].col, plan_->njoins, &df.ref));
+        df.kind = uint32_t(x.factors[f].kind);
+        if (df.kind > PGF_FACTOR_CONST_PLUS_COL) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad factor kind");
+        int fcls;
+        if (df.ref.type == PGF_T_FLOAT64) fcls = CLS_F64;
+        else if (df.ref.type == PGF_T_DECIMAL128) fcls = CLS_I128;
+        else if (is_int_type(df.ref.type)) fcls = CLS_I64;
+        else return not_eligible("aggregate argument of a type the GPU path does not compute");
+        all_i64 &= df.ref.type == PGF_T_INT64;
+        if (ecls >= 0 && ecls != fcls) return not_eligible("mixed-type arithmetic in one expression");
+        ecls = fcls;
+        const pgf_literal& c = x.factors[f].c;
+        if (df.kind != PGF_FACTOR_COL) {
+          if (fcls == CLS_F64) df.cf = c.type_tag == PGF_T_FLOAT64 ? c.f64 : double(c.i64);
+          else { df.ci_lo = c.i64; df.ci_hi = c.type_tag == PGF_T_DECIMAL128 ? c.hi : (c.i64 < 0 ? -1 : 0); }
+        }
+      }
+      // narrow integers wrap at their own width in arrow; only plain columns or all-Int64
+      // arithmetic is bit-exact with 64-bit registers
+      if (ecls == CLS_I64 && !(all_i64 || (x.nfactors == 1 && dx.f[0].kind == PGF_FACTOR_COL)))
+        return not_eligible("arithmetic on Int16/Int32 columns");
+      expr_cls_[e] = ecls;
+    }
+    // AVG over integers is computed on the Float64 cast (DataFusion coerces avg(int) to Float64)
+    for (uint32_t a = 0; a < plan_->naggs; ++a) {
+      const pgf_agg& ag = plan_->aggs[a];
+      if (ag.func < PGF_AGG_SUM || ag.func > PGF_AGG_COUNT) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad aggregate function");
+      if (ag.func == PGF_AGG_COUNT_STAR) continue;
+      if (ag.expr < 0 || uint32_t(ag.expr) >= plan_->nexprs) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "aggregate %u references expression %d", a, ag.expr);
+      if (ag.func == PGF_AGG_AVG && expr_cls_[ag.expr] == CLS_I64) expr_as_f64_[ag.expr] = true;
+    }
+    for (uint32_t e = 0; e < plan_->nexprs; ++e) {
+      int ecls = expr_cls_[e];
+      if (expr_as_f64_[e]) {
+        if (plan_->exprs[e].nfactors != 1 || plan_->exprs[e].factors[0].kind != PGF_FACTOR_COL) return not_eligible("AVG over integer arithmetic");
+        for (uint32_t a = 0; a < plan_->naggs; ++a)
+          if (plan_->aggs[a].func != PGF_AGG_COUNT_STAR && plan_->aggs[a].expr == int32_t(e) && plan_->aggs[a].func == PGF_AGG_SUM)
+            return not_eligible("SUM and AVG sharing one integer expression");
+        ecls = CLS_F64;
+      }
+      if (cls >= 0 && cls != ecls) return not_eligible("aggregates of different accumulator classes in one pipeline");
+      cls = ecls;
+    }
+    if (cls < 0) cls = CLS_I64;  // COUNT(*) only
+    const uint32_t max_exprs = cls == CLS_I128 ? kAccI128MaxExprs : kAccF64MaxExprs;
+    if (plan_->nexprs > max_exprs) return not_eligible("too many distinct aggregate arguments");
+    D.nexprs = plan_->nexprs;
+    D.acc_cls = uint32_t(cls);
+    L_->acc_cls = uint32_t(cls);
+
+    uint32_t words = 0;
+    for (uint32_t k = 0; k < plan_->nkeys; ++k) {
+      DevKeyPart& kp = D.keys[k];
+      PGF_TRY(lower_ref(plan_->keys[k], plan_->njoins, &kp.ref));
+      const int t = kp.ref.type;
+      if (is_int_type(t)) kp.nwords = 1;
+      else if (is_view(t) || t == PGF_T_DECIMAL128) kp.nwords = 2;
+      else return not_eligible("group key of a type the GPU path does not hash");
+      kp.word = uint16_t(words);
+      words += kp.nwords;
+      L_->key_types[k] = t;
+    }
+    if (words > kKeyWords) return not_eligible("group key wider than 32 bytes");
+    D.nkeys = plan_->nkeys;
+    D.nkeywords = words;
+    L_->grouped = plan_->nkeys > 0;
+    if (L_->grouped) {
+      uint64_t want = plan_->expected_groups ? plan_->expected_groups * 2 : (1ull << 16);
+      uint64_t cap = 1024;
+      while (cap < want) cap <<= 1;
+      if (cap > (1ull << 30)) cap = 1ull << 30;
+      L_->table_capacity = cap;
+    } else {
+      L_->table_capacity = 1;
+    }
+    return PGF_OK;
+  }
+
+  pgf_status lower_join_build() {
+    DevPlan& D = L_->dev;
+    D.sink = SINK_JOIN_BUILD;
+    JoinBuild& jb = D.build;
+    PGF_TRY(lower_ref(plan_->build_key, plan_->njoins, &jb.key));
+    if (!is_int_type(jb.key.type)) return not_eligible("join keys must be Int16/Int32/Int64");
+    JoinTable& jt = L_->build_table;
+    jt.key_type = jb.key.type;
+    jt.npayload = plan_->npayload;
+    uint32_t words = 0;
+    for (uint32_t p = 0; p < plan_->npayload; ++p) {
+      PGF_TRY(lower_ref(plan_->payload[p], plan_->njoins, &jb.payload[p]));
+      const uint32_t w = type_u32_words(jb.payload[p].type);
+      if (!w) return not_eligible("join payload column type");
+      jb.payload_word[p] = uint16_t(words);
+      jb.payload_nwords[p] = uint16_t(w);
+      jt.payload_type[p] = jb.payload[p].type;
+      jt.payload_word[p] = uint16_t(words);
+      words += w;
+    }
+    if (words > 5) return not_eligible("join payload wider than 20 bytes");
+    jb.npayload = plan_->npayload;
+    jb.slot_u4 = words > 1 ? 2 : 1;
+    jt.slot_u4 = jb.slot_u4;
+    uint64_t cap = 1024;
+    while (cap < L_->scan->rows * 2) cap <<= 1;
+    if (cap > (1ull << 31)) return not_eligible("join build side too large for one table");
+    jt.capacity = uint32_t(cap);
+    jb.mask = jt.capacity - 1;
+    if (plan_->build_bloom) {
+      auto bt = ctx_->blooms.find(plan_->build_bloom);
+      if (bt == ctx_->blooms.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown bloom filter %llu", (unsigned long long)plan_->build_bloom);
+      if (int(bt->second.lifecycle & 3) != PGF_RF_BUILDING)
+        return ctx_->fail(PGF_ERR_LIFECYCLE_INVALID_TRANSITION, "build_bloom must be in Building state");
+      D.build_bloom = bt->second.dev;
+      D.has_build_bloom = 1;
+    }
+    return PGF_OK;
+  }
+
+  // Shared-memory stage layout: row tiles of at most ~40 KiB, tile_rows a multiple of 128 so
+  // every column slice (and validity slice) starts 16-byte aligned.
+  pgf_status layout_stage(Scan& s) {
+    DevPlan& D = L_->dev;
+    uint32_t row_bytes8 = 0;  // bytes per row x 8 (validity counts 1 bit)
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) row_bytes8 += D.scol[c].width * 8u + (D.scol[c].nullable ? 1u : 0u);
+    const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
+    const uint64_t page_bytes = (uint64_t(row_bytes8) * max_rows + 7) / 8;
+    uint32_t ntiles = uint32_t((page_bytes + 40 * 1024 - 1) / (40 * 1024));
+    if (ntiles == 0) ntiles = 1;
+    uint32_t tile_rows = 0, stage_bytes = 0;
+    for (;; ++ntiles) {
+      tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
+      stage_bytes = 0;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+        D.scol[c].smem_off = stage_bytes;
+        stage_bytes += tile_rows * D.scol[c].width;
+      }
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+        D.scol[c].valid_off = stage_bytes;
+        if (D.scol[c].nullable) stage_bytes += tile_rows / 8;
+      }
+      stage_bytes = (stage_bytes + 127u) & ~127u;
+      if (stage_bytes <= 48 * 1024 || tile_rows == 128) break;
+    }
+    if (stage_bytes > 48 * 1024) return not_eligible("row too wide for the shared-memory stages");
+    D.tile_rows = tile_rows;
+    D.tiles_per_page = (max_rows + tile_rows - 1) / tile_rows;
+    D.stage_bytes = stage_bytes ? stage_bytes : 128;
+    D.npages = uint32_t(s.npages);
+    if (s.npages * uint64_t(D.tiles_per_page) > 0xFFFFFFF0ull) return not_eligible("scan too large for 32-bit tile ids");
+    D.nitems = uint32_t(s.npages) * D.tiles_per_page;
+    D.pages = s.d_pages;
+    D.descs = s.d_descs;
+    D.classes = s.d_classes;
+    D.page_stride = ctx_->page_size;
+    L_->smem = ((sizeof(BlockShared) + 127) & ~size_t(127)) + size_t(kStages) * D.stage_bytes;
+    return PGF_OK;
+  }
+
+  pgf_ctx* ctx_;
+  const pgf_pipeline* plan_;
+  Lowered* L_ = nullptr;
+  JoinTable* jtables_[kMaxJoins] = {nullptr, nullptr};
+  int expr_cls_[kMaxExprs] = {0};
+  bool expr_as_f64_[kMaxExprs] = {false};
+
+ public:
+  bool expr_as_f64(uint32_t e) const { return expr_as_f64_[e]; }
+};
+
+// ---- result extraction ----------------------------------------------------------------
+pgf_value key_value(int type, const uint64_t* words, bool is_null) {
+  pgf_value v{};
+  if (is_null) { v.kind = PGF_V_NULL; return v; }
+  if (is_int_type(type)) {
+    v.kind = PGF_V_I64;
+    v.lo = int64_t(words[0]);
+    v.hi = v.lo < 0 ? -1 : 0;
+  } else if (type == PGF_T_DECIMAL128) {
+    v.kind = PGF_V_I128;
+    v.lo = int64_t(words[0]);
+    v.hi = int64_t(words[1]);
+  } else {  // inline view: [len u32][12 bytes]
+    v.kind = PGF_V_STR;
+    uint8_t raw[16];
+    std::memcpy(raw, words, 16);
+    uint32_t len;
+    std::memcpy(&len, raw, 4);
+    v.slen = int32_t(len > 12 ? 12 : len);
+    std::memcpy(v.str, raw + 4, size_t(v.slen));
+  }
+  return v;
+}
+
+pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L, const std::vector<uint64_t>& state,
+                        pgf_result* res) {
+  const uint32_t nexprs = plan->nexprs;
+  const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  const uint32_t ew = entry_words(nexprs, aw);
+  const uint64_t n = state.empty() ? 0 : state[0];
+  res->ngroups = n;
+  res->nkeys = plan->nkeys;
+  res->naggs = plan->naggs;
+  res->keys = new (std::nothrow) pgf_value[n * (plan->nkeys ? plan->nkeys : 1) + 1]();
+  res->aggs = new (std::nothrow) pgf_value[n * (plan->naggs ? plan->naggs : 1) + 1]();
+  if (!res->keys || !res->aggs) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
+  for (uint64_t g = 0; g < n; ++g) {
+    const uint64_t* e = state.data() + 1 + g * ew;
+    const uint32_t knull = uint32_t(e[kKeyWords]);
+    for (uint32_t k = 0; k < plan->nkeys; ++k)
+      res->keys[g * plan->nkeys + k] = key_value(L.key_types[k], e + L.dev.keys[k].word, (knull >> k) & 1);
+    const uint64_t* acc = e + kKeyWords + 1;
+    const uint64_t* cnt = acc + nexprs * aw;
+    for (uint32_t a = 0; a < plan->naggs; ++a) {
+      pgf_value& v = res->aggs[g * plan->naggs + a];
+      const pgf_agg& ag = plan->aggs[a];
+      if (ag.func == PGF_AGG_COUNT_STAR) { v.kind = PGF_V_I64; v.lo = int64_t(cnt[nexprs]); continue; }
+      const uint64_t c = cnt[ag.expr];
+      if (ag.func == PGF_AGG_COUNT) { v.kind = PGF_V_I64; v.lo = int64_t(c); continue; }
+      if (c == 0) { v.kind = PGF_V_NULL; continue; }  // SUM / AVG over no rows is NULL
+      if (L.acc_cls == CLS_F64) {
+        double s;
+        std::memcpy(&s, acc + ag.expr, 8);
+        v.kind = PGF_V_F64;
+        v.f64 = ag.func == PGF_AGG_AVG ? s / double(c) : s;  // f64 sum / (u64 count as f64)
+      } else if (L.acc_cls == CLS_I64) {
+        v.kind = PGF_V_I64;
+        v.lo = int64_t(acc[ag.expr]);
+        v.hi = v.lo < 0 ? -1 : 0;
+        if (ag.func == PGF_AGG_AVG) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "integer AVG must be lowered to Float64");
+      } else {
+        __int128 s = (__int128)(((unsigned __int128)acc[ag.expr * 2 + 1] << 64) | acc[ag.expr * 2]);
+        if (ag.func == PGF_AGG_AVG) {
+          // DecimalAverager: sum * 10^(s_out - s) / count with s_out = s + 4, truncating
+          s = (s * 10000) / (__int128)c;
+        }
+        v.kind = PGF_V_I128;
+        v.lo = int64_t(uint64_t((unsigned __int128)s));
+        v.hi = int64_t(uint64_t((unsigned __int128)s >> 64));
+      }
+    }
+  }
+  return PGF_OK;
+}
+
+struct TableAlloc {
+  GroupTable t{};
+  uint64_t capacity = 0;
+};
+
+pgf_status alloc_table(pgf_ctx* ctx, DevAlloc& mem, uint64_t capacity, uint32_t nexprs, uint32_t acc_words, bool grouped,
+                       TableAlloc* out) {
+  GroupTable& t = out->t;
+  out->capacity = capacity;
+  if (mem.alloc(&t.state, capacity) != cudaSuccess || mem.alloc(&t.keys, capacity * kKeyWords) != cudaSuccess ||
+      mem.alloc(&t.acc, capacity * (nexprs ? nexprs : 1) * acc_words) != cudaSuccess ||
+      mem.alloc(&t.cnt, capacity * (nexprs + 1)) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a group table of %llu slots", (unsigned long long)capacity);
+  }
+  t.mask = uint32_t(capacity - 1);
+  t.acc_words = acc_words;
+  t.overflow = ctx->d_flags;
+  t.used = ctx->d_flags + 1;
+  CU(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8, ctx->compute_stream));
+  CU(ctx, cudaMemsetAsync(t.state, 0, capacity * 4, ctx->compute_stream));
+  CU(ctx, cudaMemsetAsync(t.acc, 0, capacity * (nexprs ? nexprs : 1) * acc_words * 8, ctx->compute_stream));
+  CU(ctx, cudaMemsetAsync(t.cnt, 0, capacity * (nexprs + 1) * 8, ctx->compute_stream));
+  if (!grouped) {
+    table_init_nogroup_kernel<<<1, 32, 0, ctx->compute_stream>>>(t);
+    CU(ctx, cudaGetLastError());
+  }
+  return PGF_OK;
+}
+
+// Extract the occupied slots into `d_state` ([count][entries...]) on the compute stream.
+pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, uint32_t nexprs, uint64_t* d_state,
+                         uint64_t max_entries) {
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 4);
+  CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
+  const uint32_t grid = uint32_t(std::min<uint64_t>((capacity + 255) / 256, uint64_t(ctx->sm_count) * 8));
+  table_extract_kernel<<<grid, 256, 0, ctx->compute_stream>>>(t, nexprs, d_state, max_entries, d_cnt);
+  CU(ctx, cudaGetLastError());
+  finish_count_kernel<<<1, 1, 0, ctx->compute_stream>>>(d_state, d_cnt);
+  CU(ctx, cudaGetLastError());
+  return PGF_OK;
+}
+
+}  // namespace
+
+pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
+                        uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  Lowered L;
+  Lowering low(ctx, plan);
+  PGF_TRY(low.run(&L));
+  if (check_only) return PGF_OK;
+  if (partial && plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
+  PGF_TRY(scan_sync_descs(ctx, *L.scan));
+  L.dev.descs = L.scan->d_descs;
+  L.dev.classes = L.scan->d_classes;
+  L.dev.counters = ctx->d_counters;
+
+  pgf_result* res = new (std::nothrow) pgf_result();
+  if (!res) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
+  struct ResGuard {
+    pgf_result* r;
+    ~ResGuard() { if (r) pgf_result_free(r); }
+  } guard{res};
+
+  DevAlloc mem;
+  const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.nitems ? L.dev.nitems : 1, uint64_t(ctx->sm_count)));
+  uint64_t capacity = L.table_capacity;
+  std::vector<uint64_t> h_state;
+  float total_ms = 0.f;
+  uint32_t launches = 0;
+
+  if (plan->sink == PGF_SINK_JOIN_BUILD) {
+    JoinTable& jt = L.build_table;
+    cudaError_t e = cudaMalloc(&jt.d_slots, uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
+    }
+    mem.ptrs.push_back(jt.d_slots);
+    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4), ctx->compute_stream));
+    L.dev.build.slots = jt.d_slots;
+  }
+
+  for (int attempt = 0; attempt < 6; ++attempt) {
+    TableAlloc ta;
+    DevAlloc table_mem;
+    uint64_t* d_state = nullptr;
+    if (plan->sink == PGF_SINK_AGGREGATE) {
+      PGF_TRY(alloc_table(ctx, table_mem, capacity, plan->nexprs, aw, L.grouped, &ta));
+      L.dev.table = ta.t;
+    }
+    CU(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->compute_stream));
+    CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
+    if (L.dev.nitems) {
+      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.dev, grid, L.smem, ctx->compute_stream));
+      ++launches;
+    }
+    CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute_stream));
+    CU(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    total_ms += ms;
+    if (ctx->h_counters->bad_rows)
+      return ctx->fail(PGF_ERR_UNSUPPORTED_DATA, "%llu rows carry out-of-line (> 12 byte) view values in a predicate or key column",
+                       (unsigned long long)ctx->h_counters->bad_rows);
+    if (plan->sink == PGF_SINK_AGGREGATE && ctx->h_flags[0]) {  // group table overflow: grow and re-run
+      capacity *= 16;
+      if (capacity > (1ull << 30)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "group table would exceed 2^30 slots");
+      continue;
+    }
+    if (plan->sink == PGF_SINK_AGGREGATE) {
+      const uint64_t ngroups = ctx->h_flags[1];
+      const uint32_t ew = entry_words(plan->nexprs, aw);
+      const uint64_t bytes = (1 + ngroups * ew) * 8;
+      if (partial) {
+        if (bytes > state_cap) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state needs %llu bytes, buffer has %llu", (unsigned long long)bytes, (unsigned long long)state_cap);
+        PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, static_cast<uint64_t*>(dev_state_out), ngroups));
+        CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+        *state_bytes = bytes;
+        ++launches;
+      } else {
+        if (table_mem.alloc(&d_state, 1 + ngroups * ew) != cudaSuccess) {
+          cudaGetLastError();
+          return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate the result buffer");
+        }
+        PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, d_state, ngroups));
+        h_state.resize(1 + ngroups * ew);
+        CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, bytes, cudaMemcpyDeviceToHost, ctx->compute_stream));
+        CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+        ++launches;
+        PGF_TRY(build_result(ctx, plan, L, h_state, res));
+      }
+    }
+    break;
+  }
+
+  const Counters& c = *ctx->h_counters;
+  res->rows_in = c.rows_in;
+  res->rows_bloom = c.rows_bloom;
+  res->rows_filtered = c.rows_filtered;
+  res->rows_out = c.rows_out;
+  res->bloom_rows = c.bloom_rows;
+  res->kernel_ms = total_ms;
+  res->kernel_launches = launches;
+  if (plan->sink == PGF_SINK_JOIN_BUILD) {
+    JoinTable jt = L.build_table;
+    jt.rows = c.rows_out;
+    mem.release(jt.d_slots);
+    const uint64_t id = ctx->next_handle++;
+    ctx->joins[id] = jt;
+    res->join_table = id;
+  }
+  if (out) {
+    *out = res;
+    guard.r = nullptr;
+  }
+  return PGF_OK;
+}
+
+pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states, uint64_t stride,
+                          uint32_t nstates, pgf_result** out) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
+  Lowered L;
+  Lowering low(ctx, plan);
+  PGF_TRY(low.run(&L));
+  const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  const uint32_t ew = entry_words(plan->nexprs, aw);
+  // size the final table from the partial group counts
+  std::vector<uint64_t> counts(nstates);
+  uint64_t total = 0;
+  for (uint32_t i = 0; i < nstates; ++i) {
+    CU(ctx, cudaMemcpyAsync(&counts[i], static_cast<const uint8_t*>(dev_states) + i * stride, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  }
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  for (uint32_t i = 0; i < nstates; ++i) {
+    if ((1 + counts[i] * ew) * 8 > stride) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state %u overruns its stride", i);
+    total += counts[i];
+  }
+  uint64_t capacity = 1;
+  if (L.grouped) {
+    capacity = 1024;
+    while (capacity < total * 2) capacity <<= 1;
+  }
+  DevAlloc mem;
+  TableAlloc ta;
+  PGF_TRY(alloc_table(ctx, mem, capacity, plan->nexprs, aw, L.grouped, &ta));
+  for (uint32_t i = 0; i < nstates; ++i) {  // rank order => fixed Float64 summation order
+    if (!counts[i]) continue;
+    const uint64_t* st = reinterpret_cast<const uint64_t*>(static_cast<const uint8_t*>(dev_states) + i * stride);
+    const uint32_t grid = uint32_t(std::min<uint64_t>((counts[i] + 255) / 256, uint64_t(ctx->sm_count) * 4));
+    switch (L.acc_cls) {
+      case CLS_F64: table_merge_kernel<CLS_F64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
+      case CLS_I64: table_merge_kernel<CLS_I64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
+      default: table_merge_kernel<CLS_I128><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
+    }
+    CU(ctx, cudaGetLastError());
+  }
+  CU(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  const uint64_t ngroups = ctx->h_flags[1];
+  uint64_t* d_state = nullptr;
+  if (mem.alloc(&d_state, 1 + ngroups * ew) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate the result buffer");
+  }
+  PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, d_state, ngroups));
+  std::vector<uint64_t> h_state(1 + ngroups * ew);
+  CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, h_state.size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  pgf_result* res = new (std::nothrow) pgf_result();
+  if (!res) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
+  pgf_status st = build_result(ctx, plan, L, h_state, res);
+  if (st) {
+    pgf_result_free(res);
+    return st;
+  }
+  res->kernel_launches = nstates + 2;
+  *out = res;
+  return PGF_OK;
+}
+
+}  // namespace pgf

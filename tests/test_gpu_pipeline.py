@@ -1,0 +1,256 @@
+"""GPU parity tests of the fused scan pipelines (filter / projection / aggregate) through
+the C ABI against the oracle (oracle/orc_ops.c) on the same seeded pages.
+Bar: counts, integer and Decimal128 sums bit-exact; Float64 SUM/AVG within 1e-12 relative
+(BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import pg_fusion_b200 as pg
+from oracle import pyorc as O
+from pg_fusion_b200 import AggFunc, Cmp, ColumnSpec, Factor, GenTable, TypeTag
+from pg_fusion_b200 import arrow_layout as AL
+
+from . import util as U
+
+pytestmark = pytest.mark.gpu
+E = O.Expr
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pg.Context()
+    yield c
+    c.close()
+
+
+def load(ctx, schema, pages):
+    scan = ctx.declare_scan(schema)
+    if len(pages):
+        scan.push_pages(pages)
+    scan.finish()
+    return scan
+
+
+@pytest.mark.parametrize("n,rows_per_page", [(0, None), (1, None), (999, None), (50_000, None), (20_000, 100), (3000, 1)])
+def test_q6_shape_matches_oracle(ctx, n, rows_per_page):
+    li = U.lineitem(n, 11 + n)
+    pages = U.q6_pages(li, rows_per_page=rows_per_page) if n else np.zeros((0, 65536), np.uint8)
+    scan = load(ctx, U.Q6_SCHEMA, pages)
+    res = U.gpu_q6(scan).run()
+    table = O.OTable.from_pages(pages, 65536, U.orc_cols(U.Q6_SCHEMA)) if n else None
+    if n == 0:
+        assert res.rows_in == 0 and res.aggs == [(None, 0)]  # SUM over no rows is NULL, COUNT(*) = 0
+        return
+    want = U.oracle_q6(table)
+    assert res.rows_in == n and res.rows_filtered == want.rows_filtered
+    U.assert_agg_equal(res, want)
+    # the lane-striped "arrow sum kernel" order must agree within the same tolerance
+    U.assert_agg_equal(res, U.oracle_q6(table, sum_lanes=4))
+    # fast CPU baseline loop agrees with the generic interpreter
+    s, rows_in, kept = O.q6_pages(pages, 65536, 2)
+    assert (rows_in, kept) == (n, want.rows_filtered)
+    U.assert_close(s, want.aggs[0][0], 1e-12, "orc_q6_pages")
+    scan.release()
+
+
+@pytest.mark.parametrize("n", [5, 4000, 60_000])
+def test_q1_shape_matches_oracle(ctx, n):
+    li = U.lineitem(n, 3 + n)
+    pages = U.q1_pages(li)
+    scan = load(ctx, U.Q1_SCHEMA, pages)
+    res = U.gpu_q1(scan).run()
+    want = U.oracle_q1(O.OTable.from_pages(pages, 65536, U.orc_cols(U.Q1_SCHEMA)))
+    assert res.rows_in == n and res.rows_filtered == want.rows_filtered
+    U.assert_agg_equal(res, want)
+    fast, _ = O.q1_pages(pages, 65536, 3)
+    for k, a in want.by_key().items():
+        g = fast[(k[0], k[1])]
+        U.assert_close(g["sum_charge"], a[3], 1e-12, "orc_q1_pages")
+        assert g["count"] == a[7]
+    scan.release()
+
+
+def test_generated_pages_are_valid_and_match_oracle(ctx):
+    """The device generator writes reference-format pages; the oracle decodes the same bytes."""
+    for table, schema, run_gpu, run_orc in (
+            (GenTable.LINEITEM_Q6, U.Q6_SCHEMA, U.gpu_q6, U.oracle_q6),
+            (GenTable.LINEITEM_Q1, U.Q1_SCHEMA, U.gpu_q1, U.oracle_q1)):
+        scan = ctx.gen_scan(table, 30_000, seed=42)
+        pages = scan.read_pages()
+        for p in pages[:2]:
+            assert AL.import_check(0x4152, 0, p[20:], schema) == 0
+            assert O.import_check(0x4152, 0, np.ascontiguousarray(p[20:]), U.orc_cols(schema)) == 0
+        want = run_orc(O.OTable.from_pages(pages, 65536, U.orc_cols(schema)))
+        res = run_gpu(scan).run()
+        assert res.rows_in == 30_000
+        U.assert_agg_equal(res, want)
+        if table == GenTable.LINEITEM_Q1:
+            assert sorted(res.by_key()) == [(b"A", b"F"), (b"N", b"F"), (b"N", b"O"), (b"R", b"F")]
+        scan.release()
+
+
+def test_nulls_three_valued_logic_and_null_groups(ctx):
+    r = np.random.default_rng(1)
+    n = 20_000
+    schema = [ColumnSpec(TypeTag.Int32, True), ColumnSpec(TypeTag.Float64, True), ColumnSpec(TypeTag.Float64, True),
+              ColumnSpec(TypeTag.Utf8View, True), ColumnSpec(TypeTag.Int64, True)]
+    g = r.integers(0, 3, n).astype(np.int32)
+    a = r.random(n) * 100
+    b = r.random(n)
+    s = [bytes([65 + int(x)]) * int(1 + x) for x in r.integers(0, 5, n)]
+    i = r.integers(-10**12, 10**12, n)
+    valid = [r.random(n) > p for p in (0.1, 0.2, 0.15, 0.1, 0.3)]
+    cols = [(g, valid[0]), (a, valid[1]), (b, valid[2]), (AL.inline_views(s), valid[3]), (i, valid[4])]
+    pages = AL.encode_pages(schema, cols, rows_per_page=700)
+    scan = load(ctx, schema, pages)
+    table = O.OTable.from_pages(pages, 65536, U.orc_cols(schema))
+    # WHERE a > 10 AND s >= 'BB' GROUP BY g : sum(a*b), avg(a), count(b), count(*), sum(a*(1-b))
+    res = (scan.pipeline().filter(1, Cmp.GT, 10.0).filter(3, Cmp.GE, b"BB")
+           .aggregate([0], [(AggFunc.SUM, [Factor.of(1), Factor.of(2)]), (AggFunc.AVG, [Factor.of(1)]),
+                            (AggFunc.COUNT, [Factor.of(2)]), (AggFunc.COUNT_STAR, None),
+                            (AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])]).run())
+    filt = E.col(1).gt(E.f64(10.0)).and_(E.col(3).ge(E.s(b"BB")))
+    want = O.aggregate(table, filt, [E.col(0)],
+                       [(O.AGG_SUM, E.col(1) * E.col(2)), (O.AGG_AVG, E.col(1)), (O.AGG_COUNT, E.col(2)),
+                        (O.AGG_COUNT_STAR, None), (O.AGG_SUM, E.col(1) * (E.f64(1.0) - E.col(2)))])
+    assert res.rows_filtered == want.rows_filtered
+    assert (None,) in res.by_key()  # NULL keys form one group
+    U.assert_agg_equal(res, want)
+    # integer sums are bit-exact (Int64 wrapping), grouped by a string key
+    res = scan.pipeline().aggregate([3], [(AggFunc.SUM, [Factor.of(4)]), (AggFunc.COUNT, [Factor.of(4)])]).run()
+    want = O.aggregate(table, None, [E.col(3)], [(O.AGG_SUM, E.col(4)), (O.AGG_COUNT, E.col(4))])
+    U.assert_agg_equal(res, want, rel=0)
+    scan.release()
+
+
+def test_reference_smoke_values(ctx):
+    """pg/extension/src/smoke_tests.rs:205-251 re-expressed on synthetic pages."""
+    ids = np.arange(1, 50_001, dtype=np.int64)
+    schema = [ColumnSpec(TypeTag.Int64)]
+    scan = load(ctx, schema, AL.encode_pages(schema, [(ids, None)]))
+    res = scan.pipeline().aggregate([], [(AggFunc.AVG, [Factor.of(0)])]).run()
+    assert abs(res.aggs[0][0] - 25000.5) < 1e-3            # smoke_tests.rs:205-226
+    scan.release()
+    ids = np.arange(1, 5001, dtype=np.int64)
+    schema = [ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Utf8View)]
+    pages = AL.encode_pages(schema, [(ids, None), (AL.inline_views([b"payload"] * 5000), None)])
+    scan = load(ctx, schema, pages)
+    res = scan.pipeline().aggregate([], [(AggFunc.COUNT, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(0)])]).run()
+    assert res.aggs[0] == (5000, 12502500)                  # smoke_tests.rs:228-251
+    res = scan.pipeline().filter(0, Cmp.GE, 10).filter(0, Cmp.LE, 20).aggregate([], [(AggFunc.SUM, [Factor.of(0)])]).run()
+    assert res.aggs[0] == (sum(range(10, 21)),)             # smoke_tests.rs:382-471 (BETWEEN)
+    scan.release()
+
+
+def test_many_groups_take_the_hash_path(ctx):
+    r = np.random.default_rng(3)
+    n = 200_000
+    schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Float64)]
+    k = r.integers(0, 30_000, n).astype(np.int32)
+    v = r.integers(-10**9, 10**9, n)
+    f = r.random(n) * 1000
+    pages = AL.encode_pages(schema, [(k, None), (v, None), (f, None)])
+    scan = load(ctx, schema, pages)
+    table = O.OTable.from_pages(pages, 65536, U.orc_cols(schema))
+    res = scan.pipeline().aggregate([0], [(AggFunc.SUM, [Factor.of(1)]), (AggFunc.COUNT_STAR, None)], expected_groups=100).run()
+    want = O.aggregate(table, None, [E.col(0)], [(O.AGG_SUM, E.col(1)), (O.AGG_COUNT_STAR, None)])
+    assert len(res.keys) == len(want.keys)
+    U.assert_agg_equal(res, want, rel=0)   # forces a table-overflow re-run (expected_groups far too low)
+    res = scan.pipeline().aggregate([0], [(AggFunc.SUM, [Factor.of(2)]), (AggFunc.AVG, [Factor.of(2)])]).run()
+    want = O.aggregate(table, None, [E.col(0)], [(O.AGG_SUM, E.col(2)), (O.AGG_AVG, E.col(2))])
+    U.assert_agg_equal(res, want)
+    scan.release()
+
+
+def test_decimal128_extension_is_bit_exact(ctx):
+    """Decimal128(15,2) money (SURVEY 8d "D" schema): i128 sums and products are bit-exact,
+    AVG follows DecimalAverager (sum * 10^4 / count, truncating)."""
+    r = np.random.default_rng(8)
+    n = 30_000
+    schema = [ColumnSpec(TypeTag.Decimal128), ColumnSpec(TypeTag.Decimal128), ColumnSpec(TypeTag.Decimal128), ColumnSpec(TypeTag.Int16)]
+
+    def dec(vals):
+        out = np.zeros((len(vals), 16), dtype=np.uint8)
+        for i, v in enumerate(vals):
+            out[i] = np.frombuffer((int(v) & (2**128 - 1)).to_bytes(16, "little"), dtype=np.uint8)
+        return out
+    price = r.integers(-10**13, 10**13, n)
+    disc = r.integers(0, 11, n)
+    tax = r.integers(0, 9, n)
+    grp = r.integers(0, 3, n).astype(np.int16)
+    pages = AL.encode_pages(schema, [(dec(price), None), (dec(disc), None), (dec(tax), None), (grp, None)])
+    scan = load(ctx, schema, pages)
+    table = O.OTable.from_pages(pages, 65536, U.orc_cols(schema))
+    dp = [Factor.of(0), Factor.const_minus(100, 1)]
+    res = (scan.pipeline().filter(1, Cmp.GE, 2).aggregate([3], [
+        (AggFunc.SUM, [Factor.of(0)]), (AggFunc.SUM, dp), (AggFunc.SUM, dp + [Factor.const_plus(100, 2)]),
+        (AggFunc.AVG, [Factor.of(0)]), (AggFunc.COUNT_STAR, None)]).run())
+    d_price = E.col(0) * (E.i128(100) - E.col(1))
+    want = O.aggregate(table, E.col(1).ge(E.i128(2)), [E.col(3)], [
+        (O.AGG_SUM, E.col(0)), (O.AGG_SUM, d_price), (O.AGG_SUM, d_price * (E.i128(100) + E.col(2))),
+        (O.AGG_SUM, E.col(0)), (O.AGG_COUNT_STAR, None)])
+    got, exp = res.by_key(), want.by_key()
+    assert set(got) == set(exp)
+    for k in exp:
+        s0, s1, s2, ssum, cnt = exp[k]
+        q = abs(ssum * 10000) // cnt
+        avg = q if ssum >= 0 else -q  # i128 division truncates toward zero
+        assert got[k] == (s0, s1, s2, avg, cnt)
+    scan.release()
+
+
+def test_eligibility_and_unsupported_data(ctx):
+    schema = [ColumnSpec(TypeTag.Boolean), ColumnSpec(TypeTag.Float64), ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Utf8View)]
+    n = 100
+    long_s = [b"a long string beyond twelve bytes"] * n
+    blk = O.Block(U.orc_cols(schema), n, 65516)
+    import struct
+    for r_ in range(n):
+        blk.write_bool(0, r_, True); blk.write_fixed(1, r_, struct.pack("<d", 1.0)); blk.write_fixed(2, r_, struct.pack("<i", r_))
+        assert blk.write_view_bytes(3, r_, long_s[r_]) == 0
+        blk.commit_current_row()
+    page = np.concatenate([np.frombuffer(AL.page_header(), dtype=np.uint8), blk.buf])
+    scan = load(ctx, schema, page.reshape(1, -1))
+    # out-of-line views pass ingest (they are valid pages) ...
+    assert scan.info().rows == n
+    # ... plans over unsupported shapes are declined, like install_runtime_filters declines joins
+    assert scan.pipeline().filter(0, Cmp.EQ, 1).count().check() == pg.errors.NOT_ELIGIBLE
+    assert scan.pipeline().aggregate([], [(AggFunc.SUM, [Factor.of(1), Factor.of(2)])]).check() == pg.errors.NOT_ELIGIBLE
+    assert scan.pipeline().filter(3, Cmp.EQ, b"x" * 13).count().check() == pg.errors.NOT_ELIGIBLE
+    # ... and data the kernel cannot compare fails loudly instead of returning a wrong answer
+    with pytest.raises(pg.PgfError) as e:
+        scan.pipeline().filter(3, Cmp.EQ, b"a").count().run()
+    assert e.value.name == "UNSUPPORTED_DATA"
+    assert scan.pipeline().filter(2, Cmp.LT, 10).count().run().rows_out == 10
+    scan.release()
+
+
+def test_ingest_rejects_bad_pages_on_host_and_device(ctx):
+    schema = [ColumnSpec(TypeTag.Int32, True), ColumnSpec(TypeTag.Utf8View, True)]
+    vals = np.arange(10, dtype=np.int32)
+    valid = np.array([True] * 9 + [False])
+    good = AL.encode_pages(schema, [(vals, valid), (AL.inline_views([b"ab"] * 10), valid)])
+    # host-side structural rejection: wrong kind
+    bad = good.copy(); bad[0, 10:12] = [0, 9]
+    scan = ctx.declare_scan(schema)
+    with pytest.raises(pg.PgfError) as e:
+        scan.push_pages(bad)
+    assert e.value.name == "IMPORT_WRONG_KIND"
+    with pytest.raises(pg.PgfError) as e:
+        scan.push_pages(good[:, :30000], stride=30000)
+    assert e.value.name == "LAYOUT_BLOCK_SLICE_TOO_SMALL"
+    # device-side row-level rejection: null bitmap popcount mismatch, invalid UTF-8
+    plan = AL.LayoutPlan(schema, AL.fixed_row_cap(schema), 65516)
+    for mutate, name in ((lambda p: p.__setitem__((0, 20 + plan.column_layout(0).validity_off), 0xFF), "IMPORT_NULL_BITMAP_COUNT_MISMATCH"),
+                         (lambda p: p.__setitem__((0, 20 + plan.column_layout(1).values_off + 4), 0xFF), "IMPORT_ARROW_INVALID_VIEW")):
+        bad = good.copy(); mutate(bad)
+        s2 = ctx.declare_scan(schema)
+        s2.push_pages(bad)
+        with pytest.raises(pg.PgfError) as e:
+            s2.finish()
+        assert e.value.name == name
+        s2.release()
+    scan.push_pages(good)
+    scan.finish()
+    assert scan.pipeline().count().run().rows_out == 10
+    scan.release()

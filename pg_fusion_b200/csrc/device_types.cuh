@@ -51,28 +51,46 @@ struct DevStageCol {
   uint16_t type;
 };
 
+enum : uint8_t { LD_I16 = 0, LD_I32 = 1, LD_I64 = 2, LD_F32 = 3, LD_F64 = 4, LD_VIEW = 5, LD_DEC = 6 };
+constexpr uint32_t kNoValidity = 0xFFFFFFFFu;
+
 struct DevRef {          // where a value comes from
   uint8_t src;           // SRC_PAGE or join index + 1
+  uint8_t ld;            // LD_*: how to load / widen it
   uint8_t type;          // PGF_T_*
-  uint16_t idx;          // SRC_PAGE: stage column slot; else: first u32 word in the payload
+  uint8_t pcol;          // SRC_PAGE: page column index; else: payload column index
+  uint32_t off;          // SRC_PAGE: byte offset of the column tile inside a stage; else first u32 payload word
+  uint32_t valid_off;    // SRC_PAGE + nullable: offset of the validity tile; else kNoValidity
 };
 
+// One conjunct after host-side normalisation: every LT/LE/GT/GE/EQ on a column is folded
+// into one inclusive range over the order-preserving key (signed k0, unsigned k1); NE
+// becomes "not in [c, c]".
+enum : uint32_t { TERM_IN_RANGE = 0, TERM_NOT_IN_RANGE = 1, TERM_NEVER = 2 };
 struct DevTerm {
   DevRef ref;
-  uint32_t cmp;          // PGF_CMP_*
-  int64_t k0;            // literal as an order-preserving (signed hi, unsigned lo) key
-  uint64_t k1;
+  uint32_t op;           // TERM_*
+  uint32_t wide;         // 0: one-word key, test (u64)(k0 - lo0) <= span; 1: (k0, k1) pair compare
+  int64_t lo0;
+  uint64_t lo1;          // wide: low word of the lower bound; narrow: span = hi0 - lo0
+  int64_t hi0;
+  uint64_t hi1;
 };
 
 struct DevFactor {
   DevRef ref;
   uint32_t kind;         // PGF_FACTOR_*
+  uint32_t pad;
   double cf;             // constant (CLS_F64)
   int64_t ci_lo, ci_hi;  // constant (CLS_I64 / CLS_I128)
 };
+// form: straight-line fast paths for products of Float64 scan columns
+enum : uint32_t { FORM_GENERIC = 0, FORM_X = 1, FORM_XY = 2, FORM_X_CMY = 3, FORM_X_CMY_CPZ = 4 };
 struct DevExpr {
   uint32_t nfactors;
-  uint32_t pad;
+  uint32_t form;
+  uint32_t null_cols;    // page columns (bit mask) whose validity this expression depends on
+  uint32_t has_payload;  // some factor reads a join payload (may be NULL)
   DevFactor f[3];
 };
 

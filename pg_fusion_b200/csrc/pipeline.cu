@@ -10,8 +10,8 @@
 namespace pgf {
 
 // implemented in pipeline_inst_*.cu (explicit instantiations split for parallel builds)
-cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t nj, const DevPlan& plan,
-                            uint32_t grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t nj, uint32_t maxe,
+                            const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
 
 namespace {
 
@@ -75,6 +75,7 @@ struct Lowered {
   uint32_t acc_cls = CLS_F64;
   bool grouped = false;
   uint32_t nj = 0;
+  uint32_t maxe = 2;
   size_t smem = 0;
   int32_t key_types[4] = {0, 0, 0, 0};
   JoinTable build_table{};
@@ -153,15 +154,7 @@ class Lowering {
       D.nbloom++;
     }
 
-    for (uint32_t t = 0; t < plan_->nterms; ++t) {
-      DevTerm& dt = D.terms[t];
-      PGF_TRY(lower_ref(plan_->terms[t].col, plan_->njoins, &dt.ref));
-      if (plan_->terms[t].col.source != 0) return not_eligible("predicates are evaluated on scan columns");
-      if (plan_->terms[t].cmp < PGF_CMP_LT || plan_->terms[t].cmp > PGF_CMP_NE) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad comparison operator");
-      dt.cmp = uint32_t(plan_->terms[t].cmp);
-      PGF_TRY(literal_key(plan_->terms[t].lit, dt.ref.type, &dt.k0, &dt.k1));
-    }
-    D.nterms = plan_->nterms;
+    PGF_TRY(lower_terms());
 
     switch (plan_->sink) {
       case PGF_SINK_AGGREGATE: PGF_TRY(lower_aggregate()); break;
@@ -169,13 +162,104 @@ class Lowering {
       case PGF_SINK_COUNT: D.sink = SINK_COUNT; break;
       default: return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "unknown sink %d", plan_->sink);
     }
-    return layout_stage(s);
+    PGF_TRY(layout_stage(s));
+    fix_refs();
+    return PGF_OK;
   }
 
  private:
+  // FilterExec conjuncts -> one inclusive key range per column (+ one term per NE).
+  pgf_status lower_terms() {
+    DevPlan& D = L_->dev;
+    struct Range {
+      pgf_colref col;
+      DevRef ref;
+      bool wide;
+      __int128 lo, hi;  // over the 128-bit key ((i128)k0 << 64 | k1)
+    };
+    std::vector<Range> ranges;
+    const __int128 kMin = (__int128)1 << 127, kMax = ~kMin;
+    for (uint32_t t = 0; t < plan_->nterms; ++t) {
+      const pgf_pred_term& pt = plan_->terms[t];
+      if (pt.col.source != 0) return not_eligible("predicates are evaluated on scan columns");
+      if (pt.cmp < PGF_CMP_LT || pt.cmp > PGF_CMP_NE) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad comparison operator");
+      DevRef ref;
+      PGF_TRY(lower_ref(pt.col, plan_->njoins, &ref));
+      int64_t k0;
+      uint64_t k1;
+      PGF_TRY(literal_key(pt.lit, ref.type, &k0, &k1));
+      const bool wide = ref.ld == LD_VIEW || ref.ld == LD_DEC;
+      const __int128 key = ((__int128)k0 << 64) | (__int128)k1;
+      // one-word keys only occupy k1 == 0: step over whole words so that "< c" is "<= c - 1"
+      const __int128 one = wide ? (__int128)1 : ((__int128)1 << 64);
+      if (pt.cmp == PGF_CMP_NE) {
+        if (D.nterms >= kMaxTerms) return not_eligible("too many predicate terms");
+        DevTerm& dt = D.terms[D.nterms++];
+        dt.ref = ref;
+        dt.op = TERM_NOT_IN_RANGE;
+        set_bounds(&dt, wide, key, key);
+        continue;
+      }
+      Range* rg = nullptr;
+      for (auto& r : ranges)
+        if (r.col.col == pt.col.col) rg = &r;
+      if (!rg) {
+        ranges.push_back(Range{pt.col, ref, wide, kMin, kMax});
+        rg = &ranges.back();
+      }
+      switch (pt.cmp) {
+        case PGF_CMP_LT: if (key == kMin) rg->hi = kMin, rg->lo = kMax; else rg->hi = std::min(rg->hi, key - one); break;
+        case PGF_CMP_LE: rg->hi = std::min(rg->hi, key); break;
+        case PGF_CMP_GT: if (key > kMax - one) rg->hi = kMin, rg->lo = kMax; else rg->lo = std::max(rg->lo, key + one); break;
+        case PGF_CMP_GE: rg->lo = std::max(rg->lo, key); break;
+        default: rg->lo = std::max(rg->lo, key); rg->hi = std::min(rg->hi, key); break;  // EQ
+      }
+    }
+    for (auto& r : ranges) {
+      if (D.nterms >= kMaxTerms) return not_eligible("too many predicate terms");
+      DevTerm& dt = D.terms[D.nterms++];
+      dt.ref = r.ref;
+      if (r.lo > r.hi) {
+        dt.op = TERM_NEVER;
+        set_bounds(&dt, r.wide, 0, 0);
+      } else {
+        dt.op = TERM_IN_RANGE;
+        set_bounds(&dt, r.wide, r.lo, r.hi);
+      }
+    }
+    return PGF_OK;
+  }
+
+  static void set_bounds(DevTerm* dt, bool wide, __int128 lo, __int128 hi) {
+    dt->wide = wide;
+    dt->lo0 = int64_t(lo >> 64);
+    dt->hi0 = int64_t(hi >> 64);
+    if (wide) {
+      dt->lo1 = uint64_t((unsigned __int128)lo);
+      dt->hi1 = uint64_t((unsigned __int128)hi);
+    } else {
+      dt->lo1 = uint64_t(dt->hi0) - uint64_t(dt->lo0);  // span
+      dt->hi1 = 0;
+    }
+  }
+
   pgf_status not_eligible(const char* why) { return ctx_->fail(PGF_ERR_NOT_ELIGIBLE, "pipeline not eligible for the GPU path: %s", why); }
 
-  // Resolve a column reference; scan columns get a stage slot.
+  static uint8_t ld_kind(int type) {
+    switch (type) {
+      case PGF_T_INT16: return LD_I16;
+      case PGF_T_INT32: return LD_I32;
+      case PGF_T_INT64: return LD_I64;
+      case PGF_T_FLOAT32: return LD_F32;
+      case PGF_T_FLOAT64: return LD_F64;
+      case PGF_T_DECIMAL128: return LD_DEC;
+      default: return LD_VIEW;
+    }
+  }
+
+  // Resolve a column reference; scan columns get a stage slot.  For scan columns `off`
+  // temporarily holds the slot; fix_ref() turns it into shared-memory offsets once the
+  // stage layout is known.
   pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out) {
     Scan& s = *L_->scan;
     DevPlan& D = L_->dev;
@@ -196,8 +280,11 @@ class Lowering {
         if (is_view(type)) D.view_mask |= 1u << r.col;
       }
       out->src = SRC_PAGE;
+      out->ld = ld_kind(type);
       out->type = uint8_t(type);
-      out->idx = uint16_t(slot);
+      out->pcol = uint8_t(r.col);
+      out->off = slot;
+      out->valid_off = kNoValidity;
       return PGF_OK;
     }
     const uint32_t j = uint32_t(r.source - 1);
@@ -205,12 +292,35 @@ class Lowering {
     const JoinTable& jt = *jtables_[j];
     if (r.col < 0 || uint32_t(r.col) >= jt.npayload) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "join payload %d out of range", r.col);
     out->src = uint8_t(j + 1);
+    out->ld = ld_kind(jt.payload_type[r.col]);
     out->type = uint8_t(jt.payload_type[r.col]);
-    out->idx = uint16_t(jt.payload_word[r.col] | (uint32_t(r.col) << 8));
+    out->pcol = uint8_t(r.col);
+    out->off = jt.payload_word[r.col];
+    out->valid_off = kNoValidity;
     return PGF_OK;
   }
 
-  // Literal -> order-preserving key, matching raw_to_key on the device.
+  void fix_ref(DevRef* ref) {
+    if (ref->src != SRC_PAGE) return;
+    const DevStageCol& sc = L_->dev.scol[ref->off];
+    ref->valid_off = sc.nullable ? sc.valid_off : kNoValidity;
+    ref->off = sc.smem_off;
+  }
+
+  // Second pass once layout_stage() has placed the column tiles.
+  void fix_refs() {
+    DevPlan& D = L_->dev;
+    for (uint32_t b = 0; b < D.nbloom; ++b) fix_ref(&D.bloom[b].key);
+    for (uint32_t t = 0; t < D.nterms; ++t) fix_ref(&D.terms[t].ref);
+    for (uint32_t j = 0; j < D.njoins; ++j) fix_ref(&D.joins[j].key);
+    for (uint32_t k = 0; k < D.nkeys; ++k) fix_ref(&D.keys[k].ref);
+    for (uint32_t e = 0; e < D.nexprs; ++e)
+      for (uint32_t f = 0; f < D.exprs[e].nfactors; ++f) fix_ref(&D.exprs[e].f[f].ref);
+    fix_ref(&D.build.key);
+    for (uint32_t p = 0; p < D.build.npayload; ++p) fix_ref(&D.build.payload[p]);
+  }
+
+  // Literal -> order-preserving key, matching term_pass2 on the device.
   pgf_status literal_key(const pgf_literal& lit, int col_type, int64_t* k0, uint64_t* k1) {
     *k1 = 0;
     switch (col_type) {
@@ -285,6 +395,23 @@ class Lowering {
           else { df.ci_lo = c.i64; df.ci_hi = c.type_tag == PGF_T_DECIMAL128 ? c.hi : (c.i64 < 0 ? -1 : 0); }
         }
       }
+      dx.form = FORM_GENERIC;
+      dx.null_cols = 0;
+      dx.has_payload = 0;
+      bool plain_f64 = true;
+      for (uint32_t f = 0; f < x.nfactors; ++f) {
+        const DevRef& rf = dx.f[f].ref;
+        plain_f64 &= rf.src == SRC_PAGE && rf.ld == LD_F64;
+        if (rf.src == SRC_PAGE) { if (L_->scan->schema[rf.pcol].nullable) dx.null_cols |= 1u << rf.pcol; }
+        else dx.has_payload = 1;
+      }
+      if (plain_f64) {
+        const uint32_t k0 = dx.f[0].kind, k1 = x.nfactors > 1 ? dx.f[1].kind : 0, k2 = x.nfactors > 2 ? dx.f[2].kind : 0;
+        if (x.nfactors == 1 && k0 == PGF_FACTOR_COL) dx.form = FORM_X;
+        else if (x.nfactors == 2 && k0 == PGF_FACTOR_COL && k1 == PGF_FACTOR_COL) dx.form = FORM_XY;
+        else if (x.nfactors == 2 && k0 == PGF_FACTOR_COL && k1 == PGF_FACTOR_CONST_MINUS_COL) dx.form = FORM_X_CMY;
+        else if (x.nfactors == 3 && k0 == PGF_FACTOR_COL && k1 == PGF_FACTOR_CONST_MINUS_COL && k2 == PGF_FACTOR_CONST_PLUS_COL) dx.form = FORM_X_CMY_CPZ;
+      }
       // narrow integers wrap at their own width in arrow; only plain columns or all-Int64
       // arithmetic is bit-exact with 64-bit registers
       if (ecls == CLS_I64 && !(all_i64 || (x.nfactors == 1 && dx.f[0].kind == PGF_FACTOR_COL)))
@@ -317,6 +444,10 @@ class Lowering {
     D.nexprs = plan_->nexprs;
     D.acc_cls = uint32_t(cls);
     L_->acc_cls = uint32_t(cls);
+    L_->maxe = plan_->nexprs <= 2 ? 2 : max_exprs;
+    // an integer expression averaged as Float64 must not take the raw-f64 fast forms
+    for (uint32_t e = 0; e < plan_->nexprs; ++e)
+      if (expr_as_f64_[e]) D.exprs[e].form = FORM_GENERIC;
 
     uint32_t words = 0;
     for (uint32_t k = 0; k < plan_->nkeys; ++k) {
@@ -609,7 +740,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     CU(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->compute_stream));
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
     if (L.dev.nitems) {
-      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.dev, grid, L.smem, ctx->compute_stream));
+      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
       ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));

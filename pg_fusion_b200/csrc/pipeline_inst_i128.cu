@@ -3,20 +3,25 @@
 
 namespace pgf {
 
-template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ>
+template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE>
 static cudaError_t launch_one(const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
-  auto kernel = pipeline_kernel<SINK, ACC, GROUPED, NJ>;
+  auto kernel = pipeline_kernel<SINK, ACC, GROUPED, NJ, MAXE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   kernel<<<grid, pipeline_threads(SINK, GROUPED), smem, stream>>>(plan);
   return cudaGetLastError();
 }
 
-cudaError_t launch_agg_i128(bool grouped, uint32_t nj, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
-  if (grouped) return nj ? launch_one<SINK_AGG, CLS_I128, true, 1>(plan, grid, smem, stream)
-                          : launch_one<SINK_AGG, CLS_I128, true, 0>(plan, grid, smem, stream);
-  return nj ? launch_one<SINK_AGG, CLS_I128, false, 1>(plan, grid, smem, stream)
-            : launch_one<SINK_AGG, CLS_I128, false, 0>(plan, grid, smem, stream);
+cudaError_t launch_agg_i128(bool grouped, uint32_t nj, uint32_t maxe, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
+  if (grouped == true && nj == 1 && maxe == 2) return launch_one<SINK_AGG, CLS_I128, true, 1, 2>(plan, grid, smem, stream);
+  if (grouped == true && nj == 1 && maxe == 6) return launch_one<SINK_AGG, CLS_I128, true, 1, 6>(plan, grid, smem, stream);
+  if (grouped == true && nj == 0 && maxe == 2) return launch_one<SINK_AGG, CLS_I128, true, 0, 2>(plan, grid, smem, stream);
+  if (grouped == true && nj == 0 && maxe == 6) return launch_one<SINK_AGG, CLS_I128, true, 0, 6>(plan, grid, smem, stream);
+  if (grouped == false && nj == 1 && maxe == 2) return launch_one<SINK_AGG, CLS_I128, false, 1, 2>(plan, grid, smem, stream);
+  if (grouped == false && nj == 1 && maxe == 6) return launch_one<SINK_AGG, CLS_I128, false, 1, 6>(plan, grid, smem, stream);
+  if (grouped == false && nj == 0 && maxe == 2) return launch_one<SINK_AGG, CLS_I128, false, 0, 2>(plan, grid, smem, stream);
+  if (grouped == false && nj == 0 && maxe == 6) return launch_one<SINK_AGG, CLS_I128, false, 0, 6>(plan, grid, smem, stream);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace pgf

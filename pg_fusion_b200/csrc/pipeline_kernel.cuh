@@ -137,163 +137,209 @@ struct AccOps<CLS_I128> {
   }
 };
 
-// Per-row view of the staged tile and of the matched join slots.
-struct RowCtx {
+// ---- per-row access ---------------------------------------------------------------------
+// A row of the staged tile plus (behind a join probe) the matched build-side slot.
+struct Row {
   const uint8_t* stage;
   uint32_t r;
-  uint32_t tile_nulls;        // page columns with nulls in this tile (already masked by use)
-  const uint32_t* pay[kMaxJoins];
-  uint32_t occ[kMaxJoins];    // slot occupancy word: bit 0 occupied, bit 1+p payload p is NULL
+  uint32_t tile_nulls;   // page columns with nulls in this tile (already masked by use)
+  const uint32_t* pay;   // matched join slot (u32 words: key lo, key hi, occ, payload...)
+  uint32_t occ;          // slot occupancy word: bit 0 occupied, bit 1+p payload p is NULL
 };
 
-__device__ __forceinline__ bool ref_valid(const DevPlan& P, const RowCtx& c, const DevRef ref) {
+__device__ __forceinline__ bool ref_valid(const DevRef& ref, const Row& row) {
   if (ref.src == SRC_PAGE) {
-    const DevStageCol& sc = P.scol[ref.idx];
-    if (!((c.tile_nulls >> sc.page_col) & 1)) return true;
-    return (c.stage[sc.valid_off + (c.r >> 3)] >> (c.r & 7)) & 1;
+    if (ref.valid_off == kNoValidity || !((row.tile_nulls >> ref.pcol) & 1)) return true;
+    return (row.stage[ref.valid_off + (row.r >> 3)] >> (row.r & 7)) & 1;
   }
-  const uint32_t occ = ref.src == 1 ? c.occ[0] : c.occ[1];  // static indices: RowCtx stays in registers
-  return !((occ >> (1 + (ref.idx >> 8))) & 1);
+  return !((row.occ >> (1 + ref.pcol)) & 1);
 }
 
-// Raw 128-bit load of a value (low words valid according to the type width).
-__device__ __forceinline__ uint4 ref_load(const DevPlan& P, const RowCtx& c, const DevRef ref) {
-  uint4 v = make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ int64_t load_i64(const DevRef& ref, const Row& row) {
   if (ref.src == SRC_PAGE) {
-    const DevStageCol& sc = P.scol[ref.idx];
-    const uint8_t* p = c.stage + sc.smem_off + c.r * uint32_t(sc.width);
-    switch (sc.width) {
-      case 16: v = *reinterpret_cast<const uint4*>(p); break;
-      case 8: { const uint2 t = *reinterpret_cast<const uint2*>(p); v.x = t.x; v.y = t.y; break; }
-      case 4: v.x = *reinterpret_cast<const uint32_t*>(p); break;
-      default: v.x = *reinterpret_cast<const uint16_t*>(p); break;
-    }
-  } else {
-    const uint32_t* p = (ref.src == 1 ? c.pay[0] : c.pay[1]) + 3 + (ref.idx & 0xFF);
-    const int t = ref.type;
-    v.x = __ldg(p);
-    if (t == PGF_T_INT64 || t == PGF_T_FLOAT64) v.y = __ldg(p + 1);
-    if (t == PGF_T_UTF8VIEW || t == PGF_T_BINARYVIEW || t == PGF_T_DECIMAL128 || t == PGF_T_UUID) {
-      v.y = __ldg(p + 1); v.z = __ldg(p + 2); v.w = __ldg(p + 3);
+    const uint8_t* p = row.stage + ref.off;
+    switch (ref.ld) {
+      case LD_I16: return int64_t(reinterpret_cast<const int16_t*>(p)[row.r]);
+      case LD_I32: return int64_t(reinterpret_cast<const int32_t*>(p)[row.r]);
+      default: return reinterpret_cast<const int64_t*>(p)[row.r];
     }
   }
-  return v;
-}
-
-__device__ __forceinline__ int64_t raw_to_i64(const uint4 v, int type) {
-  switch (type) {
-    case PGF_T_INT16: return int64_t(int16_t(v.x));
-    case PGF_T_INT32: return int64_t(int32_t(v.x));
-    default: return int64_t((uint64_t(v.y) << 32) | v.x);
+  const uint32_t* p = row.pay + 3 + ref.off;
+  switch (ref.ld) {
+    case LD_I16: return int64_t(int16_t(__ldg(p)));
+    case LD_I32: return int64_t(int32_t(__ldg(p)));
+    default: return int64_t((uint64_t(__ldg(p + 1)) << 32) | __ldg(p));
   }
 }
 
-// Order-preserving key (signed k0, unsigned k1) of a value: arrow's comparison kernels
-// order floats by IEEE totalOrder and strings bytewise; inline views (<= 12 bytes, zero
-// padded) compare as (big-endian first 8 bytes, big-endian next 4 bytes, length).
-__device__ __forceinline__ bool raw_to_key(const uint4 v, int type, int64_t* k0, uint64_t* k1) {
-  switch (type) {
-    case PGF_T_INT16: case PGF_T_INT32: case PGF_T_INT64:
-      *k0 = raw_to_i64(v, type); *k1 = 0; return true;
-    case PGF_T_FLOAT64: {
-      int64_t b = int64_t((uint64_t(v.y) << 32) | v.x);
-      b ^= int64_t(uint64_t(b >> 63) >> 1);
-      *k0 = b; *k1 = 0; return true;
-    }
-    case PGF_T_FLOAT32: {
-      int32_t b = int32_t(v.x);
-      b ^= int32_t(uint32_t(b >> 31) >> 1);
-      *k0 = b; *k1 = 0; return true;
-    }
-    case PGF_T_DECIMAL128:
-      *k0 = int64_t((uint64_t(v.w) << 32) | v.z); *k1 = (uint64_t(v.y) << 32) | v.x; return true;
-    case PGF_T_UTF8VIEW: case PGF_T_BINARYVIEW: {
-      const uint64_t hi = (uint64_t(bswap32(v.y)) << 32) | bswap32(v.z);
-      *k0 = int64_t(hi ^ 0x8000000000000000ull);
-      *k1 = (uint64_t(bswap32(v.w)) << 32) | v.x;
-      return v.x <= 12u;  // out-of-line views are not handled by this kernel
-    }
-    default: return false;
-  }
+__device__ __forceinline__ uint4 load_u128(const DevRef& ref, const Row& row) {
+  if (ref.src == SRC_PAGE) return reinterpret_cast<const uint4*>(row.stage + ref.off)[row.r];
+  const uint32_t* p = row.pay + 3 + ref.off;
+  return make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 
-__device__ __forceinline__ bool key_cmp(uint32_t cmp, int64_t a0, uint64_t a1, int64_t b0, uint64_t b1) {
-  const bool lt = a0 < b0 || (a0 == b0 && a1 < b1);
-  const bool eq = a0 == b0 && a1 == b1;
-  switch (cmp) {
-    case PGF_CMP_LT: return lt;
-    case PGF_CMP_LE: return lt || eq;
-    case PGF_CMP_GT: return !(lt || eq);
-    case PGF_CMP_GE: return !lt;
-    case PGF_CMP_EQ: return eq;
-    default: return !eq;
+__device__ __forceinline__ double load_f64(const DevRef& ref, const Row& row) {
+  if (ref.src == SRC_PAGE) {
+    const uint8_t* p = row.stage + ref.off;
+    switch (ref.ld) {
+      case LD_F64: return reinterpret_cast<const double*>(p)[row.r];
+      case LD_F32: return double(reinterpret_cast<const float*>(p)[row.r]);
+      default: return double(load_i64(ref, row));  // AVG over integers runs on the Float64 cast
+    }
   }
+  const uint32_t* p = row.pay + 3 + ref.off;
+  if (ref.ld == LD_F64) return __longlong_as_double((long long)((uint64_t(__ldg(p + 1)) << 32) | __ldg(p)));
+  if (ref.ld == LD_F32) return double(__uint_as_float(__ldg(p)));
+  return double(load_i64(ref, row));
 }
 
-// ---- expression evaluation ------------------------------------------------------------
-template <uint32_t ACC>
-__device__ __forceinline__ bool eval_expr(const DevPlan& P, const RowCtx& c, const DevExpr& e,
-                                          typename AccOps<ACC>::T* out);
+// ---- FilterExec: one normalised conjunct -------------------------------------------------
+// Keys are order preserving: integers as themselves, floats by IEEE totalOrder (what arrow's
+// comparison kernels use), inline views (<= 12 bytes, zero padded) as (big-endian first 8
+// bytes, big-endian next 4 bytes, length), decimals as (hi, lo).
+__device__ __forceinline__ int64_t f64_key(int64_t bits) { return bits ^ int64_t(uint64_t(bits >> 63) >> 1); }
 
-template <>
-__device__ __forceinline__ bool eval_expr<CLS_F64>(const DevPlan& P, const RowCtx& c, const DevExpr& e, double* out) {
-  double v = 1.0;
+__device__ __forceinline__ bool in_range1(int64_t k, const DevTerm& T) { return uint64_t(k - T.lo0) <= T.lo1; }
+__device__ __forceinline__ bool in_range2(int64_t k0, uint64_t k1, const DevTerm& T) {
+  const bool ge = k0 > T.lo0 || (k0 == T.lo0 && k1 >= T.lo1);
+  const bool le = k0 < T.hi0 || (k0 == T.hi0 && k1 <= T.hi1);
+  return ge && le;
+}
+__device__ __forceinline__ bool view_in_range(const uint4 v, const DevTerm& T, uint32_t& bad) {
+  const uint64_t hi = (uint64_t(bswap32(v.y)) << 32) | bswap32(v.z);
+  bad += v.x > 12u;  // out-of-line views are not compared by this kernel
+  return in_range2(int64_t(hi ^ 0x8000000000000000ull), (uint64_t(bswap32(v.w)) << 32) | v.x, T);
+}
+
+// Evaluates the conjunct for two rows of the tile with one dispatch (ILP across the rows).
+__device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stage, uint32_t r0, uint32_t r1,
+                                           uint32_t tile_nulls, uint32_t& bad, bool& p0, bool& p1) {
+  const uint8_t* p = stage + T.ref.off;
+  bool a, b;
+  switch (T.ref.ld) {
+    case LD_F64: {
+      const int64_t x0 = reinterpret_cast<const int64_t*>(p)[r0], x1 = reinterpret_cast<const int64_t*>(p)[r1];
+      a = in_range1(f64_key(x0), T); b = in_range1(f64_key(x1), T);
+      break;
+    }
+    case LD_VIEW: {
+      const uint4 v0 = reinterpret_cast<const uint4*>(p)[r0], v1 = reinterpret_cast<const uint4*>(p)[r1];
+      a = view_in_range(v0, T, bad); b = view_in_range(v1, T, bad);
+      break;
+    }
+    case LD_I32: {
+      const int32_t x0 = reinterpret_cast<const int32_t*>(p)[r0], x1 = reinterpret_cast<const int32_t*>(p)[r1];
+      a = in_range1(x0, T); b = in_range1(x1, T);
+      break;
+    }
+    case LD_I64: {
+      const int64_t x0 = reinterpret_cast<const int64_t*>(p)[r0], x1 = reinterpret_cast<const int64_t*>(p)[r1];
+      a = in_range1(x0, T); b = in_range1(x1, T);
+      break;
+    }
+    case LD_I16: {
+      const int16_t x0 = reinterpret_cast<const int16_t*>(p)[r0], x1 = reinterpret_cast<const int16_t*>(p)[r1];
+      a = in_range1(x0, T); b = in_range1(x1, T);
+      break;
+    }
+    case LD_F32: {
+      const int32_t x0 = reinterpret_cast<const int32_t*>(p)[r0], x1 = reinterpret_cast<const int32_t*>(p)[r1];
+      a = in_range1(x0 ^ int32_t(uint32_t(x0 >> 31) >> 1), T); b = in_range1(x1 ^ int32_t(uint32_t(x1 >> 31) >> 1), T);
+      break;
+    }
+    default: {  // LD_DEC
+      const uint4 v0 = reinterpret_cast<const uint4*>(p)[r0], v1 = reinterpret_cast<const uint4*>(p)[r1];
+      a = in_range2(int64_t((uint64_t(v0.w) << 32) | v0.z), (uint64_t(v0.y) << 32) | v0.x, T);
+      b = in_range2(int64_t((uint64_t(v1.w) << 32) | v1.z), (uint64_t(v1.y) << 32) | v1.x, T);
+      break;
+    }
+  }
+  if (T.op != TERM_IN_RANGE) { a = T.op == TERM_NOT_IN_RANGE && !a; b = T.op == TERM_NOT_IN_RANGE && !b; }
+  if (T.ref.valid_off != kNoValidity && ((tile_nulls >> T.ref.pcol) & 1)) {  // NULL => not TRUE => dropped
+    a &= (stage[T.ref.valid_off + (r0 >> 3)] >> (r0 & 7)) & 1;
+    b &= (stage[T.ref.valid_off + (r1 >> 3)] >> (r1 & 7)) & 1;
+  }
+  p0 &= a;
+  p1 &= b;
+}
+
+// ---- ProjectionExec / aggregate arguments -------------------------------------------------
+__device__ __forceinline__ bool expr_inputs_valid(const DevExpr& e, const Row& row) {
+  if (!(row.tile_nulls & e.null_cols) && !e.has_payload) return true;
   bool ok = true;
 #pragma unroll
-  for (uint32_t i = 0; i < 3; ++i) {
-    if (i < e.nfactors) {
-      const DevFactor& f = e.f[i];
-      ok &= ref_valid(P, c, f.ref);
-      const uint4 raw = ref_load(P, c, f.ref);
-      double x;
-      if (f.ref.type == PGF_T_FLOAT64) x = __longlong_as_double((long long)((uint64_t(raw.y) << 32) | raw.x));
-      else if (f.ref.type == PGF_T_FLOAT32) x = double(__uint_as_float(raw.x));
-      else x = double(raw_to_i64(raw, f.ref.type));  // AVG over integers runs on the Float64 cast
-      // one IEEE operation per node, no FMA contraction (explicit _rn intrinsics)
-      if (f.kind == PGF_FACTOR_CONST_MINUS_COL) x = __dsub_rn(f.cf, x);
-      else if (f.kind == PGF_FACTOR_CONST_PLUS_COL) x = __dadd_rn(f.cf, x);
-      v = i == 0 ? x : __dmul_rn(v, x);
-    }
-  }
-  *out = v;
+  for (uint32_t i = 0; i < 3; ++i)
+    if (i < e.nfactors) ok &= ref_valid(e.f[i].ref, row);
   return ok;
 }
 
+template <uint32_t ACC>
+__device__ __forceinline__ typename AccOps<ACC>::T eval_expr(const DevExpr& e, const Row& row);
+
+// Float64: one IEEE operation per node, never contracted into an FMA (explicit _rn intrinsics).
 template <>
-__device__ __forceinline__ bool eval_expr<CLS_I64>(const DevPlan& P, const RowCtx& c, const DevExpr& e, uint64_t* out) {
+__device__ __forceinline__ double eval_expr<CLS_F64>(const DevExpr& e, const Row& row) {
+  const uint8_t* st = row.stage;
+  const uint32_t r = row.r;
+  switch (e.form) {
+    case FORM_X:
+      return reinterpret_cast<const double*>(st + e.f[0].ref.off)[r];
+    case FORM_XY:
+      return __dmul_rn(reinterpret_cast<const double*>(st + e.f[0].ref.off)[r], reinterpret_cast<const double*>(st + e.f[1].ref.off)[r]);
+    case FORM_X_CMY:
+      return __dmul_rn(reinterpret_cast<const double*>(st + e.f[0].ref.off)[r],
+                       __dsub_rn(e.f[1].cf, reinterpret_cast<const double*>(st + e.f[1].ref.off)[r]));
+    case FORM_X_CMY_CPZ:
+      return __dmul_rn(__dmul_rn(reinterpret_cast<const double*>(st + e.f[0].ref.off)[r],
+                                 __dsub_rn(e.f[1].cf, reinterpret_cast<const double*>(st + e.f[1].ref.off)[r])),
+                       __dadd_rn(e.f[2].cf, reinterpret_cast<const double*>(st + e.f[2].ref.off)[r]));
+    default: {
+      double v = 1.0;
+#pragma unroll
+      for (uint32_t i = 0; i < 3; ++i) {
+        if (i < e.nfactors) {
+          const DevFactor& f = e.f[i];
+          double x = load_f64(f.ref, row);
+          if (f.kind == PGF_FACTOR_CONST_MINUS_COL) x = __dsub_rn(f.cf, x);
+          else if (f.kind == PGF_FACTOR_CONST_PLUS_COL) x = __dadd_rn(f.cf, x);
+          v = i == 0 ? x : __dmul_rn(v, x);
+        }
+      }
+      return v;
+    }
+  }
+}
+
+template <>
+__device__ __forceinline__ uint64_t eval_expr<CLS_I64>(const DevExpr& e, const Row& row) {
   uint64_t v = 1;
-  bool ok = true;
 #pragma unroll
   for (uint32_t i = 0; i < 3; ++i) {
     if (i < e.nfactors) {
       const DevFactor& f = e.f[i];
-      ok &= ref_valid(P, c, f.ref);
-      uint64_t x = uint64_t(raw_to_i64(ref_load(P, c, f.ref), f.ref.type));
+      uint64_t x = uint64_t(load_i64(f.ref, row));
       if (f.kind == PGF_FACTOR_CONST_MINUS_COL) x = uint64_t(f.ci_lo) - x;
       else if (f.kind == PGF_FACTOR_CONST_PLUS_COL) x = uint64_t(f.ci_lo) + x;
       v = i == 0 ? x : v * x;  // wrapping
     }
   }
-  *out = v;
-  return ok;
+  return v;
 }
 
 template <>
-__device__ __forceinline__ bool eval_expr<CLS_I128>(const DevPlan& P, const RowCtx& c, const DevExpr& e, I128* out) {
+__device__ __forceinline__ I128 eval_expr<CLS_I128>(const DevExpr& e, const Row& row) {
   I128 v{1, 0};
-  bool ok = true;
 #pragma unroll
   for (uint32_t i = 0; i < 3; ++i) {
     if (i < e.nfactors) {
       const DevFactor& f = e.f[i];
-      ok &= ref_valid(P, c, f.ref);
-      const uint4 raw = ref_load(P, c, f.ref);
       I128 x;
-      if (f.ref.type == PGF_T_DECIMAL128) {
+      if (f.ref.ld == LD_DEC) {
+        const uint4 raw = load_u128(f.ref, row);
         x.lo = (uint64_t(raw.y) << 32) | raw.x;
         x.hi = (uint64_t(raw.w) << 32) | raw.z;
       } else {
-        const int64_t s = raw_to_i64(raw, f.ref.type);
+        const int64_t s = load_i64(f.ref, row);
         x.lo = uint64_t(s);
         x.hi = s < 0 ? ~0ull : 0ull;
       }
@@ -303,18 +349,21 @@ __device__ __forceinline__ bool eval_expr<CLS_I128>(const DevPlan& P, const RowC
       v = i == 0 ? x : i128_mul(v, x);
     }
   }
-  *out = v;
-  return ok;
+  return v;
 }
 
 // ---- global group table ---------------------------------------------------------------
-// Returns the slot holding `key` (inserting it if absent) or -1 when the table is full.
-__device__ __forceinline__ int64_t group_slot(const GroupTable& t, const uint64_t* key, uint32_t nwords, uint32_t knull) {
+__device__ __forceinline__ uint64_t key_hash(const uint64_t* key, uint32_t nwords, uint32_t knull) {
   uint64_t h = 0x9E3779B97F4A7C15ull ^ knull;
 #pragma unroll
   for (uint32_t w = 0; w < kKeyWords; ++w)
     if (w < nwords) h = mix64(h ^ key[w]) + 0x632BE59BD9B4E019ull;
-  uint32_t i = uint32_t(h) & t.mask;
+  return h;
+}
+
+// Returns the slot holding `key` (inserting it if absent) or -1 when the table is full.
+__device__ __forceinline__ int64_t group_slot(const GroupTable& t, const uint64_t* key, uint32_t nwords, uint32_t knull) {
+  uint32_t i = uint32_t(key_hash(key, nwords, knull)) & t.mask;
   const uint32_t ready = 2u | (knull << 8);
   for (uint32_t probes = 0; probes <= t.mask; ++probes, i = (i + 1) & t.mask) {
     uint32_t s = *reinterpret_cast<volatile uint32_t*>(t.state + i);
@@ -352,6 +401,7 @@ struct BlockShared {
   StageMeta meta[kStages];
   // CTA-local dictionary of the first kRegGroups group keys (register pre-aggregation)
   uint64_t dict_keys[kRegGroups][kKeyWords];
+  uint64_t dict_hash[kRegGroups];
   uint32_t dict_null[kRegGroups];
   uint32_t dict_n;
   uint32_t dict_lock;
@@ -359,53 +409,47 @@ struct BlockShared {
   uint64_t red[kMaxConsumerWarps][2];
 };
 
-__device__ __forceinline__ int dict_find(const BlockShared* sh, const uint64_t* key, uint32_t nwords, uint32_t knull, uint32_t n) {
-  for (uint32_t g = 0; g < n; ++g) {
-    bool same = *reinterpret_cast<const volatile uint32_t*>(&sh->dict_null[g]) == knull;
+__device__ __forceinline__ bool dict_entry_equals(const BlockShared* sh, uint32_t g, const uint64_t* key, uint32_t nwords, uint32_t knull) {
+  bool same = *reinterpret_cast<const volatile uint32_t*>(&sh->dict_null[g]) == knull;
 #pragma unroll
-    for (uint32_t w = 0; w < kKeyWords; ++w)
-      if (w < nwords) same &= *reinterpret_cast<const volatile uint64_t*>(&sh->dict_keys[g][w]) == key[w];
-    if (same) return int(g);
-  }
-  return -1;
+  for (uint32_t w = 0; w < kKeyWords; ++w)
+    if (w < nwords) same &= *reinterpret_cast<const volatile uint64_t*>(&sh->dict_keys[g][w]) == key[w];
+  return same;
 }
 
-// Find the key in the CTA dictionary, appending it while there is room.  Returns -1 when
-// the key is not one of the (at most kRegGroups) register-resident groups.
-__device__ __forceinline__ int dict_lookup_or_insert(BlockShared* sh, const uint64_t* key, uint32_t nwords, uint32_t knull) {
-  uint32_t n = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
-  int g = dict_find(sh, key, nwords, knull, n);
-  if (g >= 0 || n == kRegGroups) return g;
-  // rare path: append under a CTA-wide spin lock (at most kRegGroups successful appends)
-  bool done = false;
-  while (!done) {
+// Find the key in the CTA dictionary, appending it while there is room (rare path: at most
+// kRegGroups successful appends per CTA).  Returns -1 when the key is not one of the
+// register-resident groups.
+static __device__ __noinline__ int dict_lookup_or_insert(BlockShared* sh, const uint64_t* key, uint32_t nwords, uint32_t knull, uint64_t h) {
+  for (;;) {
+    const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
+    for (uint32_t g = 0; g < n; ++g)
+      if (dict_entry_equals(sh, g, key, nwords, knull)) return int(g);
+    if (n == kRegGroups) return -1;
     if (atomicCAS(&sh->dict_lock, 0u, 1u) == 0u) {
-      n = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
-      g = dict_find(sh, key, nwords, knull, n);
-      if (g < 0 && n < kRegGroups) {
-#pragma unroll
-        for (uint32_t w = 0; w < kKeyWords; ++w)
-          if (w < nwords) sh->dict_keys[n][w] = key[w];
+      int g = -1;
+      if (*reinterpret_cast<volatile uint32_t*>(&sh->dict_n) == n) {  // nothing appended meanwhile
+        for (uint32_t w = 0; w < kKeyWords; ++w) sh->dict_keys[n][w] = w < nwords ? key[w] : 0;
         sh->dict_null[n] = knull;
+        sh->dict_hash[n] = h;
         __threadfence_block();
         *reinterpret_cast<volatile uint32_t*>(&sh->dict_n) = n + 1;
         g = int(n);
       }
       __threadfence_block();
       atomicExch(&sh->dict_lock, 0u);
-      done = true;
+      if (g >= 0) return g;
     }
   }
-  return g;
 }
 
 // ---- the kernel ----------------------------------------------------------------------
-template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ>
+template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T>
 __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED);
   using Ops = AccOps<ACC>;
   using AccT = typename Ops::T;
-  constexpr uint32_t MAXE = SINK == SINK_AGG ? Ops::kMaxExprs : 1;
+  constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -434,15 +478,23 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
 #pragma unroll
     for (uint32_t e = 0; e < MAXE; ++e) acc[g][e] = Ops::zero();
   }
+  uint64_t dh[G];  // hashes of the CTA dictionary entries, cached in registers
+  uint32_t dn = 0;
+#pragma unroll
+  for (uint32_t g = 0; g < G; ++g) dh[g] = 0;
   uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0;
 
   if (warp == 0) {
     // ===== producer: TMA bulk copies of the needed column slices of each row tile =====
     uint32_t k = 0;
-    for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
+    uint32_t item = blockIdx.x;
+    PageDesc d_next{};
+    if (item < P.nitems) d_next = P.descs[item / P.tiles_per_page];
+    for (; item < P.nitems; item += gridDim.x, ++k) {
       const uint32_t s = k % kStages;
       const uint32_t page = item / P.tiles_per_page, tile = item - page * P.tiles_per_page;
-      const PageDesc d = P.descs[page];
+      const PageDesc d = d_next;
+      if (item + gridDim.x < P.nitems) d_next = P.descs[(item + gridDim.x) / P.tiles_per_page];  // prefetch
       const LayoutClass* lc = P.classes + d.layout_class;
       const uint32_t r0 = tile * P.tile_rows;
       const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
@@ -488,164 +540,184 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       const uint32_t s = k % kStages;
       mbar_wait(&sh->full[s], (k / kStages) & 1u);
       const uint32_t nrows = sh->meta[s].nrows;
-      RowCtx c;
-      c.stage = stages + size_t(s) * P.stage_bytes;
-      c.tile_nulls = sh->meta[s].null_mask;
-      for (uint32_t r = ct; r < nrows; r += NCT) {
-        c.r = r;
-        ++n_in;
-        bool keep = true;
+      const uint8_t* stage = stages + size_t(s) * P.stage_bytes;
+      const uint32_t tile_nulls = sh->meta[s].null_mask;
+      // two rows per thread and iteration: r0 and r0 + NCT (independent chains => ILP).  The
+      // loop bound is warp-uniform so the warp votes below are executed by all 32 lanes.
+      for (uint32_t b0 = ct - lane; b0 < nrows; b0 += 2 * NCT) {
+        const bool has0 = b0 + lane < nrows, has1 = b0 + lane + NCT < nrows;
+        const uint32_t r0 = has0 ? b0 + lane : 0u;
+        const uint32_t r1 = has1 ? b0 + lane + NCT : r0;
+        bool keep0 = has0, keep1 = has1;
+        n_in += uint32_t(has0) + uint32_t(has1);
         // -- runtime Bloom probes: NULL key => DefinitelyAbsent (shared.rs:367-374)
-        for (uint32_t b = 0; b < P.nbloom && keep; ++b) {
+        for (uint32_t b = 0; b < P.nbloom; ++b) {
           const DevBloomProbe& bp = P.bloom[b];
-          keep = ref_valid(P, c, bp.key) &&
-                 bloom_contains(bp.bloom, uint64_t(raw_to_i64(ref_load(P, c, bp.key), bp.key.type)));
+          Row q{stage, r0, tile_nulls, nullptr, 0};
+          if (keep0) keep0 = ref_valid(bp.key, q) && bloom_contains(bp.bloom, uint64_t(load_i64(bp.key, q)));
+          q.r = r1;
+          if (keep1) keep1 = ref_valid(bp.key, q) && bloom_contains(bp.bloom, uint64_t(load_i64(bp.key, q)));
         }
-        if (!keep) continue;
-        ++n_bloom;
-        // -- FilterExec: every conjunct must be TRUE (NULL drops the row)
-#pragma unroll
-        for (uint32_t t = 0; t < kMaxTerms; ++t) {
-          if (t < P.nterms) {
-            const DevTerm& tm = P.terms[t];
-            int64_t k0;
-            uint64_t k1;
-            const bool ok = raw_to_key(ref_load(P, c, tm.ref), tm.ref.type, &k0, &k1);
-            const bool valid = ref_valid(P, c, tm.ref);
-            if (valid && !ok) ++n_bad;
-            keep &= valid && ok && key_cmp(tm.cmp, k0, k1, tm.k0, tm.k1);
-          }
+        n_bloom += uint32_t(keep0) + uint32_t(keep1);
+        // -- FilterExec: every conjunct must be TRUE; stop as soon as the whole warp is dead
+        for (uint32_t t = 0; t < P.nterms; ++t) {
+          if (!__any_sync(0xffffffffu, keep0 || keep1)) break;
+          term_pass2(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
         }
-        if (!keep) continue;
-        ++n_filt;
+        n_filt += uint32_t(keep0) + uint32_t(keep1);
 
-        // -- sink (optionally behind one HashJoinExec probe)
-        auto sink = [&](const RowCtx& rc) {
-          ++n_out;
-          if constexpr (SINK == SINK_AGG) {
-            AccT v[MAXE];
-            bool all_valid = true;
-            uint32_t valid_mask = 0;
+#pragma unroll 1
+        for (uint32_t half = 0; half < 2; ++half) {
+          if (!(half ? keep1 : keep0)) continue;
+          Row row{stage, half ? r1 : r0, tile_nulls, nullptr, 0};
+
+          // -- sink (optionally behind one HashJoinExec probe)
+          auto sink = [&](const Row& rc) {
+            ++n_out;
+            if constexpr (SINK == SINK_AGG) {
+              uint64_t key[kKeyWords] = {0, 0, 0, 0};
+              uint32_t knull = 0;
+              int g = 0;
+              if constexpr (GROUPED) {
 #pragma unroll
-            for (uint32_t e = 0; e < MAXE; ++e) {
-              v[e] = Ops::zero();
-              if (e < P.nexprs) {
-                const bool ok = eval_expr<ACC>(P, rc, P.exprs[e], &v[e]);
-                all_valid &= ok;
-                valid_mask |= uint32_t(ok) << e;
-              }
-            }
-            uint64_t key[kKeyWords] = {0, 0, 0, 0};
-            uint32_t knull = 0;
-            int g = 0;
-            if constexpr (GROUPED) {
-#pragma unroll
-              for (uint32_t kp = 0; kp < 4; ++kp) {
-                if (kp < P.nkeys) {
-                  const DevKeyPart& part = P.keys[kp];
-                  if (!ref_valid(P, rc, part.ref)) {
-                    knull |= 1u << kp;  // NULL keys form one group; words stay zero
-                  } else {
-                    const uint4 raw = ref_load(P, rc, part.ref);
-                    uint64_t w0, w1 = 0;
-                    if (part.nwords == 1) {
-                      w0 = uint64_t(raw_to_i64(raw, part.ref.type));
+                for (uint32_t kp = 0; kp < 4; ++kp) {
+                  if (kp < P.nkeys) {
+                    const DevKeyPart& part = P.keys[kp];
+                    if (!ref_valid(part.ref, rc)) {
+                      knull |= 1u << kp;  // NULL keys form one group; words stay zero
                     } else {
-                      if ((part.ref.type == PGF_T_UTF8VIEW || part.ref.type == PGF_T_BINARYVIEW) && raw.x > 12u) ++n_bad;
-                      w0 = (uint64_t(raw.y) << 32) | raw.x;
-                      w1 = (uint64_t(raw.w) << 32) | raw.z;
-                    }
+                      uint64_t w0, w1 = 0;
+                      if (part.nwords == 1) {
+                        w0 = uint64_t(load_i64(part.ref, rc));
+                      } else {
+                        const uint4 raw = load_u128(part.ref, rc);
+                        if (part.ref.ld == LD_VIEW && raw.x > 12u) ++n_bad;
+                        w0 = (uint64_t(raw.y) << 32) | raw.x;
+                        w1 = (uint64_t(raw.w) << 32) | raw.z;
+                      }
 #pragma unroll
-                    for (uint32_t w = 0; w < kKeyWords; ++w) {  // static indices keep key[] in registers
-                      if (w == part.word) key[w] = w0;
-                      if (part.nwords == 2 && w == part.word + 1u) key[w] = w1;
+                      for (uint32_t w = 0; w < kKeyWords; ++w) {  // static indices keep key[] in registers
+                        if (w == part.word) key[w] = w0;
+                        if (part.nwords == 2 && w == part.word + 1u) key[w] = w1;
+                      }
                     }
                   }
                 }
-              }
-              g = dict_lookup_or_insert(sh, key, P.nkeywords, knull);
-            }
-            if (all_valid && g >= 0) {
-              // fast path: register accumulators (predicated over the register groups)
+                // CTA dictionary lookup: hashes cached in registers, full compare on a hit
+                const uint64_t h = key_hash(key, P.nkeywords, knull) | 1ull;
+                g = -1;
 #pragma unroll
-              for (uint32_t gg = 0; gg < G; ++gg) {
-                if (G == 1 || gg == uint32_t(g)) {
-                  grows[gg] += 1;
+                for (uint32_t gg = 0; gg < G; ++gg)
+                  if (gg < dn && dh[gg] == h) g = int(gg);
+                if (g < 0 || !dict_entry_equals(sh, uint32_t(g), key, P.nkeywords, knull)) {
+                  g = dict_lookup_or_insert(sh, key, P.nkeywords, knull, h);
+                  dn = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
 #pragma unroll
-                  for (uint32_t e = 0; e < MAXE; ++e)
-                    if (e < P.nexprs) acc[gg][e] = Ops::add(acc[gg][e], v[e]);
+                  for (uint32_t gg = 0; gg < G; ++gg) dh[gg] = gg < dn ? *reinterpret_cast<volatile uint64_t*>(&sh->dict_hash[gg]) : 0;
                 }
               }
-            } else {
-              // slow path: straight to the global table (NULL inputs, or > kRegGroups groups)
-              const int64_t slot = GROUPED ? group_slot(P.table, key, P.nkeywords, knull) : 0;
-              if (slot >= 0) {
+              bool all_valid = true;
+              uint32_t valid_mask = 0;
+              AccT v[MAXE];
 #pragma unroll
-                for (uint32_t e = 0; e < MAXE; ++e) {
-                  if (e < P.nexprs && ((valid_mask >> e) & 1)) {
-                    Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, v[e]);
-                    atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
+              for (uint32_t e = 0; e < MAXE; ++e) {
+                v[e] = Ops::zero();
+                if (e < P.nexprs) {
+                  const bool ok = expr_inputs_valid(P.exprs[e], rc);
+                  v[e] = eval_expr<ACC>(P.exprs[e], rc);
+                  all_valid &= ok;
+                  valid_mask |= uint32_t(ok) << e;
+                }
+              }
+              if (all_valid && g >= 0) {
+                // fast path: register accumulators of the row's group
+#pragma unroll
+                for (uint32_t gg = 0; gg < G; ++gg) {
+                  if (G == 1 || gg == uint32_t(g)) {
+                    grows[gg] += 1;
+#pragma unroll
+                    for (uint32_t e = 0; e < MAXE; ++e)
+                      if (e < P.nexprs) acc[gg][e] = Ops::add(acc[gg][e], v[e]);
                   }
                 }
-                atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
-              }
-            }
-          } else if constexpr (SINK == SINK_JOIN_BUILD) {
-            const JoinBuild& jb = P.build;
-            if (ref_valid(P, rc, jb.key)) {  // NULL keys never match: not inserted
-              const int64_t key = raw_to_i64(ref_load(P, rc, jb.key), jb.key.type);
-              uint32_t pay[5] = {0, 0, 0, 0, 0};
-              uint32_t occ = 1u;
+              } else {
+                // slow path: straight to the global table (NULL inputs, or > kRegGroups groups)
+                const int64_t slot = GROUPED ? group_slot(P.table, key, P.nkeywords, knull) : 0;
+                if (slot >= 0) {
 #pragma unroll
-              for (uint32_t p = 0; p < 4; ++p) {
-                if (p >= jb.npayload) continue;
-                if (!ref_valid(P, rc, jb.payload[p])) { occ |= 2u << p; continue; }
-                const uint4 raw = ref_load(P, rc, jb.payload[p]);
-                const uint32_t w = jb.payload_word[p], nw = jb.payload_nwords[p];
-#pragma unroll
-                for (uint32_t q = 0; q < 5; ++q) {  // static indices keep pay[] in registers
-                  if (q == w) pay[q] = raw.x;
-                  if (nw >= 2 && q == w + 1) pay[q] = raw.y;
-                  if (nw == 4 && q == w + 2) pay[q] = raw.z;
-                  if (nw == 4 && q == w + 3) pay[q] = raw.w;
+                  for (uint32_t e = 0; e < MAXE; ++e) {
+                    if (e < P.nexprs && ((valid_mask >> e) & 1)) {
+                      Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, v[e]);
+                      atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
+                    }
+                  }
+                  atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
                 }
               }
-              uint32_t i = uint32_t(mix64(uint64_t(key))) & jb.mask;
-              for (;;) {  // capacity >= 2 x rows: an empty slot always exists
-                uint32_t* slot = reinterpret_cast<uint32_t*>(jb.slots + uint64_t(i) * jb.slot_u4);
-                if (atomicCAS(slot + 2, 0u, occ) == 0u) {
-                  slot[0] = uint32_t(uint64_t(key));
-                  slot[1] = uint32_t(uint64_t(key) >> 32);
-                  slot[3] = pay[0];
-                  if (jb.slot_u4 == 2) { slot[4] = pay[1]; slot[5] = pay[2]; slot[6] = pay[3]; slot[7] = pay[4]; }
-                  break;
+            } else if constexpr (SINK == SINK_JOIN_BUILD) {
+              const JoinBuild& jb = P.build;
+              if (ref_valid(jb.key, rc)) {  // NULL keys never match: not inserted
+                const int64_t key = load_i64(jb.key, rc);
+                uint32_t pay[5] = {0, 0, 0, 0, 0};
+                uint32_t occ = 1u;
+#pragma unroll
+                for (uint32_t p = 0; p < 4; ++p) {
+                  if (p >= jb.npayload) continue;
+                  if (!ref_valid(jb.payload[p], rc)) { occ |= 2u << p; continue; }
+                  const uint32_t w = jb.payload_word[p], nw = jb.payload_nwords[p];
+                  uint4 raw = make_uint4(0, 0, 0, 0);
+                  if (nw == 4) raw = load_u128(jb.payload[p], rc);
+                  else {
+                    const int64_t x = jb.payload[p].ld == LD_F64 ? __double_as_longlong(load_f64(jb.payload[p], rc))
+                                    : jb.payload[p].ld == LD_F32 ? int64_t(__float_as_uint(float(load_f64(jb.payload[p], rc))))
+                                                                 : load_i64(jb.payload[p], rc);
+                    raw.x = uint32_t(uint64_t(x));
+                    raw.y = uint32_t(uint64_t(x) >> 32);
+                  }
+#pragma unroll
+                  for (uint32_t q = 0; q < 5; ++q) {  // static indices keep pay[] in registers
+                    if (q == w) pay[q] = raw.x;
+                    if (nw >= 2 && q == w + 1) pay[q] = raw.y;
+                    if (nw == 4 && q == w + 2) pay[q] = raw.z;
+                    if (nw == 4 && q == w + 3) pay[q] = raw.w;
+                  }
                 }
-                i = (i + 1) & jb.mask;
+                uint32_t i = uint32_t(mix64(uint64_t(key))) & jb.mask;
+                for (;;) {  // capacity >= 2 x rows: an empty slot always exists
+                  uint32_t* slot = reinterpret_cast<uint32_t*>(jb.slots + uint64_t(i) * jb.slot_u4);
+                  if (atomicCAS(slot + 2, 0u, occ) == 0u) {
+                    slot[0] = uint32_t(uint64_t(key));
+                    slot[1] = uint32_t(uint64_t(key) >> 32);
+                    slot[3] = pay[0];
+                    if (jb.slot_u4 == 2) { slot[4] = pay[1]; slot[5] = pay[2]; slot[6] = pay[3]; slot[7] = pay[4]; }
+                    break;
+                  }
+                  i = (i + 1) & jb.mask;
+                }
+                if (P.has_build_bloom) { bloom_insert(P.build_bloom, uint64_t(key)); ++n_bloom_ins; }
               }
-              if (P.has_build_bloom) { bloom_insert(P.build_bloom, uint64_t(key)); ++n_bloom_ins; }
             }
-          }
-        };
+          };
 
-        if constexpr (NJ == 0) {
-          c.pay[0] = nullptr; c.occ[0] = 0;
-          sink(c);
-        } else {
-          const DevJoin& j = P.joins[0];
-          if (!ref_valid(P, c, j.key)) continue;  // NULL keys never match
-          const int64_t key = raw_to_i64(ref_load(P, c, j.key), j.key.type);
-          const uint32_t klo = uint32_t(uint64_t(key)), khi = uint32_t(uint64_t(key) >> 32);
-          uint32_t i = uint32_t(mix64(uint64_t(key))) & j.mask;
-          for (;;) {
-            const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
-            const uint4 s0 = __ldg(slot);
-            if ((s0.z & 1u) == 0u) break;
-            if (s0.x == klo && s0.y == khi) {
-              c.pay[0] = reinterpret_cast<const uint32_t*>(slot);
-              c.occ[0] = s0.z;
-              sink(c);
+          if constexpr (NJ == 0) {
+            sink(row);
+          } else {
+            const DevJoin& j = P.joins[0];
+            if (!ref_valid(j.key, row)) continue;  // NULL keys never match
+            const int64_t key = load_i64(j.key, row);
+            const uint32_t klo = uint32_t(uint64_t(key)), khi = uint32_t(uint64_t(key) >> 32);
+            uint32_t i = uint32_t(mix64(uint64_t(key))) & j.mask;
+            for (;;) {
+              const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
+              const uint4 s0 = __ldg(slot);
+              if ((s0.z & 1u) == 0u) break;
+              if (s0.x == klo && s0.y == khi) {
+                row.pay = reinterpret_cast<const uint32_t*>(slot);
+                row.occ = s0.z;
+                sink(row);
+              }
+              i = (i + 1) & j.mask;
             }
-            i = (i + 1) & j.mask;
           }
         }
       }

@@ -6,6 +6,7 @@
 #include "context.hpp"
 #include "layout.hpp"
 #include "pipeline_kernel.cuh"
+#include "pipeline_shapes.hpp"
 
 namespace pgf {
 
@@ -643,6 +644,27 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
   return PGF_OK;
 }
 
+// A specialised instantiation exists when every term is a plain range over the load kinds of
+// a registered shape and the aggregate arguments have the registered forms.
+const ShapeEntry* pick_shape(const Lowered& L) {
+  const DevPlan& D = L.dev;
+  if (D.nterms > 4 || D.nbloom > 0 && false) return nullptr;
+  ShapeSig sig{};
+  sig.sink = D.sink;
+  sig.acc = L.acc_cls;
+  sig.grouped = L.grouped;
+  sig.nj = L.nj;
+  sig.maxe = L.maxe;
+  sig.nterms = int(D.nterms);
+  for (uint32_t t = 0; t < D.nterms; ++t) {
+    if (D.terms[t].op != TERM_IN_RANGE) return nullptr;
+    sig.term_ld[t] = D.terms[t].ref.ld;
+  }
+  sig.nexprs = int(D.nexprs);
+  for (uint32_t e = 0; e < D.nexprs; ++e) sig.expr_form[e] = int(D.exprs[e].form);
+  return find_shape(sig);
+}
+
 struct TableAlloc {
   GroupTable t{};
   uint64_t capacity = 0;
@@ -740,7 +762,10 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     CU(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->compute_stream));
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
     if (L.dev.nitems) {
-      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
+      if (const ShapeEntry* se = pick_shape(L))
+        CU(ctx, se->fn(L.dev, grid, L.smem, ctx->compute_stream));
+      else
+        CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
       ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));

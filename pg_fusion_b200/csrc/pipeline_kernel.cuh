@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "../../include/pgf_b200.h"
 #include "bloom_device.cuh"
@@ -35,6 +36,37 @@ struct StageMeta {
   uint32_t null_mask;
   uint64_t row_base;
 };
+
+// ---- compile-time plan shapes ----------------------------------------------------------
+// The kernel is written once, generically over the plan grammar (every per-term / per-
+// expression decision is a warp-uniform runtime dispatch).  For the plan shapes that matter
+// most, the same code is instantiated with the load kinds of the predicate terms and the
+// forms of the aggregate arguments as compile-time constants, which folds the dispatches
+// away.  Literals, column positions and bounds stay runtime parameters in both cases.
+template <int... V>
+struct IntList {
+  static constexpr int size = int(sizeof...(V));
+  template <int I>
+  static constexpr int at() {
+    constexpr int a[] = {V..., -1};
+    return I < size ? a[I < size ? I : 0] : -1;
+  }
+};
+template <bool GENERIC, class TERMS, class EXPRS>
+struct ShapeT {
+  static constexpr bool generic = GENERIC;
+  using Terms = TERMS;   // LD_* of every (range) predicate term, in plan order
+  using Exprs = EXPRS;   // FORM_* of every aggregate argument
+};
+using GenericShape = ShapeT<true, IntList<>, IntList<>>;
+
+template <int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (N > 0) {
+    static_for<N - 1>(f);
+    f(std::integral_constant<int, N - 1>{});
+  }
+}
 
 // ---- PTX wrappers: mbarrier + TMA bulk copy -----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -212,11 +244,14 @@ __device__ __forceinline__ bool view_in_range(const uint4 v, const DevTerm& T, u
 }
 
 // Evaluates the conjunct for two rows of the tile with one dispatch (ILP across the rows).
+// LD >= 0: the term's load kind is a compile-time constant and the term is a plain range.
+template <int LD>
 __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stage, uint32_t r0, uint32_t r1,
                                            uint32_t tile_nulls, uint32_t& bad, bool& p0, bool& p1) {
   const uint8_t* p = stage + T.ref.off;
   bool a, b;
-  switch (T.ref.ld) {
+  const uint32_t ld = LD >= 0 ? uint32_t(LD) : uint32_t(T.ref.ld);
+  switch (ld) {
     case LD_F64: {
       const int64_t x0 = reinterpret_cast<const int64_t*>(p)[r0], x1 = reinterpret_cast<const int64_t*>(p)[r1];
       a = in_range1(f64_key(x0), T); b = in_range1(f64_key(x1), T);
@@ -254,7 +289,7 @@ __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stag
       break;
     }
   }
-  if (T.op != TERM_IN_RANGE) { a = T.op == TERM_NOT_IN_RANGE && !a; b = T.op == TERM_NOT_IN_RANGE && !b; }
+  if (LD < 0 && T.op != TERM_IN_RANGE) { a = T.op == TERM_NOT_IN_RANGE && !a; b = T.op == TERM_NOT_IN_RANGE && !b; }
   if (T.ref.valid_off != kNoValidity && ((tile_nulls >> T.ref.pcol) & 1)) {  // NULL => not TRUE => dropped
     a &= (stage[T.ref.valid_off + (r0 >> 3)] >> (r0 & 7)) & 1;
     b &= (stage[T.ref.valid_off + (r1 >> 3)] >> (r1 & 7)) & 1;
@@ -273,15 +308,13 @@ __device__ __forceinline__ bool expr_inputs_valid(const DevExpr& e, const Row& r
   return ok;
 }
 
-template <uint32_t ACC>
-__device__ __forceinline__ typename AccOps<ACC>::T eval_expr(const DevExpr& e, const Row& row);
-
 // Float64: one IEEE operation per node, never contracted into an FMA (explicit _rn intrinsics).
-template <>
-__device__ __forceinline__ double eval_expr<CLS_F64>(const DevExpr& e, const Row& row) {
+template <int FORM>
+__device__ __forceinline__ double eval_expr_f64(const DevExpr& e, const Row& row) {
   const uint8_t* st = row.stage;
   const uint32_t r = row.r;
-  switch (e.form) {
+  const uint32_t form = FORM >= 0 ? uint32_t(FORM) : e.form;
+  switch (form) {
     case FORM_X:
       return reinterpret_cast<const double*>(st + e.f[0].ref.off)[r];
     case FORM_XY:
@@ -310,8 +343,7 @@ __device__ __forceinline__ double eval_expr<CLS_F64>(const DevExpr& e, const Row
   }
 }
 
-template <>
-__device__ __forceinline__ uint64_t eval_expr<CLS_I64>(const DevExpr& e, const Row& row) {
+__device__ __forceinline__ uint64_t eval_expr_i64(const DevExpr& e, const Row& row) {
   uint64_t v = 1;
 #pragma unroll
   for (uint32_t i = 0; i < 3; ++i) {
@@ -326,8 +358,7 @@ __device__ __forceinline__ uint64_t eval_expr<CLS_I64>(const DevExpr& e, const R
   return v;
 }
 
-template <>
-__device__ __forceinline__ I128 eval_expr<CLS_I128>(const DevExpr& e, const Row& row) {
+__device__ __forceinline__ I128 eval_expr_i128(const DevExpr& e, const Row& row) {
   I128 v{1, 0};
 #pragma unroll
   for (uint32_t i = 0; i < 3; ++i) {
@@ -350,6 +381,13 @@ __device__ __forceinline__ I128 eval_expr<CLS_I128>(const DevExpr& e, const Row&
     }
   }
   return v;
+}
+
+template <uint32_t ACC, int FORM>
+__device__ __forceinline__ typename AccOps<ACC>::T eval_expr(const DevExpr& e, const Row& row) {
+  if constexpr (ACC == CLS_F64) return eval_expr_f64<FORM>(e, row);
+  else if constexpr (ACC == CLS_I64) return eval_expr_i64(e, row);
+  else return eval_expr_i128(e, row);
 }
 
 // ---- global group table ---------------------------------------------------------------
@@ -444,7 +482,7 @@ static __device__ __noinline__ int dict_lookup_or_insert(BlockShared* sh, const 
 }
 
 // ---- the kernel ----------------------------------------------------------------------
-template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T>
+template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
 __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED);
   using Ops = AccOps<ACC>;
@@ -560,9 +598,17 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
         }
         n_bloom += uint32_t(keep0) + uint32_t(keep1);
         // -- FilterExec: every conjunct must be TRUE; stop as soon as the whole warp is dead
-        for (uint32_t t = 0; t < P.nterms; ++t) {
-          if (!__any_sync(0xffffffffu, keep0 || keep1)) break;
-          term_pass2(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+        if constexpr (SHAPE::generic) {
+          for (uint32_t t = 0; t < P.nterms; ++t) {
+            if (!__any_sync(0xffffffffu, keep0 || keep1)) break;
+            term_pass2<-1>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+          }
+        } else {
+          static_for<SHAPE::Terms::size>([&](auto I) {
+            constexpr int t = decltype(I)::value;
+            if (__any_sync(0xffffffffu, keep0 || keep1))
+              term_pass2<SHAPE::Terms::template at<t>()>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+          });
         }
         n_filt += uint32_t(keep0) + uint32_t(keep1);
 
@@ -619,16 +665,17 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
               bool all_valid = true;
               uint32_t valid_mask = 0;
               AccT v[MAXE];
-#pragma unroll
-              for (uint32_t e = 0; e < MAXE; ++e) {
+              static_for<int(MAXE)>([&](auto I) {
+                constexpr int e = decltype(I)::value;
+                constexpr int form = SHAPE::generic ? -1 : SHAPE::Exprs::template at<e>();
                 v[e] = Ops::zero();
-                if (e < P.nexprs) {
+                if (SHAPE::generic ? uint32_t(e) < P.nexprs : e < SHAPE::Exprs::size) {
                   const bool ok = expr_inputs_valid(P.exprs[e], rc);
-                  v[e] = eval_expr<ACC>(P.exprs[e], rc);
+                  v[e] = eval_expr<ACC, form>(P.exprs[e], rc);
                   all_valid &= ok;
                   valid_mask |= uint32_t(ok) << e;
                 }
-              }
+              });
               if (all_valid && g >= 0) {
                 // fast path: register accumulators of the row's group
 #pragma unroll

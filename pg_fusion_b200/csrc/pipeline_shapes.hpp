@@ -1,0 +1,28 @@
+// Registry of plan shapes with a compile-time specialised instantiation of the fused
+// pipeline kernel (see "compile-time plan shapes" in pipeline_kernel.cuh).  Anything else
+// runs the generic instantiation of the same kernel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "device_types.cuh"
+
+namespace pgf {
+
+struct ShapeSig {
+  uint32_t sink, acc, grouped, nj, maxe;
+  int nterms;
+  int term_ld[4];
+  int nexprs;
+  int expr_form[8];
+};
+
+using ShapeLaunchFn = cudaError_t (*)(const DevPlan&, uint32_t grid, size_t smem, cudaStream_t);
+struct ShapeEntry {
+  ShapeSig sig;
+  ShapeLaunchFn fn;
+  const char* name;
+};
+
+const ShapeEntry* find_shape(const ShapeSig& sig);
+
+}  // namespace pgf

@@ -231,14 +231,21 @@ class Lowering {
     return PGF_OK;
   }
 
+  // Narrow keys: lo0 and span.  Wide keys: the device compares unsigned 128-bit values, so the
+  // signed order of (k0, k1) is mapped by flipping the sign bit; stored as lo and span = hi - lo.
   static void set_bounds(DevTerm* dt, bool wide, __int128 lo, __int128 hi) {
     dt->wide = wide;
-    dt->lo0 = int64_t(lo >> 64);
-    dt->hi0 = int64_t(hi >> 64);
     if (wide) {
-      dt->lo1 = uint64_t((unsigned __int128)lo);
-      dt->hi1 = uint64_t((unsigned __int128)hi);
+      const unsigned __int128 flip = (unsigned __int128)1 << 127;
+      const unsigned __int128 ulo = (unsigned __int128)lo ^ flip, uhi = (unsigned __int128)hi ^ flip;
+      const unsigned __int128 span = uhi - ulo;
+      dt->lo0 = int64_t(uint64_t(ulo >> 64));
+      dt->lo1 = uint64_t(ulo);
+      dt->hi0 = int64_t(uint64_t(span >> 64));
+      dt->hi1 = uint64_t(span);
     } else {
+      dt->lo0 = int64_t(lo >> 64);
+      dt->hi0 = int64_t(hi >> 64);
       dt->lo1 = uint64_t(dt->hi0) - uint64_t(dt->lo0);  // span
       dt->hi1 = 0;
     }
@@ -648,7 +655,7 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
 // a registered shape and the aggregate arguments have the registered forms.
 const ShapeEntry* pick_shape(const Lowered& L) {
   const DevPlan& D = L.dev;
-  if (D.nterms > 4 || D.nbloom > 0 && false) return nullptr;
+  if (D.nterms > 4 || D.used_null_mask != 0) return nullptr;  // registered shapes assume NOT NULL scan columns
   ShapeSig sig{};
   sig.sink = D.sink;
   sig.acc = L.acc_cls;

@@ -17,12 +17,12 @@ cudaError_t launch_shape(const DevPlan& plan, uint32_t grid, size_t smem, cudaSt
 }
 
 // Q6: WHERE date-range AND f64-range AND f64-range ; SUM(x * y)
-using Q6Shape = ShapeT<false, IntList<LD_VIEW, LD_F64, LD_F64>, IntList<FORM_XY>>;
+using Q6Shape = ShapeT<false, IntList<LD_VIEW, LD_F64, LD_F64>, IntList<FORM_XY>, true>;
 // Q1 (standard, 8 aggregates -> 5 distinct arguments) and the reference's q01.sql (7 -> 4)
-using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X_CMY_CPZ, FORM_X>>;
-using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>>;
+using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X_CMY_CPZ, FORM_X>, true>;
+using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>, true>;
 // Q3 lineitem side: WHERE date-range ; join probe ; SUM(x * (1 - y)) GROUP BY ...
-using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>>;
+using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true>;
 
 const ShapeEntry kShapes[] = {
     {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}},

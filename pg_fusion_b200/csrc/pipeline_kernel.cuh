@@ -52,9 +52,10 @@ struct IntList {
     return I < size ? a[I < size ? I : 0] : -1;
   }
 };
-template <bool GENERIC, class TERMS, class EXPRS>
+template <bool GENERIC, class TERMS, class EXPRS, bool NONULL = false>
 struct ShapeT {
   static constexpr bool generic = GENERIC;
+  static constexpr bool no_nulls = NONULL;  // no nullable scan column is referenced: validity checks compile out
   using Terms = TERMS;   // LD_* of every (range) predicate term, in plan order
   using Exprs = EXPRS;   // FORM_* of every aggregate argument
 };
@@ -229,23 +230,31 @@ __device__ __forceinline__ double load_f64(const DevRef& ref, const Row& row) {
 // Keys are order preserving: integers as themselves, floats by IEEE totalOrder (what arrow's
 // comparison kernels use), inline views (<= 12 bytes, zero padded) as (big-endian first 8
 // bytes, big-endian next 4 bytes, length), decimals as (hi, lo).
-__device__ __forceinline__ int64_t f64_key(int64_t bits) { return bits ^ int64_t(uint64_t(bits >> 63) >> 1); }
+__device__ __forceinline__ int64_t f64_key(int64_t bits) {
+  // totalOrder key on 32-bit halves: 3 instructions instead of 64-bit shifts
+  const int32_t hi = int32_t(uint64_t(bits) >> 32);
+  const int32_t m = hi >> 31;
+  const uint32_t klo = uint32_t(uint64_t(bits)) ^ uint32_t(m);
+  const uint32_t khi = uint32_t(hi) ^ (uint32_t(m) >> 1);
+  return int64_t((uint64_t(khi) << 32) | klo);
+}
 
 __device__ __forceinline__ bool in_range1(int64_t k, const DevTerm& T) { return uint64_t(k - T.lo0) <= T.lo1; }
-__device__ __forceinline__ bool in_range2(int64_t k0, uint64_t k1, const DevTerm& T) {
-  const bool ge = k0 > T.lo0 || (k0 == T.lo0 && k1 >= T.lo1);
-  const bool le = k0 < T.hi0 || (k0 == T.hi0 && k1 <= T.hi1);
-  return ge && le;
+// Wide keys are unsigned 128-bit (hi, lo); bounds are stored as lo = (lo0:lo1), span = (hi0:hi1).
+__device__ __forceinline__ bool in_range2(uint64_t khi, uint64_t klo, const DevTerm& T) {
+  const unsigned __int128 k = (static_cast<unsigned __int128>(khi) << 64) | klo;
+  const unsigned __int128 lo = (static_cast<unsigned __int128>(uint64_t(T.lo0)) << 64) | T.lo1;
+  const unsigned __int128 span = (static_cast<unsigned __int128>(uint64_t(T.hi0)) << 64) | T.hi1;
+  return (k - lo) <= span;
 }
 __device__ __forceinline__ bool view_in_range(const uint4 v, const DevTerm& T, uint32_t& bad) {
-  const uint64_t hi = (uint64_t(bswap32(v.y)) << 32) | bswap32(v.z);
   bad += v.x > 12u;  // out-of-line views are not compared by this kernel
-  return in_range2(int64_t(hi ^ 0x8000000000000000ull), (uint64_t(bswap32(v.w)) << 32) | v.x, T);
+  return in_range2((uint64_t(bswap32(v.y)) << 32) | bswap32(v.z), (uint64_t(bswap32(v.w)) << 32) | v.x, T);
 }
 
 // Evaluates the conjunct for two rows of the tile with one dispatch (ILP across the rows).
 // LD >= 0: the term's load kind is a compile-time constant and the term is a plain range.
-template <int LD>
+template <int LD, bool NONULL>
 __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stage, uint32_t r0, uint32_t r1,
                                            uint32_t tile_nulls, uint32_t& bad, bool& p0, bool& p1) {
   const uint8_t* p = stage + T.ref.off;
@@ -284,13 +293,14 @@ __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stag
     }
     default: {  // LD_DEC
       const uint4 v0 = reinterpret_cast<const uint4*>(p)[r0], v1 = reinterpret_cast<const uint4*>(p)[r1];
-      a = in_range2(int64_t((uint64_t(v0.w) << 32) | v0.z), (uint64_t(v0.y) << 32) | v0.x, T);
-      b = in_range2(int64_t((uint64_t(v1.w) << 32) | v1.z), (uint64_t(v1.y) << 32) | v1.x, T);
+      // signed hi word -> unsigned order by flipping the sign bit (bounds are flipped on the host)
+      a = in_range2(((uint64_t(v0.w) << 32) | v0.z) ^ 0x8000000000000000ull, (uint64_t(v0.y) << 32) | v0.x, T);
+      b = in_range2(((uint64_t(v1.w) << 32) | v1.z) ^ 0x8000000000000000ull, (uint64_t(v1.y) << 32) | v1.x, T);
       break;
     }
   }
   if (LD < 0 && T.op != TERM_IN_RANGE) { a = T.op == TERM_NOT_IN_RANGE && !a; b = T.op == TERM_NOT_IN_RANGE && !b; }
-  if (T.ref.valid_off != kNoValidity && ((tile_nulls >> T.ref.pcol) & 1)) {  // NULL => not TRUE => dropped
+  if (!NONULL && T.ref.valid_off != kNoValidity && ((tile_nulls >> T.ref.pcol) & 1)) {  // NULL => not TRUE => dropped
     a &= (stage[T.ref.valid_off + (r0 >> 3)] >> (r0 & 7)) & 1;
     b &= (stage[T.ref.valid_off + (r1 >> 3)] >> (r1 & 7)) & 1;
   }
@@ -299,8 +309,9 @@ __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stag
 }
 
 // ---- ProjectionExec / aggregate arguments -------------------------------------------------
+template <bool NONULL>
 __device__ __forceinline__ bool expr_inputs_valid(const DevExpr& e, const Row& row) {
-  if (!(row.tile_nulls & e.null_cols) && !e.has_payload) return true;
+  if ((NONULL || !(row.tile_nulls & e.null_cols)) && !e.has_payload) return true;
   bool ok = true;
 #pragma unroll
   for (uint32_t i = 0; i < 3; ++i)
@@ -580,12 +591,16 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       const uint32_t nrows = sh->meta[s].nrows;
       const uint8_t* stage = stages + size_t(s) * P.stage_bytes;
       const uint32_t tile_nulls = sh->meta[s].null_mask;
-      // two rows per thread and iteration: r0 and r0 + NCT (independent chains => ILP).  The
-      // loop bound is warp-uniform so the warp votes below are executed by all 32 lanes.
-      for (uint32_t b0 = ct - lane; b0 < nrows; b0 += 2 * NCT) {
-        const bool has0 = b0 + lane < nrows, has1 = b0 + lane + NCT < nrows;
+      // Two rows per thread and iteration (independent chains => ILP): a warp takes the pair of
+      // 32-row chunks (2p, 2p+1).  Pairs are dealt to the warps round-robin with a per-tile
+      // rotation so partial tiles do not always load the same warps.  The loop bound is
+      // warp-uniform: the warp votes below are executed by all 32 lanes.
+      const uint32_t npairs = (nrows + 63u) >> 6;
+      for (uint32_t pr = (warp - 1 + kConsumerWarps - (k * 5u) % kConsumerWarps) % kConsumerWarps; pr < npairs; pr += kConsumerWarps) {
+        const uint32_t b0 = pr << 6;
+        const bool has0 = b0 + lane < nrows, has1 = b0 + 32u + lane < nrows;
         const uint32_t r0 = has0 ? b0 + lane : 0u;
-        const uint32_t r1 = has1 ? b0 + lane + NCT : r0;
+        const uint32_t r1 = has1 ? b0 + 32u + lane : r0;
         bool keep0 = has0, keep1 = has1;
         n_in += uint32_t(has0) + uint32_t(has1);
         // -- runtime Bloom probes: NULL key => DefinitelyAbsent (shared.rs:367-374)
@@ -601,17 +616,18 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
         if constexpr (SHAPE::generic) {
           for (uint32_t t = 0; t < P.nterms; ++t) {
             if (!__any_sync(0xffffffffu, keep0 || keep1)) break;
-            term_pass2<-1>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+            term_pass2<-1, false>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
           }
         } else {
           static_for<SHAPE::Terms::size>([&](auto I) {
             constexpr int t = decltype(I)::value;
             if (__any_sync(0xffffffffu, keep0 || keep1))
-              term_pass2<SHAPE::Terms::template at<t>()>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+              term_pass2<SHAPE::Terms::template at<t>(), SHAPE::no_nulls>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
           });
         }
         n_filt += uint32_t(keep0) + uint32_t(keep1);
 
+        if (!__any_sync(0xffffffffu, keep0 || keep1)) continue;
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
           if (!(half ? keep1 : keep0)) continue;
@@ -670,7 +686,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                 constexpr int form = SHAPE::generic ? -1 : SHAPE::Exprs::template at<e>();
                 v[e] = Ops::zero();
                 if (SHAPE::generic ? uint32_t(e) < P.nexprs : e < SHAPE::Exprs::size) {
-                  const bool ok = expr_inputs_valid(P.exprs[e], rc);
+                  const bool ok = expr_inputs_valid<SHAPE::no_nulls>(P.exprs[e], rc);
                   v[e] = eval_expr<ACC, form>(P.exprs[e], rc);
                   all_valid &= ok;
                   valid_mask |= uint32_t(ok) << e;

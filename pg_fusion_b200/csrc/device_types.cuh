@@ -85,7 +85,8 @@ struct DevFactor {
   int64_t ci_lo, ci_hi;  // constant (CLS_I64 / CLS_I128)
 };
 // form: straight-line fast paths for products of Float64 scan columns
-enum : uint32_t { FORM_GENERIC = 0, FORM_X = 1, FORM_XY = 2, FORM_X_CMY = 3, FORM_X_CMY_CPZ = 4 };
+enum : uint32_t { FORM_GENERIC = 0, FORM_X = 1, FORM_XY = 2, FORM_X_CMY = 3, FORM_X_CMY_CPZ = 4,
+                  FORM_PREV_CPZ = 5 /* shapes only: previous argument times (c + z) */ };
 struct DevExpr {
   uint32_t nfactors;
   uint32_t form;

@@ -165,6 +165,13 @@ class Lowering {
     }
     PGF_TRY(layout_stage(s));
     fix_refs();
+    // common subexpression: x*(c-y)*(c2+z) right after x*(c-y) reuses the previous value
+    for (uint32_t e = 1; e < D.nexprs; ++e) {
+      const DevExpr &a = D.exprs[e - 1], &b = D.exprs[e];
+      if (a.form == FORM_X_CMY && b.form == FORM_X_CMY_CPZ && a.f[0].ref.off == b.f[0].ref.off &&
+          a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf)
+        D.exprs[e].form = FORM_PREV_CPZ;
+    }
     return PGF_OK;
   }
 

@@ -19,7 +19,8 @@ cudaError_t launch_shape(const DevPlan& plan, uint32_t grid, size_t smem, cudaSt
 // Q6: WHERE date-range AND f64-range AND f64-range ; SUM(x * y)
 using Q6Shape = ShapeT<false, IntList<LD_VIEW, LD_F64, LD_F64>, IntList<FORM_XY>, true>;
 // Q1 (standard, 8 aggregates -> 5 distinct arguments) and the reference's q01.sql (7 -> 4)
-using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X_CMY_CPZ, FORM_X>, true>;
+// (the 4th argument price*(1-disc)*(1+tax) reuses the 3rd: FORM_PREV_CPZ; find_shape checks the operands match)
+using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true>;
 using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>, true>;
 // Q3 lineitem side: WHERE date-range ; join probe ; SUM(x * (1 - y)) GROUP BY ...
 using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true>;
@@ -27,7 +28,7 @@ using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true>;
 const ShapeEntry kShapes[] = {
     {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}},
      launch_shape<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>, "q6_f64"},
-    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_X_CMY_CPZ, FORM_X, -1, -1, -1}},
+    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape8>, "q1_f64_8aggs"},
     {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X_CMY, FORM_X, -1, -1, -1, -1}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape7>, "q1_f64_7aggs"},

@@ -24,9 +24,9 @@
 namespace pgf {
 
 // Consumer warps per CTA: 16 for streaming sinks; 8 when kRegGroups x kMaxExprs register
-// accumulators per thread are live (GROUP BY), which needs the larger register budget.
+// accumulators per thread are live (GROUP BY), which needs the larger register budget (12 warps).
 constexpr int kMaxConsumerWarps = 16;
-__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 8 : 16; }
+__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 12 : 16; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
 constexpr int kStages = 4;
 constexpr uint32_t kAccF64MaxExprs = 8, kAccI128MaxExprs = 6;
@@ -401,6 +401,14 @@ __device__ __forceinline__ typename AccOps<ACC>::T eval_expr(const DevExpr& e, c
   else return eval_expr_i128(e, row);
 }
 
+template <class T>
+__device__ __forceinline__ T prev_times_cpz(T prev, const DevExpr& e, const Row& row) {
+  if constexpr (std::is_same<T, double>::value)
+    return __dmul_rn(prev, __dadd_rn(e.f[2].cf, reinterpret_cast<const double*>(row.stage + e.f[2].ref.off)[row.r]));
+  else
+    return prev;
+}
+
 // ---- global group table ---------------------------------------------------------------
 __device__ __forceinline__ uint64_t key_hash(const uint64_t* key, uint32_t nwords, uint32_t knull) {
   uint64_t h = 0x9E3779B97F4A7C15ull ^ knull;
@@ -408,6 +416,15 @@ __device__ __forceinline__ uint64_t key_hash(const uint64_t* key, uint32_t nword
   for (uint32_t w = 0; w < kKeyWords; ++w)
     if (w < nwords) h = mix64(h ^ key[w]) + 0x632BE59BD9B4E019ull;
   return h;
+}
+
+// Cheap fingerprint for the CTA dictionary: a collision only costs the full compare.
+__device__ __forceinline__ uint64_t key_fingerprint(const uint64_t* key, uint32_t knull) {
+  uint64_t h = key[0] ^ knull;
+  h ^= (key[1] << 17) | (key[1] >> 47);
+  h ^= (key[2] << 31) | (key[2] >> 33);
+  h ^= (key[3] << 47) | (key[3] >> 17);
+  return mix64(h) | 1ull;
 }
 
 // Returns the slot holding `key` (inserting it if absent) or -1 when the table is full.
@@ -469,15 +486,24 @@ __device__ __forceinline__ bool dict_entry_equals(const BlockShared* sh, uint32_
 // Find the key in the CTA dictionary, appending it while there is room (rare path: at most
 // kRegGroups successful appends per CTA).  Returns -1 when the key is not one of the
 // register-resident groups.
-static __device__ __noinline__ int dict_lookup_or_insert(BlockShared* sh, const uint64_t* key, uint32_t nwords, uint32_t knull, uint64_t h) {
+struct Key4 {
+  uint64_t w0, w1, w2, w3;
+};
+// Key passed by value so the caller's key words never live in local memory.
+static __device__ __noinline__ int dict_lookup_or_insert(BlockShared* sh, Key4 kv, uint32_t nwords, uint32_t knull, uint64_t h) {
+  const uint64_t key[kKeyWords] = {kv.w0, kv.w1, kv.w2, kv.w3};
   for (;;) {
     const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
-    for (uint32_t g = 0; g < n; ++g)
-      if (dict_entry_equals(sh, g, key, nwords, knull)) return int(g);
+    int found = -1;
+#pragma unroll
+    for (uint32_t g = 0; g < kRegGroups; ++g)
+      if (g < n && dict_entry_equals(sh, g, key, nwords, knull)) found = int(g);
+    if (found >= 0) return found;
     if (n == kRegGroups) return -1;
     if (atomicCAS(&sh->dict_lock, 0u, 1u) == 0u) {
       int g = -1;
       if (*reinterpret_cast<volatile uint32_t*>(&sh->dict_n) == n) {  // nothing appended meanwhile
+#pragma unroll
         for (uint32_t w = 0; w < kKeyWords; ++w) sh->dict_keys[n][w] = w < nwords ? key[w] : 0;
         sh->dict_null[n] = knull;
         sh->dict_hash[n] = h;
@@ -582,8 +608,6 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     }
   } else {
     // ===== consumers =====
-    const uint32_t ct = threadIdx.x - 32;
-    constexpr uint32_t NCT = kConsumerWarps * 32;
     uint32_t k = 0;
     for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
       const uint32_t s = k % kStages;
@@ -666,13 +690,13 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                   }
                 }
                 // CTA dictionary lookup: hashes cached in registers, full compare on a hit
-                const uint64_t h = key_hash(key, P.nkeywords, knull) | 1ull;
+                const uint64_t h = key_fingerprint(key, knull);
                 g = -1;
 #pragma unroll
                 for (uint32_t gg = 0; gg < G; ++gg)
                   if (gg < dn && dh[gg] == h) g = int(gg);
                 if (g < 0 || !dict_entry_equals(sh, uint32_t(g), key, P.nkeywords, knull)) {
-                  g = dict_lookup_or_insert(sh, key, P.nkeywords, knull, h);
+                  g = dict_lookup_or_insert(sh, Key4{key[0], key[1], key[2], key[3]}, P.nkeywords, knull, h);
                   dn = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
 #pragma unroll
                   for (uint32_t gg = 0; gg < G; ++gg) dh[gg] = gg < dn ? *reinterpret_cast<volatile uint64_t*>(&sh->dict_hash[gg]) : 0;
@@ -683,24 +707,31 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
               AccT v[MAXE];
               static_for<int(MAXE)>([&](auto I) {
                 constexpr int e = decltype(I)::value;
-                constexpr int form = SHAPE::generic ? -1 : SHAPE::Exprs::template at<e>();
+                constexpr int form = SHAPE::generic ? -1 : SHAPE::Exprs::template at<e>();  // FORM_PREV_CPZ only in shapes
                 v[e] = Ops::zero();
                 if (SHAPE::generic ? uint32_t(e) < P.nexprs : e < SHAPE::Exprs::size) {
                   const bool ok = expr_inputs_valid<SHAPE::no_nulls>(P.exprs[e], rc);
-                  v[e] = eval_expr<ACC, form>(P.exprs[e], rc);
+                  if constexpr (ACC == CLS_F64 && form == int(FORM_PREV_CPZ) && e > 0) {
+                    // common subexpression: this argument is the previous one times (c + z)
+                    v[e] = prev_times_cpz(v[e > 0 ? e - 1 : 0], P.exprs[e], rc);
+                  } else {
+                    v[e] = eval_expr<ACC, form>(P.exprs[e], rc);
+                  }
                   all_valid &= ok;
                   valid_mask |= uint32_t(ok) << e;
                 }
               });
               if (all_valid && g >= 0) {
-                // fast path: register accumulators of the row's group
+                // fast path: register accumulators of the row's group (one short divergent
+                // block per register group present in the warp)
 #pragma unroll
                 for (uint32_t gg = 0; gg < G; ++gg) {
                   if (G == 1 || gg == uint32_t(g)) {
                     grows[gg] += 1;
-#pragma unroll
-                    for (uint32_t e = 0; e < MAXE; ++e)
-                      if (e < P.nexprs) acc[gg][e] = Ops::add(acc[gg][e], v[e]);
+                    static_for<int(MAXE)>([&](auto I) {
+                      constexpr int e = decltype(I)::value;
+                      if (SHAPE::generic ? uint32_t(e) < P.nexprs : e < SHAPE::Exprs::size) acc[gg][e] = Ops::add(acc[gg][e], v[e]);
+                    });
                   }
                 }
               } else {

@@ -676,6 +676,9 @@ const ShapeEntry* pick_shape(const Lowered& L) {
   }
   sig.nexprs = int(D.nexprs);
   for (uint32_t e = 0; e < D.nexprs; ++e) sig.expr_form[e] = int(D.exprs[e].form);
+  sig.nkeys = int(D.nkeys);
+  for (uint32_t k = 0; k < D.nkeys; ++k)
+    sig.key_enc[k] = key_enc(D.keys[k].ref.ld, D.keys[k].ref.src != SRC_PAGE, D.keys[k].word);
   return find_shape(sig);
 }
 

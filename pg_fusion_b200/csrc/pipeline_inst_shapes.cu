@@ -20,19 +20,26 @@ cudaError_t launch_shape(const DevPlan& plan, uint32_t grid, size_t smem, cudaSt
 using Q6Shape = ShapeT<false, IntList<LD_VIEW, LD_F64, LD_F64>, IntList<FORM_XY>, true>;
 // Q1 (standard, 8 aggregates -> 5 distinct arguments) and the reference's q01.sql (7 -> 4)
 // (the 4th argument price*(1-disc)*(1+tax) reuses the 3rd: FORM_PREV_CPZ; find_shape checks the operands match)
-using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true>;
-using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>, true>;
+using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true,
+                        IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
+using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>, true,
+                        IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
 // Q3 lineitem side: WHERE date-range ; join probe ; SUM(x * (1 - y)) GROUP BY ...
-using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true>;
+// GROUP BY l_orderkey (scan), o_orderdate, o_shippriority (join payload)
+using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true,
+                       IntList<key_enc(LD_I32, false, 0), key_enc(LD_VIEW, true, 1), key_enc(LD_I32, true, 3)>>;
 
 const ShapeEntry kShapes[] = {
-    {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}},
+    {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>, "q6_f64"},
-    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1}},
+    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1},
+      2, {key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2), 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape8>, "q1_f64_8aggs"},
-    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X_CMY, FORM_X, -1, -1, -1, -1}},
+    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X_CMY, FORM_X, -1, -1, -1, -1},
+      2, {key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2), 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape7>, "q1_f64_7aggs"},
-    {{SINK_AGG, CLS_F64, 1, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 1, {FORM_X_CMY, -1, -1, -1, -1, -1, -1, -1}},
+    {{SINK_AGG, CLS_F64, 1, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 1, {FORM_X_CMY, -1, -1, -1, -1, -1, -1, -1},
+      3, {key_enc(LD_I32, false, 0), key_enc(LD_VIEW, true, 1), key_enc(LD_I32, true, 3), 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 1, 2, Q3Shape>, "q3_lineitem_f64"},
 };
 
@@ -43,6 +50,9 @@ bool same(const ShapeSig& a, const ShapeSig& b) {
     if (a.term_ld[i] != b.term_ld[i]) return false;
   for (int i = 0; i < a.nexprs; ++i)
     if (a.expr_form[i] != b.expr_form[i]) return false;
+  if (a.nkeys != b.nkeys) return false;
+  for (int i = 0; i < a.nkeys; ++i)
+    if (a.key_enc[i] != b.key_enc[i]) return false;
   return true;
 }
 

@@ -26,7 +26,7 @@ namespace pgf {
 // Consumer warps per CTA: 16 for streaming sinks; 8 when kRegGroups x kMaxExprs register
 // accumulators per thread are live (GROUP BY), which needs the larger register budget (12 warps).
 constexpr int kMaxConsumerWarps = 16;
-__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 12 : 16; }
+__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 14 : 16; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
 constexpr int kStages = 4;
 constexpr uint32_t kAccF64MaxExprs = 8, kAccI128MaxExprs = 6;
@@ -52,8 +52,12 @@ struct IntList {
     return I < size ? a[I < size ? I : 0] : -1;
   }
 };
-template <bool GENERIC, class TERMS, class EXPRS, bool NONULL = false>
+// Key part encoding for shapes: LD_* | (1 << 4 if the part is a join payload) | (first key word << 8)
+constexpr int key_enc(int ld, bool payload, int word) { return ld | (payload ? 16 : 0) | (word << 8); }
+
+template <bool GENERIC, class TERMS, class EXPRS, bool NONULL = false, class KEYS = IntList<>>
 struct ShapeT {
+  using Keys = KEYS;     // key_enc() of every GROUP BY key part (empty: resolved at run time)
   static constexpr bool generic = GENERIC;
   static constexpr bool no_nulls = NONULL;  // no nullable scan column is referenced: validity checks compile out
   using Terms = TERMS;   // LD_* of every (range) predicate term, in plan order
@@ -665,6 +669,46 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
               uint32_t knull = 0;
               int g = 0;
               if constexpr (GROUPED) {
+                if constexpr (!SHAPE::generic && SHAPE::Keys::size > 0) {
+                  // key layout known at compile time: every word lands in a fixed register
+                  static_for<SHAPE::Keys::size>([&](auto I) {
+                    constexpr int kp = decltype(I)::value;
+                    constexpr int enc = SHAPE::Keys::template at<kp>();
+                    constexpr int ld = enc & 15;
+                    constexpr bool pay = ((enc >> 4) & 1) != 0;
+                    constexpr int word = enc >> 8;
+                    const DevKeyPart& part = P.keys[kp];
+                    bool valid = true;
+                    if (pay || !SHAPE::no_nulls) valid = ref_valid(part.ref, rc);
+                    if (!valid) {
+                      knull |= 1u << kp;
+                    } else if constexpr (ld == LD_VIEW || ld == LD_DEC) {
+                      uint4 raw;
+                      if constexpr (pay) {
+                        const uint32_t* pp = rc.pay + 3 + part.ref.off;
+                        raw = make_uint4(__ldg(pp), __ldg(pp + 1), __ldg(pp + 2), __ldg(pp + 3));
+                      } else {
+                        raw = reinterpret_cast<const uint4*>(rc.stage + part.ref.off)[rc.r];
+                      }
+                      if (ld == LD_VIEW && raw.x > 12u) ++n_bad;
+                      key[word] = (uint64_t(raw.y) << 32) | raw.x;
+                      key[word + 1 < int(kKeyWords) ? word + 1 : word] = (uint64_t(raw.w) << 32) | raw.z;
+                    } else {
+                      int64_t x;
+                      if constexpr (pay) {
+                        const uint32_t* pp = rc.pay + 3 + part.ref.off;
+                        x = ld == LD_I64 ? int64_t((uint64_t(__ldg(pp + 1)) << 32) | __ldg(pp))
+                          : ld == LD_I32 ? int64_t(int32_t(__ldg(pp))) : int64_t(int16_t(__ldg(pp)));
+                      } else {
+                        const uint8_t* pp = rc.stage + part.ref.off;
+                        x = ld == LD_I64 ? reinterpret_cast<const int64_t*>(pp)[rc.r]
+                          : ld == LD_I32 ? int64_t(reinterpret_cast<const int32_t*>(pp)[rc.r])
+                                         : int64_t(reinterpret_cast<const int16_t*>(pp)[rc.r]);
+                      }
+                      key[word] = uint64_t(x);
+                    }
+                  });
+                } else {
 #pragma unroll
                 for (uint32_t kp = 0; kp < 4; ++kp) {
                   if (kp < P.nkeys) {
@@ -682,12 +726,13 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                         w1 = (uint64_t(raw.w) << 32) | raw.z;
                       }
 #pragma unroll
-                      for (uint32_t w = 0; w < kKeyWords; ++w) {  // static indices keep key[] in registers
+                      for (uint32_t w = 0; w < kKeyWords; ++w) {
                         if (w == part.word) key[w] = w0;
                         if (part.nwords == 2 && w == part.word + 1u) key[w] = w1;
                       }
                     }
                   }
+                }
                 }
                 // CTA dictionary lookup: hashes cached in registers, full compare on a hit
                 const uint64_t h = key_fingerprint(key, knull);

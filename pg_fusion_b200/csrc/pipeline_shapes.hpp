@@ -14,6 +14,8 @@ struct ShapeSig {
   int term_ld[4];
   int nexprs;
   int expr_form[8];
+  int nkeys;
+  int key_enc[4];  // LD_* | payload << 4 | word << 8
 };
 
 using ShapeLaunchFn = cudaError_t (*)(const DevPlan&, uint32_t grid, size_t smem, cudaStream_t);

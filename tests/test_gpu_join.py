@@ -1,0 +1,144 @@
+"""GPU parity tests of the int-key hash join (build + probe), the Bloom filter fused into
+pipelines and the TPC-H Q3 shape, against the oracle.  Join row multisets are bit-exact."""
+import numpy as np
+import pytest
+
+import pg_fusion_b200 as pg
+from oracle import pyorc as O
+from pg_fusion_b200 import AggFunc, BloomParams, Cmp, ColumnSpec, Factor, GenTable, TypeTag
+from pg_fusion_b200 import arrow_layout as AL
+
+from . import util as U
+
+pytestmark = pytest.mark.gpu
+E = O.Expr
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = pg.Context()
+    yield c
+    c.close()
+
+
+def load(ctx, schema, cols, **kw):
+    pages = AL.encode_pages(schema, cols, **kw)
+    scan = ctx.declare_scan(schema)
+    scan.push_pages(pages)
+    scan.finish()
+    return scan, O.OTable.from_pages(pages, 65536, U.orc_cols(schema))
+
+
+def test_reference_smoke_join(ctx):
+    """pg/extension/src/smoke_tests.rs:253-304: {1,2,3} |><| {2,3,4} on bigint keys = 2 rows, score 20 for key 2."""
+    s1 = [ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Int64)]
+    left, _ = load(ctx, s1, [(np.array([1, 2, 3], np.int64), None), (np.array([10, 20, 30], np.int64), None)])
+    right, _ = load(ctx, [ColumnSpec(TypeTag.Int64)], [(np.array([2, 3, 4], np.int64), None)])
+    b = left.pipeline().build_join(0, [1]).run()
+    assert b.rows_out == 3
+    r = right.pipeline().join(b.join_table, 0).aggregate([0], [(AggFunc.COUNT_STAR, None), (AggFunc.SUM, [Factor.of((1, 0))])]).run()
+    assert r.rows_out == 2
+    assert r.by_key() == {(2,): (1, 20), (3,): (1, 30)}
+
+
+@pytest.mark.parametrize("key_dtype,tag", [(np.int16, TypeTag.Int16), (np.int32, TypeTag.Int32), (np.int64, TypeTag.Int64)])
+def test_join_multiset_with_duplicates_and_nulls(ctx, key_dtype, tag):
+    r = np.random.default_rng(4)
+    nb, npr = 5000, 40_000
+    bk = r.integers(0, 2000, nb).astype(key_dtype)           # duplicates on the build side
+    pk = r.integers(-500, 2500, npr).astype(key_dtype)       # misses and duplicates on the probe side
+    bvalid, pvalid = r.random(nb) > 0.05, r.random(npr) > 0.05
+    bpay = r.integers(-10**6, 10**6, nb).astype(np.int64)
+    pval = r.integers(-10**6, 10**6, npr).astype(np.int64)
+    bs = [ColumnSpec(tag, True), ColumnSpec(TypeTag.Int64)]
+    ps = [ColumnSpec(tag, True), ColumnSpec(TypeTag.Int64)]
+    build, bt = load(ctx, bs, [(bk, bvalid), (bpay, None)], rows_per_page=900)
+    probe, pt = load(ctx, ps, [(pk, pvalid), (pval, None)], rows_per_page=1100)
+    b = build.pipeline().build_join(0, [1]).run()
+    assert b.rows_out == nb
+    # number of matched pairs == oracle HashJoinExec pair count (NULL keys never match)
+    want_b, want_p = O.hash_join_pairs(bt, 0, pt, 0)
+    got = probe.pipeline().join(b.join_table, 0).count().run()
+    assert got.rows_out == want_b.size
+    # multiset check via aggregates over (build payload, probe value) grouped by key:
+    # sum(build.pay), sum(probe.val), count(*) are bit-exact iff the pair multiset per key matches
+    res = (probe.pipeline().join(b.join_table, 0)
+           .aggregate([0], [(AggFunc.SUM, [Factor.of((1, 0))]), (AggFunc.SUM, [Factor.of(1)]), (AggFunc.COUNT_STAR, None)]).run())
+    want = O.aggregate(pt, None, [E.col(0)], [(O.AGG_SUM, E.col(1, 1)), (O.AGG_SUM, E.col(1)), (O.AGG_COUNT_STAR, None)],
+                       joins=[(bt, 0, 0, 0)])
+    U.assert_agg_equal(res, want, rel=0)
+    # a filter on the probe side and one on the build side
+    b2 = build.pipeline().filter(1, Cmp.GE, 0).build_join(0, [1]).run()
+    res = (probe.pipeline().filter(1, Cmp.LT, 0).join(b2.join_table, 0)
+           .aggregate([], [(AggFunc.SUM, [Factor.of((1, 0))]), (AggFunc.COUNT_STAR, None)]).run())
+    bt_f = bt.select(O.filter_rows(bt, E.col(1).ge(E.i64(0))))
+    want = O.aggregate(pt, E.col(1).lt(E.i64(0)), [], [(O.AGG_SUM, E.col(1, 1)), (O.AGG_COUNT_STAR, None)], joins=[(bt_f, 0, 0, 0)])
+    U.assert_agg_equal(res, want, rel=0)
+    ctx.destroy_join_table(b.join_table)
+    ctx.destroy_join_table(b2.join_table)
+
+
+def test_empty_build_and_empty_probe(ctx):
+    s = [ColumnSpec(TypeTag.Int32)]
+    empty = ctx.declare_scan(s); empty.finish()
+    some, _ = load(ctx, s, [(np.arange(100, dtype=np.int32), None)])
+    b = empty.pipeline().build_join(0).run()
+    assert b.rows_out == 0
+    assert some.pipeline().join(b.join_table, 0).count().run().rows_out == 0
+    b2 = some.pipeline().build_join(0).run()
+    assert empty.pipeline().join(b2.join_table, 0).count().run().rows_out == 0
+    assert some.pipeline().join(b2.join_table, 0).count().run().rows_out == 100
+
+
+def test_bloom_fused_into_build_and_probe_pipelines(ctx):
+    """RuntimeFilterBuildExec semantics: the build pipeline populates the filter with every non-null
+    build key (bit-exact vs the oracle); probing it in the scan pipeline never changes join results."""
+    r = np.random.default_rng(12)
+    bk = r.integers(0, 10**6, 20_000).astype(np.int32)
+    pk = r.integers(0, 10**6, 100_000).astype(np.int32)
+    bvalid = r.random(bk.size) > 0.1
+    build, bt = load(ctx, [ColumnSpec(TypeTag.Int32, True)], [(bk, bvalid)])
+    probe, pt = load(ctx, [ColumnSpec(TypeTag.Int32)], [(pk, None)])
+    p = BloomParams.new(**pg.GUC_DEFAULT_BLOOM)
+    rf = ctx.runtime_filter(p)
+    rf.try_acquire_builder()
+    b = build.pipeline().build_join(0, [], rf).run()
+    assert b.bloom_rows == int(bvalid.sum())      # RuntimeFilterBuildRowsTotal
+    rf.publish_ready()
+    ob = O.Bloom(O.bloom_params(p.bit_count, p.hash_count, p.seed))
+    ob.insert_keys(bk, np.packbits(bvalid, bitorder="little"))
+    assert (rf.words() == ob.words).all()
+    plain = probe.pipeline().join(b.join_table, 0).count().run()
+    filt = probe.pipeline().bloom_probe(rf, 0).join(b.join_table, 0).count().run()
+    keep, rejected = ob.probe_keys(pk)
+    assert filt.rows_bloom == int(keep.sum()) and filt.rows_in - filt.rows_bloom == rejected
+    assert filt.rows_out == plain.rows_out == O.hash_join_pairs(bt, 0, pt, 0)[0].size
+    # a filter that is not Ready (stale generation) must pass rows unfiltered
+    stale = probe.pipeline().bloom_probe(rf, 0, generation=rf.generation + 1).count().run()
+    assert stale.rows_bloom == stale.rows_in
+
+
+@pytest.mark.parametrize("with_bloom", [False, True])
+def test_q3_shape_matches_oracle(ctx, with_bloom):
+    ncust, nord, nli = 1500, 15_000, 60_000
+    customer = ctx.gen_scan(GenTable.CUSTOMER_Q3, ncust, seed=42)
+    orders = ctx.gen_scan(GenTable.ORDERS_Q3, nord, seed=42, scale_rows=ncust)
+    lineitem = ctx.gen_scan(GenTable.LINEITEM_Q3, nli, seed=42, scale_rows=nord)
+    ct = O.OTable.from_pages(customer.read_pages(), 65536, U.orc_cols(U.CUSTOMER_SCHEMA))
+    ot = O.OTable.from_pages(orders.read_pages(), 65536, U.orc_cols(U.ORDERS_SCHEMA))
+    lt = O.OTable.from_pages(lineitem.read_pages(), 65536, U.orc_cols(U.LINEITEM_Q3_SCHEMA))
+    want, wstats = U.oracle_q3(ct, ot, lt)
+    bp = (BloomParams.new(**pg.GUC_DEFAULT_BLOOM), BloomParams.new(1 << 16, 4, 7)) if with_bloom else None
+    res, stats = U.gpu_q3(ctx, customer, orders, lineitem, bp)
+    assert stats["customer"].rows_out == wstats["customers"]
+    assert stats["orders"].rows_out == wstats["orders"]
+    assert res.rows_out == want.rows_joined and len(res.keys) == len(want.keys) > 0
+    U.assert_agg_equal(res, want)
+    got10, want10 = U.top10(res), U.top10(want)
+    assert [(r[0], r[2], r[3]) for r in got10] == [(r[0], r[2], r[3]) for r in want10]
+    for g, w in zip(got10, want10):
+        U.assert_close(g[1], w[1], 1e-12, "revenue")
+    if with_bloom:
+        assert stats["lineitem"].rows_bloom < stats["lineitem"].rows_in   # the filter does reject rows
+    for s in (customer, orders, lineitem):
+        s.release()

@@ -115,3 +115,61 @@ def assert_agg_equal(gpu, orc, rel=1e-12):
         assert len(gk[k]) == len(ok[k])
         for j, (x, y) in enumerate(zip(gk[k], ok[k])):
             assert_close(x, y, rel, f"group {k} agg {j}")
+
+
+# ---- TPC-H Q3 shape: customer |><| orders |><| lineitem, benches/tpch/queries/q03.sql ----
+CUSTOMER_SCHEMA = [ColumnSpec(I32), ColumnSpec(VIEW)]                                    # c_custkey, c_mktsegment
+ORDERS_SCHEMA = [ColumnSpec(I32), ColumnSpec(I32), ColumnSpec(VIEW), ColumnSpec(I32)]    # o_orderkey, o_custkey, o_orderdate, o_shippriority
+LINEITEM_Q3_SCHEMA = [ColumnSpec(I32), ColumnSpec(F64), ColumnSpec(F64), ColumnSpec(VIEW)]  # l_orderkey, l_extendedprice, l_discount, l_shipdate
+Q3_DATE = b"1995-03-15"
+
+
+def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDING"):
+    """Runs the three fused pipelines of the Q3 shape; returns (result, stats dict)."""
+    import pg_fusion_b200 as pg
+    from pg_fusion_b200 import AggFunc, Cmp, Factor
+    stats = {}
+    rf1 = rf2 = None
+    if bloom_params is not None:
+        rf1 = ctx.runtime_filter(bloom_params[0])
+        rf1.try_acquire_builder()
+    # customer(BUILDING) -> join table T1 keyed by c_custkey (+ Bloom for the orders scan)
+    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1).run()
+    if rf1 is not None:
+        rf1.publish_ready()
+    # orders: [Bloom probe] -> o_orderdate < date -> probe T1 -> T2 keyed by o_orderkey with payload
+    p2 = orders.pipeline()
+    if rf1 is not None:
+        p2.bloom_probe(rf1, 1)
+        rf2 = ctx.runtime_filter(bloom_params[1])
+        rf2.try_acquire_builder()
+    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(r1.join_table, 1).build_join(0, [2, 3], rf2).run()
+    if rf2 is not None:
+        rf2.publish_ready()
+    # lineitem: [Bloom probe] -> l_shipdate > date -> probe T2 -> GROUP BY l_orderkey, o_orderdate, o_shippriority
+    p3 = lineitem.pipeline()
+    if rf2 is not None:
+        p3.bloom_probe(rf2, 0)
+    r3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(r2.join_table, 0)
+          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
+                     expected_groups=max(1024, r2.rows_out)).run())
+    ctx.destroy_join_table(r1.join_table)
+    ctx.destroy_join_table(r2.join_table)
+    stats.update(customer=r1, orders=r2, lineitem=r3, rf1=rf1, rf2=rf2)
+    return r3, stats
+
+
+def oracle_q3(customer_t, orders_t, lineitem_t, segment=b"BUILDING"):
+    cust_f = customer_t.select(O.filter_rows(customer_t, E.col(1).eq(E.s(segment))))
+    ord_f = orders_t.select(O.filter_rows(orders_t, E.col(2).lt(E.s(Q3_DATE))))
+    _, probe_rows = O.hash_join_pairs(cust_f, 0, ord_f, 1)      # HashJoinExec(customer, orders)
+    ord_j = ord_f.take(probe_rows)
+    res = O.aggregate(lineitem_t, E.col(3).gt(E.s(Q3_DATE)), [E.col(0), E.col(2, 1), E.col(3, 1)],
+                      [(O.AGG_SUM, E.col(1) * (E.f64(1.0) - E.col(2)))], joins=[(ord_j, 0, 0, 0)])
+    return res, dict(customers=cust_f.rows, orders=ord_j.rows)
+
+
+def top10(res):
+    """ORDER BY revenue DESC, o_orderdate LIMIT 10 (benches/tpch/queries/q03.sql)."""
+    rows = [(k[0], a[0], k[1], k[2]) for k, a in zip(res.keys, res.aggs)]
+    return sorted(rows, key=lambda r: (-r[1], r[2]))[:10]

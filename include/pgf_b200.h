@@ -118,6 +118,9 @@ pgf_status pgf_ctx_register_host_region(pgf_ctx *ctx, void *base, size_t len);
 pgf_status pgf_ctx_unregister_host_region(pgf_ctx *ctx, void *base);
 /* Block until all work queued on the context's streams has completed. */
 pgf_status pgf_ctx_synchronize(pgf_ctx *ctx);
+/* Device time (CUDA events on the compute stream) of the kernels of the last Bloom build /
+ * probe or pipeline call on this context, in milliseconds. */
+float pgf_ctx_last_kernel_ms(const pgf_ctx *ctx);
 /* The compute stream (cudaStream_t) so a harness can bracket it with CUDA events. */
 void *pgf_ctx_compute_stream(pgf_ctx *ctx);
 

@@ -126,6 +126,7 @@ _SIGNATURES = {
     "pgf_ctx_unregister_host_region": (i32, [vp, vp]),
     "pgf_ctx_synchronize": (i32, [vp]),
     "pgf_ctx_compute_stream": (vp, [vp]),
+    "pgf_ctx_last_kernel_ms": (C.c_float, [vp]),
     "pgf_layout_plan_new": (i32, [P(ColumnSpec), u32, u32, u32, P(LayoutPlanC)]),
     "pgf_layout_fixed_row_cap": (i32, [P(ColumnSpec), u32, u32, P(u32)]),
     "pgf_block_validate": (i32, [vp, C.c_size_t]),

@@ -217,6 +217,8 @@ pgf_status pgf_ctx_synchronize(pgf_ctx* ctx) {
   return PGF_OK;
 }
 
+float pgf_ctx_last_kernel_ms(const pgf_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
+
 void* pgf_ctx_compute_stream(pgf_ctx* ctx) { return ctx ? (void*)ctx->compute_stream : nullptr; }
 
 /* ---- host-side layout ---- */

@@ -274,11 +274,14 @@ pgf_status bloom_insert_host_keys(pgf_ctx* ctx, BloomSlot& b, const void* keys, 
   unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 8);
   CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
   KeySpan sp{dk.p, static_cast<const uint8_t*>(dv.p), n, 0};
+  CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
   bloom_insert_array_kernel<<<grid_for(ctx, n, 4), kThreads, 0, ctx->compute_stream>>>(b.dev, sp, key_width, d_cnt);
   CU(ctx, cudaGetLastError());
+  CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
   CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   if (inserted) *inserted = *h_cnt;
+  CU(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b));
   return PGF_OK;
 }
 
@@ -289,14 +292,17 @@ pgf_status bloom_insert_scan(pgf_ctx* ctx, BloomSlot& b, Scan& s, uint32_t col, 
   unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 8);
   unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 8);
   CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
+  CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
   if (s.npages) {
     const uint32_t grid = uint32_t(s.npages < uint64_t(ctx->sm_count) * 4 ? s.npages : uint64_t(ctx->sm_count) * 4);
     bloom_insert_scan_kernel<<<grid, kThreads, 0, ctx->compute_stream>>>(b.dev, sk, d_cnt);
     CU(ctx, cudaGetLastError());
   }
+  CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
   CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   if (inserted) *inserted = *h_cnt;
+  CU(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b));
   return PGF_OK;
 }
 
@@ -312,10 +318,13 @@ pgf_status run_probe(pgf_ctx* ctx, BloomSlot& b, uint64_t n, uint8_t* decisions,
   ProbeOut out{static_cast<uint8_t*>(dd.p), d_cnt, d_cnt + 1};
   const uint32_t nwords = uint32_t(b.params.word_count);
   const bool smem = b.params.word_count <= kSmemWordsMax;
+  CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
   if (n) PGF_TRY(launch(out, smem, nwords));
+  CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
   CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 16, cudaMemcpyDeviceToHost, ctx->compute_stream));
   if (n) CU(ctx, cudaMemcpyAsync(decisions, dd.p, n, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  CU(ctx, cudaEventElapsedTime(&ctx->last_kernel_ms, ctx->ev_a, ctx->ev_b));
   if (stats) {
     stats->probe_rows = n;
     stats->rejected_rows = h_cnt[0];

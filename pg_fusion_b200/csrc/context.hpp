@@ -84,6 +84,7 @@ struct pgf_ctx {
   std::mutex mu;
   std::string last_error;
   pgf_status sticky = PGF_OK;
+  float last_kernel_ms = 0.f;
 
   pgf_status fail(pgf_status st, const char* fmt, ...) {
     char buf[512];

@@ -833,6 +833,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   res->rows_out = c.rows_out;
   res->bloom_rows = c.bloom_rows;
   res->kernel_ms = total_ms;
+  ctx->last_kernel_ms = total_ms;
   res->kernel_launches = launches;
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable jt = L.build_table;

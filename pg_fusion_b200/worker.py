@@ -496,6 +496,9 @@ class Context:
     def synchronize(self) -> None:
         self._check(_lib.lib().pgf_ctx_synchronize(self.h))
 
+    def last_kernel_ms(self) -> float:
+        return float(_lib.lib().pgf_ctx_last_kernel_ms(self.h))
+
     def compute_stream(self) -> int:
         return _lib.lib().pgf_ctx_compute_stream(self.h)
 

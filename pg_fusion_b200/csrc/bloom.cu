@@ -90,22 +90,49 @@ __global__ void __launch_bounds__(kThreads) bloom_insert_scan_kernel(DevBloom b,
 // ---- probe -----------------------------------------------------------------------
 // Decision per key; `ready` is the lifecycle check hoisted out of the per-key path
 // (the reference re-loads the lifecycle word per key, shared.rs:351-354).
-template <bool SMEM>
+//
+// The probe is bound by integer issue, not by HBM: two splitmix64 rounds are ~50 SASS
+// instructions per key against 9 bytes of traffic.  Two things keep the rest cheap:
+//   * K > 0 (hash_count == K and bit_count a power of two <= 2^32): bit_i only depends on
+//     the low 32 bits of h1 + i*h2, the filter is read as 32-bit words (little endian:
+//     u64 word b/64, bit b%64 == u32 word b/32, bit b%32) and all K words are fetched
+//     before any is tested, so the K loads overlap instead of forming a dependent chain;
+//   * 4 keys per thread per iteration are loaded one iteration ahead (32 KiB in flight per SM).
+// K == 0 is the general form (any bit_count via the exact fastmod, early exit per bit).
+template <bool SMEM, int K>
+__device__ __forceinline__ bool probe_words(const DevBloom& b, const uint64_t* smem_words, uint64_t key) {
+  const uint64_t h1 = splitmix64(key ^ b.seed);
+  const uint64_t h2 = splitmix64(h1 ^ kBloomSalt) | 1ull;
+  if constexpr (K > 0) {
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(SMEM ? smem_words : b.words);
+    const uint32_t mask = uint32_t(b.bit_count - 1);
+    uint32_t v = uint32_t(h1), acc = 1u;
+    const uint32_t step = uint32_t(h2);
+#pragma unroll
+    for (int i = 0; i < K; ++i, v += step) {
+      const uint32_t bit = v & mask;
+      const uint32_t w = SMEM ? w32[bit >> 5] : __ldg(w32 + (bit >> 5));
+      acc &= w >> (bit & 31);
+    }
+    return acc & 1u;
+  } else {
+    const uint64_t* words = SMEM ? smem_words : b.words;
+    uint64_t v = h1;
+    for (uint32_t i = 0; i < b.hash_count; ++i, v += h2) {
+      const uint64_t bit = bloom_reduce(b, v);
+      const uint64_t w = SMEM ? words[bit >> 6] : __ldg(words + (bit >> 6));
+      if (((w >> (bit & 63)) & 1ull) == 0) return false;
+    }
+    return true;
+  }
+}
+
+template <bool SMEM, int K>
 __device__ __forceinline__ uint8_t decide(const DevBloom& b, const uint64_t* smem_words, bool ready,
                                           bool valid, int64_t key) {
   if (!ready) return PGF_PASS_UNFILTERED;
   if (!valid) return PGF_DEFINITELY_ABSENT;  // decision_for_null, shared.rs:367-374
-  if (SMEM) {
-    const uint64_t h1 = splitmix64(uint64_t(key) ^ b.seed);
-    const uint64_t h2 = splitmix64(h1 ^ kBloomSalt) | 1ull;
-    uint64_t v = h1;
-    for (uint32_t i = 0; i < b.hash_count; ++i, v += h2) {
-      const uint64_t bit = bloom_reduce(b, v);
-      if (((smem_words[bit >> 6] >> (bit & 63)) & 1ull) == 0) return PGF_DEFINITELY_ABSENT;
-    }
-    return PGF_MAYBE_PRESENT;
-  }
-  return bloom_contains(b, uint64_t(key)) ? PGF_MAYBE_PRESENT : PGF_DEFINITELY_ABSENT;
+  return probe_words<SMEM, K>(b, smem_words, uint64_t(key)) ? PGF_MAYBE_PRESENT : PGF_DEFINITELY_ABSENT;
 }
 
 template <bool SMEM>
@@ -125,41 +152,13 @@ struct ProbeOut {
   unsigned long long* unfiltered;
 };
 
-// Int64 keys, no nulls: each thread handles 2 keys per 128-bit load and writes 2 bytes.
-template <bool SMEM>
-__global__ void __launch_bounds__(kThreads) bloom_probe_array_kernel(DevBloom b, KeySpan sp, int width, bool ready,
-                                                                    uint32_t nwords, ProbeOut out) {
-  extern __shared__ __align__(16) uint64_t smem_words[];
-  stage_words<SMEM>(b, smem_words, nwords);
-  unsigned long long rej = 0, unf = 0;
-  const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
-  const uint64_t tid = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x;
-  if (width == 8 && sp.validity == nullptr && (reinterpret_cast<uintptr_t>(sp.keys) & 15) == 0 &&
-      (reinterpret_cast<uintptr_t>(out.decisions + sp.out_base) & 1) == 0) {
-    const longlong2* k2 = reinterpret_cast<const longlong2*>(sp.keys);
-    const uint64_t pairs = sp.n / 2;
-    for (uint64_t i = tid; i < pairs; i += stride) {
-      const longlong2 k = __ldg(k2 + i);
-      const uint8_t d0 = decide<SMEM>(b, smem_words, ready, true, k.x);
-      const uint8_t d1 = decide<SMEM>(b, smem_words, ready, true, k.y);
-      *reinterpret_cast<uchar2*>(out.decisions + sp.out_base + 2 * i) = make_uchar2(d0, d1);
-      rej += (d0 == PGF_DEFINITELY_ABSENT) + (d1 == PGF_DEFINITELY_ABSENT);
-      unf += (d0 == PGF_PASS_UNFILTERED) + (d1 == PGF_PASS_UNFILTERED);
-    }
-    if ((sp.n & 1) && tid == 0) {
-      const uint8_t d = decide<SMEM>(b, smem_words, ready, true, load_key(sp.keys, 8, sp.n - 1));
-      out.decisions[sp.out_base + sp.n - 1] = d;
-      rej += d == PGF_DEFINITELY_ABSENT;
-      unf += d == PGF_PASS_UNFILTERED;
-    }
-  } else {
-    for (uint64_t i = tid; i < sp.n; i += stride) {
-      const uint8_t d = decide<SMEM>(b, smem_words, ready, valid_bit(sp.validity, i), load_key(sp.keys, width, i));
-      out.decisions[sp.out_base + i] = d;
-      rej += d == PGF_DEFINITELY_ABSENT;
-      unf += d == PGF_PASS_UNFILTERED;
-    }
-  }
+__device__ __forceinline__ longlong2 ldg_stream_i64x2(const longlong2* p) {
+  longlong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.s64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ void finish_counts(unsigned long long rej, unsigned long long unf, const ProbeOut& out) {
   for (int o = 16; o; o >>= 1) {
     rej += __shfl_xor_sync(0xffffffffu, rej, o);
     unf += __shfl_xor_sync(0xffffffffu, unf, o);
@@ -170,29 +169,130 @@ __global__ void __launch_bounds__(kThreads) bloom_probe_array_kernel(DevBloom b,
   }
 }
 
-template <bool SMEM>
-__global__ void __launch_bounds__(kThreads) bloom_probe_scan_kernel(DevBloom b, ScanKeys s, bool ready,
-                                                                   uint32_t nwords, ProbeOut out) {
+// A block of 4 * kProbeThreads consecutive Int64 keys without NULLs: thread t owns the key
+// pairs (2t, 2t+1) of the two halves of the block.
+constexpr int kProbeThreads = 1024;
+constexpr uint32_t kBlockKeys = 4u * kProbeThreads;
+struct KeyQuad {
+  longlong2 a, b;
+};
+__device__ __forceinline__ KeyQuad load_quad(const void* keys, uint32_t n, uint32_t base) {
+  // rows past n are not loaded; pairs start at even rows so a pair is in range iff its first row is
+  KeyQuad q{{0, 0}, {0, 0}};
+  const longlong2* k2 = reinterpret_cast<const longlong2*>(keys);
+  const uint32_t r0 = base + 2u * threadIdx.x, r1 = r0 + 2u * kProbeThreads;
+  if (r0 + 1 < n) q.a = ldg_stream_i64x2(k2 + (r0 >> 1));
+  else if (r0 < n) q.a.x = reinterpret_cast<const int64_t*>(keys)[r0];
+  if (r1 + 1 < n) q.b = ldg_stream_i64x2(k2 + (r1 >> 1));
+  else if (r1 < n) q.b.x = reinterpret_cast<const int64_t*>(keys)[r1];
+  return q;
+}
+template <bool SMEM, int K>
+__device__ __forceinline__ void probe_quad(const DevBloom& b, const uint64_t* smem_words, bool ready, const KeyQuad& q,
+                                           uint32_t n, uint32_t base, uint8_t* out, unsigned long long& rej,
+                                           unsigned long long& unf) {
+  const uint8_t d0 = decide<SMEM, K>(b, smem_words, ready, true, q.a.x), d1 = decide<SMEM, K>(b, smem_words, ready, true, q.a.y);
+  const uint8_t d2 = decide<SMEM, K>(b, smem_words, ready, true, q.b.x), d3 = decide<SMEM, K>(b, smem_words, ready, true, q.b.y);
+  const uint32_t r0 = base + 2u * threadIdx.x, r1 = r0 + 2u * kProbeThreads;
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 1) == 0;
+  auto put = [&](uint32_t r, uint8_t x, uint8_t y) {
+    if (r + 1 < n) {
+      if (aligned) *reinterpret_cast<uchar2*>(out + r) = make_uchar2(x, y);
+      else { out[r] = x; out[r + 1] = y; }
+      rej += (x == PGF_DEFINITELY_ABSENT) + (y == PGF_DEFINITELY_ABSENT);
+      unf += (x == PGF_PASS_UNFILTERED) + (y == PGF_PASS_UNFILTERED);
+    } else if (r < n) {
+      out[r] = x;
+      rej += x == PGF_DEFINITELY_ABSENT;
+      unf += x == PGF_PASS_UNFILTERED;
+    }
+  };
+  put(r0, d0, d1);
+  put(r1, d2, d3);
+}
+
+// Host key arrays (copied to a device buffer).
+template <bool SMEM, int K>
+__global__ void __launch_bounds__(kProbeThreads, 1) bloom_probe_array_kernel(DevBloom b, KeySpan sp, int width, bool ready,
+                                                                            uint32_t nwords, ProbeOut out) {
   extern __shared__ __align__(16) uint64_t smem_words[];
   stage_words<SMEM>(b, smem_words, nwords);
   unsigned long long rej = 0, unf = 0;
-  for (uint32_t page = blockIdx.x; page < s.npages; page += gridDim.x) {
-    const KeySpan sp = page_span(s, page);
-    for (uint32_t i = threadIdx.x; i < sp.n; i += blockDim.x) {
-      const uint8_t d = decide<SMEM>(b, smem_words, ready, valid_bit(sp.validity, i), load_key(sp.keys, s.width, i));
+  if (width == 8 && sp.validity == nullptr && (reinterpret_cast<uintptr_t>(sp.keys) & 15) == 0 && sp.n < 0xFFFF0000ull) {
+    const uint32_t n = uint32_t(sp.n), nblocks = (n + kBlockKeys - 1) / kBlockKeys;
+    uint32_t blk = blockIdx.x;
+    KeyQuad q = blk < nblocks ? load_quad(sp.keys, n, blk * kBlockKeys) : KeyQuad{};
+    for (; blk < nblocks; blk += gridDim.x) {
+      const uint32_t nxt = blk + gridDim.x;
+      const KeyQuad qn = nxt < nblocks ? load_quad(sp.keys, n, nxt * kBlockKeys) : KeyQuad{};
+      probe_quad<SMEM, K>(b, smem_words, ready, q, n, blk * kBlockKeys, out.decisions + sp.out_base, rej, unf);
+      q = qn;
+    }
+  } else {
+    const uint64_t stride = uint64_t(gridDim.x) * blockDim.x;
+    for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < sp.n; i += stride) {
+      const uint8_t d = decide<SMEM, K>(b, smem_words, ready, valid_bit(sp.validity, i), load_key(sp.keys, width, i));
       out.decisions[sp.out_base + i] = d;
       rej += d == PGF_DEFINITELY_ABSENT;
       unf += d == PGF_PASS_UNFILTERED;
     }
   }
-  for (int o = 16; o; o >>= 1) {
-    rej += __shfl_xor_sync(0xffffffffu, rej, o);
-    unf += __shfl_xor_sync(0xffffffffu, unf, o);
+  finish_counts(rej, unf, out);
+}
+
+// One key column of a scan's pages.  Work item = one block of kBlockKeys rows of one page.
+template <bool SMEM, int K>
+__global__ void __launch_bounds__(kProbeThreads, 1) bloom_probe_scan_kernel(DevBloom b, ScanKeys s, bool ready,
+                                                                           uint32_t nwords, uint32_t blocks_per_page,
+                                                                           ProbeOut out) {
+  extern __shared__ __align__(16) uint64_t smem_words[];
+  stage_words<SMEM>(b, smem_words, nwords);
+  unsigned long long rej = 0, unf = 0;
+  const uint32_t nitems = s.npages * blocks_per_page;
+  if (s.width == 8) {
+    auto fetch = [&](uint32_t item, KeySpan& sp, uint32_t& base) -> KeyQuad {
+      sp = page_span(s, item / blocks_per_page);
+      base = (item % blocks_per_page) * kBlockKeys;
+      // pages with NULLs take the row-at-a-time path below
+      return sp.validity == nullptr ? load_quad(sp.keys, uint32_t(sp.n), base) : KeyQuad{};
+    };
+    uint32_t item = blockIdx.x;
+    KeySpan sp{}, spn{};
+    uint32_t base = 0, basen = 0;
+    KeyQuad q{};
+    if (item < nitems) q = fetch(item, sp, base);
+    for (; item < nitems; item += gridDim.x) {
+      const uint32_t nxt = item + gridDim.x;
+      KeyQuad qn{};
+      if (nxt < nitems) qn = fetch(nxt, spn, basen);
+      if (sp.validity == nullptr) {
+        probe_quad<SMEM, K>(b, smem_words, ready, q, uint32_t(sp.n), base, out.decisions + sp.out_base, rej, unf);
+      } else {
+        const uint32_t end = uint32_t(sp.n) < base + kBlockKeys ? uint32_t(sp.n) : base + kBlockKeys;
+        for (uint32_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+          const uint8_t d = decide<SMEM, K>(b, smem_words, ready, valid_bit(sp.validity, i), load_key(sp.keys, 8, i));
+          out.decisions[sp.out_base + i] = d;
+          rej += d == PGF_DEFINITELY_ABSENT;
+          unf += d == PGF_PASS_UNFILTERED;
+        }
+      }
+      q = qn; sp = spn; base = basen;
+    }
+  } else {
+    for (uint32_t item = blockIdx.x; item < nitems; item += gridDim.x) {
+      const KeySpan sp = page_span(s, item / blocks_per_page);
+      const uint32_t base = (item % blocks_per_page) * kBlockKeys;
+      const uint32_t end = uint32_t(sp.n) < base + kBlockKeys ? uint32_t(sp.n) : base + kBlockKeys;
+#pragma unroll 4
+      for (uint32_t i = base + threadIdx.x; i < end; i += blockDim.x) {
+        const uint8_t d = decide<SMEM, K>(b, smem_words, ready, valid_bit(sp.validity, i), load_key(sp.keys, s.width, i));
+        out.decisions[sp.out_base + i] = d;
+        rej += d == PGF_DEFINITELY_ABSENT;
+        unf += d == PGF_PASS_UNFILTERED;
+      }
+    }
   }
-  if ((threadIdx.x & 31) == 0) {
-    if (rej) atomicAdd(out.rejected, rej);
-    if (unf) atomicAdd(out.unfiltered, unf);
-  }
+  finish_counts(rej, unf, out);
 }
 
 __global__ void bloom_or_kernel(uint64_t* dst, const uint64_t* src, uint64_t nwords, uint32_t narrays) {
@@ -248,6 +348,7 @@ pgf_status bloom_make_dev(const pgf_bloom_params& p, uint64_t* d_words, DevBloom
   out->seed = p.seed;
   out->hash_count = uint32_t(p.hash_count > 0xFFFFFFFFull ? 0xFFFFFFFFull : p.hash_count);
   out->pow2 = (p.bit_count & (p.bit_count - 1)) == 0;
+  if (out->pow2 && p.bit_count >= 32 && p.bit_count <= (1ull << 32)) out->pow2 = 2;  // 32-bit word addressing
   // M = floor((2^128 - 1) / d) + 1
   const unsigned __int128 all = ~(unsigned __int128)0;
   const unsigned __int128 m = all / p.bit_count + 1;
@@ -334,6 +435,53 @@ pgf_status run_probe(pgf_ctx* ctx, BloomSlot& b, uint64_t n, uint8_t* decisions,
 }
 }  // namespace
 
+namespace {
+// hash_count with an unrolled instantiation (pow2 bit_count <= 2^32), else 0 = general form
+int probe_k(const BloomSlot& b) {
+  const uint64_t bits = b.params.bit_count;
+  const bool pow2 = (bits & (bits - 1)) == 0 && bits <= (1ull << 32) && bits >= 32;
+  return (pow2 && b.params.hash_count >= 1 && b.params.hash_count <= 8) ? int(b.params.hash_count) : 0;
+}
+
+template <bool SMEM, int K>
+cudaError_t launch_probe_array(uint32_t grid, size_t bytes, cudaStream_t st, const DevBloom& b, const KeySpan& sp, int width,
+                               bool ready, uint32_t nwords, const ProbeOut& out) {
+  auto kernel = bloom_probe_array_kernel<SMEM, K>;
+  if (SMEM) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e != cudaSuccess) return e;
+  }
+  kernel<<<grid, kProbeThreads, bytes, st>>>(b, sp, width, ready, nwords, out);
+  return cudaGetLastError();
+}
+template <bool SMEM, int K>
+cudaError_t launch_probe_scan(uint32_t grid, size_t bytes, cudaStream_t st, const DevBloom& b, const ScanKeys& sk, bool ready,
+                              uint32_t nwords, uint32_t blocks_per_page, const ProbeOut& out) {
+  auto kernel = bloom_probe_scan_kernel<SMEM, K>;
+  if (SMEM) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes));
+    if (e != cudaSuccess) return e;
+  }
+  kernel<<<grid, kProbeThreads, bytes, st>>>(b, sk, ready, nwords, blocks_per_page, out);
+  return cudaGetLastError();
+}
+
+#define PGF_PROBE_DISPATCH(FN, SMEM_FLAG, K, ...)                                            \
+  [&]() -> cudaError_t {                                                                     \
+    switch (K) {                                                                             \
+      case 1: return SMEM_FLAG ? FN<true, 1>(__VA_ARGS__) : FN<false, 1>(__VA_ARGS__);       \
+      case 2: return SMEM_FLAG ? FN<true, 2>(__VA_ARGS__) : FN<false, 2>(__VA_ARGS__);       \
+      case 3: return SMEM_FLAG ? FN<true, 3>(__VA_ARGS__) : FN<false, 3>(__VA_ARGS__);       \
+      case 4: return SMEM_FLAG ? FN<true, 4>(__VA_ARGS__) : FN<false, 4>(__VA_ARGS__);       \
+      case 5: return SMEM_FLAG ? FN<true, 5>(__VA_ARGS__) : FN<false, 5>(__VA_ARGS__);       \
+      case 6: return SMEM_FLAG ? FN<true, 6>(__VA_ARGS__) : FN<false, 6>(__VA_ARGS__);       \
+      case 7: return SMEM_FLAG ? FN<true, 7>(__VA_ARGS__) : FN<false, 7>(__VA_ARGS__);       \
+      case 8: return SMEM_FLAG ? FN<true, 8>(__VA_ARGS__) : FN<false, 8>(__VA_ARGS__);       \
+      default: return SMEM_FLAG ? FN<true, 0>(__VA_ARGS__) : FN<false, 0>(__VA_ARGS__);      \
+    }                                                                                        \
+  }()
+}  // namespace
+
 pgf_status bloom_probe_host_keys(pgf_ctx* ctx, BloomSlot& b, bool ready, const void* keys, int32_t key_width,
                                  const uint8_t* validity, uint64_t n, uint8_t* decisions, pgf_probe_stats* stats) {
   CU(ctx, cudaSetDevice(ctx->device));
@@ -348,15 +496,11 @@ pgf_status bloom_probe_host_keys(pgf_ctx* ctx, BloomSlot& b, bool ready, const v
   }
   KeySpan sp{dk.p, static_cast<const uint8_t*>(dv.p), n, 0};
   return run_probe(ctx, b, n, decisions, stats, [&](ProbeOut out, bool smem, uint32_t nwords) -> pgf_status {
-    const uint32_t grid = grid_for(ctx, n / 2 + 1, 1);
-    if (smem) {
-      const size_t bytes = size_t(nwords) * 8;
-      CU(ctx, cudaFuncSetAttribute(bloom_probe_array_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-      bloom_probe_array_kernel<true><<<grid, kThreads, bytes, ctx->compute_stream>>>(b.dev, sp, key_width, ready, nwords, out);
-    } else {
-      bloom_probe_array_kernel<false><<<grid, kThreads, 0, ctx->compute_stream>>>(b.dev, sp, key_width, ready, nwords, out);
-    }
-    CU(ctx, cudaGetLastError());
+    const uint64_t blocks = (n + kBlockKeys - 1) / kBlockKeys;
+    const uint32_t grid = uint32_t(blocks < uint64_t(ctx->sm_count) ? (blocks ? blocks : 1) : uint64_t(ctx->sm_count));
+    const size_t bytes = smem ? size_t(nwords) * 8 : 0;
+    const int k = probe_k(b);
+    CU(ctx, PGF_PROBE_DISPATCH(launch_probe_array, smem, k, grid, bytes, ctx->compute_stream, b.dev, sp, key_width, ready, nwords, out));
     return PGF_OK;
   });
 }
@@ -367,15 +511,14 @@ pgf_status bloom_probe_scan(pgf_ctx* ctx, BloomSlot& b, bool ready, Scan& s, uin
   ScanKeys sk;
   PGF_TRY(make_scan_keys(ctx, s, col, &sk));
   return run_probe(ctx, b, s.rows, decisions, stats, [&](ProbeOut out, bool smem, uint32_t nwords) -> pgf_status {
-    const uint32_t grid = uint32_t(s.npages < uint64_t(ctx->sm_count) ? s.npages : uint64_t(ctx->sm_count));
-    if (smem) {
-      const size_t bytes = size_t(nwords) * 8;
-      CU(ctx, cudaFuncSetAttribute(bloom_probe_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(bytes)));
-      bloom_probe_scan_kernel<true><<<grid, kThreads, bytes, ctx->compute_stream>>>(b.dev, sk, ready, nwords, out);
-    } else {
-      bloom_probe_scan_kernel<false><<<grid, kThreads, 0, ctx->compute_stream>>>(b.dev, sk, ready, nwords, out);
-    }
-    CU(ctx, cudaGetLastError());
+    const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
+    const uint32_t blocks_per_page = (max_rows + kBlockKeys - 1) / kBlockKeys;
+    const uint64_t items = s.npages * uint64_t(blocks_per_page);
+    if (items > 0xFFFFFFF0ull) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "scan too large for 32-bit probe items");
+    const uint32_t grid = uint32_t(items < uint64_t(ctx->sm_count) ? (items ? items : 1) : uint64_t(ctx->sm_count));
+    const size_t bytes = smem ? size_t(nwords) * 8 : 0;
+    const int k = probe_k(b);
+    CU(ctx, PGF_PROBE_DISPATCH(launch_probe_scan, smem, k, grid, bytes, ctx->compute_stream, b.dev, sk, ready, nwords, blocks_per_page, out));
     return PGF_OK;
   });
 }

@@ -35,12 +35,27 @@ __device__ __forceinline__ uint64_t bloom_reduce(const DevBloom& b, uint64_t v) 
   return b.pow2 ? (v & (b.bit_count - 1)) : fastmod_u64(v, b.m_lo, b.m_hi, b.bit_count);
 }
 
+// b.pow2 == 2: bit_count is a power of two in [32, 2^32].  Then bit_i only depends on the low
+// 32 bits of h1 + i*h2 and the filter can be addressed as 32-bit words (little endian: u64
+// word b/64, bit b%64 is u32 word b/32, bit b%32) -- same bits, half the register traffic.
+
 // AtomicBloomRef::insert_hash (bloom.rs:222-227).  The word is read first and the atomic
 // skipped when the bit is already set: bits are only ever set during a build, so a stale
 // "set" observation is always valid, and saturated filters stop generating atomics.
 __device__ __forceinline__ void bloom_insert(const DevBloom& b, uint64_t hash) {
   const uint64_t h1 = splitmix64(hash ^ b.seed);
   const uint64_t h2 = splitmix64(h1 ^ kBloomSalt) | 1ull;
+  if (b.pow2 == 2) {
+    unsigned int* w32 = reinterpret_cast<unsigned int*>(b.words);
+    const uint32_t mask = uint32_t(b.bit_count - 1), step = uint32_t(h2);
+    uint32_t v = uint32_t(h1);
+    for (uint32_t i = 0; i < b.hash_count; ++i, v += step) {
+      const uint32_t bit = v & mask, m = 1u << (bit & 31);
+      unsigned int* w = w32 + (bit >> 5);
+      if ((*reinterpret_cast<volatile unsigned int*>(w) & m) == 0) atomicOr(w, m);
+    }
+    return;
+  }
   uint64_t v = h1;
   for (uint32_t i = 0; i < b.hash_count; ++i, v += h2) {
     const uint64_t bit = bloom_reduce(b, v);
@@ -50,10 +65,29 @@ __device__ __forceinline__ void bloom_insert(const DevBloom& b, uint64_t hash) {
   }
 }
 
-// AtomicBloomRef::might_contain_hash (bloom.rs:233-241), early-out on the first clear bit.
+// AtomicBloomRef::might_contain_hash (bloom.rs:233-241).  The decision is the AND of the k
+// bits whatever the order of evaluation: the first bit is tested alone (a sparse filter
+// rejects most absent keys there), the remaining ones are fetched three at a time so their
+// L1/L2 latencies overlap instead of forming a dependent chain.
 __device__ __forceinline__ bool bloom_contains(const DevBloom& b, uint64_t hash) {
   const uint64_t h1 = splitmix64(hash ^ b.seed);
   const uint64_t h2 = splitmix64(h1 ^ kBloomSalt) | 1ull;
+  if (b.pow2 == 2) {
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(b.words);
+    const uint32_t mask = uint32_t(b.bit_count - 1), step = uint32_t(h2);
+    uint32_t v = uint32_t(h1);
+    uint32_t bit = v & mask;
+    if (((__ldg(w32 + (bit >> 5)) >> (bit & 31)) & 1u) == 0) return false;
+    for (uint32_t i = 1; i < b.hash_count; i += 3) {
+      const uint32_t b0 = (v + step) & mask, b1 = (v + 2u * step) & mask, b2 = (v + 3u * step) & mask;
+      uint32_t x0 = __ldg(w32 + (b0 >> 5)) >> (b0 & 31), x1 = ~0u, x2 = ~0u;
+      if (i + 1 < b.hash_count) x1 = __ldg(w32 + (b1 >> 5)) >> (b1 & 31);
+      if (i + 2 < b.hash_count) x2 = __ldg(w32 + (b2 >> 5)) >> (b2 & 31);
+      if (((x0 & x1 & x2) & 1u) == 0) return false;
+      v += 3u * step;
+    }
+    return true;
+  }
   uint64_t v = h1;
   for (uint32_t i = 0; i < b.hash_count; ++i, v += h2) {
     const uint64_t bit = bloom_reduce(b, v);

@@ -35,7 +35,7 @@ struct DevBloom {
   uint64_t seed;
   uint64_t m_lo, m_hi;   // ceil(2^128 / bit_count) for the exact 64-bit fastmod
   uint32_t hash_count;
-  uint32_t pow2;         // bit_count is a power of two: use mask
+  uint32_t pow2;         // 1: bit_count is a power of two (mask instead of modulo); 2: and in [32, 2^32]
 };
 
 // ---- pipeline plan -----------------------------------------------------------------

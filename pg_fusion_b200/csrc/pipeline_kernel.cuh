@@ -522,6 +522,116 @@ static __device__ __noinline__ int dict_lookup_or_insert(BlockShared* sh, Key4 k
   }
 }
 
+// ---- register-group fast path (compile-time shapes, NOT NULL scan columns, no join) ------
+// Everything below is straight-line code for the two rows a thread handles per iteration, so
+// the scheduler can overlap the shared-memory latencies of one row with the arithmetic of the
+// other.  The group of a row is resolved against the CTA dictionary with a 32-bit fingerprint
+// held in registers plus one exact 128/256-bit compare; the register accumulators are updated
+// with predicated adds (no divergent blocks, no jump table).
+template <class KEYS>
+struct ShapeKeyInfo {
+  template <int I>
+  static constexpr int words_until() {  // key words used by parts [0, I)
+    if constexpr (I == 0) return 0;
+    else {
+      constexpr int enc = KEYS::template at<I - 1>();
+      constexpr int ld = enc & 15;
+      constexpr int end = (enc >> 8) + ((ld == LD_VIEW || ld == LD_DEC) ? 2 : 1);
+      constexpr int prev = words_until<I - 1>();
+      return end > prev ? end : prev;
+    }
+  }
+  static constexpr int nwords = words_until<KEYS::size>();
+};
+
+template <class KEYS>
+__device__ __forceinline__ void load_key_fast(const DevPlan& P, const uint8_t* stage, uint32_t r, uint64_t (&key)[kKeyWords],
+                                              uint32_t& bad) {
+  static_for<KEYS::size>([&](auto I) {
+    constexpr int kp = decltype(I)::value;
+    constexpr int enc = KEYS::template at<kp>();
+    constexpr int ld = enc & 15;
+    constexpr int word = enc >> 8;
+    const uint8_t* col = stage + P.keys[kp].ref.off;
+    if constexpr (ld == LD_VIEW || ld == LD_DEC) {
+      const uint4 raw = reinterpret_cast<const uint4*>(col)[r];
+      if (ld == LD_VIEW) bad += raw.x > 12u;
+      key[word] = (uint64_t(raw.y) << 32) | raw.x;
+      key[word + 1 < int(kKeyWords) ? word + 1 : word] = (uint64_t(raw.w) << 32) | raw.z;
+    } else if constexpr (ld == LD_I64) {
+      key[word] = uint64_t(reinterpret_cast<const int64_t*>(col)[r]);
+    } else if constexpr (ld == LD_I32) {
+      key[word] = uint64_t(int64_t(reinterpret_cast<const int32_t*>(col)[r]));
+    } else {
+      key[word] = uint64_t(int64_t(reinterpret_cast<const int16_t*>(col)[r]));
+    }
+  });
+}
+
+// 32-bit fingerprint over the used key words; odd, so it never equals an empty (0) entry.
+template <int NW>
+__device__ __forceinline__ uint32_t key_fp32(const uint64_t (&key)[kKeyWords]) {
+  uint32_t f = 0x9E3779B9u;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) {
+    const uint32_t lo = uint32_t(key[w]), hi = uint32_t(key[w] >> 32);
+    f = __funnelshift_l(f, f, 5) ^ lo ^ __funnelshift_l(hi, hi, 13);
+  }
+  return f | 1u;
+}
+
+template <int NW>
+__device__ __forceinline__ bool dict_equal_fast(const BlockShared* sh, int g, const uint64_t (&key)[kKeyWords]) {
+  const ulonglong2* e = reinterpret_cast<const ulonglong2*>(&sh->dict_keys[g < 0 ? 0 : g][0]);
+  uint64_t diff = 0;
+  const ulonglong2 a = e[0];
+  diff |= a.x ^ key[0];
+  if (NW > 1) diff |= a.y ^ key[1];
+  if constexpr (NW > 2) {
+    const ulonglong2 b = e[1];
+    diff |= b.x ^ key[2];
+    if (NW > 3) diff |= b.y ^ key[3];
+  }
+  return g >= 0 && diff == 0;
+}
+
+__device__ __forceinline__ void pred_dadd(double& acc, double v, int g, int gg) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"(g), "r"(gg));
+}
+__device__ __forceinline__ void pred_inc(uint32_t& n, int g, int gg) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(n) : "r"(g), "r"(gg));
+}
+
+// Float64 argument forms over NOT NULL scan columns (compile-time FORM)
+template <int FORM>
+__device__ __forceinline__ double eval_fast_f64(const DevExpr& e, const uint8_t* stage, uint32_t r, double prev) {
+  auto col = [&](int f) { return reinterpret_cast<const double*>(stage + e.f[f].ref.off)[r]; };
+  if constexpr (FORM == int(FORM_X)) return col(0);
+  else if constexpr (FORM == int(FORM_XY)) return __dmul_rn(col(0), col(1));
+  else if constexpr (FORM == int(FORM_X_CMY)) return __dmul_rn(col(0), __dsub_rn(e.f[1].cf, col(1)));
+  else if constexpr (FORM == int(FORM_X_CMY_CPZ)) return __dmul_rn(__dmul_rn(col(0), __dsub_rn(e.f[1].cf, col(1))), __dadd_rn(e.f[2].cf, col(2)));
+  else return __dmul_rn(prev, __dadd_rn(e.f[2].cf, col(2)));  // FORM_PREV_CPZ
+}
+
+// Rare path of the fast sink: the row's group is not register resident (more than kRegGroups
+// groups in this CTA): accumulate straight into the global table.
+template <int NE>
+struct ValuesF64 {
+  double v[NE];
+};
+template <int NE>
+static __device__ __noinline__ void fast_slow_accumulate(const DevPlan& P, Key4 kv, ValuesF64<NE> vals) {
+  const uint64_t key[kKeyWords] = {kv.w0, kv.w1, kv.w2, kv.w3};
+  const int64_t slot = group_slot(P.table, key, P.nkeywords, 0);
+  if (slot < 0) return;
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    atomicAdd(reinterpret_cast<double*>(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words), vals.v[e]);
+    atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
+}
+
 // ---- the kernel ----------------------------------------------------------------------
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
 __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_kernel(const __grid_constant__ DevPlan P) {
@@ -530,6 +640,9 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
+  // straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 sums, no join
+  constexpr bool kFastGrouped = SINK == SINK_AGG && GROUPED && NJ == 0 && ACC == CLS_F64 && !SHAPE::generic &&
+                                SHAPE::no_nulls && SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   BlockShared* sh = reinterpret_cast<BlockShared*>(smem_raw);
@@ -656,6 +769,57 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
         n_filt += uint32_t(keep0) + uint32_t(keep1);
 
         if (!__any_sync(0xffffffffu, keep0 || keep1)) continue;
+        if constexpr (kFastGrouped) {
+          constexpr int NW = ShapeKeyInfo<typename SHAPE::Keys>::nwords;
+          constexpr int NE = SHAPE::Exprs::size;
+          n_out += uint32_t(keep0) + uint32_t(keep1);
+          uint64_t key0[kKeyWords] = {0, 0, 0, 0}, key1[kKeyWords] = {0, 0, 0, 0};
+          load_key_fast<typename SHAPE::Keys>(P, stage, r0, key0, n_bad);
+          load_key_fast<typename SHAPE::Keys>(P, stage, r1, key1, n_bad);
+          const uint32_t f0 = key_fp32<NW>(key0), f1 = key_fp32<NW>(key1);
+          int g0 = -1, g1 = -1;
+#pragma unroll
+          for (uint32_t gg = 0; gg < G; ++gg) {
+            if (uint32_t(dh[gg]) == f0) g0 = int(gg);
+            if (uint32_t(dh[gg]) == f1) g1 = int(gg);
+          }
+          const bool hit0 = dict_equal_fast<NW>(sh, g0, key0), hit1 = dict_equal_fast<NW>(sh, g1, key1);
+          if ((keep0 && !hit0) || (keep1 && !hit1)) {  // first rows of a group in this CTA, or > kRegGroups groups
+            if (keep0 && !hit0) g0 = dict_lookup_or_insert(sh, Key4{key0[0], key0[1], key0[2], key0[3]}, uint32_t(NW), 0u, f0);
+            if (keep1 && !hit1) g1 = dict_lookup_or_insert(sh, Key4{key1[0], key1[1], key1[2], key1[3]}, uint32_t(NW), 0u, f1);
+            const uint32_t n = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
+#pragma unroll
+            for (uint32_t gg = 0; gg < G; ++gg) dh[gg] = gg < n ? *reinterpret_cast<volatile uint64_t*>(&sh->dict_hash[gg]) : 0;
+          }
+          double v0[NE], v1[NE];
+          static_for<NE>([&](auto I) {
+            constexpr int e = decltype(I)::value;
+            constexpr int form = SHAPE::Exprs::template at<e>();
+            v0[e] = eval_fast_f64<form>(P.exprs[e], stage, r0, v0[e > 0 ? e - 1 : 0]);
+            v1[e] = eval_fast_f64<form>(P.exprs[e], stage, r1, v1[e > 0 ? e - 1 : 0]);
+          });
+          const int a0 = keep0 ? g0 : -2, a1 = keep1 ? g1 : -2;
+#pragma unroll
+          for (uint32_t gg = 0; gg < G; ++gg) {
+            pred_inc(grows[gg], a0, int(gg));
+#pragma unroll
+            for (int e = 0; e < NE; ++e) pred_dadd(acc[gg][e], v0[e], a0, int(gg));
+          }
+#pragma unroll
+          for (uint32_t gg = 0; gg < G; ++gg) {
+            pred_inc(grows[gg], a1, int(gg));
+#pragma unroll
+            for (int e = 0; e < NE; ++e) pred_dadd(acc[gg][e], v1[e], a1, int(gg));
+          }
+          if (a0 == -1 || a1 == -1) {
+            ValuesF64<NE> x0, x1;
+#pragma unroll
+            for (int e = 0; e < NE; ++e) { x0.v[e] = v0[e]; x1.v[e] = v1[e]; }
+            if (a0 == -1) fast_slow_accumulate<NE>(P, Key4{key0[0], key0[1], key0[2], key0[3]}, x0);
+            if (a1 == -1) fast_slow_accumulate<NE>(P, Key4{key1[0], key1[1], key1[2], key1[3]}, x1);
+          }
+          continue;
+        }
 #pragma unroll 1
         for (uint32_t half = 0; half < 2; ++half) {
           if (!(half ? keep1 : keep0)) continue;

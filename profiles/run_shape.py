@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Run one plan shape a few times (for ncu captures): python profiles/run_shape.py {q6|q1} [rows] [iters]"""
+"""Run one plan shape a few times (for ncu captures):
+    python profiles/run_shape.py {q6|q1|q3|q3bloom|bloom} [rows] [iters]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pg_fusion_b200 as pg
@@ -8,11 +9,47 @@ from tests import util as U
 shape = sys.argv[1] if len(sys.argv) > 1 else "q6"
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 12_000_000
 iters = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+
+
+def pow2(n):
+    b = 1
+    while b < n:
+        b <<= 1
+    return b
+
+
 with pg.Context(0) as ctx:
-    if shape == "q6":
-        scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q6, rows, seed=42); plan = U.gpu_q6(scan); bpr = 40
-    else:
-        scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q1, rows, seed=42); plan = U.gpu_q1(scan); bpr = 80
-    for i in range(iters):
-        r = plan.run()
-        print(f"{shape} iter {i}: kernel {r.kernel_ms:.4f} ms, {rows * bpr / r.kernel_ms / 1e6:.1f} GB/s, rows_out {r.rows_out}")
+    if shape in ("q6", "q1"):
+        if shape == "q6":
+            scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q6, rows, seed=42); plan = U.gpu_q6(scan); bpr = 40
+        else:
+            scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q1, rows, seed=42); plan = U.gpu_q1(scan); bpr = 80
+        for i in range(iters):
+            r = plan.run()
+            print(f"{shape} iter {i}: kernel {r.kernel_ms:.4f} ms, {rows * bpr / r.kernel_ms / 1e6:.1f} GB/s, rows_out {r.rows_out}")
+    elif shape in ("q3", "q3bloom"):
+        scale = rows / 59_986_052
+        ncust, nord = max(1000, int(1_500_000 * scale)), max(10000, int(15_000_000 * scale))
+        cust = ctx.gen_scan(pg.GenTable.CUSTOMER_Q3, ncust, seed=42)
+        orders = ctx.gen_scan(pg.GenTable.ORDERS_Q3, nord, seed=42, scale_rows=ncust)
+        li = ctx.gen_scan(pg.GenTable.LINEITEM_Q3, rows, seed=42, scale_rows=nord)
+        bp = None
+        if shape == "q3bloom":
+            bp = (pg.BloomParams.new(pow2(16 * ncust // 5), 4, 7), pg.BloomParams.new(pow2(16 * nord // 10), 4, 7))
+        for i in range(iters):
+            res, st = U.gpu_q3(ctx, cust, orders, li, bp)
+            t = (st["customer"].kernel_ms, st["orders"].kernel_ms, st["lineitem"].kernel_ms)
+            print(f"{shape} iter {i}: kernels {t[0]:.4f} {t[1]:.4f} {t[2]:.4f} ms; lineitem {rows * 36 / t[2] / 1e6:.1f} GB/s; "
+                  f"bloom->{st['lineitem'].rows_bloom} filter->{st['lineitem'].rows_filtered} joined {st['lineitem'].rows_out} groups {len(res.keys)}")
+    elif shape == "bloom":
+        p = pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM)
+        keys = ctx.gen_scan(pg.GenTable.KEYS_I64, 1_000_000, seed=7)
+        probe = ctx.gen_scan(pg.GenTable.KEYS_I64, rows, seed=7)
+        rf = ctx.runtime_filter(p)
+        rf.try_acquire_builder(); rf.insert_scan(keys, 0)
+        print(f"bloom build: {ctx.last_kernel_ms():.4f} ms")
+        rf.publish_ready()
+        for i in range(iters):
+            d, st = rf.probe_scan(probe, 0)
+            k = ctx.last_kernel_ms()
+            print(f"bloom probe iter {i}: kernel {k:.4f} ms, {rows / k / 1e6:.2f} G probes/s, {rows * 9 / k / 1e6:.1f} GB/s, rejected {st.rejected_rows}")

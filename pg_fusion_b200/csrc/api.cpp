@@ -150,6 +150,7 @@ pgf_status pgf_ctx_create(const pgf_config* config, pgf_ctx** ctx_out) {
   if (cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
   if (cudaMalloc(&ctx->d_flags, 64 * sizeof(uint32_t)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
   if (cudaMallocHost(&ctx->h_flags, 64 * sizeof(uint32_t)) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
+  if (cudaMallocHost(&ctx->h_arena, 64 * 1024) != cudaSuccess) return bail(PGF_ERR_OUT_OF_MEMORY);
   *ctx_out = ctx;
   return PGF_OK;
 }
@@ -176,6 +177,9 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   if (ctx->d_flags) cudaFree(ctx->d_flags);
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
+  if (ctx->d_arena) cudaFree(ctx->d_arena);
+  if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
   if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);

@@ -41,7 +41,8 @@ __device__ __forceinline__ uint64_t bloom_reduce(const DevBloom& b, uint64_t v) 
 
 // AtomicBloomRef::insert_hash (bloom.rs:222-227).  The word is read first and the atomic
 // skipped when the bit is already set: bits are only ever set during a build, so a stale
-// "set" observation is always valid, and saturated filters stop generating atomics.
+// "set" observation is always valid, and saturated filters stop generating atomics.  The
+// reads of up to four bit positions are issued together (independent L2 round trips).
 __device__ __forceinline__ void bloom_insert(const DevBloom& b, uint64_t hash) {
   const uint64_t h1 = splitmix64(hash ^ b.seed);
   const uint64_t h2 = splitmix64(h1 ^ kBloomSalt) | 1ull;
@@ -49,10 +50,19 @@ __device__ __forceinline__ void bloom_insert(const DevBloom& b, uint64_t hash) {
     unsigned int* w32 = reinterpret_cast<unsigned int*>(b.words);
     const uint32_t mask = uint32_t(b.bit_count - 1), step = uint32_t(h2);
     uint32_t v = uint32_t(h1);
-    for (uint32_t i = 0; i < b.hash_count; ++i, v += step) {
-      const uint32_t bit = v & mask, m = 1u << (bit & 31);
-      unsigned int* w = w32 + (bit >> 5);
-      if ((*reinterpret_cast<volatile unsigned int*>(w) & m) == 0) atomicOr(w, m);
+    for (uint32_t i = 0; i < b.hash_count; i += 4, v += 4u * step) {
+      uint32_t bit[4], cur[4];
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) {
+        bit[q] = (v + q * step) & mask;
+        cur[q] = ~0u;
+        if (i + q < b.hash_count) cur[q] = *reinterpret_cast<volatile unsigned int*>(w32 + (bit[q] >> 5));
+      }
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) {
+        const uint32_t m = 1u << (bit[q] & 31);
+        if ((cur[q] & m) == 0) atomicOr(w32 + (bit[q] >> 5), m);
+      }
     }
     return;
   }
@@ -94,6 +104,55 @@ __device__ __forceinline__ bool bloom_contains(const DevBloom& b, uint64_t hash)
     if (((__ldg(b.words + (bit >> 6)) >> (bit & 63)) & 1ull) == 0) return false;
   }
   return true;
+}
+
+// N keys at once (the fused pipeline handles N rows per thread): the hashes and the loads of
+// all keys are interleaved so their latencies overlap.  keep[] says which keys are live on
+// entry and holds the decisions on return.
+template <uint32_t N>
+__device__ __forceinline__ void bloom_contains_n(const DevBloom& b, const uint64_t (&key)[N], bool (&keep)[N]) {
+  if (b.pow2 != 2) {
+#pragma unroll
+    for (uint32_t q = 0; q < N; ++q)
+      if (keep[q]) keep[q] = bloom_contains(b, key[q]);
+    return;
+  }
+  const uint32_t* w32 = reinterpret_cast<const uint32_t*>(b.words);
+  const uint32_t mask = uint32_t(b.bit_count - 1);
+  uint64_t h1[N];
+  uint32_t v[N], x[N], step[N];
+  // first bit of every key
+#pragma unroll
+  for (uint32_t q = 0; q < N; ++q) {
+    h1[q] = splitmix64(key[q] ^ b.seed);
+    v[q] = uint32_t(h1[q]);
+    const uint32_t bit = v[q] & mask;
+    x[q] = 0;
+    if (keep[q]) x[q] = __ldg(w32 + (bit >> 5)) >> (bit & 31);
+  }
+  // second hash while the loads are in flight
+#pragma unroll
+  for (uint32_t q = 0; q < N; ++q) step[q] = uint32_t(splitmix64(h1[q] ^ kBloomSalt)) | 1u;
+  bool any = false;
+#pragma unroll
+  for (uint32_t q = 0; q < N; ++q) { keep[q] = keep[q] && (x[q] & 1u); any |= keep[q]; }
+  for (uint32_t i = 1; i < b.hash_count && any; i += 3) {
+#pragma unroll
+    for (uint32_t q = 0; q < N; ++q) x[q] = ~0u;
+#pragma unroll
+    for (uint32_t t = 1; t <= 3; ++t) {
+      if (i + t - 1 < b.hash_count) {
+#pragma unroll
+        for (uint32_t q = 0; q < N; ++q) {
+          const uint32_t bit = (v[q] + t * step[q]) & mask;
+          if (keep[q]) x[q] &= __ldg(w32 + (bit >> 5)) >> (bit & 31);
+        }
+      }
+    }
+    any = false;
+#pragma unroll
+    for (uint32_t q = 0; q < N; ++q) { keep[q] = keep[q] && (x[q] & 1u); v[q] += 3u * step[q]; any |= keep[q]; }
+  }
 }
 #endif
 

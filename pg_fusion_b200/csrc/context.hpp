@@ -76,6 +76,14 @@ struct pgf_ctx {
   pgf::Counters* h_counters = nullptr;  // pinned
   uint32_t* d_flags = nullptr;          // [0] group-table overflow, [1] table used, [2..] scratch
   uint32_t* h_flags = nullptr;          // pinned
+  // Grow-only scratch of the aggregate pipelines: [header][group table][result entries], so a
+  // run costs one memset, the fused kernel, the extract kernel and two small D2H copies
+  // instead of a cudaMalloc/cudaFree cycle per table array.
+  uint8_t* d_arena = nullptr;
+  size_t d_arena_cap = 0;
+  uint8_t* d_out = nullptr;             // result entries of tables too large for the arena prefix
+  size_t d_out_cap = 0;
+  uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
   std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;
   std::map<uint64_t, pgf::BloomSlot> blooms;
   std::map<uint64_t, pgf::JoinTable> joins;

@@ -101,8 +101,13 @@ struct DevKeyPart {
   uint16_t nwords;       // 1 or 2
 };
 
+// Join table: open addressing with linear probing.  `tags` is a one-byte directory (0 = empty
+// slot, else the top hash bits | 1) that stays L2 resident: probes walk the tags and touch a
+// 16/32-byte slot only when the tag matches, so misses (most probes of a selective join)
+// never read the slots.
 struct DevJoin {
   const uint4* slots;    // slot_u4 x uint4 per slot: {key lo, key hi, occupied, pay0} [, pay1..4]
+  const uint8_t* tags;   // capacity bytes
   uint32_t mask;         // capacity - 1
   uint32_t slot_u4;      // 1 (16-byte slot) or 2 (32-byte slot)
   DevRef key;
@@ -128,6 +133,7 @@ struct GroupTable {
 
 struct JoinBuild {
   uint4* slots;
+  uint8_t* tags;
   uint32_t mask;
   uint32_t slot_u4;
   DevRef key;

@@ -17,25 +17,20 @@ cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t 
 namespace {
 
 // ---- device helpers for the group table ------------------------------------------------
-__global__ void table_init_nogroup_kernel(GroupTable t) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    t.state[0] = 2u;  // the single output row of an aggregate without GROUP BY always exists
-    *t.used = 1u;
-  }
-}
-
 // Partial-state entry: [kKeyWords key][1 null mask][nexprs * acc_words acc][nexprs + 1 counts]
 __host__ __device__ inline uint32_t entry_words(uint32_t nexprs, uint32_t acc_words) {
   return kKeyWords + 1 + nexprs * acc_words + nexprs + 1;
 }
 
-__global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, uint64_t* out, uint64_t max_entries,
-                                     unsigned long long* count) {
+// Compacts the occupied slots into out = [count][entries...]; out[0] must be zero on entry.
+// An aggregate without GROUP BY always has its single output row (slot 0).
+__global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, bool grouped, uint64_t* out, uint64_t max_entries) {
   const uint32_t ew = entry_words(nexprs, t.acc_words);
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i <= t.mask; i += uint64_t(gridDim.x) * blockDim.x) {
+  const uint64_t nslots = grouped ? uint64_t(t.mask) + 1 : 1;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nslots; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint32_t s = t.state[i];
-    if ((s & 3u) != 2u) continue;
-    const unsigned long long pos = atomicAdd(count, 1ull);
+    if (grouped && (s & 3u) != 2u) continue;
+    const unsigned long long pos = atomicAdd(reinterpret_cast<unsigned long long*>(out), 1ull);
     if (pos >= max_entries) continue;
     uint64_t* e = out + 1 + pos * ew;
     for (uint32_t w = 0; w < kKeyWords; ++w) e[w] = t.keys[i * kKeyWords + w];
@@ -44,8 +39,6 @@ __global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, uint64_t* ou
     for (uint32_t w = 0; w <= nexprs; ++w) e[kKeyWords + 1 + nexprs * t.acc_words + w] = t.cnt[i * (nexprs + 1) + w];
   }
 }
-
-__global__ void finish_count_kernel(uint64_t* out, const unsigned long long* count) { out[0] = *count; }
 
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
 // rank order, so Float64 sums are added in a fixed order on every rank.
@@ -132,6 +125,7 @@ class Lowering {
     for (uint32_t j = 0; j < plan_->njoins; ++j) {
       DevJoin& dj = D.joins[j];
       dj.slots = jtables_[j]->d_slots;
+      dj.tags = reinterpret_cast<const uint8_t*>(jtables_[j]->d_slots) + uint64_t(jtables_[j]->capacity) * jtables_[j]->slot_u4 * sizeof(uint4);
       dj.mask = jtables_[j]->capacity - 1;
       dj.slot_u4 = jtables_[j]->slot_u4;
       PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key));
@@ -543,6 +537,8 @@ class Lowering {
     uint32_t ntiles = uint32_t((page_bytes + 40 * 1024 - 1) / (40 * 1024));
     if (ntiles == 0) ntiles = 1;
     uint32_t tile_rows = 0, stage_bytes = 0;
+    // GROUP BY pipelines also hold the per-warp deferred-sink queues in shared memory
+    const uint32_t max_stage = (D.sink == SINK_AGG && L_->grouped) ? 44 * 1024 : 48 * 1024;
     for (;; ++ntiles) {
       tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
       stage_bytes = 0;
@@ -555,9 +551,9 @@ class Lowering {
         if (D.scol[c].nullable) stage_bytes += tile_rows / 8;
       }
       stage_bytes = (stage_bytes + 127u) & ~127u;
-      if (stage_bytes <= 48 * 1024 || tile_rows == 128) break;
+      if (stage_bytes <= max_stage || tile_rows == 128) break;
     }
-    if (stage_bytes > 48 * 1024) return not_eligible("row too wide for the shared-memory stages");
+    if (stage_bytes > max_stage) return not_eligible("row too wide for the shared-memory stages");
     D.tile_rows = tile_rows;
     D.tiles_per_page = (max_rows + tile_rows - 1) / tile_rows;
     D.stage_bytes = stage_bytes ? stage_bytes : 128;
@@ -569,6 +565,7 @@ class Lowering {
     D.classes = s.d_classes;
     D.page_stride = ctx_->page_size;
     L_->smem = ((sizeof(BlockShared) + 127) & ~size_t(127)) + size_t(kStages) * D.stage_bytes;
+    if (D.sink == SINK_AGG && L_->grouped) L_->smem += size_t(kMaxConsumerWarps) * kQueueBytesPerWarp;  // deferred-sink queues
     return PGF_OK;
   }
 
@@ -682,45 +679,87 @@ const ShapeEntry* pick_shape(const Lowered& L) {
   return find_shape(sig);
 }
 
+// Device header at the start of the arena (one memset clears header + table).
+struct ArenaHeader {
+  Counters counters;         // 48 bytes
+  uint32_t overflow, used;   // group-table overflow flag, occupied slots
+  uint64_t pad;
+};
+static_assert(sizeof(ArenaHeader) == 64, "arena header layout");
+constexpr uint64_t kSmallTable = 1ull << 16;   // tables up to this many slots keep their result entries in the arena
+constexpr size_t kHostArena = 64 * 1024;       // pinned mirror: header + first result entries
+
 struct TableAlloc {
   GroupTable t{};
   uint64_t capacity = 0;
+  ArenaHeader* d_header = nullptr;
+  size_t zero_bytes = 0;     // header + table
+  uint64_t* d_out = nullptr; // [count][entries] (small tables only)
+  uint64_t out_entries = 0;
 };
 
-pgf_status alloc_table(pgf_ctx* ctx, DevAlloc& mem, uint64_t capacity, uint32_t nexprs, uint32_t acc_words, bool grouped,
-                       TableAlloc* out) {
-  GroupTable& t = out->t;
-  out->capacity = capacity;
-  if (mem.alloc(&t.state, capacity) != cudaSuccess || mem.alloc(&t.keys, capacity * kKeyWords) != cudaSuccess ||
-      mem.alloc(&t.acc, capacity * (nexprs ? nexprs : 1) * acc_words) != cudaSuccess ||
-      mem.alloc(&t.cnt, capacity * (nexprs + 1)) != cudaSuccess) {
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+pgf_status grow(pgf_ctx* ctx, uint8_t** buf, size_t* cap, size_t need, const char* what) {
+  if (*cap >= need) return PGF_OK;
+  if (*buf) {
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+  }
+  const size_t want = align_up(need + need / 4, 1 << 20);
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
     cudaGetLastError();
-    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a group table of %llu slots", (unsigned long long)capacity);
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %zu bytes for %s", want, what);
   }
-  t.mask = uint32_t(capacity - 1);
-  t.acc_words = acc_words;
-  t.overflow = ctx->d_flags;
-  t.used = ctx->d_flags + 1;
-  CU(ctx, cudaMemsetAsync(ctx->d_flags, 0, 8, ctx->compute_stream));
-  CU(ctx, cudaMemsetAsync(t.state, 0, capacity * 4, ctx->compute_stream));
-  CU(ctx, cudaMemsetAsync(t.acc, 0, capacity * (nexprs ? nexprs : 1) * acc_words * 8, ctx->compute_stream));
-  CU(ctx, cudaMemsetAsync(t.cnt, 0, capacity * (nexprs + 1) * 8, ctx->compute_stream));
-  if (!grouped) {
-    table_init_nogroup_kernel<<<1, 32, 0, ctx->compute_stream>>>(t);
-    CU(ctx, cudaGetLastError());
-  }
+  *buf = static_cast<uint8_t*>(p);
+  *cap = want;
   return PGF_OK;
 }
 
-// Extract the occupied slots into `d_state` ([count][entries...]) on the compute stream.
-pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, uint32_t nexprs, uint64_t* d_state,
-                         uint64_t max_entries) {
-  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 4);
-  CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
-  const uint32_t grid = uint32_t(std::min<uint64_t>((capacity + 255) / 256, uint64_t(ctx->sm_count) * 8));
-  table_extract_kernel<<<grid, 256, 0, ctx->compute_stream>>>(t, nexprs, d_state, max_entries, d_cnt);
-  CU(ctx, cudaGetLastError());
-  finish_count_kernel<<<1, 1, 0, ctx->compute_stream>>>(d_state, d_cnt);
+// Places header, group table and (for small tables) the result entries in the context's
+// grow-only arena and clears header + table with one memset on the compute stream.
+pgf_status arena_table(pgf_ctx* ctx, uint64_t capacity, uint32_t nexprs, uint32_t acc_words, TableAlloc* out) {
+  const uint32_t ne = nexprs ? nexprs : 1;
+  const uint32_t ew = entry_words(nexprs, acc_words);
+  size_t off = sizeof(ArenaHeader);
+  const size_t o_state = off; off = align_up(off + capacity * 4, 16);
+  const size_t o_keys = off;  off += capacity * kKeyWords * 8;
+  const size_t o_acc = off;   off += capacity * ne * acc_words * 8;
+  const size_t o_cnt = off;   off += capacity * (nexprs + 1) * 8;
+  out->zero_bytes = off;
+  const bool small = capacity <= kSmallTable;
+  const size_t o_out = off = align_up(off, 16);
+  if (small) off += (1 + capacity * ew) * 8;
+  PGF_TRY(grow(ctx, &ctx->d_arena, &ctx->d_arena_cap, off, "the group table"));
+  uint8_t* base = ctx->d_arena;
+  out->capacity = capacity;
+  out->d_header = reinterpret_cast<ArenaHeader*>(base);
+  GroupTable& t = out->t;
+  t.state = reinterpret_cast<uint32_t*>(base + o_state);
+  t.keys = reinterpret_cast<uint64_t*>(base + o_keys);
+  t.acc = reinterpret_cast<uint64_t*>(base + o_acc);
+  t.cnt = reinterpret_cast<uint64_t*>(base + o_cnt);
+  t.mask = uint32_t(capacity - 1);
+  t.acc_words = acc_words;
+  t.overflow = &out->d_header->overflow;
+  t.used = &out->d_header->used;
+  out->d_out = small ? reinterpret_cast<uint64_t*>(base + o_out) : nullptr;
+  out->out_entries = small ? capacity : 0;
+  CU(ctx, cudaMemsetAsync(base, 0, out->zero_bytes, ctx->compute_stream));
+  if (small) CU(ctx, cudaMemsetAsync(out->d_out, 0, 8, ctx->compute_stream));
+  return PGF_OK;
+}
+
+// Extract the occupied slots into `d_state` ([count][entries...]) on the compute stream;
+// d_state[0] must already be zero.
+pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, uint32_t nexprs, bool grouped,
+                         uint64_t* d_state, uint64_t max_entries) {
+  const uint64_t nslots = grouped ? capacity : 1;
+  const uint32_t grid = uint32_t(std::min<uint64_t>((nslots + 255) / 256, uint64_t(ctx->sm_count) * 8));
+  table_extract_kernel<<<grid, 256, 0, ctx->compute_stream>>>(t, nexprs, grouped, d_state, max_entries);
   CU(ctx, cudaGetLastError());
   return PGF_OK;
 }
@@ -739,7 +778,6 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   PGF_TRY(scan_sync_descs(ctx, *L.scan));
   L.dev.descs = L.scan->d_descs;
   L.dev.classes = L.scan->d_classes;
-  L.dev.counters = ctx->d_counters;
 
   pgf_result* res = new (std::nothrow) pgf_result();
   if (!res) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
@@ -749,34 +787,38 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   } guard{res};
 
   DevAlloc mem;
+  const bool agg = plan->sink == PGF_SINK_AGGREGATE;
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  const uint32_t ew = entry_words(plan->nexprs, aw);
   uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.nitems ? L.dev.nitems : 1, uint64_t(ctx->sm_count)));
   uint64_t capacity = L.table_capacity;
-  std::vector<uint64_t> h_state;
   float total_ms = 0.f;
   uint32_t launches = 0;
+  ArenaHeader* h_header = reinterpret_cast<ArenaHeader*>(ctx->h_arena);
+  uint64_t* h_out = reinterpret_cast<uint64_t*>(ctx->h_arena + sizeof(ArenaHeader));
+  const uint64_t h_out_entries = (kHostArena - sizeof(ArenaHeader) - 8) / (uint64_t(ew) * 8);
 
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable& jt = L.build_table;
-    cudaError_t e = cudaMalloc(&jt.d_slots, uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4));
+    // slots followed by the one-byte tag directory
+    const uint64_t slot_bytes = uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4);
+    cudaError_t e = cudaMalloc(&jt.d_slots, slot_bytes + jt.capacity);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
     }
     mem.ptrs.push_back(jt.d_slots);
-    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4), ctx->compute_stream));
+    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + jt.capacity, ctx->compute_stream));
     L.dev.build.slots = jt.d_slots;
+    L.dev.build.tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
   }
 
   for (int attempt = 0; attempt < 6; ++attempt) {
     TableAlloc ta;
-    DevAlloc table_mem;
-    uint64_t* d_state = nullptr;
-    if (plan->sink == PGF_SINK_AGGREGATE) {
-      PGF_TRY(alloc_table(ctx, table_mem, capacity, plan->nexprs, aw, L.grouped, &ta));
-      L.dev.table = ta.t;
-    }
-    CU(ctx, cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), ctx->compute_stream));
+    // header (+ group table + result entries) live in the arena; other sinks only use the header
+    PGF_TRY(arena_table(ctx, agg ? capacity : 1, agg ? plan->nexprs : 0, aw, &ta));
+    L.dev.table = ta.t;
+    L.dev.counters = &ta.d_header->counters;
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
     if (L.dev.nitems) {
       if (const ShapeEntry* se = pick_shape(L))
@@ -786,47 +828,66 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
       ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
-    CU(ctx, cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, ctx->compute_stream));
-    CU(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+    // small tables: extract right away so header and result travel with one synchronisation
+    const bool inline_out = agg && !partial && ta.d_out != nullptr;
+    uint64_t prefix_entries = 0;
+    if (inline_out) {
+      PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, ta.d_out, ta.out_entries));
+      ++launches;
+      prefix_entries = std::min<uint64_t>(ta.out_entries, h_out_entries);
+      CU(ctx, cudaMemcpyAsync(h_out, ta.d_out, (1 + prefix_entries * ew) * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+    }
+    CU(ctx, cudaMemcpyAsync(h_header, ta.d_header, sizeof(ArenaHeader), cudaMemcpyDeviceToHost, ctx->compute_stream));
     CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
     float ms = 0.f;
     CU(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
     total_ms += ms;
-    if (ctx->h_counters->bad_rows)
+    if (h_header->counters.bad_rows)
       return ctx->fail(PGF_ERR_UNSUPPORTED_DATA, "%llu rows carry out-of-line (> 12 byte) view values in a predicate or key column",
-                       (unsigned long long)ctx->h_counters->bad_rows);
-    if (plan->sink == PGF_SINK_AGGREGATE && ctx->h_flags[0]) {  // group table overflow: grow and re-run
+                       (unsigned long long)h_header->counters.bad_rows);
+    if (agg && h_header->overflow) {  // group table overflow: grow and re-run
       capacity *= 16;
       if (capacity > (1ull << 30)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "group table would exceed 2^30 slots");
       continue;
     }
-    if (plan->sink == PGF_SINK_AGGREGATE) {
-      const uint64_t ngroups = ctx->h_flags[1];
-      const uint32_t ew = entry_words(plan->nexprs, aw);
+    if (agg) {
+      const uint64_t ngroups = L.grouped ? h_header->used : 1;
       const uint64_t bytes = (1 + ngroups * ew) * 8;
       if (partial) {
         if (bytes > state_cap) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state needs %llu bytes, buffer has %llu", (unsigned long long)bytes, (unsigned long long)state_cap);
-        PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, static_cast<uint64_t*>(dev_state_out), ngroups));
+        CU(ctx, cudaMemsetAsync(dev_state_out, 0, 8, ctx->compute_stream));
+        PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, static_cast<uint64_t*>(dev_state_out), ngroups));
         CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
         *state_bytes = bytes;
         ++launches;
       } else {
-        if (table_mem.alloc(&d_state, 1 + ngroups * ew) != cudaSuccess) {
-          cudaGetLastError();
-          return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate the result buffer");
+        std::vector<uint64_t> h_state(1 + ngroups * ew);
+        if (inline_out) {
+          const uint64_t have = std::min<uint64_t>(ngroups, prefix_entries);
+          std::memcpy(h_state.data(), h_out, (1 + have * ew) * 8);
+          if (ngroups > have) {
+            CU(ctx, cudaMemcpyAsync(h_state.data() + 1 + have * ew, ta.d_out + 1 + have * ew, (ngroups - have) * ew * 8,
+                                    cudaMemcpyDeviceToHost, ctx->compute_stream));
+            CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+          }
+        } else {
+          PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
+          uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
+          CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
+          PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
+          CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, bytes, cudaMemcpyDeviceToHost, ctx->compute_stream));
+          CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+          ++launches;
         }
-        PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, d_state, ngroups));
-        h_state.resize(1 + ngroups * ew);
-        CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, bytes, cudaMemcpyDeviceToHost, ctx->compute_stream));
-        CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
-        ++launches;
+        if (h_state[0] != ngroups) return ctx->fail(PGF_ERR_STATE, "group table extraction found %llu groups, expected %llu",
+                                                    (unsigned long long)h_state[0], (unsigned long long)ngroups);
         PGF_TRY(build_result(ctx, plan, L, h_state, res));
       }
     }
     break;
   }
 
-  const Counters& c = *ctx->h_counters;
+  const Counters& c = h_header->counters;
   res->rows_in = c.rows_in;
   res->rows_bloom = c.rows_bloom;
   res->rows_filtered = c.rows_filtered;
@@ -876,9 +937,8 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     capacity = 1024;
     while (capacity < total * 2) capacity <<= 1;
   }
-  DevAlloc mem;
   TableAlloc ta;
-  PGF_TRY(alloc_table(ctx, mem, capacity, plan->nexprs, aw, L.grouped, &ta));
+  PGF_TRY(arena_table(ctx, capacity, plan->nexprs, aw, &ta));
   for (uint32_t i = 0; i < nstates; ++i) {  // rank order => fixed Float64 summation order
     if (!counts[i]) continue;
     const uint64_t* st = reinterpret_cast<const uint64_t*>(static_cast<const uint8_t*>(dev_states) + i * stride);
@@ -890,15 +950,15 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     }
     CU(ctx, cudaGetLastError());
   }
-  CU(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  ArenaHeader* h_header = reinterpret_cast<ArenaHeader*>(ctx->h_arena);
+  CU(ctx, cudaMemcpyAsync(h_header, ta.d_header, sizeof(ArenaHeader), cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
-  const uint64_t ngroups = ctx->h_flags[1];
-  uint64_t* d_state = nullptr;
-  if (mem.alloc(&d_state, 1 + ngroups * ew) != cudaSuccess) {
-    cudaGetLastError();
-    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate the result buffer");
-  }
-  PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, d_state, ngroups));
+  const uint64_t ngroups = L.grouped ? h_header->used : 1;
+  const uint64_t bytes = (1 + ngroups * ew) * 8;
+  PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
+  uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
+  CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
+  PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
   std::vector<uint64_t> h_state(1 + ngroups * ew);
   CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, h_state.size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));

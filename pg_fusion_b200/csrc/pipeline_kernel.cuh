@@ -29,6 +29,11 @@ constexpr int kMaxConsumerWarps = 16;
 __host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 14 : 16; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
 constexpr int kStages = 4;
+// Deferred sink: rows whose group is not register resident are queued per warp (in shared
+// memory behind the stage ring) and applied to the global table 32 at a time from a converged
+// point, instead of one or two lanes at a time from inside the divergent probe loop.
+constexpr uint32_t kQueueBytesPerWarp = 2048;
+__host__ __device__ constexpr uint32_t queue_entry_words(uint32_t maxe, uint32_t acc_words) { return kKeyWords + 1 + maxe * acc_words; }
 constexpr uint32_t kAccF64MaxExprs = 8, kAccI128MaxExprs = 6;
 
 struct StageMeta {
@@ -112,6 +117,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+// Join tables: slot = low hash bits, directory tag = top hash byte | 1 (never 0 = empty).
+__device__ __forceinline__ uint32_t join_tag(uint64_t h) { return uint32_t(h >> 56) | 1u; }
 
 struct I128 {
   uint64_t lo, hi;
@@ -477,6 +484,8 @@ struct BlockShared {
   uint32_t dict_lock;
   // block reduction scratch
   uint64_t red[kMaxConsumerWarps][2];
+  // per-warp deferred-sink queues (entries live behind the stage ring)
+  uint32_t qcount[kMaxConsumerWarps];
 };
 
 __device__ __forceinline__ bool dict_entry_equals(const BlockShared* sh, uint32_t g, const uint64_t* key, uint32_t nwords, uint32_t knull) {
@@ -632,6 +641,23 @@ static __device__ __noinline__ void fast_slow_accumulate(const DevPlan& P, Key4 
   atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
 }
 
+// One row straight into the global group table (NULL inputs, groups beyond the register set).
+template <uint32_t ACC, uint32_t MAXE>
+__device__ __forceinline__ void global_accumulate(const DevPlan& P, bool grouped, const uint64_t* key, uint32_t knull,
+                                                  uint32_t valid_mask, const typename AccOps<ACC>::T* v) {
+  using Ops = AccOps<ACC>;
+  const int64_t slot = grouped ? group_slot(P.table, key, P.nkeywords, knull) : 0;
+  if (slot < 0) return;
+#pragma unroll
+  for (uint32_t e = 0; e < MAXE; ++e) {
+    if (e < P.nexprs && ((valid_mask >> e) & 1)) {
+      Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, v[e]);
+      atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
+    }
+  }
+  atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
+}
+
 // ---- the kernel ----------------------------------------------------------------------
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
 __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_kernel(const __grid_constant__ DevPlan P) {
@@ -640,6 +666,11 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
+  constexpr uint32_t kRows = NJ != 0 ? 4 : 2;  // rows per thread and iteration
+  constexpr uint32_t kAccWords = ACC == CLS_I128 ? 2 : 1;
+  [[maybe_unused]] constexpr uint32_t kQueueEntryWords = queue_entry_words(MAXE, kAccWords);
+  [[maybe_unused]] constexpr uint32_t kQueueCap = kQueueBytesPerWarp / (8 * kQueueEntryWords);
+  [[maybe_unused]] constexpr uint32_t kQueueDrainAt = kQueueCap > 12 ? kQueueCap - 8 : kQueueCap / 2;
   // straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 sums, no join
   constexpr bool kFastGrouped = SINK == SINK_AGG && GROUPED && NJ == 0 && ACC == CLS_F64 && !SHAPE::generic &&
                                 SHAPE::no_nulls && SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0;
@@ -656,6 +687,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     }
     sh->dict_n = 0;
     sh->dict_lock = 0;
+    for (int w = 0; w < kMaxConsumerWarps; ++w) sh->qcount[w] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -725,6 +757,30 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     }
   } else {
     // ===== consumers =====
+    [[maybe_unused]] uint64_t* myqueue = reinterpret_cast<uint64_t*>(stages + size_t(kStages) * P.stage_bytes) +
+                                         size_t(warp - 1) * (kQueueBytesPerWarp / 8);
+    [[maybe_unused]] auto drain_queue = [&]() {
+      if constexpr (SINK == SINK_AGG && GROUPED) {
+        __syncwarp();
+        const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - 1]), kQueueCap);
+        for (uint32_t base = 0; base < n; base += 32u) {
+          const uint32_t idx = base + lane;
+          if (idx < n) {
+            const uint64_t* qe = myqueue + idx * kQueueEntryWords;
+            uint64_t key[kKeyWords];
+            AccT v[MAXE];
+#pragma unroll
+            for (uint32_t w = 0; w < kKeyWords; ++w) key[w] = qe[w];
+#pragma unroll
+            for (uint32_t e = 0; e < MAXE; ++e) v[e] = *reinterpret_cast<const AccT*>(qe + kKeyWords + 1 + e * kAccWords);
+            global_accumulate<ACC, MAXE>(P, true, key, uint32_t(qe[kKeyWords]), uint32_t(qe[kKeyWords] >> 32), v);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) sh->qcount[warp - 1] = 0;
+        __syncwarp();
+      }
+    };
     uint32_t k = 0;
     for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
       const uint32_t s = k % kStages;
@@ -732,43 +788,70 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       const uint32_t nrows = sh->meta[s].nrows;
       const uint8_t* stage = stages + size_t(s) * P.stage_bytes;
       const uint32_t tile_nulls = sh->meta[s].null_mask;
-      // Two rows per thread and iteration (independent chains => ILP): a warp takes the pair of
-      // 32-row chunks (2p, 2p+1).  Pairs are dealt to the warps round-robin with a per-tile
-      // rotation so partial tiles do not always load the same warps.  The loop bound is
-      // warp-uniform: the warp votes below are executed by all 32 lanes.
-      const uint32_t npairs = (nrows + 63u) >> 6;
-      for (uint32_t pr = (warp - 1 + kConsumerWarps - (k * 5u) % kConsumerWarps) % kConsumerWarps; pr < npairs; pr += kConsumerWarps) {
-        const uint32_t b0 = pr << 6;
-        const bool has0 = b0 + lane < nrows, has1 = b0 + 32u + lane < nrows;
-        const uint32_t r0 = has0 ? b0 + lane : 0u;
-        const uint32_t r1 = has1 ? b0 + 32u + lane : r0;
-        bool keep0 = has0, keep1 = has1;
-        n_in += uint32_t(has0) + uint32_t(has1);
+      // R rows per thread and iteration (independent chains => ILP / memory-level parallelism):
+      // a warp takes R consecutive 32-row chunks.  R = 2 for streaming pipelines; R = 4 behind a
+      // join probe, where every row carries a chain of dependent L2/HBM round trips and the rows
+      // in flight per SM bound the throughput.  Chunk groups are dealt to the warps round-robin
+      // with a per-tile rotation so partial tiles do not always load the same warps.  The loop
+      // bound is warp-uniform: the warp votes below are executed by all 32 lanes.
+      constexpr uint32_t R = kRows;
+      const uint32_t ngroups = (nrows + 32u * R - 1u) / (32u * R);
+      for (uint32_t pr = (warp - 1 + kConsumerWarps - (k * 5u) % kConsumerWarps) % kConsumerWarps; pr < ngroups; pr += kConsumerWarps) {
+        const uint32_t b0 = pr * (32u * R);
+        uint32_t rr[R];
+        bool keep[R];
+#pragma unroll
+        for (uint32_t q = 0; q < R; ++q) {
+          const bool has = b0 + 32u * q + lane < nrows;
+          rr[q] = has ? b0 + 32u * q + lane : 0u;  // row 0 of a tile always exists
+          keep[q] = has;
+          n_in += uint32_t(has);
+        }
         // -- runtime Bloom probes: NULL key => DefinitelyAbsent (shared.rs:367-374)
         for (uint32_t b = 0; b < P.nbloom; ++b) {
           const DevBloomProbe& bp = P.bloom[b];
-          Row q{stage, r0, tile_nulls, nullptr, 0};
-          if (keep0) keep0 = ref_valid(bp.key, q) && bloom_contains(bp.bloom, uint64_t(load_i64(bp.key, q)));
-          q.r = r1;
-          if (keep1) keep1 = ref_valid(bp.key, q) && bloom_contains(bp.bloom, uint64_t(load_i64(bp.key, q)));
+          uint64_t bk[R];
+#pragma unroll
+          for (uint32_t q = 0; q < R; ++q) {
+            const Row rq{stage, rr[q], tile_nulls, nullptr, 0};
+            keep[q] = keep[q] && ref_valid(bp.key, rq);
+            bk[q] = uint64_t(load_i64(bp.key, rq));
+          }
+          bloom_contains_n<R>(bp.bloom, bk, keep);
         }
-        n_bloom += uint32_t(keep0) + uint32_t(keep1);
+        bool any_keep = false;
+#pragma unroll
+        for (uint32_t q = 0; q < R; ++q) { n_bloom += uint32_t(keep[q]); any_keep |= keep[q]; }
         // -- FilterExec: every conjunct must be TRUE; stop as soon as the whole warp is dead
         if constexpr (SHAPE::generic) {
           for (uint32_t t = 0; t < P.nterms; ++t) {
-            if (!__any_sync(0xffffffffu, keep0 || keep1)) break;
-            term_pass2<-1, false>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+            if (!__any_sync(0xffffffffu, any_keep)) break;
+            any_keep = false;
+#pragma unroll
+            for (uint32_t q = 0; q < R; q += 2) {
+              term_pass2<-1, false>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, n_bad, keep[q], keep[q + 1]);
+              any_keep |= keep[q] || keep[q + 1];
+            }
           }
         } else {
           static_for<SHAPE::Terms::size>([&](auto I) {
             constexpr int t = decltype(I)::value;
-            if (__any_sync(0xffffffffu, keep0 || keep1))
-              term_pass2<SHAPE::Terms::template at<t>(), SHAPE::no_nulls>(P.terms[t], stage, r0, r1, tile_nulls, n_bad, keep0, keep1);
+            if (__any_sync(0xffffffffu, any_keep)) {
+              any_keep = false;
+#pragma unroll
+              for (uint32_t q = 0; q < R; q += 2) {
+                term_pass2<SHAPE::Terms::template at<t>(), SHAPE::no_nulls>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, n_bad, keep[q], keep[q + 1]);
+                any_keep |= keep[q] || keep[q + 1];
+              }
+            }
           });
         }
-        n_filt += uint32_t(keep0) + uint32_t(keep1);
+#pragma unroll
+        for (uint32_t q = 0; q < R; ++q) n_filt += uint32_t(keep[q]);
 
-        if (!__any_sync(0xffffffffu, keep0 || keep1)) continue;
+        if (!__any_sync(0xffffffffu, any_keep)) continue;
+        [[maybe_unused]] const uint32_t r0 = rr[0], r1 = rr[1];
+        [[maybe_unused]] const bool keep0 = keep[0], keep1 = keep[1];
         if constexpr (kFastGrouped) {
           constexpr int NW = ShapeKeyInfo<typename SHAPE::Keys>::nwords;
           constexpr int NE = SHAPE::Exprs::size;
@@ -820,10 +903,38 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
           }
           continue;
         }
+        // HashJoinExec probe: hash both rows and fetch their first directory tags together so
+        // the two L2 latencies overlap; NULL keys never match.
+        uint32_t ji[R], jtag[R], jt0[R];
+        int64_t jkey[R];
+#pragma unroll
+        for (uint32_t h = 0; h < R; ++h) { ji[h] = 0; jtag[h] = 0; jt0[h] = 0; jkey[h] = 0; }
+        if constexpr (NJ != 0) {
+          const DevJoin& j = P.joins[0];
+#pragma unroll
+          for (uint32_t h = 0; h < R; ++h) {
+            const Row q{stage, rr[h], tile_nulls, nullptr, 0};
+            if (keep[h] && ref_valid(j.key, q)) {
+              jkey[h] = load_i64(j.key, q);
+              const uint64_t hk = mix64(uint64_t(jkey[h]));
+              ji[h] = uint32_t(hk) & j.mask;
+              jtag[h] = join_tag(hk);
+            }
+          }
+#pragma unroll
+          for (uint32_t h = 0; h < R; ++h)
+            if (jtag[h]) jt0[h] = __ldg(j.tags + ji[h]);
+        }
 #pragma unroll 1
-        for (uint32_t half = 0; half < 2; ++half) {
-          if (!(half ? keep1 : keep0)) continue;
-          Row row{stage, half ? r1 : r0, tile_nulls, nullptr, 0};
+        for (uint32_t half = 0; half < R; ++half) {
+          uint32_t rsel = rr[0], isel = ji[0], tagsel = jtag[0], tsel = jt0[0];
+          int64_t keysel = jkey[0];
+          bool ksel = keep[0];
+#pragma unroll
+          for (uint32_t h = 1; h < R; ++h)
+            if (half == h) { rsel = rr[h]; isel = ji[h]; tagsel = jtag[h]; tsel = jt0[h]; keysel = jkey[h]; ksel = keep[h]; }
+          if (!ksel) continue;
+          Row row{stage, rsel, tile_nulls, nullptr, 0};
 
           // -- sink (optionally behind one HashJoinExec probe)
           auto sink = [&](const Row& rc) {
@@ -904,7 +1015,9 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
 #pragma unroll
                 for (uint32_t gg = 0; gg < G; ++gg)
                   if (gg < dn && dh[gg] == h) g = int(gg);
-                if (g < 0 || !dict_entry_equals(sh, uint32_t(g), key, P.nkeywords, knull)) {
+                // the dictionary is append-only: once it is full a key without a fingerprint hit is not in it
+                if (g < 0 && dn == G) {
+                } else if (g < 0 || !dict_entry_equals(sh, uint32_t(g), key, P.nkeywords, knull)) {
                   g = dict_lookup_or_insert(sh, Key4{key[0], key[1], key[2], key[3]}, P.nkeywords, knull, h);
                   dn = *reinterpret_cast<volatile uint32_t*>(&sh->dict_n);
 #pragma unroll
@@ -944,18 +1057,22 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                   }
                 }
               } else {
-                // slow path: straight to the global table (NULL inputs, or > kRegGroups groups)
-                const int64_t slot = GROUPED ? group_slot(P.table, key, P.nkeywords, knull) : 0;
-                if (slot >= 0) {
+                // slow path (NULL inputs, or > kRegGroups groups): queue the evaluated row; the warp
+                // applies its queue to the global table from a converged point
+                bool queued = false;
+                if constexpr (GROUPED) {
+                  const uint32_t pos = atomicAdd(&sh->qcount[warp - 1], 1u);
+                  if (pos < kQueueCap) {
+                    uint64_t* qe = myqueue + pos * kQueueEntryWords;
 #pragma unroll
-                  for (uint32_t e = 0; e < MAXE; ++e) {
-                    if (e < P.nexprs && ((valid_mask >> e) & 1)) {
-                      Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, v[e]);
-                      atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
-                    }
+                    for (uint32_t w = 0; w < kKeyWords; ++w) qe[w] = key[w];
+                    qe[kKeyWords] = uint64_t(knull) | (uint64_t(valid_mask) << 32);
+#pragma unroll
+                    for (uint32_t e = 0; e < MAXE; ++e) *reinterpret_cast<AccT*>(qe + kKeyWords + 1 + e * kAccWords) = v[e];
+                    queued = true;
                   }
-                  atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
                 }
+                if (!queued) global_accumulate<ACC, MAXE>(P, GROUPED, key, knull, valid_mask, v);
               }
             } else if constexpr (SINK == SINK_JOIN_BUILD) {
               const JoinBuild& jb = P.build;
@@ -985,10 +1102,12 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                     if (nw == 4 && q == w + 3) pay[q] = raw.w;
                   }
                 }
-                uint32_t i = uint32_t(mix64(uint64_t(key))) & jb.mask;
+                const uint64_t hk = mix64(uint64_t(key));
+                uint32_t i = uint32_t(hk) & jb.mask;
                 for (;;) {  // capacity >= 2 x rows: an empty slot always exists
                   uint32_t* slot = reinterpret_cast<uint32_t*>(jb.slots + uint64_t(i) * jb.slot_u4);
                   if (atomicCAS(slot + 2, 0u, occ) == 0u) {
+                    jb.tags[i] = uint8_t(join_tag(hk));
                     slot[0] = uint32_t(uint64_t(key));
                     slot[1] = uint32_t(uint64_t(key) >> 32);
                     slot[3] = pay[0];
@@ -1006,27 +1125,36 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
             sink(row);
           } else {
             const DevJoin& j = P.joins[0];
-            if (!ref_valid(j.key, row)) continue;  // NULL keys never match
-            const int64_t key = load_i64(j.key, row);
+            const uint32_t tag = tagsel;
+            if (!tag) continue;  // NULL key
+            const int64_t key = keysel;
             const uint32_t klo = uint32_t(uint64_t(key)), khi = uint32_t(uint64_t(key) >> 32);
-            uint32_t i = uint32_t(mix64(uint64_t(key))) & j.mask;
-            for (;;) {
-              const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
-              const uint4 s0 = __ldg(slot);
-              if ((s0.z & 1u) == 0u) break;
-              if (s0.x == klo && s0.y == khi) {
-                row.pay = reinterpret_cast<const uint32_t*>(slot);
-                row.occ = s0.z;
-                sink(row);
+            uint32_t i = isel;
+            uint32_t t = tsel;
+            while (t != 0u) {
+              if (t == tag) {
+                const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
+                const uint4 s0 = __ldg(slot);
+                if (s0.x == klo && s0.y == khi) {
+                  row.pay = reinterpret_cast<const uint32_t*>(slot);
+                  row.occ = s0.z;
+                  sink(row);
+                }
               }
               i = (i + 1) & j.mask;
+              t = __ldg(j.tags + i);
             }
           }
+        }
+        if constexpr (SINK == SINK_AGG && GROUPED) {
+          __syncwarp();
+          if (*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - 1]) >= kQueueDrainAt) drain_queue();
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->empty[s]);
     }
+    drain_queue();
   }
   __syncthreads();
 

@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libpgf_b200.so")
+LIB_PATH = os.environ.get("PGF_B200_LIB") or os.path.join(_PKG_DIR, "libpgf_b200.so")  # override: kernel A/B experiments
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 MAX_COLS = 16

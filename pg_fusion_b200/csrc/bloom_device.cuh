@@ -20,6 +20,23 @@ __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t v) {  // bloom.
 constexpr uint64_t kBloomSalt = 0xD1B54A32D192ED03ull;  // bloom.rs:10
 
 #ifdef __CUDACC__
+// Predicated read-only loads.  A load under `if (p)` becomes a branch, and loads behind
+// different branches are issued and waited for one after the other; a predicated instruction
+// keeps the code straight-line so independent loads of several rows overlap.
+__device__ __forceinline__ uint32_t ldg_u32_if(const uint32_t* p, bool pred, uint32_t otherwise) {
+  uint32_t v = otherwise;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p ld.global.nc.u32 %0, [%1];\n\t}" : "+r"(v) : "l"(p), "r"(uint32_t(pred)));
+  return v;
+}
+__device__ __forceinline__ uint4 ldg_u128_if(const uint4* p, bool pred) {
+  uint4 v = make_uint4(0, 0, 0, 0);
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];\n\t}"
+      : "+r"(v.x), "+r"(v.y), "+r"(v.z), "+r"(v.w) : "l"(p), "r"(uint32_t(pred)));
+  return v;
+}
+#endif
+
+#ifdef __CUDACC__
 // Exact a % d for 64-bit operands without a divide (Lemire, Kaser, Kurz 2019):
 // M = ceil(2^128 / d) (128 bit), lowbits = M * a mod 2^128, result = (lowbits * d) >> 128.
 __device__ __forceinline__ uint64_t fastmod_u64(uint64_t a, uint64_t m_lo, uint64_t m_hi, uint64_t d) {
@@ -127,8 +144,7 @@ __device__ __forceinline__ void bloom_contains_n(const DevBloom& b, const uint64
     h1[q] = splitmix64(key[q] ^ b.seed);
     v[q] = uint32_t(h1[q]);
     const uint32_t bit = v[q] & mask;
-    x[q] = 0;
-    if (keep[q]) x[q] = __ldg(w32 + (bit >> 5)) >> (bit & 31);
+    x[q] = ldg_u32_if(w32 + (bit >> 5), keep[q], 0u) >> (bit & 31);
   }
   // second hash while the loads are in flight
 #pragma unroll
@@ -145,7 +161,7 @@ __device__ __forceinline__ void bloom_contains_n(const DevBloom& b, const uint64
 #pragma unroll
         for (uint32_t q = 0; q < N; ++q) {
           const uint32_t bit = (v[q] + t * step[q]) & mask;
-          if (keep[q]) x[q] &= __ldg(w32 + (bit >> 5)) >> (bit & 31);
+          x[q] &= ldg_u32_if(w32 + (bit >> 5), keep[q], ~0u) >> (bit & 31);
         }
       }
     }

@@ -534,11 +534,17 @@ class Lowering {
     for (uint32_t c = 0; c < D.nstage_cols; ++c) row_bytes8 += D.scol[c].width * 8u + (D.scol[c].nullable ? 1u : 0u);
     const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
     const uint64_t page_bytes = (uint64_t(row_bytes8) * max_rows + 7) / 8;
-    uint32_t ntiles = uint32_t((page_bytes + 40 * 1024 - 1) / (40 * 1024));
+    // Pipelines behind a join probe stage whole pages in a 3-deep ring: their throughput is bound
+    // by the rows in flight per SM (4 rows per thread x all consumer warps), not by ring depth.
+    const uint32_t nstages = uint32_t(pipeline_stages(L_->nj));
+    const uint32_t queue_bytes = (D.sink == SINK_AGG && L_->grouped) ? kMaxConsumerWarps * kQueueBytesPerWarp : 0u;
+    const uint32_t smem_budget = 227u * 1024u - uint32_t((sizeof(BlockShared) + 127) & ~size_t(127)) - queue_bytes;
+    const bool whole_pages = L_->nj != 0 && nstages <= 3;
+    const uint32_t max_stage = std::min<uint32_t>((smem_budget / nstages) & ~127u, whole_pages ? 66u * 1024u : 48u * 1024u);
+    const uint32_t target = whole_pages ? max_stage : 40u * 1024u;
+    uint32_t ntiles = uint32_t((page_bytes + target - 1) / target);
     if (ntiles == 0) ntiles = 1;
     uint32_t tile_rows = 0, stage_bytes = 0;
-    // GROUP BY pipelines also hold the per-warp deferred-sink queues in shared memory
-    const uint32_t max_stage = (D.sink == SINK_AGG && L_->grouped) ? 44 * 1024 : 48 * 1024;
     for (;; ++ntiles) {
       tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
       stage_bytes = 0;
@@ -564,8 +570,7 @@ class Lowering {
     D.descs = s.d_descs;
     D.classes = s.d_classes;
     D.page_stride = ctx_->page_size;
-    L_->smem = ((sizeof(BlockShared) + 127) & ~size_t(127)) + size_t(kStages) * D.stage_bytes;
-    if (D.sink == SINK_AGG && L_->grouped) L_->smem += size_t(kMaxConsumerWarps) * kQueueBytesPerWarp;  // deferred-sink queues
+    L_->smem = ((sizeof(BlockShared) + 127) & ~size_t(127)) + size_t(nstages) * D.stage_bytes + queue_bytes;  // ring + deferred-sink queues
     return PGF_OK;
   }
 
@@ -802,13 +807,14 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     JoinTable& jt = L.build_table;
     // slots followed by the one-byte tag directory
     const uint64_t slot_bytes = uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4);
-    cudaError_t e = cudaMalloc(&jt.d_slots, slot_bytes + jt.capacity);
+    const uint64_t tag_bytes = uint64_t(jt.capacity) + 16;  // + mirror of the first tags (windows never wrap)
+    cudaError_t e = cudaMalloc(&jt.d_slots, slot_bytes + tag_bytes);
     if (e != cudaSuccess) {
       cudaGetLastError();
       return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
     }
     mem.ptrs.push_back(jt.d_slots);
-    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + jt.capacity, ctx->compute_stream));
+    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream));
     L.dev.build.slots = jt.d_slots;
     L.dev.build.tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
   }

@@ -28,7 +28,15 @@ namespace pgf {
 constexpr int kMaxConsumerWarps = 16;
 __host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 14 : 16; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
-constexpr int kStages = 4;
+constexpr int kStages = 4;     // ring depth of streaming pipelines
+#ifndef PGF_JOIN_STAGES
+#define PGF_JOIN_STAGES 3
+#endif
+#ifndef PGF_JOIN_ROWS
+#define PGF_JOIN_ROWS 4
+#endif
+constexpr int kJoinStages = PGF_JOIN_STAGES; // pipelines behind a join probe: 3 = whole pages (one tile per page)
+__host__ __device__ constexpr int pipeline_stages(uint32_t nj) { return nj != 0 ? kJoinStages : kStages; }
 // Deferred sink: rows whose group is not register resident are queued per warp (in shared
 // memory behind the stage ring) and applied to the global table 32 at a time from a converged
 // point, instead of one or two lanes at a time from inside the divergent probe loop.
@@ -666,7 +674,8 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
-  constexpr uint32_t kRows = NJ != 0 ? 4 : 2;  // rows per thread and iteration
+  constexpr uint32_t kRows = NJ != 0 ? PGF_JOIN_ROWS : 2;  // rows per thread and iteration
+  constexpr uint32_t kNumStages = uint32_t(pipeline_stages(NJ));
   constexpr uint32_t kAccWords = ACC == CLS_I128 ? 2 : 1;
   [[maybe_unused]] constexpr uint32_t kQueueEntryWords = queue_entry_words(MAXE, kAccWords);
   [[maybe_unused]] constexpr uint32_t kQueueCap = kQueueBytesPerWarp / (8 * kQueueEntryWords);
@@ -681,7 +690,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNumStages; ++s) {
       mbar_init(&sh->full[s], 1);
       mbar_init(&sh->empty[s], kConsumerWarps);
     }
@@ -715,7 +724,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     PageDesc d_next{};
     if (item < P.nitems) d_next = P.descs[item / P.tiles_per_page];
     for (; item < P.nitems; item += gridDim.x, ++k) {
-      const uint32_t s = k % kStages;
+      const uint32_t s = k % kNumStages;
       const uint32_t page = item / P.tiles_per_page, tile = item - page * P.tiles_per_page;
       const PageDesc d = d_next;
       if (item + gridDim.x < P.nitems) d_next = P.descs[(item + gridDim.x) / P.tiles_per_page];  // prefetch
@@ -745,7 +754,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       uint32_t total = bytes;
 #pragma unroll
       for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      mbar_wait(&sh->empty[s], ((k / kStages) & 1u) ^ 1u);
+      mbar_wait(&sh->empty[s], ((k / kNumStages) & 1u) ^ 1u);
       if (lane == 0) {
         sh->meta[s].nrows = n;
         sh->meta[s].null_mask = d.null_mask & P.used_null_mask;
@@ -757,7 +766,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     }
   } else {
     // ===== consumers =====
-    [[maybe_unused]] uint64_t* myqueue = reinterpret_cast<uint64_t*>(stages + size_t(kStages) * P.stage_bytes) +
+    [[maybe_unused]] uint64_t* myqueue = reinterpret_cast<uint64_t*>(stages + size_t(kNumStages) * P.stage_bytes) +
                                          size_t(warp - 1) * (kQueueBytesPerWarp / 8);
     [[maybe_unused]] auto drain_queue = [&]() {
       if constexpr (SINK == SINK_AGG && GROUPED) {
@@ -783,8 +792,8 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
     };
     uint32_t k = 0;
     for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
-      const uint32_t s = k % kStages;
-      mbar_wait(&sh->full[s], (k / kStages) & 1u);
+      const uint32_t s = k % kNumStages;
+      mbar_wait(&sh->full[s], (k / kNumStages) & 1u);
       const uint32_t nrows = sh->meta[s].nrows;
       const uint8_t* stage = stages + size_t(s) * P.stage_bytes;
       const uint32_t tile_nulls = sh->meta[s].null_mask;
@@ -903,37 +912,90 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
           }
           continue;
         }
-        // HashJoinExec probe: hash both rows and fetch their first directory tags together so
-        // the two L2 latencies overlap; NULL keys never match.
-        uint32_t ji[R], jtag[R], jt0[R];
+        // HashJoinExec probe, batched over the R rows of this thread so the memory round trips
+        // overlap: (A) hash every row and fetch a window of four directory tags starting at its
+        // home slot, (B) scan the windows (SIMD-in-register byte compares) for the first tag hit
+        // and the end of the probe chain, (C) fetch the heads of the candidate slots.  Only rows
+        // with a tag hit or a chain longer than the window enter the per-row loop below (a bit
+        // mask per thread), so the common miss costs no control flow.  NULL keys never match.
+        constexpr uint32_t kNone = 0xFFFFFFFFu;
+        uint32_t ji[R], jtag[R], jcand[R], jres[R];
         int64_t jkey[R];
-#pragma unroll
-        for (uint32_t h = 0; h < R; ++h) { ji[h] = 0; jtag[h] = 0; jt0[h] = 0; jkey[h] = 0; }
-        if constexpr (NJ != 0) {
-          const DevJoin& j = P.joins[0];
+        uint4 js0[R];
+        uint32_t pending = 0;  // bit h: row h needs the per-row loop
+        if constexpr (NJ == 0) {
 #pragma unroll
           for (uint32_t h = 0; h < R; ++h) {
-            const Row q{stage, rr[h], tile_nulls, nullptr, 0};
-            if (keep[h] && ref_valid(j.key, q)) {
-              jkey[h] = load_i64(j.key, q);
-              const uint64_t hk = mix64(uint64_t(jkey[h]));
-              ji[h] = uint32_t(hk) & j.mask;
-              jtag[h] = join_tag(hk);
+            ji[h] = 0; jtag[h] = 0; jcand[h] = kNone; jres[h] = kNone; jkey[h] = 0; js0[h] = make_uint4(0, 0, 0, 0);
+            pending |= uint32_t(keep[h]) << h;
+          }
+        } else {
+          const DevJoin& j = P.joins[0];
+          // keys of all rows with one dispatch on the key width
+          {
+            const uint8_t* kp = stage + j.key.off;
+            if (j.key.ld == LD_I32) {
+#pragma unroll
+              for (uint32_t h = 0; h < R; ++h) jkey[h] = int64_t(reinterpret_cast<const int32_t*>(kp)[rr[h]]);
+            } else if (j.key.ld == LD_I64) {
+#pragma unroll
+              for (uint32_t h = 0; h < R; ++h) jkey[h] = reinterpret_cast<const int64_t*>(kp)[rr[h]];
+            } else {
+#pragma unroll
+              for (uint32_t h = 0; h < R; ++h) jkey[h] = int64_t(reinterpret_cast<const int16_t*>(kp)[rr[h]]);
+            }
+          }
+#pragma unroll
+          for (uint32_t h = 0; h < R; ++h) {
+            bool live = keep[h];
+            if constexpr (!SHAPE::no_nulls) live = live && ref_valid(j.key, Row{stage, rr[h], tile_nulls, nullptr, 0});
+            const uint64_t hk = mix64(uint64_t(jkey[h]));
+            ji[h] = uint32_t(hk) & j.mask;
+            jtag[h] = live ? join_tag(hk) : 0u;
+          }
+          // the loads of all rows sit in one straight-line block (no control flow in between)
+          uint32_t wlo[R], whi[R];
+#pragma unroll
+          for (uint32_t h = 0; h < R; ++h) {
+            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(j.tags + (ji[h] & ~3u));
+            wlo[h] = ldg_u32_if(w32, jtag[h] != 0u, 0u);
+            whi[h] = ldg_u32_if(w32 + 1, jtag[h] != 0u, 0u);
+          }
+#pragma unroll
+          for (uint32_t h = 0; h < R; ++h) {
+            const uint32_t win = __funnelshift_r(wlo[h], whi[h], (ji[h] & 3u) * 8u);  // tags[i .. i+3]
+            // 0x80 in every byte of the window that is zero (end of chain) / equals the tag: exact
+            // zero-byte detection, no carries between bytes
+            const uint32_t x = win ^ (jtag[h] * 0x01010101u);
+            const uint32_t mz = ~(((win & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | win | 0x7F7F7F7Fu);
+            const uint32_t mt = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+            const uint32_t below_end = mz ? ((mz & (0u - mz)) - 1u) : 0xFFFFFFFFu;  // bytes before the first zero tag
+            uint32_t hits = mt & below_end;
+            jcand[h] = kNone;
+            jres[h] = kNone;
+            if (jtag[h] != 0u) {
+              if (hits) {
+                jcand[h] = (ji[h] + ((31u - __clz(hits & (0u - hits))) >> 3)) & j.mask;
+                hits &= hits - 1u;
+                if (hits) jres[h] = (ji[h] + ((31u - __clz(hits & (0u - hits))) >> 3)) & j.mask;  // second hit: walk from there
+              }
+              if (jres[h] == kNone && mz == 0u) jres[h] = (ji[h] + 4u) & j.mask;  // chain continues past the window
+              pending |= uint32_t(jcand[h] != kNone || jres[h] != kNone) << h;
             }
           }
 #pragma unroll
           for (uint32_t h = 0; h < R; ++h)
-            if (jtag[h]) jt0[h] = __ldg(j.tags + ji[h]);
+            js0[h] = ldg_u128_if(j.slots + uint64_t(jcand[h] != kNone ? jcand[h] : 0u) * j.slot_u4, jcand[h] != kNone);
         }
-#pragma unroll 1
-        for (uint32_t half = 0; half < R; ++half) {
-          uint32_t rsel = rr[0], isel = ji[0], tagsel = jtag[0], tsel = jt0[0];
+        while (pending) {
+          const uint32_t half = 31u - __clz(pending & (0u - pending));
+          pending &= pending - 1u;
+          uint32_t rsel = rr[0], tagsel = jtag[0], candsel = jcand[0], ressel = jres[0];
           int64_t keysel = jkey[0];
-          bool ksel = keep[0];
+          uint4 s0sel = js0[0];
 #pragma unroll
           for (uint32_t h = 1; h < R; ++h)
-            if (half == h) { rsel = rr[h]; isel = ji[h]; tagsel = jtag[h]; tsel = jt0[h]; keysel = jkey[h]; ksel = keep[h]; }
-          if (!ksel) continue;
+            if (half == h) { rsel = rr[h]; tagsel = jtag[h]; candsel = jcand[h]; ressel = jres[h]; keysel = jkey[h]; s0sel = js0[h]; }
           Row row{stage, rsel, tile_nulls, nullptr, 0};
 
           // -- sink (optionally behind one HashJoinExec probe)
@@ -1108,6 +1170,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
                   uint32_t* slot = reinterpret_cast<uint32_t*>(jb.slots + uint64_t(i) * jb.slot_u4);
                   if (atomicCAS(slot + 2, 0u, occ) == 0u) {
                     jb.tags[i] = uint8_t(join_tag(hk));
+                    if (i < 4u) jb.tags[jb.mask + 1u + i] = uint8_t(join_tag(hk));  // mirror: tag windows never wrap
                     slot[0] = uint32_t(uint64_t(key));
                     slot[1] = uint32_t(uint64_t(key) >> 32);
                     slot[3] = pay[0];
@@ -1129,20 +1192,27 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
             if (!tag) continue;  // NULL key
             const int64_t key = keysel;
             const uint32_t klo = uint32_t(uint64_t(key)), khi = uint32_t(uint64_t(key) >> 32);
-            uint32_t i = isel;
-            uint32_t t = tsel;
-            while (t != 0u) {
-              if (t == tag) {
-                const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
-                const uint4 s0 = __ldg(slot);
-                if (s0.x == klo && s0.y == khi) {
-                  row.pay = reinterpret_cast<const uint32_t*>(slot);
-                  row.occ = s0.z;
-                  sink(row);
+            if (candsel != kNone && s0sel.x == klo && s0sel.y == khi) {
+              row.pay = reinterpret_cast<const uint32_t*>(j.slots + uint64_t(candsel) * j.slot_u4);
+              row.occ = s0sel.z;
+              sink(row);
+            }
+            if (ressel != kNone) {  // rest of the chain, one tag at a time
+              uint32_t i = ressel;
+              uint32_t t = __ldg(j.tags + i);
+              while (t != 0u) {
+                if (t == tag) {
+                  const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
+                  const uint4 s0 = __ldg(slot);
+                  if (s0.x == klo && s0.y == khi) {
+                    row.pay = reinterpret_cast<const uint32_t*>(slot);
+                    row.occ = s0.z;
+                    sink(row);
+                  }
                 }
+                i = (i + 1) & j.mask;
+                t = __ldg(j.tags + i);
               }
-              i = (i + 1) & j.mask;
-              t = __ldg(j.tags + i);
             }
           }
         }

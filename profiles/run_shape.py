@@ -53,3 +53,23 @@ with pg.Context(0) as ctx:
             d, st = rf.probe_scan(probe, 0)
             k = ctx.last_kernel_ms()
             print(f"bloom probe iter {i}: kernel {k:.4f} ms, {rows / k / 1e6:.2f} G probes/s, {rows * 9 / k / 1e6:.1f} GB/s, rejected {st.rejected_rows}")
+    elif shape == "q3var":
+        # isolate the cost components of the Q3 lineitem pipeline (probe side)
+        from pg_fusion_b200 import AggFunc, Cmp, Factor
+        scale = rows / 59_986_052
+        ncust, nord = max(1000, int(1_500_000 * scale)), max(10000, int(15_000_000 * scale))
+        cust = ctx.gen_scan(pg.GenTable.CUSTOMER_Q3, ncust, seed=42)
+        orders = ctx.gen_scan(pg.GenTable.ORDERS_Q3, nord, seed=42, scale_rows=ncust)
+        li = ctx.gen_scan(pg.GenTable.LINEITEM_Q3, rows, seed=42, scale_rows=nord)
+        r1 = cust.pipeline().filter(1, Cmp.EQ, b"BUILDING").build_join(0, []).run()
+        full = orders.pipeline().filter(2, Cmp.LT, U.Q3_DATE).join(r1.join_table, 1).build_join(0, [2, 3]).run()
+        empty = orders.pipeline().filter(2, Cmp.LT, b"0000-00-00").build_join(0, [2, 3]).run()
+        allord = orders.pipeline().build_join(0, [2, 3]).run()
+        for label, table, date in (("full", full, U.Q3_DATE), ("nothing passes the filter", full, b"9999-99-99"),
+                                   ("empty build side", empty, U.Q3_DATE), ("all orders build side (every probe matches)", allord, U.Q3_DATE)):
+            p3 = (li.pipeline().filter(3, Cmp.GT, date).join(table.join_table, 0)
+                  .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
+                             expected_groups=max(1024, table.rows_out)))
+            for i in range(iters):
+                r = p3.run()
+            print(f"q3var [{label}]: kernel {r.kernel_ms:.4f} ms, filter->{r.rows_filtered} joined {r.rows_out} groups {len(r.keys)}")

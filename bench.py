@@ -113,9 +113,8 @@ def cpu_q6(pages, nthreads, min_seconds=5.0):
             return rows_total / dt, passes, rows_in
 
 
-def side_measurements(ctx, pg, U, rows, peak):
-    """Kernel-time throughput of the other BASELINE.json shapes at SF10 (device events inside the library)."""
-    import numpy as np
+def side_measurements(ctx, pg, U, rows, peak, label="sf10", bloom=True):
+    """Kernel-time throughput of the other BASELINE.json shapes (device events inside the library)."""
     extras = {}
     # Q1 shape, 8 aggregates, 4 groups
     q1 = ctx.gen_scan(pg.GenTable.LINEITEM_Q1, rows, seed=42)
@@ -124,10 +123,10 @@ def side_measurements(ctx, pg, U, rows, peak):
         p1.run()
     k = statistics.mean(p1.run().kernel_ms for _ in range(5))
     gbps = rows * Q1_BYTES_PER_ROW / (k / 1e3) / 1e9
-    extras["tpch_q1_sf10"] = {"rows_per_s": rows / (k / 1e3), "kernel_ms": k, "achieved_GBps": gbps,
-                              "frac_of_measured_peak": gbps / peak, "bytes_per_row": Q1_BYTES_PER_ROW}
+    extras[f"tpch_q1_{label}"] = {"rows_per_s": rows / (k / 1e3), "kernel_ms": k, "achieved_GBps": gbps,
+                                  "frac_of_measured_peak": gbps / peak, "bytes_per_row": Q1_BYTES_PER_ROW}
     q1.release()
-    # Q3 shape: customer |><| orders |><| lineitem with runtime Bloom filters sized 16 bits per build key
+    # Q3 shape: customer |><| orders |><| lineitem, without and with runtime Bloom filters
     scale = rows / SF10_LINEITEM
     ncust, nord = max(1000, int(SF10_CUSTOMER * scale)), max(10000, int(SF10_ORDERS * scale))
     cust = ctx.gen_scan(pg.GenTable.CUSTOMER_Q3, ncust, seed=42)
@@ -139,9 +138,10 @@ def side_measurements(ctx, pg, U, rows, peak):
         while b < n:
             b <<= 1
         return b
-    for label, bp in (("no_bloom", None),
-                      ("bloom_guc_default", (pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM), pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM))),
-                      ("bloom_16_bits_per_key", (pg.BloomParams.new(pow2(16 * ncust // 5), 4, 7), pg.BloomParams.new(pow2(16 * nord // 10), 4, 7)))):
+    variants = [("no_bloom", None),
+                ("bloom_guc_default", (pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM), pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM))),
+                ("bloom_16_bits_per_key", (pg.BloomParams.new(pow2(16 * ncust // 5), 4, 7), pg.BloomParams.new(pow2(16 * nord // 10), 4, 7)))]
+    for name, bp in variants:
         best = None
         for _ in range(3):
             res, st = U.gpu_q3(ctx, cust, orders, li, bp)
@@ -149,16 +149,20 @@ def side_measurements(ctx, pg, U, rows, peak):
             if best is None or sum(t) < sum(best[0]):
                 best = (t, res, st)
         t, res, st = best
-        extras["tpch_q3_sf10_" + label] = {
+        scanned = ncust * 20 + nord * 28 + rows * 36   # bytes of the scanned columns
+        extras[f"tpch_q3_{label}_" + name] = {
             "kernel_ms": {"customer_build": t[0], "orders_probe_build": t[1], "lineitem_probe_aggregate": t[2], "total": sum(t)},
             "lineitem_rows_per_s": rows / (t[2] / 1e3), "lineitem_achieved_GBps": rows * 36 / (t[2] / 1e3) / 1e9,
             "lineitem_frac_of_measured_peak": rows * 36 / (t[2] / 1e3) / 1e9 / peak,
+            "all_scans_achieved_GBps": scanned / (sum(t) / 1e3) / 1e9, "all_scans_frac_of_measured_peak": scanned / (sum(t) / 1e3) / 1e9 / peak,
             "join_probes_per_s": st["lineitem"].rows_filtered / (t[2] / 1e3),
             "rows": {"customer_build": st["customer"].rows_out, "orders_build": st["orders"].rows_out,
                      "lineitem_after_bloom": st["lineitem"].rows_bloom, "lineitem_after_filter": st["lineitem"].rows_filtered,
                      "joined": st["lineitem"].rows_out, "groups": len(res.keys)}}
     for s in (cust, orders, li):
         s.release()
+    if not bloom:
+        return extras
     # Bloom, BASELINE.json configs[0] shape: 1M Int64 keys, GUC-default filter; probes over 64M keys
     p = pg.BloomParams.new(**pg.GUC_DEFAULT_BLOOM)
     keys = ctx.gen_scan(pg.GenTable.KEYS_I64, 1_000_000, seed=7)
@@ -181,10 +185,29 @@ def side_measurements(ctx, pg, U, rows, peak):
         "build_keys_per_s": 1e6 / (kb / 1e3), "build_kernel_ms": kb,
         "probes_per_s": 64e6 / (kp / 1e3), "probe_kernel_ms": kp, "probe_keys": 64_000_000,
         "probe_achieved_GBps": 64e6 * 9 / (kp / 1e3) / 1e9, "probe_frac_of_measured_peak": 64e6 * 9 / (kp / 1e3) / 1e9 / peak,
-        "rejected": int(stp.rejected_rows), "bytes_per_probe": 9}
+        "rejected": int(stp.rejected_rows), "bytes_per_probe": 9,
+        "bound": "integer issue (two splitmix64 rounds per key), not HBM"}
     keys.release()
     probe.release()
     return extras
+
+
+def sf100_measurements(ctx, pg, U, peak):
+    """The same three shapes at SF100 on one GPU (BASELINE.json configs[4], 1-GPU leg): pages are
+    generated on the device, so SF100 never exists on the host."""
+    rows = 10 * SF10_LINEITEM + 177_382   # 600 037 902
+    out = {}
+    q6 = ctx.gen_scan(pg.GenTable.LINEITEM_Q6, rows, seed=42)
+    p6 = U.gpu_q6(q6)
+    for _ in range(2):
+        p6.run()
+    k = statistics.mean(p6.run().kernel_ms for _ in range(5))
+    gbps = rows * Q6_BYTES_PER_ROW / (k / 1e3) / 1e9
+    out["tpch_q6_sf100"] = {"rows_per_s": rows / (k / 1e3), "kernel_ms": k, "achieved_GBps": gbps,
+                            "frac_of_measured_peak": gbps / peak, "frac_of_nominal_8TBs": gbps / 8000.0, "bytes_per_row": Q6_BYTES_PER_ROW}
+    q6.release()
+    out.update(side_measurements(ctx, pg, U, rows, peak, label="sf100", bloom=False))
+    return out
 
 
 def run_reference(args):
@@ -210,13 +233,18 @@ def run_reference(args):
             per_step.append(dt)
     ms = 1e3 * sum(per_step) / len(per_step)
     value = sample_rows / (ms / 1e3)
+    t0 = time.perf_counter()
+    O.q6_pages(pages, PAGE, 1)
+    one_thread = sample_rows / (time.perf_counter() - t0)
     sample = f"{sample_rows} rows ({pages.shape[0]} pages, 256 MiB) of the Q6 F-schema lineitem shape per step"
     print(json.dumps({
         "impl": "reference", "metric": "lineitem rows/s (TPC-H Q6 shape)", "value": value, "unit": "rows/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "tpch_q6_sf10_lineitem_F_schema", "rows": SF10_LINEITEM, "bounded_sample_rows": sample_rows},
-        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample,
+                         "one_thread": {"value": one_thread, "note": "the reference plans with target_partitions = 1 "
+                                        "(worker_runtime/src/runtime.rs:748-758): its operators run on one thread"}},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -228,7 +256,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=SF10_LINEITEM, help="lineitem rows per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-extras", action="store_true", help="skip the Q1 / Bloom side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -302,35 +330,47 @@ def main():
     total_rows = rows * world
     value = total_rows / (ms_per_step / 1e3)
 
-    # ---- end to end through the C ABI from pinned host pages (H2D inside the timed region)
-    e2e = None
-    if world == 1:
-        host = torch.empty(info.pages * PAGE, dtype=torch.uint8, pin_memory=True)
-        from pg_fusion_b200 import _lib
-        import ctypes as C
-        ctx._check(_lib.lib().pgf_scan_read_pages(ctx.h, scan.scan_id, 0, info.pages, C.c_void_p(host.data_ptr())))
-        e2e_scan = ctx.declare_scan(scan.schema, expected_pages=info.pages)
-        e2e_plan = U.gpu_q6(e2e_scan)
+    # ---- end to end through the C ABI from pinned host pages (H2D inside the timed region).
+    # Every rank pushes its own page shard from pinned host memory through its own PCIe link;
+    # at N > 1 a step also carries the NCCL all-gather of the partial states and the final merge.
+    host = torch.empty(info.pages * PAGE, dtype=torch.uint8, pin_memory=True)
+    from pg_fusion_b200 import _lib
+    import ctypes as C
+    ctx._check(_lib.lib().pgf_scan_read_pages(ctx.h, scan.scan_id, 0, info.pages, C.c_void_p(host.data_ptr())))
+    e2e_scan = ctx.declare_scan(scan.schema, expected_pages=info.pages)
+    e2e_plan = U.gpu_q6(e2e_scan)
 
-        def e2e_step():
-            e2e_scan.reset()
-            e2e_scan.push_pages_ptr(host.data_ptr(), info.pages, PAGE)
-            e2e_scan.finish()
+    def e2e_step():
+        e2e_scan.reset()
+        e2e_scan.push_pages_ptr(host.data_ptr(), info.pages, PAGE)
+        e2e_scan.finish()
+        if world == 1:
             return e2e_plan.run()
+        e2e_plan.run_partial(state.data_ptr(), state_bytes)
+        dist.all_gather_into_tensor(gathered, state)
+        torch.cuda.current_stream().synchronize()
+        return e2e_plan.merge_partials(gathered.data_ptr(), state_bytes, world)
 
+    r2 = e2e_step()
+    assert r2.aggs[0][1] == res.aggs[0][1], "e2e result differs from the HBM-resident result"
+    assert abs(r2.aggs[0][0] - res.aggs[0][0]) <= 1e-12 * abs(res.aggs[0][0]), "e2e result differs from the HBM-resident result"
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
         r2 = e2e_step()
-        assert r2.rows_in == rows and r2.aggs[0][1] == res.aggs[0][1], "e2e result differs from the HBM-resident result"
-        assert abs(r2.aggs[0][0] - res.aggs[0][0]) <= 1e-12 * abs(res.aggs[0][0]), "e2e result differs from the HBM-resident result"
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(args.e2e_steps):
-            r2 = e2e_step()
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / args.e2e_steps
-        e2e = {"value": rows / dt, "unit": "rows/s", "h2d_bytes_per_step": int(info.pages * PAGE),
-               "d2h_bytes_per_step": 8 * (1 + 4 + 1 + 1 + 2) + 64, "ms_per_step": dt * 1e3,
-               "note": "pinned host pages -> pgf_scan_push_pages (H2D) -> pgf_scan_finish (device import checks) -> pgf_pipeline_run -> result on host"}
-        e2e_scan.release()
+    barrier()
+    dt = (time.perf_counter() - t0) / args.e2e_steps
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    h2d = int(info.pages * PAGE)
+    e2e = {"value": total_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": (64 + 8 * (1 + 7)) * world, "ms_per_step": dt * 1e3, "h2d_GBps_per_gpu": h2d / dt / 1e9,
+           "note": "pinned host pages -> pgf_scan_push_pages (host admission checks + H2D) -> pgf_scan_finish (device import checks) "
+                   "-> pgf_pipeline_run -> result on host; bound by the PCIe link of each GPU"}
+    e2e_scan.release()
+    del host
 
     out = None
     peak, peak_src = measured_peak()
@@ -348,6 +388,15 @@ def main():
                    "sample": f"first {sample_pages} pages ({sample_rows} rows) of the same generated SF10 lineitem, {passes} passes; "
                              "1 thread mirrors the reference's single-partition execution (worker_runtime/src/runtime.rs:748-758)",
                    "all_cores": {"value": vn, "cores": cores}}
+        # DRAM traffic of one launch of the dominant kernel, from the committed ncu --set full capture of this workload
+        traffic, traffic_src = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "q6_sf10_traffic.json")) as f:
+                tj = json.load(f)
+            if int(tj["rows"]) == rows:
+                traffic, traffic_src = float(tj["dram_bytes_per_launch"]) / 1e9, tj["source"]
+        except Exception:
+            pass
         out = {
             "metric": "lineitem rows/s (TPC-H Q6 shape)", "value": value, "unit": "rows/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -357,7 +406,9 @@ def main():
                        "l2_policy": "inputs (2.4 GB per GPU) are larger than the 126 MB L2",
                        "parallelism": f"pages sharded over {world} GPU(s); partial aggregate states merged with NCCL all-gather" if world > 1 else "1 GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, false, 0>",
+                         "traffic": traffic, "traffic_unit": "GB per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
+                         "traffic_source": traffic_src, "algorithmic_GB_per_launch": rows * Q6_BYTES_PER_ROW / 1e9,
+                         "peak_source": peak_src, "kernel": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>",
                          "kernel_ms": kms, "frac_of_nominal_8TBs": achieved / 8000.0},
             "cpu_baseline": cpu,
             "e2e": e2e,
@@ -367,10 +418,13 @@ def main():
             "result": {"revenue": res.aggs[0][0], "rows_kept": res.aggs[0][1]},
         }
 
-    # ---- side measurements (not the headline): Q1 / Q3 shapes and Bloom, HBM resident
+    # ---- side measurements (not the headline): Q1 / Q3 shapes and Bloom, HBM resident, SF10 and SF100
     if rank == 0 and world == 1 and not args.no_extras:
         scan.release()
         out["other_workloads"] = side_measurements(ctx, pg, U, rows, peak)
+        free_b, _ = torch.cuda.mem_get_info()
+        if free_b > 120 * (1 << 30) and rows == SF10_LINEITEM:
+            out["other_workloads"].update(sf100_measurements(ctx, pg, U, peak))
     if rank == 0:
         print(json.dumps(out))
     ctx.close()

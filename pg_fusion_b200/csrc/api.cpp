@@ -305,26 +305,45 @@ pgf_status pgf_scan_push_pages(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pa
   PGF_TRY(scan_reserve(ctx, s, s.npages + npages));
   const uint32_t len = uint32_t(stride < ctx->page_size ? stride : ctx->page_size);
   const uint64_t first = s.npages;
+  const bool pinned = host_ptr_is_pinned(pages);
+  auto rollback = [&]() {  // forget the pages admitted by this call
+    s.h_descs.resize(first);
+    s.rows = first ? s.h_descs.back().row_base + s.h_descs.back().row_count : 0;
+    s.npages = first;
+  };
+  if (pinned) {
+    // caller-owned pinned (or registered shared-memory) pages: DMA straight from them, in
+    // chunks, so the host-side admission checks of chunk k+1 run under the copy of chunk k
+    const uint64_t chunk = 2048;
+    for (uint64_t p0 = 0; p0 < npages; p0 += chunk) {
+      const uint64_t n = npages - p0 < chunk ? npages - p0 : chunk;
+      for (uint64_t p = p0; p < p0 + n; ++p) {
+        pgf_status st = scan_admit_page(ctx, s, pages + p * stride, len);
+        if (st) {
+          cudaStreamSynchronize(ctx->copy_stream);
+          rollback();
+          return st;
+        }
+        s.npages++;
+      }
+      uint8_t* dst = s.d_pages + (first + p0) * uint64_t(ctx->page_size);
+      if (stride == ctx->page_size)
+        CU(ctx, cudaMemcpyAsync(dst, pages + p0 * stride, n * stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+      else
+        CU(ctx, cudaMemcpy2DAsync(dst, ctx->page_size, pages + p0 * stride, stride, len, n, cudaMemcpyHostToDevice, ctx->copy_stream));
+    }
+    s.pending_async += npages;
+    return PGF_OK;
+  }
   for (uint64_t p = 0; p < npages; ++p) {
     pgf_status st = scan_admit_page(ctx, s, pages + p * stride, len);
-    if (st) {  // roll back the pages admitted by this call
-      s.h_descs.resize(first);
-      s.rows = first ? s.h_descs.back().row_base + s.h_descs.back().row_count : 0;
-      s.npages = first;
+    if (st) {
+      rollback();
       return st;
     }
     s.npages++;
   }
   uint8_t* dst = s.d_pages + first * uint64_t(ctx->page_size);
-  if (host_ptr_is_pinned(pages)) {
-    // caller-owned pinned (or registered shared-memory) pages: DMA straight from them
-    if (stride == ctx->page_size)
-      CU(ctx, cudaMemcpyAsync(dst, pages, npages * stride, cudaMemcpyHostToDevice, ctx->copy_stream));
-    else
-      CU(ctx, cudaMemcpy2DAsync(dst, ctx->page_size, pages, stride, len, npages, cudaMemcpyHostToDevice, ctx->copy_stream));
-    s.pending_async += npages;
-    return PGF_OK;
-  }
   // pageable memory: bounce through the pinned staging chunks (double buffered)
   std::lock_guard<std::mutex> gs(ctx->mu);
   const uint64_t chunk = ctx->staging_pages;

@@ -293,13 +293,12 @@ def main():
     def step():
         if world == 1:
             return plan.run()
-        nbytes, stats = plan.run_partial(state.data_ptr(), state_bytes)
-        dist.all_gather_into_tensor(gathered, state)
-        torch.cuda.current_stream().synchronize()
-        res = plan.merge_partials(gathered.data_ptr(), state_bytes, world)
-        res.kernel_ms = stats.kernel_ms
-        res.kernel_launches += stats.kernel_launches
-        return res
+        # everything is enqueued on the library's compute stream (NCCL orders itself against the
+        # current stream); the merge synchronises once for the result
+        with torch.cuda.stream(stream):
+            plan.run_partial_async(state.data_ptr(), state_bytes)
+            dist.all_gather_into_tensor(gathered, state)
+            return plan.merge_partials_bounded(gathered.data_ptr(), state_bytes, world)
 
     def barrier():
         if world > 1:
@@ -346,10 +345,10 @@ def main():
         e2e_scan.finish()
         if world == 1:
             return e2e_plan.run()
-        e2e_plan.run_partial(state.data_ptr(), state_bytes)
-        dist.all_gather_into_tensor(gathered, state)
-        torch.cuda.current_stream().synchronize()
-        return e2e_plan.merge_partials(gathered.data_ptr(), state_bytes, world)
+        with torch.cuda.stream(stream):
+            e2e_plan.run_partial_async(state.data_ptr(), state_bytes)
+            dist.all_gather_into_tensor(gathered, state)
+            return e2e_plan.merge_partials_bounded(gathered.data_ptr(), state_bytes, world)
 
     r2 = e2e_step()
     assert r2.aggs[0][1] == res.aggs[0][1], "e2e result differs from the HBM-resident result"

@@ -349,6 +349,18 @@ pgf_status pgf_pipeline_merge_partials(pgf_ctx *ctx, const pgf_pipeline *plan,
                                        const void *dev_states, uint64_t state_stride_bytes,
                                        uint32_t nstates, pgf_result **result_out);
 
+/* One-synchronisation form of the multi-GPU step.  pgf_pipeline_run_partial_async enqueues the
+ * fused kernel and the extraction of the partial state on the compute stream and returns
+ * without synchronising (errors of the run surface in the merge).  After the all-gather has
+ * been enqueued on the same stream, pgf_pipeline_merge_partials_bounded sizes the final table
+ * from what the strides can hold instead of reading the counts back, merges in rank order
+ * and synchronises once for the result. */
+pgf_status pgf_pipeline_run_partial_async(pgf_ctx *ctx, const pgf_pipeline *plan, void *dev_state_out,
+                                          uint64_t state_capacity_bytes);
+pgf_status pgf_pipeline_merge_partials_bounded(pgf_ctx *ctx, const pgf_pipeline *plan,
+                                               const void *dev_states, uint64_t state_stride_bytes,
+                                               uint32_t nstates, pgf_result **result_out);
+
 /* -------------------------------------------------- synthetic TPC-H-shaped data
  * Counter-based generator (row id -> values) writing reference-format pages directly in
  * HBM, so SF100 never exists on the host.  `table` selects the scan shape. */

@@ -168,6 +168,8 @@ _SIGNATURES = {
     "pgf_pipeline_run_partial": (i32, [vp, P(Pipeline), vp, u64, P(u64), P(P(Result))]),
     "pgf_pipeline_merge_partials": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_partial_state_bytes": (i32, [P(Pipeline), u64, P(u64)]),
+    "pgf_pipeline_run_partial_async": (i32, [vp, P(Pipeline), vp, u64]),
+    "pgf_pipeline_merge_partials_bounded": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_gen_scan": (i32, [vp, u64, P(GenSpec)]),
     "pgf_gen_schema": (i32, [i32, P(ColumnSpec), P(u32)]),
 }

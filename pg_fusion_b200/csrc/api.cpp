@@ -680,7 +680,19 @@ pgf_status pgf_pipeline_merge_partials(pgf_ctx* ctx, const pgf_pipeline* plan, c
                                        uint64_t state_stride_bytes, uint32_t nstates, pgf_result** result_out) {
   if (!ctx || !plan || !dev_states || !result_out) return PGF_ERR_INVALID_ARGUMENT;
   if (ctx->sticky) return ctx->sticky;
-  return pipeline_merge(ctx, plan, dev_states, state_stride_bytes, nstates, result_out);
+  return pipeline_merge(ctx, plan, dev_states, state_stride_bytes, nstates, false, result_out);
+}
+pgf_status pgf_pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out,
+                                          uint64_t state_capacity_bytes) {
+  if (!ctx || !plan || !dev_state_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return pipeline_run_partial_async(ctx, plan, dev_state_out, state_capacity_bytes);
+}
+pgf_status pgf_pipeline_merge_partials_bounded(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states,
+                                               uint64_t state_stride_bytes, uint32_t nstates, pgf_result** result_out) {
+  if (!ctx || !plan || !dev_states || !result_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  return pipeline_merge(ctx, plan, dev_states, state_stride_bytes, nstates, true, result_out);
 }
 pgf_status pgf_partial_state_bytes(const pgf_pipeline* plan, uint64_t max_groups, uint64_t* bytes_out) {
   if (!plan || !bytes_out) return PGF_ERR_INVALID_ARGUMENT;

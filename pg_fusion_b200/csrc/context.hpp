@@ -84,6 +84,7 @@ struct pgf_ctx {
   uint8_t* d_out = nullptr;             // result entries of tables too large for the arena prefix
   size_t d_out_cap = 0;
   uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
+  bool partial_pending = false;         // an asynchronous partial run awaits its merge
   std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;
   std::map<uint64_t, pgf::BloomSlot> blooms;
   std::map<uint64_t, pgf::JoinTable> joins;
@@ -138,8 +139,9 @@ pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, ui
                            uint32_t narrays);
 pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
                         uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out);
+pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out, uint64_t state_cap);
 pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states,
-                          uint64_t stride, uint32_t nstates, pgf_result** out);
+                          uint64_t stride, uint32_t nstates, bool bounded, pgf_result** out);
 pgf_status gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec);
 pgf_status gen_schema(int32_t table, pgf_column_spec* schema, uint32_t* ncols);
 }  // namespace pgf

@@ -43,9 +43,13 @@ __global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, bool grouped
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
 // rank order, so Float64 sums are added in a fixed order on every rank.
 template <uint32_t ACC>
-__global__ void table_merge_kernel(GroupTable t, uint32_t nexprs, uint32_t nkeywords, const uint64_t* state) {
+__global__ void table_merge_kernel(GroupTable t, uint32_t nexprs, uint32_t nkeywords, const uint64_t* state, uint64_t max_entries) {
   using Ops = AccOps<ACC>;
-  const uint64_t n = state[0];
+  uint64_t n = state[0];
+  if (n > max_entries) {  // the producing rank had more groups than its state buffer holds
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(t.overflow, 2u);
+    n = max_entries;
+  }
   const uint32_t ew = entry_words(nexprs, t.acc_words);
   for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < n; i += uint64_t(gridDim.x) * blockDim.x) {
     const uint64_t* e = state + 1 + i * ew;
@@ -801,7 +805,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   uint32_t launches = 0;
   ArenaHeader* h_header = reinterpret_cast<ArenaHeader*>(ctx->h_arena);
   uint64_t* h_out = reinterpret_cast<uint64_t*>(ctx->h_arena + sizeof(ArenaHeader));
-  const uint64_t h_out_entries = (kHostArena - sizeof(ArenaHeader) - 8) / (uint64_t(ew) * 8);
+  const uint64_t h_out_entries = (kHostArena / 2 - sizeof(ArenaHeader) - 8) / (uint64_t(ew) * 8);
 
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable& jt = L.build_table;
@@ -917,8 +921,48 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   return PGF_OK;
 }
 
+// Asynchronous partial run for the multi-GPU step: fused kernel + extraction of the partial
+// state are enqueued on the compute stream; nothing is synchronised.  The run's header
+// (counters, overflow flag) is copied to the second half of the pinned mirror and checked by
+// the bounded merge that follows on the same stream.
+constexpr size_t kPartialHeaderOff = kHostArena / 2;
+
+pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out, uint64_t state_cap) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
+  Lowered L;
+  Lowering low(ctx, plan);
+  PGF_TRY(low.run(&L));
+  PGF_TRY(scan_sync_descs(ctx, *L.scan));
+  L.dev.descs = L.scan->d_descs;
+  L.dev.classes = L.scan->d_classes;
+  const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  const uint32_t ew = entry_words(plan->nexprs, aw);
+  if (state_cap < (1 + uint64_t(ew)) * 8) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state buffer too small");
+  const uint64_t max_entries = (state_cap / 8 - 1) / ew;
+  TableAlloc ta;
+  PGF_TRY(arena_table(ctx, L.table_capacity, plan->nexprs, aw, &ta));
+  L.dev.table = ta.t;
+  L.dev.counters = &ta.d_header->counters;
+  const uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.nitems ? L.dev.nitems : 1, uint64_t(ctx->sm_count)));
+  CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
+  if (L.dev.nitems) {
+    if (const ShapeEntry* se = pick_shape(L))
+      CU(ctx, se->fn(L.dev, grid, L.smem, ctx->compute_stream));
+    else
+      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
+  }
+  CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
+  CU(ctx, cudaMemsetAsync(dev_state_out, 0, 8, ctx->compute_stream));
+  PGF_TRY(extract_table(ctx, ta.t, L.table_capacity, plan->nexprs, L.grouped, static_cast<uint64_t*>(dev_state_out), max_entries));
+  CU(ctx, cudaMemcpyAsync(ctx->h_arena + kPartialHeaderOff, ta.d_header, sizeof(ArenaHeader), cudaMemcpyDeviceToHost, ctx->compute_stream));
+  ctx->partial_pending = true;
+  return PGF_OK;
+}
+
 pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states, uint64_t stride,
-                          uint32_t nstates, pgf_result** out) {
+                          uint32_t nstates, bool bounded, pgf_result** out) {
   std::lock_guard<std::mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
@@ -927,15 +971,20 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   PGF_TRY(low.run(&L));
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
-  // size the final table from the partial group counts
-  std::vector<uint64_t> counts(nstates);
+  if (stride < (1 + uint64_t(ew)) * 8) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state stride too small");
+  const uint64_t max_entries = (stride / 8 - 1) / ew;
+  // size the final table from the partial group counts (bounded: from what the strides can hold,
+  // without reading the counts back -- the whole multi-GPU step then synchronises once)
+  std::vector<uint64_t> counts(nstates, max_entries);
   uint64_t total = 0;
-  for (uint32_t i = 0; i < nstates; ++i) {
-    CU(ctx, cudaMemcpyAsync(&counts[i], static_cast<const uint8_t*>(dev_states) + i * stride, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  if (!bounded) {
+    for (uint32_t i = 0; i < nstates; ++i) {
+      CU(ctx, cudaMemcpyAsync(&counts[i], static_cast<const uint8_t*>(dev_states) + i * stride, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   }
-  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   for (uint32_t i = 0; i < nstates; ++i) {
-    if ((1 + counts[i] * ew) * 8 > stride) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state %u overruns its stride", i);
+    if (counts[i] > max_entries) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state %u overruns its stride", i);
     total += counts[i];
   }
   uint64_t capacity = 1;
@@ -950,24 +999,53 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     const uint64_t* st = reinterpret_cast<const uint64_t*>(static_cast<const uint8_t*>(dev_states) + i * stride);
     const uint32_t grid = uint32_t(std::min<uint64_t>((counts[i] + 255) / 256, uint64_t(ctx->sm_count) * 4));
     switch (L.acc_cls) {
-      case CLS_F64: table_merge_kernel<CLS_F64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
-      case CLS_I64: table_merge_kernel<CLS_I64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
-      default: table_merge_kernel<CLS_I128><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st); break;
+      case CLS_F64: table_merge_kernel<CLS_F64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, max_entries); break;
+      case CLS_I64: table_merge_kernel<CLS_I64><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, max_entries); break;
+      default: table_merge_kernel<CLS_I128><<<grid, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, max_entries); break;
     }
     CU(ctx, cudaGetLastError());
   }
   ArenaHeader* h_header = reinterpret_cast<ArenaHeader*>(ctx->h_arena);
+  uint64_t* h_out = reinterpret_cast<uint64_t*>(ctx->h_arena + sizeof(ArenaHeader));
+  const uint64_t h_out_entries = (kPartialHeaderOff - sizeof(ArenaHeader) - 8) / (uint64_t(ew) * 8);
+  uint64_t prefix_entries = 0;
+  if (ta.d_out) {  // small table: extract now, header and result travel with one synchronisation
+    PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, ta.d_out, ta.out_entries));
+    prefix_entries = std::min<uint64_t>(ta.out_entries, h_out_entries);
+    CU(ctx, cudaMemcpyAsync(h_out, ta.d_out, (1 + prefix_entries * ew) * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  }
   CU(ctx, cudaMemcpyAsync(h_header, ta.d_header, sizeof(ArenaHeader), cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  const ArenaHeader* ph = reinterpret_cast<const ArenaHeader*>(ctx->h_arena + kPartialHeaderOff);
+  const bool had_partial = ctx->partial_pending;
+  ctx->partial_pending = false;
+  if (had_partial) {
+    if (ph->counters.bad_rows)
+      return ctx->fail(PGF_ERR_UNSUPPORTED_DATA, "%llu rows carry out-of-line (> 12 byte) view values in a predicate or key column",
+                       (unsigned long long)ph->counters.bad_rows);
+    if (ph->overflow) return ctx->fail(PGF_ERR_STATE, "group table overflow in the partial run: pass a larger expected_groups");
+  }
+  if (h_header->overflow == 2u) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "a partial state holds more groups than its stride can carry");
+  if (h_header->overflow) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "final group table overflow");
   const uint64_t ngroups = L.grouped ? h_header->used : 1;
   const uint64_t bytes = (1 + ngroups * ew) * 8;
-  PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
-  uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
-  CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
-  PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
   std::vector<uint64_t> h_state(1 + ngroups * ew);
-  CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, h_state.size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
-  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  if (ta.d_out) {
+    const uint64_t have = std::min<uint64_t>(ngroups, prefix_entries);
+    std::memcpy(h_state.data(), h_out, (1 + have * ew) * 8);
+    if (ngroups > have) {
+      CU(ctx, cudaMemcpyAsync(h_state.data() + 1 + have * ew, ta.d_out + 1 + have * ew, (ngroups - have) * ew * 8,
+                              cudaMemcpyDeviceToHost, ctx->compute_stream));
+      CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    }
+  } else {
+    PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
+    uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
+    CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
+    PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
+    CU(ctx, cudaMemcpyAsync(h_state.data(), d_state, bytes, cudaMemcpyDeviceToHost, ctx->compute_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  }
   pgf_result* res = new (std::nothrow) pgf_result();
   if (!res) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
   pgf_status st = build_result(ctx, plan, L, h_state, res);
@@ -975,7 +1053,19 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     pgf_result_free(res);
     return st;
   }
-  res->kernel_launches = nstates + 2;
+  res->kernel_launches = nstates + 1;
+  if (had_partial) {  // statistics of the asynchronous partial run that fed this merge
+    const Counters& c = ph->counters;
+    res->rows_in = c.rows_in;
+    res->rows_bloom = c.rows_bloom;
+    res->rows_filtered = c.rows_filtered;
+    res->rows_out = c.rows_out;
+    float ms = 0.f;
+    CU(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+    res->kernel_ms = ms;
+    ctx->last_kernel_ms = ms;
+    res->kernel_launches += 2;
+  }
   *out = res;
   return PGF_OK;
 }

@@ -282,6 +282,16 @@ class PipelineBuilder:
                                                             C.byref(nbytes), C.byref(res)))
         return nbytes.value, self.ctx._take_result(res)
 
+    def run_partial_async(self, dev_ptr: int, capacity_bytes: int) -> None:
+        """Enqueue kernel + partial-state extraction on the compute stream; no synchronisation."""
+        self.ctx._check(_lib.lib().pgf_pipeline_run_partial_async(self.ctx.h, C.byref(self.p), dev_ptr, capacity_bytes))
+
+    def merge_partials_bounded(self, dev_ptr: int, stride_bytes: int, nstates: int) -> PipelineResult:
+        res = C.POINTER(_lib.Result)()
+        self.ctx._check(_lib.lib().pgf_pipeline_merge_partials_bounded(self.ctx.h, C.byref(self.p), dev_ptr, stride_bytes,
+                                                                       nstates, C.byref(res)))
+        return self.ctx._take_result(res)
+
     def merge_partials(self, dev_ptr: int, stride_bytes: int, nstates: int) -> PipelineResult:
         res = C.POINTER(_lib.Result)()
         self.ctx._check(_lib.lib().pgf_pipeline_merge_partials(self.ctx.h, C.byref(self.p), dev_ptr, stride_bytes,

@@ -50,6 +50,37 @@ def test_partial_states_merge_to_the_single_pass_result(ctx, shape, world):
         s.release()
 
 
+@pytest.mark.parametrize("shape", ["q6", "q1"])
+def test_async_partial_and_bounded_merge(ctx, shape):
+    """The one-synchronisation form of the multi-GPU step gives the single-pass result."""
+    rows, world, stride = 150_000, 3, 8192
+    table, gpu = (GenTable.LINEITEM_Q6, U.gpu_q6) if shape == "q6" else (GenTable.LINEITEM_Q1, U.gpu_q1)
+    states = torch.zeros(world * stride, dtype=torch.uint8, device="cuda")
+    shards = []
+    for r in range(world):
+        lo, hi = MG.shard_range(rows, r, world)
+        s = ctx.gen_scan(table, hi - lo, seed=42, first_row=lo)
+        shards.append(s)
+        if r < world - 1:
+            gpu(s).run_partial(states.data_ptr() + r * stride, stride)
+    last = gpu(shards[-1])
+    last.run_partial_async(states.data_ptr() + (world - 1) * stride, stride)   # no synchronisation here
+    merged = last.merge_partials_bounded(states.data_ptr(), stride, world)
+    lo, hi = MG.shard_range(rows, world - 1, world)
+    assert merged.rows_in == hi - lo and merged.kernel_ms > 0
+    whole = ctx.gen_scan(table, rows, seed=42)
+    U.assert_agg_equal(merged, gpu(whole).run())
+    # a stride that cannot carry the groups of a rank is reported, not truncated
+    if shape == "q1":
+        tiny = 8 * (1 + 19 * 2)   # room for two of the four groups
+        small = torch.zeros(tiny, dtype=torch.uint8, device="cuda")
+        last.run_partial_async(small.data_ptr(), tiny)
+        with pytest.raises(pg.PgfError):
+            last.merge_partials_bounded(small.data_ptr(), tiny, 1)
+    for s in shards + [whole]:
+        s.release()
+
+
 def test_bloom_or_merge_on_device(ctx):
     p = BloomParams.new(**pg.GUC_DEFAULT_BLOOM)
     keys = np.random.default_rng(2).integers(-2**60, 2**60, 100_000, dtype=np.int64)

@@ -336,6 +336,19 @@ pgf_status pgf_pipeline_run(pgf_ctx *ctx, const pgf_pipeline *plan, pgf_result *
 void pgf_result_free(pgf_result *result);
 pgf_status pgf_join_table_destroy(pgf_ctx *ctx, uint64_t join_table);
 
+/* Broadcast join across GPUs (HashJoinExec CollectLeft with the build side sharded by page;
+ * SURVEY.md 8e): every rank builds a table from its own pages, exports its rows as
+ * self-contained slot records (row_bytes each: key, NULL flags, payload), the host all-gathers
+ * the fragments (NCCL) and every rank rebuilds the full table from them.  `like_table`
+ * supplies the key / payload schema. */
+typedef struct { uint64_t rows; uint32_t capacity, row_bytes, npayload, reserved; } pgf_join_info;
+pgf_status pgf_join_table_get_info(pgf_ctx *ctx, uint64_t join_table, pgf_join_info *out);
+pgf_status pgf_join_table_export(pgf_ctx *ctx, uint64_t join_table, void *dev_rows_out,
+                                 uint64_t capacity_rows, uint64_t *rows_out);
+pgf_status pgf_join_table_from_fragments(pgf_ctx *ctx, uint64_t like_table, const void *dev_rows,
+                                         uint64_t stride_bytes, const uint64_t *counts,
+                                         uint32_t nfragments, uint64_t *table_out);
+
 /* Partial / Final aggregation across GPUs (AggregateExec Partial -> FinalPartitioned):
  * run the pipeline but leave the per-group partial states in a device buffer; gather the
  * buffers of all ranks (NCCL all-gather by the host) and merge them in rank order into a

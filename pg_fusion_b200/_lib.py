@@ -111,6 +111,10 @@ class Result(C.Structure):
                 ("join_table", u64), ("bloom_rows", u64), ("kernel_ms", C.c_float), ("kernel_launches", u32)]
 
 
+class JoinInfo(C.Structure):
+    _fields_ = [("rows", u64), ("capacity", u32), ("row_bytes", u32), ("npayload", u32), ("reserved", u32)]
+
+
 class GenSpec(C.Structure):
     _fields_ = [("table", i32), ("dense_keys", i32), ("seed", u64), ("first_row", u64), ("rows", u64),
                 ("scale_rows", u64)]
@@ -168,6 +172,9 @@ _SIGNATURES = {
     "pgf_pipeline_run_partial": (i32, [vp, P(Pipeline), vp, u64, P(u64), P(P(Result))]),
     "pgf_pipeline_merge_partials": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_partial_state_bytes": (i32, [P(Pipeline), u64, P(u64)]),
+    "pgf_join_table_get_info": (i32, [vp, u64, P(JoinInfo)]),
+    "pgf_join_table_export": (i32, [vp, u64, vp, u64, P(u64)]),
+    "pgf_join_table_from_fragments": (i32, [vp, u64, vp, u64, P(u64), u32, P(u64)]),
     "pgf_pipeline_run_partial_async": (i32, [vp, P(Pipeline), vp, u64]),
     "pgf_pipeline_merge_partials_bounded": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_gen_scan": (i32, [vp, u64, P(GenSpec)]),

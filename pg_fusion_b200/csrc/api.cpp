@@ -718,6 +718,32 @@ pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
   return PGF_OK;
 }
 
+pgf_status pgf_join_table_get_info(pgf_ctx* ctx, uint64_t join_table, pgf_join_info* out) {
+  if (!ctx || !out) return PGF_ERR_INVALID_ARGUMENT;
+  auto it = ctx->joins.find(join_table);
+  if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)join_table);
+  out->rows = it->second.rows;
+  out->capacity = it->second.capacity;
+  out->row_bytes = it->second.slot_u4 * 16u;
+  out->npayload = it->second.npayload;
+  return PGF_OK;
+}
+pgf_status pgf_join_table_export(pgf_ctx* ctx, uint64_t join_table, void* dev_rows_out, uint64_t capacity_rows, uint64_t* rows_out) {
+  if (!ctx || !dev_rows_out || !rows_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  auto it = ctx->joins.find(join_table);
+  if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)join_table);
+  return join_export(ctx, it->second, dev_rows_out, capacity_rows, rows_out);
+}
+pgf_status pgf_join_table_from_fragments(pgf_ctx* ctx, uint64_t like_table, const void* dev_rows, uint64_t stride_bytes,
+                                         const uint64_t* counts, uint32_t nfragments, uint64_t* table_out) {
+  if (!ctx || (!dev_rows && nfragments) || (!counts && nfragments) || !table_out) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  auto it = ctx->joins.find(like_table);
+  if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)like_table);
+  return join_from_fragments(ctx, it->second, dev_rows, stride_bytes, counts, nfragments, table_out);
+}
+
 pgf_status pgf_gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec) {
   if (!ctx || !spec) return PGF_ERR_INVALID_ARGUMENT;
   if (ctx->sticky) return ctx->sticky;

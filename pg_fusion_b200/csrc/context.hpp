@@ -142,6 +142,9 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
 pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out, uint64_t state_cap);
 pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states,
                           uint64_t stride, uint32_t nstates, bool bounded, pgf_result** out);
+pgf_status join_export(pgf_ctx* ctx, const JoinTable& jt, void* dev_rows_out, uint64_t capacity_rows, uint64_t* rows_out);
+pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* dev_rows, uint64_t stride_bytes,
+                               const uint64_t* counts, uint32_t nfragments, uint64_t* table_out);
 pgf_status gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec);
 pgf_status gen_schema(int32_t table, pgf_column_spec* schema, uint32_t* ncols);
 }  // namespace pgf

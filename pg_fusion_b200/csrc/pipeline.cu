@@ -40,6 +40,42 @@ __global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, bool grouped
   }
 }
 
+// ---- broadcast-join exchange: a built table travels between GPUs as its occupied
+// slots.  Slots are self-contained records {key lo, key hi, occupancy/NULL flags, payload...}.
+__global__ void join_export_kernel(const uint4* slots, uint32_t capacity, uint32_t slot_u4, uint4* out,
+                                   unsigned long long max_rows, unsigned long long* count) {
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < capacity; i += uint64_t(gridDim.x) * blockDim.x) {
+    const uint4 s0 = slots[i * slot_u4];
+    if ((s0.z & 1u) == 0u) continue;
+    const unsigned long long pos = atomicAdd(count, 1ull);
+    if (pos >= max_rows) continue;
+    out[pos * slot_u4] = s0;
+    if (slot_u4 == 2) out[pos * 2 + 1] = slots[i * 2 + 1];
+  }
+}
+
+__global__ void join_import_kernel(uint4* slots, uint8_t* tags, uint32_t mask, uint32_t slot_u4, const uint4* rows, uint64_t nrows) {
+  for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < nrows; r += uint64_t(gridDim.x) * blockDim.x) {
+    const uint4 s0 = rows[r * slot_u4];
+    const uint64_t key = (uint64_t(s0.y) << 32) | s0.x;
+    const uint64_t hk = mix64(key);
+    uint32_t i = uint32_t(hk) & mask;
+    for (;;) {  // capacity >= 2 x rows: an empty slot always exists
+      uint32_t* slot = reinterpret_cast<uint32_t*>(slots + uint64_t(i) * slot_u4);
+      if (atomicCAS(slot + 2, 0u, s0.z) == 0u) {
+        tags[i] = uint8_t(join_tag(hk));
+        if (i < 4u) tags[mask + 1u + i] = uint8_t(join_tag(hk));
+        slot[0] = s0.x;
+        slot[1] = s0.y;
+        slot[3] = s0.w;
+        if (slot_u4 == 2) slots[uint64_t(i) * 2 + 1] = rows[r * 2 + 1];
+        break;
+      }
+      i = (i + 1) & mask;
+    }
+  }
+}
+
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
 // rank order, so Float64 sums are added in a fixed order on every rank.
 template <uint32_t ACC>
@@ -1067,6 +1103,65 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     res->kernel_launches += 2;
   }
   *out = res;
+  return PGF_OK;
+}
+
+pgf_status join_export(pgf_ctx* ctx, const JoinTable& jt, void* dev_rows_out, uint64_t capacity_rows, uint64_t* rows_out) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 4);
+  unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 4);
+  CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
+  const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(jt.capacity) + 255) / 256, uint64_t(ctx->sm_count) * 8));
+  join_export_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, jt.capacity, jt.slot_u4, static_cast<uint4*>(dev_rows_out),
+                                                           capacity_rows, d_cnt);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  if (*h_cnt > capacity_rows)
+    return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "join table holds %llu rows, export buffer has room for %llu", *h_cnt, (unsigned long long)capacity_rows);
+  *rows_out = *h_cnt;
+  return PGF_OK;
+}
+
+pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* dev_rows, uint64_t stride_bytes,
+                               const uint64_t* counts, uint32_t nfragments, uint64_t* table_out) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  uint64_t total = 0;
+  const uint64_t row_bytes = uint64_t(like.slot_u4) * sizeof(uint4);
+  for (uint32_t f = 0; f < nfragments; ++f) {
+    if (counts[f] * row_bytes > stride_bytes) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "fragment %u overruns its stride", f);
+    total += counts[f];
+  }
+  uint64_t cap = 1024;
+  while (cap < total * 2) cap <<= 1;
+  if (cap > (1ull << 31)) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "join build side too large for one table");
+  JoinTable jt = like;
+  jt.capacity = uint32_t(cap);
+  jt.rows = total;
+  const uint64_t slot_bytes = cap * row_bytes, tag_bytes = cap + 16;
+  if (cudaMalloc(&jt.d_slots, slot_bytes + tag_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
+  }
+  cudaError_t e = cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream);
+  uint8_t* tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
+  for (uint32_t f = 0; f < nfragments && e == cudaSuccess; ++f) {
+    if (!counts[f]) continue;
+    const uint4* rows = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(dev_rows) + f * stride_bytes);
+    const uint32_t grid = uint32_t(std::min<uint64_t>((counts[f] + 255) / 256, uint64_t(ctx->sm_count) * 8));
+    join_import_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, tags, jt.capacity - 1, jt.slot_u4, rows, counts[f]);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute_stream);
+  if (e != cudaSuccess) {
+    cudaFree(jt.d_slots);
+    return ctx->cuda_fail(e, "join_from_fragments", __FILE__, __LINE__);
+  }
+  const uint64_t id = ctx->next_handle++;
+  ctx->joins[id] = jt;
+  *table_out = id;
   return PGF_OK;
 }
 

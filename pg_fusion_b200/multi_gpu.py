@@ -45,3 +45,55 @@ def merge_partial_sums(parts: Sequence[dict]) -> dict:
             else:
                 out[k] = (s, c)
     return out
+
+
+# ---- collectives over torch.distributed (NCCL on GPUs); the compute stays in the library ----
+def all_gather_counts(n: int, world: int, device) -> List[int]:
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([int(n)], dtype=torch.int64, device=device)
+    out = torch.empty(world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, t)
+    return [int(x) for x in out.tolist()]
+
+
+def broadcast_join_table(ctx, handle: int, world: int, device) -> int:
+    """Broadcast join: every rank exports the rows of the table it built from its own
+    pages, the fragments are all-gathered (padded to the largest) and every rank rebuilds the full
+    table.  Returns the handle of the full table; the local fragment table is destroyed."""
+    import torch
+    info = ctx.join_table_info(handle)
+    counts = all_gather_counts(info.rows, world, device)
+    stride = max(1, max(counts)) * info.row_bytes
+    local = torch.zeros(stride, dtype=torch.uint8, device=device)
+    n = ctx.join_table_export(handle, local.data_ptr(), stride // info.row_bytes)
+    assert n == info.rows
+    gathered = all_gather_bytes(local, world)
+    torch.cuda.synchronize(device)
+    full = ctx.join_table_from_fragments(handle, gathered.data_ptr(), stride, counts)
+    ctx.destroy_join_table(handle)
+    return full
+
+
+def or_merge_filter(rf, world: int, device) -> None:
+    """Bloom OR-merge: all-gather the word arrays of every rank's filter (still in
+    Building state) and OR them into the local one; bit exact by idempotence."""
+    import torch
+    words = torch.from_numpy(rf.words().view(np.uint8)).to(device)
+    gathered = all_gather_bytes(words, world)
+    torch.cuda.synchronize(device)
+    rf.or_device_words(gathered.data_ptr(), world)
+
+
+def merge_partial_aggregate(plan, world: int, device, max_groups: int):
+    """AggregateExec Partial -> Final across ranks: run the fused pipeline into a partial state,
+    all-gather the states (padded to the largest) and merge them in rank order on every rank."""
+    import torch
+    cap = plan.partial_state_bytes(max_groups)
+    state = torch.zeros(cap, dtype=torch.uint8, device=device)
+    nbytes, stats = plan.run_partial(state.data_ptr(), cap)
+    sizes = all_gather_counts(nbytes, world, device)
+    stride = (max(sizes) + 15) // 16 * 16
+    gathered = all_gather_bytes(state[:stride].contiguous() if stride <= cap else torch.nn.functional.pad(state, (0, stride - cap)), world)
+    torch.cuda.synchronize(device)
+    return plan.merge_partials(gathered.data_ptr(), stride, world), stats

@@ -282,6 +282,11 @@ class PipelineBuilder:
                                                             C.byref(nbytes), C.byref(res)))
         return nbytes.value, self.ctx._take_result(res)
 
+    def partial_state_bytes(self, max_groups: int) -> int:
+        n = C.c_uint64()
+        self.ctx._check(_lib.lib().pgf_partial_state_bytes(C.byref(self.p), max_groups, C.byref(n)))
+        return n.value
+
     def run_partial_async(self, dev_ptr: int, capacity_bytes: int) -> None:
         """Enqueue kernel + partial-state extraction on the compute stream; no synchronisation."""
         self.ctx._check(_lib.lib().pgf_pipeline_run_partial_async(self.ctx.h, C.byref(self.p), dev_ptr, capacity_bytes))
@@ -499,6 +504,24 @@ class Context:
 
     def unregister_host_region(self, ptr: int) -> None:
         self._check(_lib.lib().pgf_ctx_unregister_host_region(self.h, ptr))
+
+    def join_table_info(self, handle: int):
+        info = _lib.JoinInfo()
+        self._check(_lib.lib().pgf_join_table_get_info(self.h, handle, C.byref(info)))
+        return info
+
+    def join_table_export(self, handle: int, dev_ptr: int, capacity_rows: int) -> int:
+        """Occupied slots of a built table as self-contained records in a device buffer; returns the row count."""
+        n = C.c_uint64()
+        self._check(_lib.lib().pgf_join_table_export(self.h, handle, dev_ptr, capacity_rows, C.byref(n)))
+        return n.value
+
+    def join_table_from_fragments(self, like: int, dev_ptr: int, stride_bytes: int, counts: Sequence[int]) -> int:
+        """Rebuild one table from the exported fragments of several ranks (broadcast join)."""
+        arr = (C.c_uint64 * len(counts))(*[int(c) for c in counts])
+        out = C.c_uint64()
+        self._check(_lib.lib().pgf_join_table_from_fragments(self.h, like, dev_ptr, stride_bytes, arr, len(counts), C.byref(out)))
+        return out.value
 
     def destroy_join_table(self, handle: int) -> None:
         self._check(_lib.lib().pgf_join_table_destroy(self.h, handle))

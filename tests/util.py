@@ -173,3 +173,40 @@ def top10(res):
     """ORDER BY revenue DESC, o_orderdate LIMIT 10 (benches/tpch/queries/q03.sql)."""
     rows = [(k[0], a[0], k[1], k[2]) for k, a in zip(res.keys, res.aggs)]
     return sorted(rows, key=lambda r: (-r[1], r[2]))[:10]
+
+
+def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=None, segment=b"BUILDING"):
+    """The Q3 shape with every scan sharded by pages over `world` ranks (one process per GPU):
+    broadcast joins, OR-merged runtime filters, Partial -> Final aggregate."""
+    from pg_fusion_b200 import AggFunc, Cmp, Factor
+    from pg_fusion_b200 import multi_gpu as MG
+    rf1 = rf2 = None
+    if bloom_params is not None:
+        rf1 = ctx.runtime_filter(bloom_params[0])
+        rf1.try_acquire_builder()
+    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1).run()
+    t1 = MG.broadcast_join_table(ctx, r1.join_table, world, device)
+    if rf1 is not None:
+        MG.or_merge_filter(rf1, world, device)
+        rf1.publish_ready()
+    p2 = orders.pipeline()
+    if rf1 is not None:
+        p2.bloom_probe(rf1, 1)
+        rf2 = ctx.runtime_filter(bloom_params[1])
+        rf2.try_acquire_builder()
+    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(t1, 1).build_join(0, [2, 3], rf2).run()
+    t2 = MG.broadcast_join_table(ctx, r2.join_table, world, device)
+    if rf2 is not None:
+        MG.or_merge_filter(rf2, world, device)
+        rf2.publish_ready()
+    p3 = lineitem.pipeline()
+    if rf2 is not None:
+        p3.bloom_probe(rf2, 0)
+    total_orders = ctx.join_table_info(t2).rows
+    p3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(t2, 0)
+          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
+                     expected_groups=max(1024, total_orders)))
+    res, stats = MG.merge_partial_aggregate(p3, world, device, max_groups=max(1024, total_orders))
+    ctx.destroy_join_table(t1)
+    ctx.destroy_join_table(t2)
+    return res, dict(customer=r1, orders=r2, lineitem=stats)

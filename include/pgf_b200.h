@@ -288,6 +288,11 @@ enum {
 #define PGF_MAX_EXPRS 8u
 #define PGF_MAX_AGGS 16u
 #define PGF_MAX_PAYLOAD 4u
+#define PGF_MAX_SORT 4u
+#define PGF_TOPK_DEVICE_MAX 64u
+
+/* One ORDER BY term: output column (group key `index` or aggregate `index`), direction, NULL order. */
+typedef struct { int32_t is_agg; int32_t index; int32_t descending; int32_t nulls_first; } pgf_sort_key;
 
 typedef struct {
   uint64_t scan_id;
@@ -305,6 +310,12 @@ typedef struct {
   pgf_colref build_key;
   uint32_t npayload; pgf_colref payload[PGF_MAX_PAYLOAD];
   uint64_t build_bloom;           /* 0 = none; else a filter in Building state to populate */
+  /* PGF_SINK_AGGREGATE: SortExec / TopK above the aggregate (ORDER BY ... [LIMIT n], e.g.
+   * benches/tpch/queries/q03.sql "ORDER BY revenue DESC, o_orderdate LIMIT 10").  Output rows are
+   * returned in this order; with limit <= PGF_TOPK_DEVICE_MAX the selection runs on the device
+   * and only `limit` rows leave the GPU.  DataFusion defaults: ASC NULLS LAST, DESC NULLS FIRST. */
+  uint32_t nsort;  pgf_sort_key sort[PGF_MAX_SORT];
+  uint64_t limit;                 /* 0 = no limit */
 } pgf_pipeline;
 
 /* Result values */
@@ -329,11 +340,30 @@ typedef struct {
   uint64_t bloom_rows;     /* keys inserted into build_bloom (RuntimeFilterBuildRowsTotal) */
   float kernel_ms;         /* device time of the fused kernel(s), CUDA events */
   uint32_t kernel_launches;
+  /* Transport types of the output columns (PGF_T_*), keys first, then aggregates: group keys
+   * keep their page type; SUM/AVG(Float64) and AVG(int) -> Float64, SUM(int) and COUNT -> Int64,
+   * SUM/AVG(Decimal128) -> Decimal128 (same mapping as DataFusion's aggregate return types
+   * after worker_runtime/src/result_pages.rs:201-249 normalize_result_transport_schema). */
+  int32_t key_type[PGF_MAX_KEYS];
+  int32_t agg_type[PGF_MAX_AGGS];
 } pgf_result;
 
 pgf_status pgf_pipeline_check(pgf_ctx *ctx, const pgf_pipeline *plan); /* eligibility only */
 pgf_status pgf_pipeline_run(pgf_ctx *ctx, const pgf_pipeline *plan, pgf_result **result_out);
 void pgf_result_free(pgf_result *result);
+
+/* Result pages.  Replaces ResultPageProducer::encode_pending_page + BatchPageEncoder
+ * (worker_runtime/src/result_pages.rs:150-196; page/batch_encoder/src/encoder.rs:49-298) for
+ * the aggregate output of a pipeline: rows are encoded into transfer pages (20-byte header, kind
+ * 0x4152, payload = one arrow_layout block of page_size - 20 bytes with max_rows = the fixed row
+ * cap of the schema) that slot_import / ArrowPageDecoder consume unchanged.  Keys are nullable
+ * columns; SUM / AVG are nullable, COUNT is not.  Strings are inline views (<= 12 bytes).
+ * `first_row` / `max_pages` allow page-at-a-time production like next_step(); *rows_done is the
+ * number of rows encoded by this call. */
+pgf_status pgf_result_schema(const pgf_result *result, pgf_column_spec *schema_out, uint32_t *ncols_out);
+pgf_status pgf_result_encode_pages(const pgf_result *result, uint32_t page_size, uint64_t first_row,
+                                   uint8_t *pages_out, uint64_t max_pages, uint64_t *npages_out,
+                                   uint64_t *rows_done);
 pgf_status pgf_join_table_destroy(pgf_ctx *ctx, uint64_t join_table);
 
 /* Broadcast join across GPUs (HashJoinExec CollectLeft with the build side sharded by page;

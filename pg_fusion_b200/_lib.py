@@ -84,6 +84,10 @@ class BloomProbe(C.Structure):
     _fields_ = [("bloom", u64), ("expected_generation", u64), ("key", ColRef)]
 
 
+class SortKey(C.Structure):
+    _fields_ = [("is_agg", i32), ("index", i32), ("descending", i32), ("nulls_first", i32)]
+
+
 class Pipeline(C.Structure):
     _fields_ = [
         ("scan_id", u64),
@@ -98,6 +102,8 @@ class Pipeline(C.Structure):
         ("build_key", ColRef),
         ("npayload", u32), ("payload", ColRef * MAX_PAYLOAD),
         ("build_bloom", u64),
+        ("nsort", u32), ("sort", SortKey * 4),
+        ("limit", u64),
     ]
 
 
@@ -108,7 +114,8 @@ class Value(C.Structure):
 class Result(C.Structure):
     _fields_ = [("rows_in", u64), ("rows_bloom", u64), ("rows_filtered", u64), ("rows_out", u64),
                 ("ngroups", u64), ("nkeys", u32), ("naggs", u32), ("keys", P(Value)), ("aggs", P(Value)),
-                ("join_table", u64), ("bloom_rows", u64), ("kernel_ms", C.c_float), ("kernel_launches", u32)]
+                ("join_table", u64), ("bloom_rows", u64), ("kernel_ms", C.c_float), ("kernel_launches", u32),
+                ("key_type", i32 * 4), ("agg_type", i32 * 16)]
 
 
 class JoinInfo(C.Structure):
@@ -172,6 +179,8 @@ _SIGNATURES = {
     "pgf_pipeline_run_partial": (i32, [vp, P(Pipeline), vp, u64, P(u64), P(P(Result))]),
     "pgf_pipeline_merge_partials": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_partial_state_bytes": (i32, [P(Pipeline), u64, P(u64)]),
+    "pgf_result_schema": (i32, [P(Result), P(ColumnSpec), P(u32)]),
+    "pgf_result_encode_pages": (i32, [P(Result), u32, u64, vp, u64, P(u64), P(u64)]),
     "pgf_join_table_get_info": (i32, [vp, u64, P(JoinInfo)]),
     "pgf_join_table_export": (i32, [vp, u64, vp, u64, P(u64)]),
     "pgf_join_table_from_fragments": (i32, [vp, u64, vp, u64, P(u64), u32, P(u64)]),

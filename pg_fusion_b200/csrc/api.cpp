@@ -1,5 +1,6 @@
 // extern "C" surface of libpgf_b200.so: context, host-side layout, scan ingest and the
 // Bloom lifecycle.  Kernels live in the .cu files.
+#include <algorithm>
 #include <cstring>
 
 #include "context.hpp"
@@ -179,6 +180,7 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   if (ctx->h_flags) cudaFreeHost(ctx->h_flags);
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->d_out) cudaFree(ctx->d_out);
+  if (ctx->d_topk) cudaFree(ctx->d_topk);
   if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
@@ -707,6 +709,89 @@ void pgf_result_free(pgf_result* r) {
   delete[] r->aggs;
   delete r;
 }
+/* ---- result pages (ResultPageProducer / BatchPageEncoder) ---- */
+pgf_status pgf_result_schema(const pgf_result* r, pgf_column_spec* schema_out, uint32_t* ncols_out) {
+  if (!r || !schema_out || !ncols_out) return PGF_ERR_INVALID_ARGUMENT;
+  uint32_t n = 0;
+  for (uint32_t k = 0; k < r->nkeys; ++k) schema_out[n++] = pgf_column_spec{uint16_t(r->key_type[k]), 1};
+  for (uint32_t a = 0; a < r->naggs; ++a) {
+    // COUNT never yields NULL; SUM / AVG over no (non-null) rows do
+    bool nullable = false;
+    for (uint64_t g = 0; g < r->ngroups && !nullable; ++g) nullable = r->aggs[g * r->naggs + a].kind == PGF_V_NULL;
+    const bool is_count = r->agg_type[a] == PGF_T_INT64 && !nullable;
+    schema_out[n++] = pgf_column_spec{uint16_t(r->agg_type[a]), uint16_t(is_count ? 0 : 1)};
+  }
+  *ncols_out = n;
+  return n ? PGF_OK : PGF_ERR_INVALID_ARGUMENT;
+}
+
+namespace {
+// one output cell -> its fixed-width slot (integers narrow to the column width; strings become
+// inline ByteViews: len + up to 12 bytes, zero padded, page/arrow_layout/src/raw.rs:114-126)
+void put_cell(uint8_t* dst, int type, const pgf_value& v) {
+  switch (type) {
+    case PGF_T_INT16: { const int16_t x = int16_t(v.lo); std::memcpy(dst, &x, 2); break; }
+    case PGF_T_INT32: { const int32_t x = int32_t(v.lo); std::memcpy(dst, &x, 4); break; }
+    case PGF_T_INT64: std::memcpy(dst, &v.lo, 8); break;
+    case PGF_T_FLOAT32: { const float x = float(v.f64); std::memcpy(dst, &x, 4); break; }
+    case PGF_T_FLOAT64: std::memcpy(dst, &v.f64, 8); break;
+    case PGF_T_DECIMAL128: std::memcpy(dst, &v.lo, 8); std::memcpy(dst + 8, &v.hi, 8); break;
+    default: {  // views
+      std::memset(dst, 0, 16);
+      const int32_t len = v.slen;
+      std::memcpy(dst, &len, 4);
+      std::memcpy(dst + 4, v.str, size_t(len > 12 ? 12 : len));
+    }
+  }
+}
+}  // namespace
+
+pgf_status pgf_result_encode_pages(const pgf_result* r, uint32_t page_size, uint64_t first_row, uint8_t* pages_out,
+                                   uint64_t max_pages, uint64_t* npages_out, uint64_t* rows_done) {
+  if (!r || !npages_out || (!pages_out && max_pages)) return PGF_ERR_INVALID_ARGUMENT;
+  if (page_size <= kPageHeaderLen + 64 || first_row > r->ngroups) return PGF_ERR_INVALID_ARGUMENT;
+  pgf_column_spec schema[PGF_MAX_KEYS + PGF_MAX_AGGS];
+  uint32_t ncols = 0;
+  PGF_TRY(pgf_result_schema(r, schema, &ncols));
+  const uint32_t block_size = page_size - kPageHeaderLen;
+  uint32_t cap = 0;
+  PGF_TRY(fixed_row_cap(schema, ncols, block_size, &cap));
+  if (cap == 0) return PGF_ERR_LAYOUT_DOES_NOT_FIT;
+  pgf_layout_plan plan;
+  PGF_TRY(plan_layout(schema, ncols, cap, block_size, &plan));
+  uint64_t row = first_row, pages = 0;
+  std::vector<uint8_t> values(size_t(cap) * 16), validity((cap + 7) / 8);
+  while (row < r->ngroups && pages < max_pages) {
+    const uint32_t n = uint32_t(std::min<uint64_t>(cap, r->ngroups - row));
+    uint8_t* page = pages_out + pages * uint64_t(page_size);
+    std::memset(page, 0, page_size);
+    encode_page_header(uint16_t(PGF_ARROW_LAYOUT_BATCH_KIND), 0, block_size, page);
+    uint8_t* block = page + kPageHeaderLen;
+    PGF_TRY(init_block(block, block_size, plan));
+    for (uint32_t c = 0; c < ncols; ++c) {
+      const int type = schema[c].type_tag;
+      const uint32_t w = row_width(type);
+      std::fill(validity.begin(), validity.end(), uint8_t(0));
+      for (uint32_t i = 0; i < n; ++i) {
+        const pgf_value& v = c < r->nkeys ? r->keys[(row + i) * r->nkeys + c] : r->aggs[(row + i) * r->naggs + (c - r->nkeys)];
+        if (v.kind == PGF_V_NULL) {
+          std::memset(values.data() + size_t(i) * w, 0, w);
+        } else {
+          validity[i >> 3] |= uint8_t(1u << (i & 7));
+          put_cell(values.data() + size_t(i) * w, type, v);
+        }
+      }
+      PGF_TRY(write_column(block, block_size, c, n, values.data(), schema[c].nullable ? validity.data() : nullptr));
+    }
+    PGF_TRY(set_row_count(block, block_size, n));
+    row += n;
+    ++pages;
+  }
+  *npages_out = pages;
+  if (rows_done) *rows_done = row - first_row;
+  return PGF_OK;
+}
+
 pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
   if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
   auto it = ctx->joins.find(join_table);

@@ -83,6 +83,8 @@ struct pgf_ctx {
   size_t d_arena_cap = 0;
   uint8_t* d_out = nullptr;             // result entries of tables too large for the arena prefix
   size_t d_out_cap = 0;
+  uint8_t* d_topk = nullptr;            // scratch of the device top-k selection
+  size_t d_topk_cap = 0;
   uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
   bool partial_pending = false;         // an asynchronous partial run awaits its merge
   std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;

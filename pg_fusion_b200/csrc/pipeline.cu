@@ -76,6 +76,126 @@ __global__ void join_import_kernel(uint4* slots, uint8_t* tags, uint32_t mask, u
   }
 }
 
+// ---- SortExec / TopK above the aggregate -------------------------------------------------
+// ORDER BY over the extracted group entries.  With a small LIMIT the k best entries are
+// selected on the device (k rounds of a parallel arg-best reduction under the ORDER BY
+// comparator) and only those leave the GPU; the host puts the k rows in their final order.
+enum : uint32_t { SK_KEY_INT = 0, SK_KEY_VIEW = 1, SK_KEY_DEC = 2, SK_F64_SUM = 3, SK_F64_AVG = 4, SK_I64_SUM = 5,
+                  SK_I128_SUM = 6, SK_I128_AVG = 7, SK_COUNT = 8 };
+struct DevSortKey {
+  uint32_t kind, word, cnt_word, null_bit, desc, nulls_first;
+};
+struct DevSort {
+  uint32_t n, ew;
+  DevSortKey k[PGF_MAX_SORT];
+};
+
+__device__ __forceinline__ int cmp_u64(uint64_t a, uint64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+__device__ __forceinline__ int cmp_i64(int64_t a, int64_t b) { return a < b ? -1 : (a > b ? 1 : 0); }
+__device__ __forceinline__ int cmp_f64_total(double a, double b) {  // IEEE totalOrder, as arrow's sort
+  int64_t x = __double_as_longlong(a), y = __double_as_longlong(b);
+  x ^= int64_t(uint64_t(x >> 63) >> 1);
+  y ^= int64_t(uint64_t(y >> 63) >> 1);
+  return cmp_i64(x, y);
+}
+__device__ __forceinline__ int cmp_i128(const uint64_t* a, const uint64_t* b) {
+  const int c = cmp_i64(int64_t(a[1]), int64_t(b[1]));
+  return c ? c : cmp_u64(a[0], b[0]);
+}
+__device__ __forceinline__ int cmp_view(const uint64_t* a, const uint64_t* b) {  // bytes, then length
+  auto be = [](uint32_t v) { return __byte_perm(v, 0, 0x0123); };
+  const uint32_t pa[3] = {be(uint32_t(a[0] >> 32)), be(uint32_t(a[1])), be(uint32_t(a[1] >> 32))};
+  const uint32_t pb[3] = {be(uint32_t(b[0] >> 32)), be(uint32_t(b[1])), be(uint32_t(b[1] >> 32))};
+  for (int i = 0; i < 3; ++i)
+    if (pa[i] != pb[i]) return pa[i] < pb[i] ? -1 : 1;
+  return cmp_u64(uint32_t(a[0]), uint32_t(b[0]));
+}
+
+// < 0: entry a sorts before entry b.  Ties are broken by the raw key words so the order is total.
+__device__ int sort_compare(const DevSort& S, const uint64_t* a, const uint64_t* b) {
+  for (uint32_t i = 0; i < S.n; ++i) {
+    const DevSortKey& k = S.k[i];
+    bool na, nb;
+    if (k.kind <= SK_KEY_DEC) {
+      na = (a[kKeyWords] >> k.null_bit) & 1;
+      nb = (b[kKeyWords] >> k.null_bit) & 1;
+    } else if (k.kind == SK_COUNT) {
+      na = nb = false;
+    } else {
+      na = a[k.cnt_word] == 0;
+      nb = b[k.cnt_word] == 0;
+    }
+    if (na || nb) {
+      if (na && nb) continue;
+      return (na == bool(k.nulls_first)) ? -1 : 1;
+    }
+    int c;
+    switch (k.kind) {
+      case SK_KEY_INT: c = cmp_i64(int64_t(a[k.word]), int64_t(b[k.word])); break;
+      case SK_KEY_VIEW: c = cmp_view(a + k.word, b + k.word); break;
+      case SK_KEY_DEC: c = cmp_i128(a + k.word, b + k.word); break;
+      case SK_F64_SUM: c = cmp_f64_total(__longlong_as_double(a[k.word]), __longlong_as_double(b[k.word])); break;
+      case SK_F64_AVG:
+        c = cmp_f64_total(__longlong_as_double(a[k.word]) / double(a[k.cnt_word]), __longlong_as_double(b[k.word]) / double(b[k.cnt_word]));
+        break;
+      case SK_I64_SUM: c = cmp_i64(int64_t(a[k.word]), int64_t(b[k.word])); break;
+      case SK_I128_SUM: c = cmp_i128(a + k.word, b + k.word); break;
+      case SK_I128_AVG: {
+        const __int128 x = (__int128)(((unsigned __int128)a[k.word + 1] << 64) | a[k.word]) * 10000 / (__int128)a[k.cnt_word];
+        const __int128 y = (__int128)(((unsigned __int128)b[k.word + 1] << 64) | b[k.word]) * 10000 / (__int128)b[k.cnt_word];
+        c = x < y ? -1 : (x > y ? 1 : 0);
+        break;
+      }
+      default: c = cmp_u64(a[k.cnt_word], b[k.cnt_word]); break;  // COUNT
+    }
+    if (c) return k.desc ? -c : c;
+  }
+  for (uint32_t w = 0; w <= kKeyWords; ++w)
+    if (a[w] != b[w]) return a[w] < b[w] ? -1 : 1;
+  return 0;
+}
+
+constexpr uint32_t kTopkThreads = 256;
+constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t better(const DevSort& S, const uint64_t* entries, uint32_t x, uint32_t y) {
+  if (x == kNoEntry) return y;
+  if (y == kNoEntry) return x;
+  return sort_compare(S, entries + uint64_t(x) * S.ew, entries + uint64_t(y) * S.ew) <= 0 ? x : y;
+}
+
+__device__ uint32_t block_best(const DevSort& S, const uint64_t* entries, uint32_t mine) {
+  __shared__ uint32_t sbest[kTopkThreads];
+  sbest[threadIdx.x] = mine;
+  __syncthreads();
+  for (uint32_t o = kTopkThreads / 2; o; o >>= 1) {
+    if (threadIdx.x < o) sbest[threadIdx.x] = better(S, entries, sbest[threadIdx.x], sbest[threadIdx.x + o]);
+    __syncthreads();
+  }
+  return sbest[0];
+}
+
+// one selection round: every block proposes its best entry that is not taken yet
+__global__ void __launch_bounds__(kTopkThreads) topk_round_kernel(DevSort S, const uint64_t* entries, uint32_t n,
+                                                                 const uint8_t* taken, uint32_t* blk_best) {
+  uint32_t mine = kNoEntry;
+  for (uint32_t i = blockIdx.x * kTopkThreads + threadIdx.x; i < n; i += gridDim.x * kTopkThreads)
+    if (!taken[i]) mine = better(S, entries, mine, i);
+  const uint32_t b = block_best(S, entries, mine);
+  if (threadIdx.x == 0) blk_best[blockIdx.x] = b;
+}
+
+// ... and one block picks the winner of the round, marks it and copies it to the output
+__global__ void __launch_bounds__(kTopkThreads) topk_pick_kernel(DevSort S, const uint64_t* entries, uint32_t nblocks,
+                                                                const uint32_t* blk_best, uint8_t* taken, uint64_t* out, uint32_t round) {
+  uint32_t mine = kNoEntry;
+  for (uint32_t i = threadIdx.x; i < nblocks; i += kTopkThreads) mine = better(S, entries, mine, blk_best[i]);
+  const uint32_t b = block_best(S, entries, mine);
+  if (b == kNoEntry) return;
+  if (threadIdx.x == 0) { taken[b] = 1; out[0] = round + 1; }
+  for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out[1 + uint64_t(round) * S.ew + w] = entries[uint64_t(b) * S.ew + w];
+}
+
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
 // rank order, so Float64 sums are added in a fixed order on every rank.
 template <uint32_t ACC>
@@ -658,6 +778,12 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
   res->ngroups = n;
   res->nkeys = plan->nkeys;
   res->naggs = plan->naggs;
+  for (uint32_t k = 0; k < plan->nkeys; ++k) res->key_type[k] = L.key_types[k];
+  for (uint32_t a = 0; a < plan->naggs; ++a) {
+    const pgf_agg& ag = plan->aggs[a];
+    if (ag.func == PGF_AGG_COUNT_STAR || ag.func == PGF_AGG_COUNT) res->agg_type[a] = PGF_T_INT64;
+    else res->agg_type[a] = L.acc_cls == CLS_F64 ? PGF_T_FLOAT64 : L.acc_cls == CLS_I64 ? PGF_T_INT64 : PGF_T_DECIMAL128;
+  }
   res->keys = new (std::nothrow) pgf_value[n * (plan->nkeys ? plan->nkeys : 1) + 1]();
   res->aggs = new (std::nothrow) pgf_value[n * (plan->naggs ? plan->naggs : 1) + 1]();
   if (!res->keys || !res->aggs) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
@@ -698,6 +824,148 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
     }
   }
   return PGF_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+pgf_status grow(pgf_ctx* ctx, uint8_t** buf, size_t* cap, size_t need, const char* what) {
+  if (*cap >= need) return PGF_OK;
+  if (*buf) {
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    cudaFree(*buf);
+    *buf = nullptr;
+    *cap = 0;
+  }
+  const size_t want = align_up(need + need / 4, 1 << 20);
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %zu bytes for %s", want, what);
+  }
+  *buf = static_cast<uint8_t*>(p);
+  *cap = want;
+  return PGF_OK;
+}
+
+// ---- ORDER BY / LIMIT: lowering, device top-k driver, host ordering of the returned rows ----
+pgf_status lower_sort(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L, DevSort* S) {
+  const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
+  S->n = plan->nsort;
+  S->ew = entry_words(plan->nexprs, aw);
+  if (plan->nsort > PGF_MAX_SORT) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "too many ORDER BY terms");
+  const uint32_t acc0 = kKeyWords + 1, cnt0 = acc0 + plan->nexprs * aw;
+  for (uint32_t i = 0; i < plan->nsort; ++i) {
+    const pgf_sort_key& sk = plan->sort[i];
+    DevSortKey& d = S->k[i];
+    d = DevSortKey{};
+    d.desc = sk.descending != 0;
+    d.nulls_first = sk.nulls_first != 0;
+    if (!sk.is_agg) {
+      if (sk.index < 0 || uint32_t(sk.index) >= plan->nkeys) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "ORDER BY key %d out of range", sk.index);
+      const int t = L.key_types[sk.index];
+      d.kind = is_int_type(t) ? SK_KEY_INT : (t == PGF_T_DECIMAL128 ? SK_KEY_DEC : SK_KEY_VIEW);
+      d.word = L.dev.keys[sk.index].word;
+      d.null_bit = uint32_t(sk.index);
+    } else {
+      if (sk.index < 0 || uint32_t(sk.index) >= plan->naggs) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "ORDER BY aggregate %d out of range", sk.index);
+      const pgf_agg& ag = plan->aggs[sk.index];
+      if (ag.func == PGF_AGG_COUNT_STAR) { d.kind = SK_COUNT; d.cnt_word = cnt0 + plan->nexprs; continue; }
+      d.word = acc0 + uint32_t(ag.expr) * aw;
+      d.cnt_word = cnt0 + uint32_t(ag.expr);
+      if (ag.func == PGF_AGG_COUNT) d.kind = SK_COUNT;
+      else if (L.acc_cls == CLS_F64) d.kind = ag.func == PGF_AGG_AVG ? SK_F64_AVG : SK_F64_SUM;
+      else if (L.acc_cls == CLS_I64) d.kind = SK_I64_SUM;
+      else d.kind = ag.func == PGF_AGG_AVG ? SK_I128_AVG : SK_I128_SUM;
+    }
+  }
+  return PGF_OK;
+}
+
+// Selects the k first entries under the ORDER BY on the device; h_state receives [k][entries].
+pgf_status device_topk(pgf_ctx* ctx, const DevSort& S, const uint64_t* d_entries, uint64_t n, uint32_t k,
+                       std::vector<uint64_t>* h_state, uint32_t* launches) {
+  const uint32_t nblocks = uint32_t(std::min<uint64_t>((n + kTopkThreads - 1) / kTopkThreads, uint64_t(ctx->sm_count) * 4));
+  const size_t o_taken = 0, o_best = align_up(n, 16), o_out = align_up(o_best + nblocks * 4, 16);
+  const size_t bytes = o_out + (1 + size_t(k) * S.ew) * 8;
+  PGF_TRY(grow(ctx, &ctx->d_topk, &ctx->d_topk_cap, bytes, "the top-k scratch"));
+  uint8_t* taken = ctx->d_topk + o_taken;
+  uint32_t* blk_best = reinterpret_cast<uint32_t*>(ctx->d_topk + o_best);
+  uint64_t* out = reinterpret_cast<uint64_t*>(ctx->d_topk + o_out);
+  CU(ctx, cudaMemsetAsync(ctx->d_topk, 0, bytes, ctx->compute_stream));
+  for (uint32_t r = 0; r < k; ++r) {
+    topk_round_kernel<<<nblocks, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, uint32_t(n), taken, blk_best);
+    topk_pick_kernel<<<1, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, nblocks, blk_best, taken, out, r);
+  }
+  CU(ctx, cudaGetLastError());
+  *launches += 2 * k;
+  h_state->assign(1 + size_t(k) * S.ew, 0);
+  CU(ctx, cudaMemcpyAsync(h_state->data(), out, h_state->size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  return PGF_OK;
+}
+
+int cmp_value(const pgf_value& a, const pgf_value& b) {  // ascending, both non-NULL
+  switch (a.kind) {
+    case PGF_V_F64: {
+      int64_t x, y;
+      std::memcpy(&x, &a.f64, 8);
+      std::memcpy(&y, &b.f64, 8);
+      x ^= int64_t(uint64_t(x >> 63) >> 1);  // IEEE totalOrder
+      y ^= int64_t(uint64_t(y >> 63) >> 1);
+      return x < y ? -1 : (x > y ? 1 : 0);
+    }
+    case PGF_V_I64: return a.lo < b.lo ? -1 : (a.lo > b.lo ? 1 : 0);
+    case PGF_V_I128:
+      if (a.hi != b.hi) return a.hi < b.hi ? -1 : 1;
+      return uint64_t(a.lo) < uint64_t(b.lo) ? -1 : (uint64_t(a.lo) > uint64_t(b.lo) ? 1 : 0);
+    default: {
+      const int n = std::min(a.slen, b.slen);
+      const int c = std::memcmp(a.str, b.str, size_t(n));
+      if (c) return c < 0 ? -1 : 1;
+      return a.slen < b.slen ? -1 : (a.slen > b.slen ? 1 : 0);
+    }
+  }
+}
+
+// Orders the rows of a result by the plan's ORDER BY and applies the LIMIT (host side: the rows
+// are either few, or already the device-selected top k).
+void sort_result(const pgf_pipeline* plan, pgf_result* res) {
+  if (!plan->nsort && !plan->limit) return;
+  const uint64_t n = res->ngroups;
+  std::vector<uint64_t> idx(n);
+  for (uint64_t i = 0; i < n; ++i) idx[i] = i;
+  auto cell = [&](uint64_t row, const pgf_sort_key& sk) -> const pgf_value& {
+    return sk.is_agg ? res->aggs[row * res->naggs + sk.index] : res->keys[row * res->nkeys + sk.index];
+  };
+  if (plan->nsort)
+    std::stable_sort(idx.begin(), idx.end(), [&](uint64_t x, uint64_t y) {
+      for (uint32_t i = 0; i < plan->nsort; ++i) {
+        const pgf_sort_key& sk = plan->sort[i];
+        const pgf_value &a = cell(x, sk), &b = cell(y, sk);
+        const bool na = a.kind == PGF_V_NULL, nb = b.kind == PGF_V_NULL;
+        if (na || nb) {
+          if (na && nb) continue;
+          return na == (sk.nulls_first != 0);
+        }
+        const int c = cmp_value(a, b);
+        if (c) return sk.descending ? c > 0 : c < 0;
+      }
+      return false;
+    });
+  const uint64_t keep = plan->limit && plan->limit < n ? plan->limit : n;
+  const uint32_t nk = res->nkeys ? res->nkeys : 1, na = res->naggs ? res->naggs : 1;
+  pgf_value* keys = new (std::nothrow) pgf_value[keep * nk + 1]();
+  pgf_value* aggs = new (std::nothrow) pgf_value[keep * na + 1]();
+  if (!keys || !aggs) { delete[] keys; delete[] aggs; return; }
+  for (uint64_t i = 0; i < keep; ++i) {
+    for (uint32_t k = 0; k < res->nkeys; ++k) keys[i * res->nkeys + k] = res->keys[idx[i] * res->nkeys + k];
+    for (uint32_t a = 0; a < res->naggs; ++a) aggs[i * res->naggs + a] = res->aggs[idx[i] * res->naggs + a];
+  }
+  delete[] res->keys;
+  delete[] res->aggs;
+  res->keys = keys;
+  res->aggs = aggs;
+  res->ngroups = keep;
 }
 
 // A specialised instantiation exists when every term is a plain range over the load kinds of
@@ -742,27 +1010,6 @@ struct TableAlloc {
   uint64_t* d_out = nullptr; // [count][entries] (small tables only)
   uint64_t out_entries = 0;
 };
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-pgf_status grow(pgf_ctx* ctx, uint8_t** buf, size_t* cap, size_t need, const char* what) {
-  if (*cap >= need) return PGF_OK;
-  if (*buf) {
-    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
-    cudaFree(*buf);
-    *buf = nullptr;
-    *cap = 0;
-  }
-  const size_t want = align_up(need + need / 4, 1 << 20);
-  void* p = nullptr;
-  if (cudaMalloc(&p, want) != cudaSuccess) {
-    cudaGetLastError();
-    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %zu bytes for %s", want, what);
-  }
-  *buf = static_cast<uint8_t*>(p);
-  *cap = want;
-  return PGF_OK;
-}
 
 // Places header, group table and (for small tables) the result entries in the context's
 // grow-only arena and clears header + table with one memset on the compute stream.
@@ -908,7 +1155,25 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
         ++launches;
       } else {
         std::vector<uint64_t> h_state(1 + ngroups * ew);
-        if (inline_out) {
+        const bool topk = plan->nsort && plan->limit && plan->limit <= PGF_TOPK_DEVICE_MAX && ngroups > plan->limit;
+        if (topk) {
+          // TopK: only `limit` rows leave the GPU
+          const uint64_t* d_entries = nullptr;
+          if (inline_out) {
+            d_entries = ta.d_out + 1;
+          } else {
+            PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
+            uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
+            CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
+            PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
+            ++launches;
+            d_entries = d_state + 1;
+          }
+          DevSort S;
+          PGF_TRY(lower_sort(ctx, plan, L, &S));
+          PGF_TRY(device_topk(ctx, S, d_entries, ngroups, uint32_t(plan->limit), &h_state, &launches));
+          if (h_state[0] != plan->limit) return ctx->fail(PGF_ERR_STATE, "top-k selection returned %llu rows", (unsigned long long)h_state[0]);
+        } else if (inline_out) {
           const uint64_t have = std::min<uint64_t>(ngroups, prefix_entries);
           std::memcpy(h_state.data(), h_out, (1 + have * ew) * 8);
           if (ngroups > have) {
@@ -925,9 +1190,14 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
           CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
           ++launches;
         }
-        if (h_state[0] != ngroups) return ctx->fail(PGF_ERR_STATE, "group table extraction found %llu groups, expected %llu",
-                                                    (unsigned long long)h_state[0], (unsigned long long)ngroups);
+        if (!topk && h_state[0] != ngroups) return ctx->fail(PGF_ERR_STATE, "group table extraction found %llu groups, expected %llu",
+                                                             (unsigned long long)h_state[0], (unsigned long long)ngroups);
+        if (plan->nsort) {  // validates the ORDER BY terms even when the host orders the rows
+          DevSort S;
+          PGF_TRY(lower_sort(ctx, plan, L, &S));
+        }
         PGF_TRY(build_result(ctx, plan, L, h_state, res));
+        sort_result(plan, res);
       }
     }
     break;
@@ -1089,6 +1359,7 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     pgf_result_free(res);
     return st;
   }
+  sort_result(plan, res);  // ORDER BY / LIMIT of the final (merged) result
   res->kernel_launches = nstates + 1;
   if (had_partial) {  // statistics of the asynchronous partial run that fed this merge
     const Counters& c = ph->counters;

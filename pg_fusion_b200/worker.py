@@ -105,6 +105,30 @@ def _value_py(v: _lib.Value):
     raise ValueError(f"bad value kind {v.kind}")
 
 
+def encode_result_pages(res, page_size: int = 65536):
+    """pgf_result -> (transport schema, pages) through pgf_result_schema / pgf_result_encode_pages."""
+    L = _lib.lib()
+    arr = (_lib.ColumnSpec * 20)()
+    n = C.c_uint32()
+    rc = L.pgf_result_schema(res, arr, C.byref(n))
+    if rc:
+        raise PgfError(rc, "pgf_result_schema")
+    schema = [ColumnSpec(TypeTag(arr[i].type_tag), bool(arr[i].nullable)) for i in range(n.value)]
+    cap = C.c_uint32()
+    rc = L.pgf_layout_fixed_row_cap(arr, n.value, page_size - 20, C.byref(cap))
+    if rc or cap.value == 0:
+        raise PgfError(rc or 113, "result row does not fit a page")
+    ngroups = res.contents.ngroups
+    npages = (ngroups + cap.value - 1) // cap.value
+    pages = np.zeros((max(npages, 1), page_size), dtype=np.uint8)
+    got, rows = C.c_uint64(), C.c_uint64()
+    rc = L.pgf_result_encode_pages(res, page_size, 0, pages.ctypes.data_as(C.c_void_p), npages, C.byref(got), C.byref(rows))
+    if rc:
+        raise PgfError(rc, "pgf_result_encode_pages")
+    assert got.value == npages and rows.value == ngroups
+    return schema, pages[:npages]
+
+
 @dataclass
 class PipelineResult:
     rows_in: int
@@ -117,6 +141,8 @@ class PipelineResult:
     bloom_rows: int
     kernel_ms: float
     kernel_launches: int
+    result_schema: Optional[List[ColumnSpec]] = None   # transport schema of the result pages
+    result_pages: Optional[np.ndarray] = None          # [npages, page_size] uint8, reference page format
 
     def by_key(self) -> Dict[tuple, tuple]:
         return dict(zip(self.keys, self.aggs))
@@ -253,6 +279,17 @@ class PipelineBuilder:
         self.p.expected_groups = expected_groups
         return self
 
+    def order_by(self, terms: Sequence[tuple], limit: int = 0) -> "PipelineBuilder":
+        """SortExec / TopK above the aggregate.  terms: ("key"|"agg", index, descending[, nulls_first]);
+        NULL order defaults to DataFusion's (ASC NULLS LAST, DESC NULLS FIRST)."""
+        self.p.nsort = len(terms)
+        for i, t in enumerate(terms):
+            which, index, desc = t[0], t[1], bool(t[2])
+            nulls_first = bool(t[3]) if len(t) > 3 else desc
+            self.p.sort[i] = _lib.SortKey(1 if which == "agg" else 0, index, int(desc), int(nulls_first))
+        self.p.limit = limit
+        return self
+
     def build_join(self, key: ColRefLike, payload: Sequence[ColRefLike] = (),
                    bloom: Optional["RuntimeFilter"] = None) -> "PipelineBuilder":
         self.p.sink = 2
@@ -270,10 +307,11 @@ class PipelineBuilder:
     def check(self) -> int:
         return _lib.lib().pgf_pipeline_check(self.ctx.h, C.byref(self.p))
 
-    def run(self) -> PipelineResult:
+    def run(self, pages: bool = False) -> PipelineResult:
+        """pages=True also encodes the output rows as reference result pages (ResultPageProducer)."""
         res = C.POINTER(_lib.Result)()
         self.ctx._check(_lib.lib().pgf_pipeline_run(self.ctx.h, C.byref(self.p), C.byref(res)))
-        return self.ctx._take_result(res)
+        return self.ctx._take_result(res, pages)
 
     def run_partial(self, dev_ptr: int, capacity_bytes: int) -> Tuple[int, PipelineResult]:
         res = C.POINTER(_lib.Result)()
@@ -465,14 +503,17 @@ class Context:
         if rc:
             raise PgfError(rc, (_lib.lib().pgf_last_error(self.h) or b"").decode(errors="replace"))
 
-    def _take_result(self, res) -> PipelineResult:
+    def _take_result(self, res, pages: bool = False) -> PipelineResult:
         try:
             r = res.contents
             nk, na = r.nkeys, r.naggs
             keys = [tuple(_value_py(r.keys[g * nk + k]) for k in range(nk)) for g in range(r.ngroups)]
             aggs = [tuple(_value_py(r.aggs[g * na + a]) for a in range(na)) for g in range(r.ngroups)]
-            return PipelineResult(r.rows_in, r.rows_bloom, r.rows_filtered, r.rows_out, keys, aggs, r.join_table,
-                                  r.bloom_rows, r.kernel_ms, r.kernel_launches)
+            out = PipelineResult(r.rows_in, r.rows_bloom, r.rows_filtered, r.rows_out, keys, aggs, r.join_table,
+                                 r.bloom_rows, r.kernel_ms, r.kernel_launches)
+            if pages and (nk or na):
+                out.result_schema, out.result_pages = encode_result_pages(res, self.page_size)
+            return out
         finally:
             _lib.lib().pgf_result_free(res)
 

@@ -257,3 +257,21 @@ def test_ingest_rejects_bad_pages_on_host_and_device(ctx):
     scan.finish()
     assert scan.pipeline().count().run().rows_out == 10
     scan.release()
+
+
+def test_q1_result_pages_round_trip(ctx):
+    """R1: the aggregate output leaves as reference result pages (ResultPageProducer format) that
+    the import path (oracle restatement of ArrowPageDecoder::import_owned) decodes to the same rows."""
+    scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q1, 50_000, seed=42)
+    res = U.gpu_q1(scan).run(pages=True)
+    cols = [(int(c.type_tag), bool(c.nullable)) for c in res.result_schema]
+    assert [c[0] for c in cols] == [8, 8] + [6] * 7 + [4]      # 2 Utf8View keys, 7 Float64, COUNT(*) Int64
+    assert cols[-1][1] is False and all(c[1] for c in cols[:-1])
+    t = O.OTable.from_pages(res.result_pages, 65536, cols)
+    assert t.rows == len(res.keys) == 4
+    decoded = {}
+    for g in range(t.rows):
+        key = (t.column(0)[g], t.column(1)[g])
+        decoded[key] = tuple(float(t.column(2 + j)[0][g]) for j in range(7)) + (int(t.column(9)[0][g]),)
+    assert decoded == {k: tuple(v) for k, v in res.by_key().items()}
+    scan.release()

@@ -1,0 +1,95 @@
+"""Result pages: pgf_result_encode_pages produces the page format that
+ResultPageProducer emits (worker_runtime/src/result_pages.rs:150-196) and that ArrowPageDecoder
+(page/import/src/lib.rs:117-206) accepts.  Checked with the oracle's restatement of import_owned
+and with the product's own host-side import checks.  CPU only: the pgf_result is built by hand."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyorc as O
+from pg_fusion_b200 import _lib
+from pg_fusion_b200.worker import encode_result_pages
+
+V_NULL, V_F64, V_I64, V_I128, V_STR = 0, 1, 2, 3, 4
+T_I32, T_I64, T_F64, T_VIEW = 3, 4, 6, 8
+
+
+def make_result(rows):
+    """rows: list of (key_str|None, key_i32|None, sum_f64|None, count_i64)"""
+    n = len(rows)
+    keys = (_lib.Value * (2 * n + 1))()
+    aggs = (_lib.Value * (2 * n + 1))()
+    for g, (ks, ki, sf, cnt) in enumerate(rows):
+        k0, k1, a0, a1 = keys[2 * g], keys[2 * g + 1], aggs[2 * g], aggs[2 * g + 1]
+        if ks is None:
+            k0.kind = V_NULL
+        else:
+            k0.kind, k0.slen = V_STR, len(ks)
+            for i, b in enumerate(ks):
+                k0.str[i] = b
+        if ki is None:
+            k1.kind = V_NULL
+        else:
+            k1.kind, k1.lo, k1.hi = V_I64, ki, -1 if ki < 0 else 0
+        if sf is None:
+            a0.kind = V_NULL
+        else:
+            a0.kind, a0.f64 = V_F64, sf
+        a1.kind, a1.lo = V_I64, cnt
+    r = _lib.Result()
+    r.ngroups, r.nkeys, r.naggs = n, 2, 2
+    r.keys, r.aggs = C.cast(keys, C.POINTER(_lib.Value)), C.cast(aggs, C.POINTER(_lib.Value))
+    r.key_type[0], r.key_type[1] = T_VIEW, T_I32
+    r.agg_type[0], r.agg_type[1] = T_F64, T_I64
+    return r, (keys, aggs)
+
+
+def sample_rows(n, seed=3):
+    rng = np.random.default_rng(seed)
+    rows = []
+    for g in range(n):
+        ks = None if g % 97 == 5 else bytes(rng.integers(65, 91, int(rng.integers(0, 13))).astype(np.uint8))
+        ki = None if g % 89 == 7 else int(rng.integers(-2**31, 2**31))
+        sf = None if g % 101 == 3 else float(rng.normal() * 1e6)
+        rows.append((ks, ki, sf, int(rng.integers(0, 2**40))))
+    return rows
+
+
+@pytest.mark.parametrize("page_size,n", [(65536, 10_000), (4096, 1_000), (65536, 1), (8192, 0)])
+def test_result_pages_decode_to_the_same_rows(page_size, n):
+    rows = sample_rows(n)
+    r, keep = make_result(rows)
+    schema, pages = encode_result_pages(C.pointer(r), page_size)
+    assert [(int(c.type_tag), c.nullable) for c in schema] == [(T_VIEW, True), (T_I32, True), (T_F64, True), (T_I64, False)]
+    cols = [(int(c.type_tag), bool(c.nullable)) for c in schema]
+    # the reference's fixed row cap decides the page count (page/row_estimator/src/lib.rs:353-371)
+    cap = O.fixed_row_cap(cols, page_size - 20)
+    assert pages.shape[0] == (n + cap - 1) // cap
+    L = _lib.lib()
+    specs = (_lib.ColumnSpec * 4)(*[_lib.ColumnSpec(int(c.type_tag), int(c.nullable)) for c in schema])
+    for p in range(pages.shape[0]):
+        page = np.ascontiguousarray(pages[p])
+        kind, flags, plen = C.c_uint16(), C.c_uint16(), C.c_uint32()
+        assert L.pgf_page_header_decode(page.ctypes.data_as(C.c_void_p), C.byref(kind), C.byref(flags), C.byref(plen)) == 0
+        assert (kind.value, flags.value, plen.value) == (0x4152, 0, page_size - 20)
+        block = page[20:]
+        assert L.pgf_block_import_check(kind.value, flags.value, block.ctypes.data_as(C.c_void_p), block.size, specs, 4) == 0
+        assert O.import_check(kind.value, flags.value, np.ascontiguousarray(block), cols) == 0
+    if n == 0:
+        return
+    t = O.OTable.from_pages(pages, page_size, cols)   # oracle restatement of import_owned
+    assert t.rows == n
+
+    def values(i):
+        c = t.column(i)
+        if isinstance(c, list):
+            return c
+        arr, valid = c
+        return [None if (valid is not None and not valid[r]) else arr[r] for r in range(len(arr))]
+    c0, c1, c2, c3 = (values(i) for i in range(4))
+    for g, (ks, ki, sf, cnt) in enumerate(rows):
+        assert c0[g] == ks, (g, c0[g], ks)
+        assert (None if c1[g] is None else int(c1[g])) == ki
+        assert (None if c2[g] is None else float(c2[g])) == sf
+        assert int(c3[g]) == cnt

@@ -234,6 +234,29 @@ pgf_status pgf_bloom_probe_scan(pgf_ctx *ctx, uint64_t bloom, uint64_t expected_
                                 uint64_t scan_id, uint32_t col, uint8_t *decisions_out,
                                 pgf_probe_stats *stats);
 
+/* ---- shared-memory runtime-filter pool (runtime_filter/src/pool.rs)
+ * The worker side of the reference's pool protocol, so a filter built on the GPU is probed by
+ * unchanged PostgreSQL backends before tuples are encoded (pg/backend_service/src/source.rs:
+ * 121-149,496-532).  `base` is the mapped pool region; (slot_count, params) is the pool
+ * configuration (RuntimeFilterPoolConfig).  allocate_build = RuntimeFilterPool::allocate_build
+ * (pool.rs:378-430; *slot_index_out = -1 when the pool is exhausted, a soft miss),
+ * publish = insert + RuntimeFilterBuildHandle::publish_ready, release_owner = handle drop. */
+typedef struct { uint64_t session_epoch, scan_id; uint32_t output_column, key_type; /* 1=i16 2=i32 3=i64 */ } pgf_rf_target;
+pgf_status pgf_shm_pool_layout(uint32_t slot_count, const pgf_bloom_params *params, uint64_t *size_out, uint64_t *align_out);
+pgf_status pgf_shm_pool_init(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params);
+pgf_status pgf_shm_pool_attach_check(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params);
+pgf_status pgf_shm_pool_allocate_build(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                       const pgf_rf_target *target, int32_t *slot_index_out, uint64_t *generation_out);
+pgf_status pgf_shm_pool_publish_words(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                      int32_t slot_index, uint64_t generation, const uint64_t *words, uint64_t nwords);
+pgf_status pgf_shm_pool_disable_build(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                      int32_t slot_index, uint64_t generation);
+pgf_status pgf_shm_pool_release_owner(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                      int32_t slot_index);
+/* Copy the words of a GPU-built filter (any lifecycle state) into the pool slot and publish it. */
+pgf_status pgf_bloom_publish_to_pool(pgf_ctx *ctx, uint64_t bloom, void *base, uint64_t len, uint32_t slot_count,
+                                     int32_t slot_index, uint64_t generation);
+
 /* ------------------------------------------------------------------ pipelines
  * Replaces the operator chain DataFusion plans over a scan
  * (worker_runtime/src/runtime.rs:667-698): CoalesceBatchesExec/FilterExec ->

@@ -118,6 +118,10 @@ class Result(C.Structure):
                 ("key_type", i32 * 4), ("agg_type", i32 * 16)]
 
 
+class RfTarget(C.Structure):
+    _fields_ = [("session_epoch", u64), ("scan_id", u64), ("output_column", u32), ("key_type", u32)]
+
+
 class JoinInfo(C.Structure):
     _fields_ = [("rows", u64), ("capacity", u32), ("row_bytes", u32), ("npayload", u32), ("reserved", u32)]
 
@@ -179,6 +183,14 @@ _SIGNATURES = {
     "pgf_pipeline_run_partial": (i32, [vp, P(Pipeline), vp, u64, P(u64), P(P(Result))]),
     "pgf_pipeline_merge_partials": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_partial_state_bytes": (i32, [P(Pipeline), u64, P(u64)]),
+    "pgf_shm_pool_layout": (i32, [u32, P(BloomParamsC), P(u64), P(u64)]),
+    "pgf_shm_pool_init": (i32, [vp, u64, u32, P(BloomParamsC)]),
+    "pgf_shm_pool_attach_check": (i32, [vp, u64, u32, P(BloomParamsC)]),
+    "pgf_shm_pool_allocate_build": (i32, [vp, u64, u32, P(BloomParamsC), P(RfTarget), P(i32), P(u64)]),
+    "pgf_shm_pool_publish_words": (i32, [vp, u64, u32, P(BloomParamsC), i32, u64, vp, u64]),
+    "pgf_shm_pool_disable_build": (i32, [vp, u64, u32, P(BloomParamsC), i32, u64]),
+    "pgf_shm_pool_release_owner": (i32, [vp, u64, u32, P(BloomParamsC), i32]),
+    "pgf_bloom_publish_to_pool": (i32, [vp, u64, vp, u64, u32, i32, u64]),
     "pgf_result_schema": (i32, [P(Result), P(ColumnSpec), P(u32)]),
     "pgf_result_encode_pages": (i32, [P(Result), u32, u64, vp, u64, P(u64), P(u64)]),
     "pgf_join_table_get_info": (i32, [vp, u64, P(JoinInfo)]),

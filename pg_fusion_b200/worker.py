@@ -448,6 +448,11 @@ class RuntimeFilter:
         words = np.ascontiguousarray(words, dtype=np.uint64)
         self.ctx._check(_lib.lib().pgf_bloom_or_words(self.ctx.h, self.handle, words.ctypes.data_as(C.c_void_p), words.size))
 
+    def publish_to_pool(self, base_ptr: int, length: int, slot_count: int, slot_index: int, generation: int) -> None:
+        """Copy the GPU-built words into a slot of the shared-memory pool and publish it Ready
+        (runtime_filter/src/pool.rs: insert + publish_ready), so backends probe it unchanged."""
+        self.ctx._check(_lib.lib().pgf_bloom_publish_to_pool(self.ctx.h, self.handle, base_ptr, length, slot_count, slot_index, generation))
+
     def device_words_ptr(self) -> int:
         return _lib.lib().pgf_bloom_device_words(self.ctx.h, self.handle)
 

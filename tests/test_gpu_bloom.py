@@ -193,3 +193,33 @@ def test_empty_inputs(ctx):
     assert n == 0 and int(rf.words().sum()) == 0
     d, st = rf.probe_keys(np.zeros(0, dtype=np.int64))
     assert d.size == 0 and st.probe_rows == 0
+
+
+def test_gpu_built_filter_is_published_into_the_shared_memory_pool(ctx):
+    """RuntimeFilterBuildExec on the GPU, probes by unchanged backends: the words
+    built in HBM land bit-exact in the pool slot and the slot goes Building -> Ready."""
+    import ctypes as C
+    import struct
+    from pg_fusion_b200 import _lib
+    p = BloomParams.new(**pg.GUC_DEFAULT_BLOOM)
+    pc = _lib.BloomParamsC(p.bit_count, p.word_count, p.hash_count, p.seed)
+    L, slots = _lib.lib(), 4
+    size = C.c_uint64()
+    assert L.pgf_shm_pool_layout(slots, C.byref(pc), C.byref(size), None) == 0
+    buf = np.zeros(size.value // 8, dtype=np.uint64)
+    base = buf.ctypes.data_as(C.c_void_p)
+    assert L.pgf_shm_pool_init(base, size.value, slots, C.byref(pc)) == 0
+    target = _lib.RfTarget(3, 99, 1, 3)
+    slot, gen = C.c_int32(), C.c_uint64()
+    assert L.pgf_shm_pool_allocate_build(base, size.value, slots, C.byref(pc), C.byref(target), C.byref(slot), C.byref(gen)) == 0
+    keys = np.random.default_rng(9).integers(-2**62, 2**62, 300_000, dtype=np.int64)
+    rf, n = built(ctx, p, keys)
+    rf.publish_to_pool(buf.ctypes.data, size.value, slots, slot.value, gen.value)
+    ob = oracle_bloom(p)
+    ob.insert_keys(keys)
+    off = (56 + 48 * slots) // 8 + slot.value * p.word_count
+    assert (buf[off:off + p.word_count] == ob.words).all()
+    lifecycle = struct.unpack_from("<Q", buf.view(np.uint8), 56 + 48 * slot.value + 40)[0]
+    assert lifecycle == (gen.value << 2) | int(RuntimeFilterState.Ready)
+    with pytest.raises(pg.PgfError):   # a second publish of the same generation is refused
+        rf.publish_to_pool(buf.ctypes.data, size.value, slots, slot.value, gen.value)

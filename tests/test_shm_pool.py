@@ -1,0 +1,137 @@
+"""Shared-memory runtime-filter pool interop: the worker side of
+runtime_filter/src/pool.rs spoken by the library, checked against the pool's binary layout
+(pool.rs:152-217), its lifecycle transitions (shared.rs:159-260) and the oracle's Bloom bits.
+Follows the reference's pool tests (runtime_filter/src/tests.rs: pool allocate / publish /
+probe / release / reuse).  CPU only: the words come from the oracle."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import pyorc as O
+from pg_fusion_b200 import _lib
+
+MAGIC = 0x5047465552465031
+FREE, BUILDING, READY, DISABLED = 0, 1, 2, 3
+SLOT_FREE, SLOT_ALLOCATED, SLOT_RETIRING = 0, 1, 2
+
+
+def params(bits=4096, k=4, seed=42):
+    p = _lib.BloomParamsC()
+    assert _lib.lib().pgf_bloom_params_new(bits, k, seed, C.byref(p)) == 0
+    return p
+
+
+class Pool:
+    def __init__(self, slots, p):
+        self.L, self.slots, self.p = _lib.lib(), slots, p
+        size, align = C.c_uint64(), C.c_uint64()
+        assert self.L.pgf_shm_pool_layout(slots, C.byref(p), C.byref(size), C.byref(align)) == 0
+        assert size.value == 56 + 48 * slots + 8 * slots * p.word_count and align.value == 8
+        self.buf = np.full(size.value // 8, 0xAB, dtype=np.uint64)   # scratch, not zero: init must clear it
+        self.base, self.len = self.buf.ctypes.data_as(C.c_void_p), size.value
+        assert self.L.pgf_shm_pool_init(self.base, self.len, slots, C.byref(p)) == 0
+
+    def raw(self):
+        return self.buf.view(np.uint8)
+
+    def header(self):
+        return struct.unpack_from("<QIIQIIQQQ", self.raw(), 0)
+
+    def slot(self, i):
+        state, refs, gen, epoch, scan, col, kt, lifecycle = struct.unpack_from("<IIQQQIIQ", self.raw(), 56 + 48 * i)
+        return dict(state=state, refs=refs, generation=gen, session_epoch=epoch, scan_id=scan, output_column=col,
+                    key_type=kt, lifecycle=lifecycle)
+
+    def bits(self, i):
+        off = (56 + 48 * self.slots) // 8 + i * self.p.word_count
+        return self.buf[off:off + self.p.word_count]
+
+    def allocate(self, epoch, scan, col=0, key_type=3):
+        t = _lib.RfTarget(epoch, scan, col, key_type)
+        slot, gen = C.c_int32(), C.c_uint64()
+        rc = self.L.pgf_shm_pool_allocate_build(self.base, self.len, self.slots, C.byref(self.p), C.byref(t), C.byref(slot), C.byref(gen))
+        return rc, slot.value, gen.value
+
+    def publish(self, slot, gen, words):
+        w = np.ascontiguousarray(words, dtype=np.uint64)
+        return self.L.pgf_shm_pool_publish_words(self.base, self.len, self.slots, C.byref(self.p), slot, gen,
+                                                 w.ctypes.data_as(C.c_void_p), w.size)
+
+    def release(self, slot):
+        return self.L.pgf_shm_pool_release_owner(self.base, self.len, self.slots, C.byref(self.p), slot)
+
+
+def test_layout_and_header_match_the_reference_structs():
+    p = params()
+    pool = Pool(3, p)
+    magic, version, slots, bit_count, hash_count, _r, seed, word_count, region = pool.header()
+    assert (magic, version, slots, bit_count, hash_count, seed, word_count) == (MAGIC, 1, 3, 4096, 4, 42, 64)
+    assert region == pool.len
+    for i in range(3):
+        assert pool.slot(i) == dict(state=SLOT_FREE, refs=0, generation=0, session_epoch=0, scan_id=0, output_column=0, key_type=0, lifecycle=0)
+        assert not pool.bits(i).any()
+    L = _lib.lib()
+    assert L.pgf_shm_pool_attach_check(pool.base, pool.len, 3, C.byref(p)) == 0
+    assert L.pgf_shm_pool_attach_check(pool.base, pool.len, 4, C.byref(p)) != 0           # TooSmall / ConfigMismatch
+    assert L.pgf_shm_pool_attach_check(pool.base, pool.len, 3, C.byref(params(seed=43))) != 0   # ConfigMismatch
+    assert L.pgf_shm_pool_attach_check(C.c_void_p(pool.buf.ctypes.data + 4), pool.len - 4, 3, C.byref(p)) != 0  # Misaligned
+
+
+def test_allocate_publish_probe_release_and_reuse():
+    p = params(bits=1 << 15, k=4, seed=0x7067667573696f6e)
+    pool = Pool(2, p)
+    keys = np.random.default_rng(5).integers(-2**62, 2**62, 2000, dtype=np.int64)
+    ob = O.Bloom(O.bloom_params(p.bit_count, p.hash_count, p.seed))
+    ob.insert_keys(keys)
+
+    rc, slot, gen = pool.allocate(epoch=7, scan=11, col=2, key_type=3)
+    assert (rc, slot, gen) == (0, 0, 1)
+    s = pool.slot(0)
+    assert (s["state"], s["refs"], s["generation"], s["session_epoch"], s["scan_id"], s["output_column"], s["key_type"]) == (SLOT_ALLOCATED, 1, 1, 7, 11, 2, 3)
+    assert s["lifecycle"] == (1 << 2) | BUILDING
+    # a second build takes the next slot; a third finds the pool exhausted (soft miss, not an error)
+    assert pool.allocate(7, 12)[:2] == (0, 1)
+    assert pool.allocate(7, 13)[:2] == (0, -1)
+    # publishing with a stale generation is refused and leaves the slot Building
+    assert pool.publish(0, 2, ob.words) != 0
+    assert pool.slot(0)["lifecycle"] == (1 << 2) | BUILDING
+    assert pool.publish(0, 1, ob.words) == 0
+    assert pool.slot(0)["lifecycle"] == (1 << 2) | READY
+    assert (pool.bits(0) == ob.words).all() and not pool.bits(1).any()
+    # what a backend probe sees: the reference's might_contain over the slot's bits
+    probe = O.Bloom(O.bloom_params(p.bit_count, p.hash_count, p.seed))
+    probe.words[:] = pool.bits(0)
+    assert all(probe.might_contain_u64(int(k) & (2**64 - 1)) for k in keys[:200])
+    assert pool.publish(0, 1, ob.words) != 0            # already Ready: not Building any more
+    # owner drop with no probe attached: Ready -> Disabled, slot metadata cleared, slot Free again
+    assert pool.release(0) == 0
+    s = pool.slot(0)
+    assert (s["state"], s["refs"], s["generation"], s["session_epoch"], s["scan_id"], s["key_type"]) == (SLOT_FREE, 0, 0, 0, 0, 0)
+    assert s["lifecycle"] == (1 << 2) | DISABLED
+    # reuse: next generation, bits cleared by the new builder lease
+    rc, slot, gen = pool.allocate(8, 21, key_type=2)
+    assert (rc, slot, gen) == (0, 0, 2)
+    assert pool.slot(0)["lifecycle"] == (2 << 2) | BUILDING and not pool.bits(0).any()
+    # a build that fails is disabled, never published
+    L = _lib.lib()
+    assert L.pgf_shm_pool_disable_build(pool.base, pool.len, 2, C.byref(p), 0, 2) == 0
+    assert pool.slot(0)["lifecycle"] == (2 << 2) | DISABLED
+    assert pool.publish(0, 2, ob.words) != 0
+    assert pool.release(0) == 0 and pool.slot(0)["state"] == SLOT_FREE
+
+
+def test_release_waits_for_the_last_probe_reference():
+    """release_ref (pool.rs:527-556): the slot is only retired by whoever drops the last reference."""
+    p = params()
+    pool = Pool(1, p)
+    rc, slot, gen = pool.allocate(1, 2)
+    assert pool.publish(slot, gen, np.ones(p.word_count, dtype=np.uint64)) == 0
+    # a backend attached a probe: refs 1 -> 2 (lookup_probes, pool.rs:432-476)
+    refs_off = 56 + 4
+    struct.pack_into("<I", pool.raw(), refs_off, 2)
+    assert pool.release(slot) == 0
+    s = pool.slot(0)
+    assert (s["state"], s["refs"]) == (SLOT_RETIRING, 1) and s["lifecycle"] == (gen << 2) | READY   # still probe-able
+    assert pool.allocate(1, 3)[:2] == (0, -1)   # not reusable yet

@@ -275,3 +275,28 @@ def test_q1_result_pages_round_trip(ctx):
         decoded[key] = tuple(float(t.column(2 + j)[0][g]) for j in range(7)) + (int(t.column(9)[0][g]),)
     assert decoded == {k: tuple(v) for k, v in res.by_key().items()}
     scan.release()
+
+
+def test_q1_shape_with_non_finite_values(ctx):
+    """Inf / NaN arguments stay inside their own group and aggregate (IEEE semantics per group, as
+    DataFusion's per-group accumulators): no selector trick in the sink may leak them elsewhere."""
+    import math
+    li = U.lineitem(30_000, 5)
+    li["price"][::1000] = np.inf
+    li["qty"][7::1500] = -np.inf
+    li["disc"][11::2000] = np.nan
+    pages = U.q1_pages(li)
+    scan = load(ctx, U.Q1_SCHEMA, pages)
+    res = U.gpu_q1(scan).run()
+    want = U.oracle_q1(O.OTable.from_pages(pages, 65536, U.orc_cols(U.Q1_SCHEMA)))
+    gk, ok = res.by_key(), want.by_key()
+    assert set(gk) == set(ok)
+    for k in ok:
+        for j, (x, y) in enumerate(zip(gk[k], ok[k])):
+            if isinstance(y, float) and not math.isfinite(y):
+                assert (math.isnan(x) and math.isnan(y)) or x == y, (k, j, x, y)
+            else:
+                U.assert_close(x, y, 1e-12, f"group {k} agg {j}")
+    # a group without any non-finite input keeps finite sums
+    assert any(all(math.isfinite(v) for v in vals if isinstance(v, float)) for vals in gk.values()) or len(gk) < 4
+    scan.release()

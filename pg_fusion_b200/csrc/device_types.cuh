@@ -156,6 +156,7 @@ struct DevPlan {
   uint64_t page_stride;
   uint32_t npages, tiles_per_page, tile_rows, nitems;
   uint32_t stage_bytes, nstage_cols;
+  uint32_t nstages, pad0;   // ring depth: kStages partial-page tiles or 3 whole pages
   uint32_t used_null_mask;  // page columns whose validity matters to this plan
   uint32_t view_mask;       // page columns read as views (must be inline)
   DevStageCol scol[kMaxStageCols];

@@ -694,32 +694,55 @@ class Lowering {
     for (uint32_t c = 0; c < D.nstage_cols; ++c) row_bytes8 += D.scol[c].width * 8u + (D.scol[c].nullable ? 1u : 0u);
     const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
     const uint64_t page_bytes = (uint64_t(row_bytes8) * max_rows + 7) / 8;
-    // Pipelines behind a join probe stage whole pages in a 3-deep ring: their throughput is bound
-    // by the rows in flight per SM (4 rows per thread x all consumer warps), not by ring depth.
-    const uint32_t nstages = uint32_t(pipeline_stages(L_->nj));
+    // Ring shape.  Streaming pipelines: kStages tiles of ~40 KiB (a fraction of a page).  Behind a
+    // join probe a thread carries 4 rows, so a tile must hold consumer_warps x 128 rows to keep
+    // every warp busy: whole pages in a 3-deep ring.  (Measured on Q1: whole-page tiles raise the
+    // share of busy warp slots from 46 % to 93 % but do not help -- the kernel is issue bound, and
+    // the deeper ring of smaller tiles hides the TMA latency better.)
     const uint32_t queue_bytes = (D.sink == SINK_AGG && L_->grouped) ? kMaxConsumerWarps * kQueueBytesPerWarp : 0u;
     const uint32_t smem_budget = 227u * 1024u - uint32_t((sizeof(BlockShared) + 127) & ~size_t(127)) - queue_bytes;
-    const bool whole_pages = L_->nj != 0 && nstages <= 3;
-    const uint32_t max_stage = std::min<uint32_t>((smem_budget / nstages) & ~127u, whole_pages ? 66u * 1024u : 48u * 1024u);
-    const uint32_t target = whole_pages ? max_stage : 40u * 1024u;
-    uint32_t ntiles = uint32_t((page_bytes + target - 1) / target);
-    if (ntiles == 0) ntiles = 1;
-    uint32_t tile_rows = 0, stage_bytes = 0;
-    for (;; ++ntiles) {
-      tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
-      stage_bytes = 0;
-      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
-        D.scol[c].smem_off = stage_bytes;
-        stage_bytes += tile_rows * D.scol[c].width;
-      }
-      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
-        D.scol[c].valid_off = stage_bytes;
+    auto shape = [&](uint32_t ntiles, uint32_t* tile_rows_out, uint32_t* stage_bytes_out) {
+      const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
+      uint32_t stage_bytes = 0;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += tile_rows * D.scol[c].width;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c)
         if (D.scol[c].nullable) stage_bytes += tile_rows / 8;
+      *tile_rows_out = tile_rows;
+      *stage_bytes_out = (stage_bytes + 127u) & ~127u;
+    };
+    uint32_t best_tiles = 0, best_stages = 0;
+    {
+      uint32_t tile_rows, stage_bytes;
+      shape(1, &tile_rows, &stage_bytes);
+      if (L_->nj != 0 && stage_bytes <= ((smem_budget / 3u) & ~127u)) {
+        best_tiles = 1;
+        best_stages = 3;
+      } else {
+        const uint32_t cap = std::min<uint32_t>((smem_budget / kStages) & ~127u, 48u * 1024u);
+        uint32_t ntiles = uint32_t((page_bytes + 40u * 1024u - 1) / (40u * 1024u));
+        for (ntiles = ntiles ? ntiles : 1;; ++ntiles) {
+          shape(ntiles, &tile_rows, &stage_bytes);
+          if (stage_bytes <= cap) { best_tiles = ntiles; best_stages = kStages; break; }
+          if (tile_rows == 128) break;
+        }
       }
-      stage_bytes = (stage_bytes + 127u) & ~127u;
-      if (stage_bytes <= max_stage || tile_rows == 128) break;
     }
-    if (stage_bytes > max_stage) return not_eligible("row too wide for the shared-memory stages");
+    if (!best_tiles) return not_eligible("row too wide for the shared-memory stages");
+    uint32_t tile_rows = 0, stage_bytes = 0;
+    shape(best_tiles, &tile_rows, &stage_bytes);
+    {
+      uint32_t off = 0;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+        D.scol[c].smem_off = off;
+        off += tile_rows * D.scol[c].width;
+      }
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+        D.scol[c].valid_off = off;
+        if (D.scol[c].nullable) off += tile_rows / 8;
+      }
+    }
+    const uint32_t nstages = best_stages;
+    D.nstages = nstages;
     D.tile_rows = tile_rows;
     D.tiles_per_page = (max_rows + tile_rows - 1) / tile_rows;
     D.stage_bytes = stage_bytes ? stage_bytes : 128;

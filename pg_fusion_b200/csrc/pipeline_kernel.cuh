@@ -29,14 +29,12 @@ constexpr int kMaxConsumerWarps = 16;
 __host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 14 : 16; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
 constexpr int kStages = 4;     // ring depth of streaming pipelines
-#ifndef PGF_JOIN_STAGES
-#define PGF_JOIN_STAGES 3
-#endif
 #ifndef PGF_JOIN_ROWS
 #define PGF_JOIN_ROWS 4
 #endif
-constexpr int kJoinStages = PGF_JOIN_STAGES; // pipelines behind a join probe: 3 = whole pages (one tile per page)
-__host__ __device__ constexpr int pipeline_stages(uint32_t nj) { return nj != 0 ? kJoinStages : kStages; }
+// The ring depth is a plan parameter (DevPlan::nstages): kStages tiles of a fraction of a page,
+// or 3 whole pages -- whichever keeps more consumer warps busy per tile (see layout_stage()).
+__host__ __device__ constexpr uint32_t rows_per_thread(uint32_t nj) { return nj != 0 ? PGF_JOIN_ROWS : 2; }
 // Deferred sink: rows whose group is not register resident are queued per warp (in shared
 // memory behind the stage ring) and applied to the global table 32 at a time from a converged
 // point, instead of one or two lanes at a time from inside the divergent probe loop.
@@ -674,8 +672,8 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
-  constexpr uint32_t kRows = NJ != 0 ? PGF_JOIN_ROWS : 2;  // rows per thread and iteration
-  constexpr uint32_t kNumStages = uint32_t(pipeline_stages(NJ));
+  constexpr uint32_t kRows = rows_per_thread(NJ);  // rows per thread and iteration
+  const uint32_t kNumStages = P.nstages;  // 3 or kStages
   constexpr uint32_t kAccWords = ACC == CLS_I128 ? 2 : 1;
   [[maybe_unused]] constexpr uint32_t kQueueEntryWords = queue_entry_words(MAXE, kAccWords);
   [[maybe_unused]] constexpr uint32_t kQueueCap = kQueueBytesPerWarp / (8 * kQueueEntryWords);
@@ -690,7 +688,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kNumStages; ++s) {
+    for (int s = 0; s < kStages; ++s) {
       mbar_init(&sh->full[s], 1);
       mbar_init(&sh->empty[s], kConsumerWarps);
     }
@@ -719,12 +717,12 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
 
   if (warp == 0) {
     // ===== producer: TMA bulk copies of the needed column slices of each row tile =====
-    uint32_t k = 0;
+    uint32_t k = 0, ps = 0, pphase = 0;  // ring stage and mbarrier phase of the producer
     uint32_t item = blockIdx.x;
     PageDesc d_next{};
     if (item < P.nitems) d_next = P.descs[item / P.tiles_per_page];
     for (; item < P.nitems; item += gridDim.x, ++k) {
-      const uint32_t s = k % kNumStages;
+      const uint32_t s = ps;
       const uint32_t page = item / P.tiles_per_page, tile = item - page * P.tiles_per_page;
       const PageDesc d = d_next;
       if (item + gridDim.x < P.nitems) d_next = P.descs[(item + gridDim.x) / P.tiles_per_page];  // prefetch
@@ -754,7 +752,8 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       uint32_t total = bytes;
 #pragma unroll
       for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      mbar_wait(&sh->empty[s], ((k / kNumStages) & 1u) ^ 1u);
+      mbar_wait(&sh->empty[s], pphase ^ 1u);
+      if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
       if (lane == 0) {
         sh->meta[s].nrows = n;
         sh->meta[s].null_mask = d.null_mask & P.used_null_mask;
@@ -790,10 +789,11 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
         __syncwarp();
       }
     };
-    uint32_t k = 0;
+    uint32_t k = 0, cs = 0, cphase = 0;  // ring stage and mbarrier phase of this consumer
     for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
-      const uint32_t s = k % kNumStages;
-      mbar_wait(&sh->full[s], (k / kNumStages) & 1u);
+      const uint32_t s = cs;
+      mbar_wait(&sh->full[s], cphase);
+      if (++cs == kNumStages) { cs = 0; cphase ^= 1u; }
       const uint32_t nrows = sh->meta[s].nrows;
       const uint8_t* stage = stages + size_t(s) * P.stage_bytes;
       const uint32_t tile_nulls = sh->meta[s].null_mask;

@@ -98,6 +98,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(device: int):
+    """Pin this process (and therefore its first-touch pinned allocations) to the CPUs NVML reports as
+    local to the GPU: with one process per GPU every rank then feeds its own PCIe link from its own
+    socket's memory.  Returns the CPU list, or None when NVML / affinity is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def cpu_q6(pages, nthreads, min_seconds=5.0):
     """Time the oracle's tight Q6 loop (reference semantics) over a bounded page sample."""
     from oracle import pyorc as O
@@ -274,6 +295,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the pg_fusion_b200 hot path has no CPU fallback")
     torch.cuda.set_device(local)
+    full_affinity = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)   # pinned host pages must live on the GPU's own socket
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -365,7 +388,7 @@ def main():
         dt = float(t.item())
     h2d = int(info.pages * PAGE)
     e2e = {"value": total_rows / dt, "unit": "rows/s", "h2d_bytes_per_step": h2d * world,
-           "d2h_bytes_per_step": (64 + 8 * (1 + 7)) * world, "ms_per_step": dt * 1e3, "h2d_GBps_per_gpu": h2d / dt / 1e9,
+           "d2h_bytes_per_step": (64 + 8 * (1 + 7)) * world, "ms_per_step": dt * 1e3, "h2d_GBps_per_gpu": h2d / dt / 1e9, "numa_bound_cpus": len(numa) if numa else None,
            "note": "pinned host pages -> pgf_scan_push_pages (host admission checks + H2D) -> pgf_scan_finish (device import checks) "
                    "-> pgf_pipeline_run -> result on host; bound by the PCIe link of each GPU"}
     e2e_scan.release()
@@ -378,6 +401,7 @@ def main():
         achieved = rows * Q6_BYTES_PER_ROW / (kms / 1e3) / 1e9
         cpu = None
         if world == 1:
+            os.sched_setaffinity(0, full_affinity)   # the CPU baseline may use every host core
             sample_pages = min(info.pages, 4096)
             pages = scan.read_pages(0, sample_pages)
             v1, passes, sample_rows = cpu_q6(pages, 1)

@@ -222,6 +222,38 @@ __global__ void table_merge_kernel(GroupTable t, uint32_t nexprs, uint32_t nkeyw
   }
 }
 
+// Small states (the bounded multi-GPU step): one CTA merges every rank's state, rank after rank
+// with a barrier in between, so the fixed summation order costs one launch instead of one per rank.
+template <uint32_t ACC>
+__global__ void table_merge_all_kernel(GroupTable t, uint32_t nexprs, uint32_t nkeywords, const uint8_t* states, uint64_t stride,
+                                       uint32_t nstates, uint64_t max_entries) {
+  using Ops = AccOps<ACC>;
+  const uint32_t ew = entry_words(nexprs, t.acc_words);
+  for (uint32_t s = 0; s < nstates; ++s) {
+    const uint64_t* state = reinterpret_cast<const uint64_t*>(states + s * stride);
+    uint64_t n = state[0];
+    if (n > max_entries) {
+      if (threadIdx.x == 0) atomicExch(t.overflow, 2u);
+      n = max_entries;
+    }
+    for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t* e = state + 1 + i * ew;
+      const int64_t slot = nkeywords ? group_slot(t, e, nkeywords, uint32_t(e[kKeyWords])) : 0;
+      if (slot < 0) continue;
+      for (uint32_t x = 0; x < nexprs; ++x) {
+        typename Ops::T v;
+        memcpy(&v, e + kKeyWords + 1 + x * t.acc_words, sizeof v);
+        Ops::atomic_add(t.acc + (uint64_t(slot) * nexprs + x) * t.acc_words, v);
+      }
+      for (uint32_t x = 0; x <= nexprs; ++x)
+        atomicAdd(reinterpret_cast<unsigned long long*>(t.cnt + uint64_t(slot) * (nexprs + 1) + x),
+                  (unsigned long long)e[kKeyWords + 1 + nexprs * t.acc_words + x]);
+    }
+    __threadfence();
+    __syncthreads();
+  }
+}
+
 // ---- lowering ----------------------------------------------------------------------
 struct Lowered {
   DevPlan dev{};
@@ -1323,7 +1355,17 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   }
   TableAlloc ta;
   PGF_TRY(arena_table(ctx, capacity, plan->nexprs, aw, &ta));
-  for (uint32_t i = 0; i < nstates; ++i) {  // rank order => fixed Float64 summation order
+  const bool one_launch = bounded && max_entries <= 1024;
+  if (one_launch) {
+    const uint8_t* st = static_cast<const uint8_t*>(dev_states);
+    switch (L.acc_cls) {
+      case CLS_F64: table_merge_all_kernel<CLS_F64><<<1, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, stride, nstates, max_entries); break;
+      case CLS_I64: table_merge_all_kernel<CLS_I64><<<1, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, stride, nstates, max_entries); break;
+      default: table_merge_all_kernel<CLS_I128><<<1, 256, 0, ctx->compute_stream>>>(ta.t, plan->nexprs, L.dev.nkeywords, st, stride, nstates, max_entries); break;
+    }
+    CU(ctx, cudaGetLastError());
+  }
+  for (uint32_t i = 0; i < nstates && !one_launch; ++i) {  // rank order => fixed Float64 summation order
     if (!counts[i]) continue;
     const uint64_t* st = reinterpret_cast<const uint64_t*>(static_cast<const uint8_t*>(dev_states) + i * stride);
     const uint32_t grid = uint32_t(std::min<uint64_t>((counts[i] + 255) / 256, uint64_t(ctx->sm_count) * 4));

@@ -147,6 +147,17 @@ def side_measurements(ctx, pg, U, rows, peak, label="sf10", bloom=True):
     extras[f"tpch_q1_{label}"] = {"rows_per_s": rows / (k / 1e3), "kernel_ms": k, "achieved_GBps": gbps,
                                   "frac_of_measured_peak": gbps / peak, "bytes_per_row": Q1_BYTES_PER_ROW}
     q1.release()
+    # "D" variants: Decimal128 money, Date32 dates, Int16 flags -- exact i128 sums
+    for name, table, plan, bpr in (("q6", pg.GenTable.LINEITEM_Q6_D, U.gpu_q6_d, 52), ("q1", pg.GenTable.LINEITEM_Q1_D, U.gpu_q1_d, 72)):
+        sd = ctx.gen_scan(table, rows, seed=42)
+        pd_ = plan(sd)
+        for _ in range(2):
+            pd_.run()
+        k = statistics.mean(pd_.run().kernel_ms for _ in range(5))
+        gbps = rows * bpr / (k / 1e3) / 1e9
+        extras[f"tpch_{name}_{label}_decimal"] = {"rows_per_s": rows / (k / 1e3), "kernel_ms": k, "achieved_GBps": gbps,
+                                                  "frac_of_measured_peak": gbps / peak, "bytes_per_row": bpr}
+        sd.release()
     # Q3 shape: customer |><| orders |><| lineitem, without and with runtime Bloom filters
     scale = rows / SF10_LINEITEM
     ncust, nord = max(1000, int(SF10_CUSTOMER * scale)), max(10000, int(SF10_ORDERS * scale))

@@ -436,7 +436,11 @@ enum {
   PGF_GEN_LINEITEM_Q3 = 3,  /* l_orderkey i32; l_extendedprice, l_discount f64; l_shipdate */
   PGF_GEN_ORDERS_Q3 = 4,    /* o_orderkey, o_custkey i32; o_orderdate utf8view; o_shippriority i32 */
   PGF_GEN_CUSTOMER_Q3 = 5,  /* c_custkey i32; c_mktsegment utf8view */
-  PGF_GEN_KEYS_I64 = 6      /* one Int64 key column: key = splitmix64(seed + i) or i + 1 */
+  PGF_GEN_KEYS_I64 = 6,     /* one Int64 key column: key = splitmix64(seed + i) or i + 1 */
+  /* D variants: the same rows with money as Decimal128(15,2), dates as Date32
+   * (Int32 days since 1970-01-01) and flags as Int16 character codes */
+  PGF_GEN_LINEITEM_Q6_D = 7, /* l_quantity, l_extendedprice, l_discount decimal; l_shipdate i32 */
+  PGF_GEN_LINEITEM_Q1_D = 8  /* + l_tax decimal; l_returnflag, l_linestatus i16; l_shipdate i32 */
 };
 typedef struct {
   int32_t table;

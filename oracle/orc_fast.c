@@ -13,6 +13,7 @@
  */
 #include "orc.h"
 
+#include <math.h>
 #include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
@@ -29,8 +30,9 @@ typedef struct {
   orc_q6_result q6;
   /* q1 */
   uint8_t date_le[12];
-  int with_tax;
+  int with_tax;            /* bit 0: sum_charge with tax; bit 1: compensated (Neumaier) sums */
   orc_q1_result q1;
+  double comp[16][5];      /* compensation terms of the per-group sums (bit 1) */
   int rc;
 } job;
 
@@ -172,9 +174,21 @@ static orc_q1_group *q1_group(orc_q1_result *r, char rf, char ls) {
   return g;
 }
 
+/* Neumaier's compensated addition: s + c is the running sum with O(1) ulp error whatever the
+ * number of terms.  Used by the full-size parity tests, where the plain reference-order sum's
+ * own rounding error (~sqrt(n)..n ulps) exceeds the 1e-12 bar that is being checked. */
+static inline void nadd(double *s, double *c, double x) {
+  const double t = *s + x;
+  if (fabs(*s) >= fabs(x)) *c += (*s - t) + x;
+  else *c += (x - t) + *s;
+  *s = t;
+}
+
 static void *q1_worker(void *arg) {
   job *j = arg;
   orc_q1_result *res = &j->q1;
+  const int compensated = (j->with_tax & 2) != 0;
+  double (*comp)[5] = j->comp;
   for (uint64_t p = j->p0; p < j->p1; ++p) {
     const uint8_t *ptr[7];
     uint32_t rows;
@@ -190,10 +204,20 @@ static void *q1_worker(void *arg) {
       orc_q1_group *g = q1_group(res, (char)rf[r].data[0], (char)ls[r].data[0]);
       if (!g) { j->rc = -1; return NULL; }
       const double disc_price = price[r] * (1.0 - disc[r]);
+      if (compensated) {
+        double *c = comp[g - res->groups];
+        nadd(&g->sum_qty, &c[0], qty[r]);
+        nadd(&g->sum_base_price, &c[1], price[r]);
+        nadd(&g->sum_disc_price, &c[2], disc_price);
+        if (j->with_tax & 1) nadd(&g->sum_charge, &c[3], disc_price * (1.0 + tax[r]));
+        nadd(&g->sum_disc, &c[4], disc[r]);
+        g->count += 1;
+        continue;
+      }
       g->sum_qty += qty[r];
       g->sum_base_price += price[r];
       g->sum_disc_price += disc_price;
-      if (j->with_tax) g->sum_charge += disc_price * (1.0 + tax[r]);
+      if (j->with_tax & 1) g->sum_charge += disc_price * (1.0 + tax[r]);
       g->sum_disc += disc[r];
       g->count += 1;
     }
@@ -212,12 +236,25 @@ int orc_q1_pages(const uint8_t *pages, uint64_t npages, uint64_t page_stride, in
   }
   const int rc = run_jobs(jobs, nthreads, q1_worker);
   memset(out, 0, sizeof *out);
+  double comp[16][5];
+  memset(comp, 0, sizeof comp);
   for (int t = 0; t < nthreads && rc == 0; ++t) {
     out->rows_in += jobs[t].q1.rows_in;
     for (uint32_t g = 0; g < jobs[t].q1.ngroups; ++g) {
       const orc_q1_group *s = &jobs[t].q1.groups[g];
       orc_q1_group *d = q1_group(out, s->returnflag, s->linestatus);
       if (!d) { free(jobs); return -1; }
+      if (with_tax & 2) {  /* compensated merge: partial sums and their compensation terms */
+        double *c = comp[d - out->groups];
+        const double *sc = jobs[t].comp[g];
+        nadd(&d->sum_qty, &c[0], s->sum_qty); nadd(&d->sum_qty, &c[0], sc[0]);
+        nadd(&d->sum_base_price, &c[1], s->sum_base_price); nadd(&d->sum_base_price, &c[1], sc[1]);
+        nadd(&d->sum_disc_price, &c[2], s->sum_disc_price); nadd(&d->sum_disc_price, &c[2], sc[2]);
+        nadd(&d->sum_charge, &c[3], s->sum_charge); nadd(&d->sum_charge, &c[3], sc[3]);
+        nadd(&d->sum_disc, &c[4], s->sum_disc); nadd(&d->sum_disc, &c[4], sc[4]);
+        d->count += s->count;
+        continue;
+      }
       d->sum_qty += s->sum_qty;
       d->sum_base_price += s->sum_base_price;
       d->sum_disc_price += s->sum_disc_price;
@@ -226,6 +263,14 @@ int orc_q1_pages(const uint8_t *pages, uint64_t npages, uint64_t page_stride, in
       d->count += s->count;
     }
   }
+  if (with_tax & 2)
+    for (uint32_t g = 0; g < out->ngroups; ++g) {
+      out->groups[g].sum_qty += comp[g][0];
+      out->groups[g].sum_base_price += comp[g][1];
+      out->groups[g].sum_disc_price += comp[g][2];
+      out->groups[g].sum_charge += comp[g][3];
+      out->groups[g].sum_disc += comp[g][4];
+    }
   free(jobs);
   return rc;
 }

@@ -605,12 +605,13 @@ def q6_pages(pages: np.ndarray, page_stride: int, nthreads: int, cols=(0, 1, 2, 
 
 
 def q1_pages(pages: np.ndarray, page_stride: int, nthreads: int, cols=(0, 1, 2, 3, 4, 5, 6),
-             date_le=b"1998-09-02", with_tax=True):
+             date_le=b"1998-09-02", with_tax=True, compensated=False):
+    """compensated=True: Neumaier sums, i.e. the correctly rounded sums (full-size parity tests)."""
     pages = np.ascontiguousarray(pages).reshape(-1)
     res = Q1Result()
     carr = (C.c_int32 * 7)(*cols)
     rc = lib().orc_q1_pages(_ptr(pages), pages.size // page_stride, page_stride, nthreads, carr, date_le,
-                            int(with_tax), C.byref(res))
+                            int(with_tax) | (2 if compensated else 0), C.byref(res))
     if rc:
         raise OracleError(rc, "q1_pages")
     out = {}

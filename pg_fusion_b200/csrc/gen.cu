@@ -74,6 +74,7 @@ constexpr uint32_t kCutoffDays = 1263;  // 1995-06-17 as days since 1992-01-01
 
 struct LineItem {
   double quantity, extendedprice, discount, tax;
+  int64_t qty_c, price_c, disc_c, tax_c;  // the same values as Decimal128(15,2): unscaled hundredths
   uint32_t ship_days;
   char returnflag, linestatus;
 };
@@ -84,8 +85,12 @@ __device__ __forceinline__ LineItem lineitem_row(uint64_t seed, uint64_t row) {
   const uint32_t part_cents = 90000 + uint32_t(rnd(seed, row, 1) % 120001);  // 900.00 .. 2100.00
   li.quantity = double(qty);
   li.extendedprice = double(uint64_t(qty) * part_cents) / 100.0;
-  li.discount = double(rnd(seed, row, 2) % 11) / 100.0;
-  li.tax = double(rnd(seed, row, 3) % 9) / 100.0;
+  li.disc_c = int64_t(rnd(seed, row, 2) % 11);
+  li.tax_c = int64_t(rnd(seed, row, 3) % 9);
+  li.discount = double(li.disc_c) / 100.0;
+  li.tax = double(li.tax_c) / 100.0;
+  li.qty_c = int64_t(qty) * 100;
+  li.price_c = int64_t(uint64_t(qty) * part_cents);
   li.ship_days = 1 + uint32_t(rnd(seed, row, 4) % 2526);  // 1992-01-02 .. 1998-12-01
   const uint32_t receipt = li.ship_days + 1 + uint32_t(rnd(seed, row, 5) % 30);
   li.linestatus = li.ship_days > kCutoffDays ? 'O' : 'F';
@@ -188,6 +193,25 @@ __global__ void __launch_bounds__(kGenThreads) gen_pages_kernel(const GenParams 
         viewcol(1)[r] = live ? str_view(seg[k], len[k]) : make_uint4(0, 0, 0, 0);
         break;
       }
+      case PGF_GEN_LINEITEM_Q6_D: {
+        // the D variant: money Decimal128(15,2) in 16-byte slots, dates Date32 (days since 1970)
+        LineItem li{};
+        if (live) li = lineitem_row(p.seed, row);
+        auto dec = [&](uint32_t c, int64_t v) { reinterpret_cast<longlong2*>(block + p.values_off[c])[r] = make_longlong2(v, v < 0 ? -1 : 0); };
+        dec(0, li.qty_c); dec(1, li.price_c); dec(2, li.disc_c);
+        i32col(3)[r] = live ? int32_t(li.ship_days + 8035) : 0;
+        break;
+      }
+      case PGF_GEN_LINEITEM_Q1_D: {
+        LineItem li{};
+        if (live) li = lineitem_row(p.seed, row);
+        auto dec = [&](uint32_t c, int64_t v) { reinterpret_cast<longlong2*>(block + p.values_off[c])[r] = make_longlong2(v, v < 0 ? -1 : 0); };
+        dec(0, li.qty_c); dec(1, li.price_c); dec(2, li.disc_c); dec(3, li.tax_c);
+        reinterpret_cast<int16_t*>(block + p.values_off[4])[r] = live ? int16_t(li.returnflag) : 0;   // flag codes
+        reinterpret_cast<int16_t*>(block + p.values_off[5])[r] = live ? int16_t(li.linestatus) : 0;
+        i32col(6)[r] = live ? int32_t(li.ship_days + 8035) : 0;
+        break;
+      }
       default: {  // PGF_GEN_KEYS_I64
         int64_t* col = reinterpret_cast<int64_t*>(block + p.values_off[0]);
         col[r] = live ? (p.dense_keys ? int64_t(row + 1) : int64_t(splitmix64(p.seed + row))) : 0;
@@ -212,6 +236,8 @@ pgf_status gen_schema(int32_t table, pgf_column_spec* schema, uint32_t* ncols) {
     case PGF_GEN_ORDERS_Q3: set({PGF_T_INT32, PGF_T_INT32, PGF_T_UTF8VIEW, PGF_T_INT32}); break;
     case PGF_GEN_CUSTOMER_Q3: set({PGF_T_INT32, PGF_T_UTF8VIEW}); break;
     case PGF_GEN_KEYS_I64: set({PGF_T_INT64}); break;
+    case PGF_GEN_LINEITEM_Q6_D: set({PGF_T_DECIMAL128, PGF_T_DECIMAL128, PGF_T_DECIMAL128, PGF_T_INT32}); break;
+    case PGF_GEN_LINEITEM_Q1_D: set({PGF_T_DECIMAL128, PGF_T_DECIMAL128, PGF_T_DECIMAL128, PGF_T_DECIMAL128, PGF_T_INT16, PGF_T_INT16, PGF_T_INT32}); break;
     default: return PGF_ERR_INVALID_ARGUMENT;
   }
   return PGF_OK;

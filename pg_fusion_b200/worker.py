@@ -55,6 +55,8 @@ class GenTable(IntEnum):
     ORDERS_Q3 = 4
     CUSTOMER_Q3 = 5
     KEYS_I64 = 6
+    LINEITEM_Q6_D = 7   # Decimal128 money, Date32 dates (SURVEY 8d "D" variant)
+    LINEITEM_Q1_D = 8
 
 
 @dataclass(frozen=True)

@@ -19,7 +19,15 @@ def pow2(n):
 
 
 with pg.Context(0) as ctx:
-    if shape in ("q6", "q1"):
+    if shape in ("q6d", "q1d"):
+        if shape == "q6d":
+            scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q6_D, rows, seed=42); plan = U.gpu_q6_d(scan); bpr = 52
+        else:
+            scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q1_D, rows, seed=42); plan = U.gpu_q1_d(scan); bpr = 72
+        for i in range(iters):
+            r = plan.run()
+            print(f"{shape} iter {i}: kernel {r.kernel_ms:.4f} ms, {rows * bpr / r.kernel_ms / 1e6:.1f} GB/s, rows_out {r.rows_out}")
+    elif shape in ("q6", "q1"):
         if shape == "q6":
             scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q6, rows, seed=42); plan = U.gpu_q6(scan); bpr = 40
         else:

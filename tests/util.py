@@ -210,3 +210,48 @@ def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=
     ctx.destroy_join_table(t1)
     ctx.destroy_join_table(t2)
     return res, dict(customer=r1, orders=r2, lineitem=stats)
+
+
+# ---- "D" schema variants: money Decimal128(15,2) as unscaled hundredths in 16-byte slots,
+# dates Date32 (Int32 days since 1970-01-01), flags Int16 character codes.  Decimal arithmetic follows
+# DataFusion's type rules: 1 - disc -> (100 - disc) at scale 2, products are plain i128 products.
+DEC = TypeTag.Decimal128
+Q6_D_SCHEMA = [ColumnSpec(DEC), ColumnSpec(DEC), ColumnSpec(DEC), ColumnSpec(I32)]
+Q1_D_SCHEMA = [ColumnSpec(DEC)] * 4 + [ColumnSpec(I16), ColumnSpec(I16), ColumnSpec(I32)]
+D_1994, D_1995, D_1998_09_02 = 8766, 9131, 10471   # days since 1970-01-01
+
+
+def gpu_q6_d(scan):
+    from pg_fusion_b200 import AggFunc, Cmp, Factor
+    return (scan.pipeline().filter(3, Cmp.GE, D_1994).filter(3, Cmp.LT, D_1995)
+            .filter(2, Cmp.GE, 5).filter(2, Cmp.LE, 7).filter(0, Cmp.LT, 2400)
+            .aggregate([], [(AggFunc.SUM, [Factor.of(1), Factor.of(2)]), (AggFunc.COUNT_STAR, None)]))
+
+
+def oracle_q6_d(table: O.OTable) -> O.AggOut:
+    filt = (E.col(3).ge(E.i64(D_1994))).and_(E.col(3).lt(E.i64(D_1995))) \
+        .and_(E.col(2).ge(E.i128(5))).and_(E.col(2).le(E.i128(7))).and_(E.col(0).lt(E.i128(2400)))
+    return O.aggregate(table, filt, [], [(O.AGG_SUM, E.col(1) * E.col(2)), (O.AGG_COUNT_STAR, None)])
+
+
+def gpu_q1_d(scan):
+    from pg_fusion_b200 import AggFunc, Cmp, Factor
+    disc_price = [Factor.of(1), Factor.const_minus(100, 2)]
+    charge = disc_price + [Factor.const_plus(100, 3)]
+    aggs = [(AggFunc.SUM, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(1)]), (AggFunc.SUM, disc_price), (AggFunc.SUM, charge),
+            (AggFunc.AVG, [Factor.of(0)]), (AggFunc.AVG, [Factor.of(1)]), (AggFunc.AVG, [Factor.of(2)]), (AggFunc.COUNT_STAR, None)]
+    return scan.pipeline().filter(6, Cmp.LE, D_1998_09_02).aggregate([4, 5], aggs)
+
+
+def oracle_q1_d(table: O.OTable):
+    """Returns {key: tuple} with DecimalAverager semantics for AVG (sum * 10^4 / count, truncating)."""
+    disc_price = E.col(1) * (E.i128(100) - E.col(2))
+    charge = disc_price * (E.i128(100) + E.col(3))
+    res = O.aggregate(table, E.col(6).le(E.i64(D_1998_09_02)), [E.col(4), E.col(5)],
+                      [(O.AGG_SUM, E.col(0)), (O.AGG_SUM, E.col(1)), (O.AGG_SUM, disc_price), (O.AGG_SUM, charge),
+                       (O.AGG_SUM, E.col(2)), (O.AGG_COUNT_STAR, None)])
+    out = {}
+    for k, (sq, sp, sdp, sch, sd, cnt) in res.by_key().items():
+        avg = lambda s: (abs(s * 10000) // cnt) * (1 if s >= 0 else -1)
+        out[k] = (sq, sp, sdp, sch, avg(sq), avg(sp), avg(sd), cnt)
+    return out, res

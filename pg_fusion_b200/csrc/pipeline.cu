@@ -291,6 +291,8 @@ uint32_t type_u32_words(int t) {
   }
 }
 
+const ShapeEntry* pick_shape(const Lowered& L);
+
 class Lowering {
  public:
   Lowering(pgf_ctx* ctx, const pgf_pipeline* plan) : ctx_(ctx), plan_(plan) {}
@@ -349,15 +351,16 @@ class Lowering {
       case PGF_SINK_COUNT: D.sink = SINK_COUNT; break;
       default: return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "unknown sink %d", plan_->sink);
     }
-    PGF_TRY(layout_stage(s));
-    fix_refs();
     // common subexpression: x*(c-y)*(c2+z) right after x*(c-y) reuses the previous value
+    // (ref.off still holds the stage slot of the column here: equal slots <=> equal columns)
     for (uint32_t e = 1; e < D.nexprs; ++e) {
       const DevExpr &a = D.exprs[e - 1], &b = D.exprs[e];
       if (a.form == FORM_X_CMY && b.form == FORM_X_CMY_CPZ && a.f[0].ref.off == b.f[0].ref.off &&
           a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf)
         D.exprs[e].form = FORM_PREV_CPZ;
     }
+    PGF_TRY(layout_stage(s));
+    fix_refs();
     return PGF_OK;
   }
 
@@ -731,10 +734,17 @@ class Lowering {
     // every warp busy: whole pages in a 3-deep ring.  (Measured on Q1: whole-page tiles raise the
     // share of busy warp slots from 46 % to 93 % but do not help -- the kernel is issue bound, and
     // the deeper ring of smaller tiles hides the TMA latency better.)
-    const uint32_t queue_bytes = (D.sink == SINK_AGG && L_->grouped) ? kMaxConsumerWarps * kQueueBytesPerWarp : 0u;
+    uint32_t queue_bytes = (D.sink == SINK_AGG && L_->grouped) ? kMaxConsumerWarps * kQueueBytesPerWarp : 0u;
+    if (const ShapeEntry* se = pick_shape(*L_))
+      if (se->fast_group_exprs) queue_bytes += fast_group_acc_bytes(se->fast_group_exprs);  // + accumulator slots
     const uint32_t smem_budget = 227u * 1024u - uint32_t((sizeof(BlockShared) + 127) & ~size_t(127)) - queue_bytes;
+    // tile starts must be 16-byte aligned in every staged buffer: 128 rows when a validity bitmap
+    // is staged, else 16 rows (2-byte values)
+    uint32_t gran = 16;
+    for (uint32_t c = 0; c < D.nstage_cols; ++c)
+      if (D.scol[c].nullable) gran = 128;
     auto shape = [&](uint32_t ntiles, uint32_t* tile_rows_out, uint32_t* stage_bytes_out) {
-      const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + 127u) & ~127u;
+      const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + gran - 1) / gran * gran;
       uint32_t stage_bytes = 0;
       for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += tile_rows * D.scol[c].width;
       for (uint32_t c = 0; c < D.nstage_cols; ++c)
@@ -755,7 +765,7 @@ class Lowering {
         for (ntiles = ntiles ? ntiles : 1;; ++ntiles) {
           shape(ntiles, &tile_rows, &stage_bytes);
           if (stage_bytes <= cap) { best_tiles = ntiles; best_stages = kStages; break; }
-          if (tile_rows == 128) break;
+          if (tile_rows <= gran) break;
         }
       }
     }
@@ -1137,7 +1147,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   const bool agg = plan->sink == PGF_SINK_AGGREGATE;
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
-  uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.nitems ? L.dev.nitems : 1, uint64_t(ctx->sm_count)));
+  uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
   uint64_t capacity = L.table_capacity;
   float total_ms = 0.f;
   uint32_t launches = 0;
@@ -1306,7 +1316,7 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
   PGF_TRY(arena_table(ctx, L.table_capacity, plan->nexprs, aw, &ta));
   L.dev.table = ta.t;
   L.dev.counters = &ta.d_header->counters;
-  const uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.nitems ? L.dev.nitems : 1, uint64_t(ctx->sm_count)));
+  const uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
   CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
   if (L.dev.nitems) {
     if (const ShapeEntry* se = pick_shape(L))

@@ -40,6 +40,8 @@ __host__ __device__ constexpr uint32_t rows_per_thread(uint32_t nj) { return nj 
 // point, instead of one or two lanes at a time from inside the divergent probe loop.
 constexpr uint32_t kQueueBytesPerWarp = 2048;
 __host__ __device__ constexpr uint32_t queue_entry_words(uint32_t maxe, uint32_t acc_words) { return kKeyWords + 1 + maxe * acc_words; }
+// shared-memory accumulator slots of the fast GROUP BY path: groups x (arguments + row count) x consumer threads x 8 B
+__host__ __device__ constexpr uint32_t fast_group_acc_bytes(uint32_t nexprs) { return kRegGroups * (nexprs + 1) * uint32_t(consumer_warps(SINK_AGG, true)) * 32u * 8u; }
 constexpr uint32_t kAccF64MaxExprs = 8, kAccI128MaxExprs = 6;
 
 struct StageMeta {
@@ -673,6 +675,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
   constexpr uint32_t G = (SINK == SINK_AGG && GROUPED) ? kRegGroups : 1;
   constexpr uint32_t kRows = rows_per_thread(NJ);  // rows per thread and iteration
+  constexpr uint32_t kAccThreads = uint32_t(kConsumerWarps) * 32u;  // threads with shared-memory accumulator slots
   const uint32_t kNumStages = P.nstages;  // 3 or kStages
   constexpr uint32_t kAccWords = ACC == CLS_I128 ? 2 : 1;
   [[maybe_unused]] constexpr uint32_t kQueueEntryWords = queue_entry_words(MAXE, kAccWords);
@@ -715,53 +718,63 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   for (uint32_t g = 0; g < G; ++g) dh[g] = 0;
   uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0;
 
+  // shared-memory accumulator slots of the fast GROUP BY path (behind the ring and the queues)
+  [[maybe_unused]] double* myacc = reinterpret_cast<double*>(stages + size_t(kNumStages) * P.stage_bytes +
+                                                             size_t(kMaxConsumerWarps) * kQueueBytesPerWarp) +
+                                   (threadIdx.x >= 32 ? threadIdx.x - 32 : 0);
+  if constexpr (kFastGrouped) {
+    if (warp > 0)
+      for (uint32_t q = 0; q < G * (SHAPE::Exprs::size + 1); ++q) myacc[q * kAccThreads] = 0.0;  // +0.0 == integer 0
+  }
+
   if (warp == 0) {
     // ===== producer: TMA bulk copies of the needed column slices of each row tile =====
-    uint32_t k = 0, ps = 0, pphase = 0;  // ring stage and mbarrier phase of the producer
-    uint32_t item = blockIdx.x;
+    // One warp feeds the whole CTA, so its per-tile path is kept short: pages are walked with a
+    // nested page / tile loop (no divisions), each lane keeps its column's plan entry and the
+    // offsets of the current layout class in registers, the byte count is one warp reduction.
+    uint32_t ps = 0, pphase = 0;  // ring stage and mbarrier phase of the producer
+    // lanes 0..15: values slice of staged column `lane`; lanes 16..31: its validity slice
+    const uint32_t mycol = lane & 15u;
+    const bool is_validity = lane >= 16;
+    const bool has_col = mycol < P.nstage_cols;
+    DevStageCol sc{};
+    if (has_col) sc = P.scol[mycol];
+    const bool want = has_col && (!is_validity || sc.nullable);
+    const uint32_t width = is_validity ? 0u : uint32_t(sc.width);
+    const uint32_t smem_off = is_validity ? sc.valid_off : sc.smem_off;
+    uint32_t cur_class = 0xFFFFFFFFu, col_off = 0;
+    uint32_t page = blockIdx.x;
     PageDesc d_next{};
-    if (item < P.nitems) d_next = P.descs[item / P.tiles_per_page];
-    for (; item < P.nitems; item += gridDim.x, ++k) {
-      const uint32_t s = ps;
-      const uint32_t page = item / P.tiles_per_page, tile = item - page * P.tiles_per_page;
+    if (page < P.npages) d_next = P.descs[page];
+    for (; page < P.npages; page += gridDim.x) {
       const PageDesc d = d_next;
-      if (item + gridDim.x < P.nitems) d_next = P.descs[(item + gridDim.x) / P.tiles_per_page];  // prefetch
-      const LayoutClass* lc = P.classes + d.layout_class;
-      const uint32_t r0 = tile * P.tile_rows;
-      const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
-      const uint8_t* page_base = P.pages + uint64_t(page) * P.page_stride;
-      uint8_t* stage = stages + size_t(s) * P.stage_bytes;
-      uint32_t bytes = 0;
-      const uint8_t* src = nullptr;
-      uint8_t* dst = nullptr;
-      if (n) {
-        if (lane < P.nstage_cols) {
-          const DevStageCol sc = P.scol[lane];
-          bytes = (n * sc.width + 15u) & ~15u;
-          src = page_base + lc->values_off[sc.page_col] + r0 * uint32_t(sc.width);
-          dst = stage + sc.smem_off;
-        } else if (lane >= 16 && lane - 16 < P.nstage_cols) {
-          const DevStageCol sc = P.scol[lane - 16];
-          if (sc.nullable && ((d.null_mask & P.used_null_mask) >> sc.page_col) & 1) {
-            bytes = (((n + 7u) >> 3) + 15u) & ~15u;
-            src = page_base + lc->validity_off[sc.page_col] + (r0 >> 3);
-            dst = stage + sc.valid_off;
-          }
+      if (page + gridDim.x < P.npages) d_next = P.descs[page + gridDim.x];  // prefetch
+      if (d.layout_class != cur_class) {  // rare: pages of one scan share their layout class
+        cur_class = d.layout_class;
+        const LayoutClass* lc = P.classes + cur_class;
+        col_off = want ? (is_validity ? lc->validity_off[sc.page_col] : lc->values_off[sc.page_col]) : 0u;
+      }
+      const uint8_t* col_base = P.pages + uint64_t(page) * P.page_stride + col_off;
+      const uint32_t null_mask = d.null_mask & P.used_null_mask;
+      const bool active = want && (!is_validity || ((null_mask >> sc.page_col) & 1u));
+      for (uint32_t tile = 0, r0 = 0; tile < P.tiles_per_page; ++tile, r0 += P.tile_rows) {
+        const uint32_t s = ps;
+        const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
+        uint32_t bytes = 0;
+        if (active && n) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * width + 15u) & ~15u);
+        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+        mbar_wait(&sh->empty[s], pphase ^ 1u);
+        if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
+        if (lane == 0) {
+          sh->meta[s].nrows = n;
+          sh->meta[s].null_mask = null_mask;
+          sh->meta[s].row_base = d.row_base + r0;
+          mbar_arrive_expect_tx(&sh->full[s], total);
         }
+        __syncwarp();
+        if (bytes)
+          tma_load_1d(stages + size_t(s) * P.stage_bytes + smem_off, col_base + (is_validity ? (r0 >> 3) : r0 * width), bytes, &sh->full[s]);
       }
-      uint32_t total = bytes;
-#pragma unroll
-      for (int o = 16; o; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-      mbar_wait(&sh->empty[s], pphase ^ 1u);
-      if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
-      if (lane == 0) {
-        sh->meta[s].nrows = n;
-        sh->meta[s].null_mask = d.null_mask & P.used_null_mask;
-        sh->meta[s].row_base = d.row_base + r0;
-        mbar_arrive_expect_tx(&sh->full[s], total);
-      }
-      __syncwarp();
-      if (bytes) tma_load_1d(dst, src, bytes, &sh->full[s]);
     }
   } else {
     // ===== consumers =====
@@ -790,7 +803,10 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
       }
     };
     uint32_t k = 0, cs = 0, cphase = 0;  // ring stage and mbarrier phase of this consumer
-    for (uint32_t item = blockIdx.x; item < P.nitems; item += gridDim.x, ++k) {
+    // tiles arrive in the producer's order: the pages blockIdx.x, blockIdx.x + gridDim.x, ... tile by tile
+    const uint32_t my_pages = P.npages > blockIdx.x ? (P.npages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+    const uint32_t my_items = my_pages * P.tiles_per_page;
+    for (uint32_t item = 0; item < my_items; ++item, ++k) {
       const uint32_t s = cs;
       mbar_wait(&sh->full[s], cphase);
       if (++cs == kNumStages) { cs = 0; cphase ^= 1u; }
@@ -891,17 +907,21 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
             v1[e] = eval_fast_f64<form>(P.exprs[e], stage, r1, v1[e > 0 ? e - 1 : 0]);
           });
           const int a0 = keep0 ? g0 : -2, a1 = keep1 ? g1 : -2;
+          // Accumulators of the register-resident groups live in shared memory, one private slot per
+          // (group, argument, thread): `accs[(g * (NE + 1) + e) * T + tid]`.  Indexing by the row's
+          // group costs one load-add-store per argument and no divergence; selecting among register
+          // accumulators costs three instructions per (group, argument) -- 64 vs 20 per row for Q1.
+          if (a0 >= 0) {
+            double* p0 = myacc + uint32_t(a0) * ((NE + 1) * kAccThreads);
 #pragma unroll
-          for (uint32_t gg = 0; gg < G; ++gg) {
-            pred_inc(grows[gg], a0, int(gg));
-#pragma unroll
-            for (int e = 0; e < NE; ++e) pred_dadd(acc[gg][e], v0[e], a0, int(gg));
+            for (int e = 0; e < NE; ++e) p0[e * kAccThreads] = __dadd_rn(p0[e * kAccThreads], v0[e]);
+            reinterpret_cast<unsigned long long*>(p0)[NE * kAccThreads] += 1ull;
           }
+          if (a1 >= 0) {
+            double* p1 = myacc + uint32_t(a1) * ((NE + 1) * kAccThreads);
 #pragma unroll
-          for (uint32_t gg = 0; gg < G; ++gg) {
-            pred_inc(grows[gg], a1, int(gg));
-#pragma unroll
-            for (int e = 0; e < NE; ++e) pred_dadd(acc[gg][e], v1[e], a1, int(gg));
+            for (int e = 0; e < NE; ++e) p1[e * kAccThreads] = __dadd_rn(p1[e * kAccThreads], v1[e]);
+            reinterpret_cast<unsigned long long*>(p1)[NE * kAccThreads] += 1ull;
           }
           if (a0 == -1 || a1 == -1) {
             ValuesF64<NE> x0, x1;
@@ -1243,13 +1263,21 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
         // e == nexprs reduces the row count of the group
         AccT a = Ops::zero();
         uint64_t rows = 0;
+        if constexpr (kFastGrouped) {
+          constexpr uint32_t NE = SHAPE::Exprs::size;
+          if (warp > 0) {
+            if (e < NE) a = myacc[(g * (NE + 1) + e) * kAccThreads];
+            else if (e == P.nexprs) rows = reinterpret_cast<const unsigned long long*>(myacc)[(g * (NE + 1) + NE) * kAccThreads];
+          }
+        } else {
 #pragma unroll
-        for (uint32_t gg = 0; gg < G; ++gg) {
-          if (gg == g) {
-            rows = grows[gg];
+          for (uint32_t gg = 0; gg < G; ++gg) {
+            if (gg == g) {
+              rows = grows[gg];
 #pragma unroll
-            for (uint32_t ee = 0; ee < MAXE; ++ee)
-              if (ee == e) a = acc[gg][ee];
+              for (uint32_t ee = 0; ee < MAXE; ++ee)
+                if (ee == e) a = acc[gg][ee];
+            }
           }
         }
         if (warp == 0) { a = Ops::zero(); rows = 0; }

@@ -23,6 +23,9 @@ struct ShapeEntry {
   ShapeSig sig;
   ShapeLaunchFn fn;
   const char* name;
+  // > 0: the instantiation takes the fast GROUP BY path (Float64 sums over NOT NULL scan columns,
+  // no join) and needs shared-memory accumulator slots for this many arguments
+  uint32_t fast_group_exprs;
 };
 
 const ShapeEntry* find_shape(const ShapeSig& sig);

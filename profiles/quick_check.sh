@@ -1,1 +1,4 @@
-python -m pytest tests/test_gpu_full_size.py -x -q 2>&1 | tail -15
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python profiles/run_shape.py q1 59986052 4
+python profiles/run_shape.py q6 59986052 3
+python profiles/run_shape.py q3 59986052 3

@@ -26,8 +26,13 @@ namespace pgf {
 // Consumer warps per CTA: 16 for streaming sinks; 8 when kRegGroups x kMaxExprs register
 // accumulators per thread are live (GROUP BY), which needs the larger register budget (12 warps).
 constexpr int kMaxConsumerWarps = 16;
-__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped) { return (sink == SINK_AGG && grouped) ? 14 : 16; }
-__host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped) { return (consumer_warps(sink, grouped) + 1) * 32; }
+// `fast`: the fast GROUP BY path keeps its accumulators in shared memory, so it fits 16 warps too.
+__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped, bool fast = false) {
+  return (sink == SINK_AGG && grouped && !fast) ? 14 : 16;
+}
+__host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped, bool fast = false) {
+  return (consumer_warps(sink, grouped, fast) + 1) * 32;
+}
 constexpr int kStages = 4;     // ring depth of streaming pipelines
 #ifndef PGF_JOIN_ROWS
 #define PGF_JOIN_ROWS 4
@@ -41,7 +46,7 @@ __host__ __device__ constexpr uint32_t rows_per_thread(uint32_t nj) { return nj 
 constexpr uint32_t kQueueBytesPerWarp = 2048;
 __host__ __device__ constexpr uint32_t queue_entry_words(uint32_t maxe, uint32_t acc_words) { return kKeyWords + 1 + maxe * acc_words; }
 // shared-memory accumulator slots of the fast GROUP BY path: groups x (arguments + row count) x consumer threads x 8 B
-__host__ __device__ constexpr uint32_t fast_group_acc_bytes(uint32_t nexprs) { return kRegGroups * (nexprs + 1) * uint32_t(consumer_warps(SINK_AGG, true)) * 32u * 8u; }
+__host__ __device__ constexpr uint32_t fast_group_acc_bytes(uint32_t nexprs) { return kRegGroups * (nexprs + 1) * uint32_t(consumer_warps(SINK_AGG, true, true)) * 32u * 8u; }
 constexpr uint32_t kAccF64MaxExprs = 8, kAccI128MaxExprs = 6;
 
 struct StageMeta {
@@ -667,9 +672,18 @@ __device__ __forceinline__ void global_accumulate(const DevPlan& P, bool grouped
 }
 
 // ---- the kernel ----------------------------------------------------------------------
+// straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 sums, no join
+template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, class SHAPE>
+constexpr bool is_fast_grouped() {
+  return SINK == SINK_AGG && GROUPED && NJ == 0 && ACC == CLS_F64 && !SHAPE::generic && SHAPE::no_nulls &&
+         SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0;
+}
+
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
-__global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_kernel(const __grid_constant__ DevPlan P) {
-  constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED);
+__global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED, is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>()), 1)
+pipeline_kernel(const __grid_constant__ DevPlan P) {
+  constexpr bool kFastGrouped = is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>();
+  constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED, kFastGrouped);
   using Ops = AccOps<ACC>;
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
@@ -681,9 +695,6 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED), 1) pipeline_k
   [[maybe_unused]] constexpr uint32_t kQueueEntryWords = queue_entry_words(MAXE, kAccWords);
   [[maybe_unused]] constexpr uint32_t kQueueCap = kQueueBytesPerWarp / (8 * kQueueEntryWords);
   [[maybe_unused]] constexpr uint32_t kQueueDrainAt = kQueueCap > 12 ? kQueueCap - 8 : kQueueCap / 2;
-  // straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 sums, no join
-  constexpr bool kFastGrouped = SINK == SINK_AGG && GROUPED && NJ == 0 && ACC == CLS_F64 && !SHAPE::generic &&
-                                SHAPE::no_nulls && SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   BlockShared* sh = reinterpret_cast<BlockShared*>(smem_raw);

@@ -300,3 +300,32 @@ def test_q1_shape_with_non_finite_values(ctx):
     # a group without any non-finite input keeps finite sums
     assert any(all(math.isfinite(v) for v in vals if isinstance(v, float)) for vals in gk.values()) or len(gk) < 4
     scan.release()
+
+
+def test_scan_with_several_layout_classes_and_ragged_pages(ctx):
+    """Pages of one scan may differ in max_rows (each page is self-describing, raw.rs:21-46): the
+    producer switches layout classes per page; the last page of each run is partially filled."""
+    parts, pages = [], []
+    for n, seed, rpp in ((5_000, 1, 700), (3_333, 2, 1614), (777, 3, 128), (4_100, 4, 1000)):
+        li = U.lineitem(n, seed)
+        parts.append(li)
+        pages.append(U.q6_pages(li, rows_per_page=rpp))
+    allp = np.concatenate(pages)
+    scan = ctx.declare_scan(U.Q6_SCHEMA)
+    for p in pages:            # four pushes, interleaving the classes would work the same
+        scan.push_pages(p)
+    scan.finish()
+    res = U.gpu_q6(scan).run()
+    want = U.oracle_q6(O.OTable.from_pages(allp, 65536, U.orc_cols(U.Q6_SCHEMA)))
+    assert res.rows_in == sum(len(p["qty"]) for p in parts) and res.rows_filtered == want.rows_filtered
+    U.assert_agg_equal(res, want)
+    # the same pages in an interleaved order (class changes on almost every page)
+    order = np.random.default_rng(0).permutation(allp.shape[0])
+    scan2 = ctx.declare_scan(U.Q6_SCHEMA)
+    scan2.push_pages(np.ascontiguousarray(allp[order]))
+    scan2.finish()
+    res2 = U.gpu_q6(scan2).run()
+    assert res2.rows_filtered == want.rows_filtered and res2.aggs[0][1] == want.aggs[0][1]
+    U.assert_close(res2.aggs[0][0], want.aggs[0][0], 1e-12, "revenue, interleaved classes")
+    scan.release()
+    scan2.release()

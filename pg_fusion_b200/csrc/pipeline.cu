@@ -356,7 +356,7 @@ class Lowering {
     for (uint32_t e = 1; e < D.nexprs; ++e) {
       const DevExpr &a = D.exprs[e - 1], &b = D.exprs[e];
       if (a.form == FORM_X_CMY && b.form == FORM_X_CMY_CPZ && a.f[0].ref.off == b.f[0].ref.off &&
-          a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf)
+          a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf && a.f[1].ci_lo == b.f[1].ci_lo && a.f[1].ci_hi == b.f[1].ci_hi)
         D.exprs[e].form = FORM_PREV_CPZ;
     }
     PGF_TRY(layout_stage(s));
@@ -602,14 +602,15 @@ class Lowering {
       dx.form = FORM_GENERIC;
       dx.null_cols = 0;
       dx.has_payload = 0;
-      bool plain_f64 = true;
+      bool plain_f64 = true, plain_dec = true;
       for (uint32_t f = 0; f < x.nfactors; ++f) {
         const DevRef& rf = dx.f[f].ref;
         plain_f64 &= rf.src == SRC_PAGE && rf.ld == LD_F64;
+        plain_dec &= rf.src == SRC_PAGE && rf.ld == LD_DEC;
         if (rf.src == SRC_PAGE) { if (L_->scan->schema[rf.pcol].nullable) dx.null_cols |= 1u << rf.pcol; }
         else dx.has_payload = 1;
       }
-      if (plain_f64) {
+      if (plain_f64 || plain_dec) {  // straight-line forms (the generic evaluators ignore them)
         const uint32_t k0 = dx.f[0].kind, k1 = x.nfactors > 1 ? dx.f[1].kind : 0, k2 = x.nfactors > 2 ? dx.f[2].kind : 0;
         if (x.nfactors == 1 && k0 == PGF_FACTOR_COL) dx.form = FORM_X;
         else if (x.nfactors == 2 && k0 == PGF_FACTOR_COL && k1 == PGF_FACTOR_COL) dx.form = FORM_XY;

@@ -30,16 +30,16 @@ using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true,
                        IntList<key_enc(LD_I32, false, 0), key_enc(LD_VIEW, true, 1), key_enc(LD_I32, true, 3)>>;
 
 // "D" variants: Decimal128 money, Date32 dates, Int16 flag codes; wrapping i128 arithmetic
-using Q6ShapeD = ShapeT<false, IntList<LD_I32, LD_DEC, LD_DEC>, IntList<FORM_GENERIC>, true>;
-using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_GENERIC, FORM_GENERIC, FORM_GENERIC, FORM_GENERIC, FORM_GENERIC>, true,
+using Q6ShapeD = ShapeT<false, IntList<LD_I32, LD_DEC, LD_DEC>, IntList<FORM_XY>, true>;
+using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true,
                         IntList<key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1)>>;
 
 const ShapeEntry kShapes[] = {
-    {{SINK_AGG, CLS_I128, 0, 0, 2, 3, {LD_I32, LD_DEC, LD_DEC, -1}, 1, {FORM_GENERIC, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
+    {{SINK_AGG, CLS_I128, 0, 0, 2, 3, {LD_I32, LD_DEC, LD_DEC, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_I128, false, 0, 2, Q6ShapeD>, "q6_decimal", 0},
-    {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_GENERIC, FORM_GENERIC, FORM_GENERIC, FORM_GENERIC, FORM_GENERIC, -1, -1, -1},
+    {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1},
       2, {key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1), 0, 0}},
-     launch_shape<SINK_AGG, CLS_I128, true, 0, kAccI128MaxExprs, Q1ShapeD>, "q1_decimal_8aggs", 0},
+     launch_shape<SINK_AGG, CLS_I128, true, 0, kAccI128MaxExprs, Q1ShapeD>, "q1_decimal_8aggs", 5},
     {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>, "q6_f64", 0},
     {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1},

@@ -635,23 +635,80 @@ __device__ __forceinline__ double eval_fast_f64(const DevExpr& e, const uint8_t*
   else return __dmul_rn(prev, __dadd_rn(e.f[2].cf, col(2)));  // FORM_PREV_CPZ
 }
 
-// Rare path of the fast sink: the row's group is not register resident (more than kRegGroups
-// groups in this CTA): accumulate straight into the global table.
-template <int NE>
-struct ValuesF64 {
-  double v[NE];
+// Decimal128 argument forms over NOT NULL Decimal128 scan columns: wrapping i128, no rescale
+template <int FORM>
+__device__ __forceinline__ I128 eval_fast_i128(const DevExpr& e, const uint8_t* stage, uint32_t r, I128 prev) {
+  auto col = [&](int f) {
+    const uint4 raw = reinterpret_cast<const uint4*>(stage + e.f[f].ref.off)[r];
+    return I128{(uint64_t(raw.y) << 32) | raw.x, (uint64_t(raw.w) << 32) | raw.z};
+  };
+  auto cst = [&](int f) { return I128{uint64_t(e.f[f].ci_lo), uint64_t(e.f[f].ci_hi)}; };
+  if constexpr (FORM == int(FORM_X)) return col(0);
+  else if constexpr (FORM == int(FORM_XY)) return i128_mul(col(0), col(1));
+  else if constexpr (FORM == int(FORM_X_CMY)) return i128_mul(col(0), i128_sub(cst(1), col(1)));
+  else if constexpr (FORM == int(FORM_X_CMY_CPZ)) return i128_mul(i128_mul(col(0), i128_sub(cst(1), col(1))), i128_add(cst(2), col(2)));
+  else return i128_mul(prev, i128_add(cst(2), col(2)));  // FORM_PREV_CPZ
+}
+
+template <uint32_t ACC, int FORM>
+__device__ __forceinline__ typename AccOps<ACC>::T eval_fast(const DevExpr& e, const uint8_t* stage, uint32_t r, typename AccOps<ACC>::T prev) {
+  if constexpr (ACC == CLS_F64) return eval_fast_f64<FORM>(e, stage, r, prev);
+  else return eval_fast_i128<FORM>(e, stage, r, prev);
+}
+
+// One 8-byte shared-memory accumulator slot.  Float64: the running sum.  Decimal128: a signed 64-bit
+// partial sum -- values that do not fit 64 bits, or an addition that would overflow the slot, are
+// reported (false) and go to the 128-bit accumulator of the global table instead, so the total is the
+// exact wrapping i128 sum whatever the magnitudes.
+template <uint32_t ACC>
+__device__ __forceinline__ bool slot_add(unsigned long long* slot, typename AccOps<ACC>::T v) {
+  if constexpr (ACC == CLS_F64) {
+    *reinterpret_cast<double*>(slot) = __dadd_rn(*reinterpret_cast<double*>(slot), v);
+    return true;
+  } else {
+    const int64_t x = int64_t(v.lo), s = int64_t(*slot);
+    const int64_t r = int64_t(uint64_t(s) + uint64_t(x));
+    const bool fits = v.hi == uint64_t(x >> 63);
+    const bool overflow = ((s ^ r) & (x ^ r)) < 0;
+    if (fits && !overflow) *slot = uint64_t(r);
+    return fits && !overflow;
+  }
+}
+template <uint32_t ACC>
+__device__ __forceinline__ typename AccOps<ACC>::T slot_value(const unsigned long long* slot) {
+  if constexpr (ACC == CLS_F64) return *reinterpret_cast<const double*>(slot);
+  else {
+    const int64_t s = int64_t(*slot);
+    return I128{uint64_t(s), s < 0 ? ~0ull : 0ull};
+  }
+}
+
+// Rare paths of the fast sink.  (a) The row's group is not slot resident (more than kRegGroups groups
+// in this CTA): the whole row goes straight to the global table.  (b) One Decimal128 value could not
+// be added to its 64-bit slot: only that value goes to the global accumulator (the row is still
+// counted by its slot).
+template <uint32_t ACC, int NE>
+struct FastValues {
+  typename AccOps<ACC>::T v[NE];
 };
-template <int NE>
-static __device__ __noinline__ void fast_slow_accumulate(const DevPlan& P, Key4 kv, ValuesF64<NE> vals) {
+template <uint32_t ACC, int NE>
+static __device__ __noinline__ void fast_slow_accumulate(const DevPlan& P, Key4 kv, FastValues<ACC, NE> vals) {
+  using Ops = AccOps<ACC>;
   const uint64_t key[kKeyWords] = {kv.w0, kv.w1, kv.w2, kv.w3};
   const int64_t slot = group_slot(P.table, key, P.nkeywords, 0);
   if (slot < 0) return;
 #pragma unroll
   for (int e = 0; e < NE; ++e) {
-    atomicAdd(reinterpret_cast<double*>(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words), vals.v[e]);
+    Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, vals.v[e]);
     atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + e), 1ull);
   }
   atomicAdd(reinterpret_cast<unsigned long long*>(P.table.cnt + uint64_t(slot) * (P.nexprs + 1) + P.nexprs), 1ull);
+}
+template <uint32_t ACC>
+static __device__ __noinline__ void fast_value_to_global(const DevPlan& P, Key4 kv, uint32_t e, typename AccOps<ACC>::T v) {
+  const uint64_t key[kKeyWords] = {kv.w0, kv.w1, kv.w2, kv.w3};
+  const int64_t slot = group_slot(P.table, key, P.nkeywords, 0);
+  if (slot >= 0) AccOps<ACC>::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, v);
 }
 
 // One row straight into the global group table (NULL inputs, groups beyond the register set).
@@ -672,11 +729,12 @@ __device__ __forceinline__ void global_accumulate(const DevPlan& P, bool grouped
 }
 
 // ---- the kernel ----------------------------------------------------------------------
-// straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 sums, no join
+// straight-line two-row sink: registered shape over NOT NULL scan columns, Float64 or Decimal128 sums of
+// arguments with a compile-time form, no join
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, class SHAPE>
 constexpr bool is_fast_grouped() {
-  return SINK == SINK_AGG && GROUPED && NJ == 0 && ACC == CLS_F64 && !SHAPE::generic && SHAPE::no_nulls &&
-         SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0;
+  return SINK == SINK_AGG && GROUPED && NJ == 0 && (ACC == CLS_F64 || ACC == CLS_I128) && !SHAPE::generic && SHAPE::no_nulls &&
+         SHAPE::Keys::size > 0 && SHAPE::Exprs::size > 0 && SHAPE::Exprs::template at<0>() != int(FORM_GENERIC);
 }
 
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
@@ -730,12 +788,12 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
   uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0;
 
   // shared-memory accumulator slots of the fast GROUP BY path (behind the ring and the queues)
-  [[maybe_unused]] double* myacc = reinterpret_cast<double*>(stages + size_t(kNumStages) * P.stage_bytes +
-                                                             size_t(kMaxConsumerWarps) * kQueueBytesPerWarp) +
-                                   (threadIdx.x >= 32 ? threadIdx.x - 32 : 0);
+  [[maybe_unused]] unsigned long long* myacc =
+      reinterpret_cast<unsigned long long*>(stages + size_t(kNumStages) * P.stage_bytes + size_t(kMaxConsumerWarps) * kQueueBytesPerWarp) +
+      (threadIdx.x >= 32 ? threadIdx.x - 32 : 0);
   if constexpr (kFastGrouped) {
     if (warp > 0)
-      for (uint32_t q = 0; q < G * (SHAPE::Exprs::size + 1); ++q) myacc[q * kAccThreads] = 0.0;  // +0.0 == integer 0
+      for (uint32_t q = 0; q < G * (SHAPE::Exprs::size + 1); ++q) myacc[q * kAccThreads] = 0ull;  // +0.0 / integer 0
   }
 
   if (warp == 0) {
@@ -910,36 +968,46 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
 #pragma unroll
             for (uint32_t gg = 0; gg < G; ++gg) dh[gg] = gg < n ? *reinterpret_cast<volatile uint64_t*>(&sh->dict_hash[gg]) : 0;
           }
-          double v0[NE], v1[NE];
+          AccT v0[NE], v1[NE];
           static_for<NE>([&](auto I) {
             constexpr int e = decltype(I)::value;
             constexpr int form = SHAPE::Exprs::template at<e>();
-            v0[e] = eval_fast_f64<form>(P.exprs[e], stage, r0, v0[e > 0 ? e - 1 : 0]);
-            v1[e] = eval_fast_f64<form>(P.exprs[e], stage, r1, v1[e > 0 ? e - 1 : 0]);
+            v0[e] = eval_fast<ACC, form>(P.exprs[e], stage, r0, v0[e > 0 ? e - 1 : 0]);
+            v1[e] = eval_fast<ACC, form>(P.exprs[e], stage, r1, v1[e > 0 ? e - 1 : 0]);
           });
           const int a0 = keep0 ? g0 : -2, a1 = keep1 ? g1 : -2;
-          // Accumulators of the register-resident groups live in shared memory, one private slot per
+          // Accumulators of the slot-resident groups live in shared memory, one private 8-byte slot per
           // (group, argument, thread): `accs[(g * (NE + 1) + e) * T + tid]`.  Indexing by the row's
           // group costs one load-add-store per argument and no divergence; selecting among register
           // accumulators costs three instructions per (group, argument) -- 64 vs 20 per row for Q1.
+          uint32_t spill0 = 0, spill1 = 0;  // Decimal128 values that did not fit their slot
           if (a0 >= 0) {
-            double* p0 = myacc + uint32_t(a0) * ((NE + 1) * kAccThreads);
+            unsigned long long* p0 = myacc + uint32_t(a0) * ((NE + 1) * kAccThreads);
 #pragma unroll
-            for (int e = 0; e < NE; ++e) p0[e * kAccThreads] = __dadd_rn(p0[e * kAccThreads], v0[e]);
-            reinterpret_cast<unsigned long long*>(p0)[NE * kAccThreads] += 1ull;
+            for (int e = 0; e < NE; ++e) spill0 |= uint32_t(!slot_add<ACC>(p0 + e * kAccThreads, v0[e])) << e;
+            p0[NE * kAccThreads] += 1ull;
           }
           if (a1 >= 0) {
-            double* p1 = myacc + uint32_t(a1) * ((NE + 1) * kAccThreads);
+            unsigned long long* p1 = myacc + uint32_t(a1) * ((NE + 1) * kAccThreads);
 #pragma unroll
-            for (int e = 0; e < NE; ++e) p1[e * kAccThreads] = __dadd_rn(p1[e * kAccThreads], v1[e]);
-            reinterpret_cast<unsigned long long*>(p1)[NE * kAccThreads] += 1ull;
+            for (int e = 0; e < NE; ++e) spill1 |= uint32_t(!slot_add<ACC>(p1 + e * kAccThreads, v1[e])) << e;
+            p1[NE * kAccThreads] += 1ull;
           }
           if (a0 == -1 || a1 == -1) {
-            ValuesF64<NE> x0, x1;
+            FastValues<ACC, NE> x0, x1;
 #pragma unroll
             for (int e = 0; e < NE; ++e) { x0.v[e] = v0[e]; x1.v[e] = v1[e]; }
-            if (a0 == -1) fast_slow_accumulate<NE>(P, Key4{key0[0], key0[1], key0[2], key0[3]}, x0);
-            if (a1 == -1) fast_slow_accumulate<NE>(P, Key4{key1[0], key1[1], key1[2], key1[3]}, x1);
+            if (a0 == -1) fast_slow_accumulate<ACC, NE>(P, Key4{key0[0], key0[1], key0[2], key0[3]}, x0);
+            if (a1 == -1) fast_slow_accumulate<ACC, NE>(P, Key4{key1[0], key1[1], key1[2], key1[3]}, x1);
+          }
+          if constexpr (ACC != CLS_F64) {
+            if (spill0 | spill1) {
+#pragma unroll
+              for (int e = 0; e < NE; ++e) {
+                if ((spill0 >> e) & 1) fast_value_to_global<ACC>(P, Key4{key0[0], key0[1], key0[2], key0[3]}, uint32_t(e), v0[e]);
+                if ((spill1 >> e) & 1) fast_value_to_global<ACC>(P, Key4{key1[0], key1[1], key1[2], key1[3]}, uint32_t(e), v1[e]);
+              }
+            }
           }
           continue;
         }
@@ -1277,8 +1345,8 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         if constexpr (kFastGrouped) {
           constexpr uint32_t NE = SHAPE::Exprs::size;
           if (warp > 0) {
-            if (e < NE) a = myacc[(g * (NE + 1) + e) * kAccThreads];
-            else if (e == P.nexprs) rows = reinterpret_cast<const unsigned long long*>(myacc)[(g * (NE + 1) + NE) * kAccThreads];
+            if (e < NE) a = slot_value<ACC>(myacc + (g * (NE + 1) + e) * kAccThreads);
+            else if (e == P.nexprs) rows = myacc[(g * (NE + 1) + NE) * kAccThreads];
           }
         } else {
 #pragma unroll

@@ -329,3 +329,41 @@ def test_scan_with_several_layout_classes_and_ragged_pages(ctx):
     U.assert_close(res2.aggs[0][0], want.aggs[0][0], 1e-12, "revenue, interleaved classes")
     scan.release()
     scan2.release()
+
+
+def test_decimal_fast_group_by_is_exact_beyond_64_bits(ctx):
+    """The registered Decimal128 Q1 shape keeps signed 64-bit partial sums in shared memory: values
+    that do not fit 64 bits and additions that would overflow a slot must reach the 128-bit global
+    accumulators, so the result is the exact wrapping i128 sum whatever the magnitudes."""
+    r = np.random.default_rng(21)
+    n = 40_000
+
+    def dec(vals):
+        out = np.zeros((len(vals), 16), dtype=np.uint8)
+        for i, v in enumerate(vals):
+            out[i] = np.frombuffer((int(v) & (2**128 - 1)).to_bytes(16, "little"), dtype=np.uint8)
+        return out
+    qty = [int(x) for x in r.integers(1, 51, n) * 100]
+    price = [int(x) for x in r.integers(-10**13, 10**13, n)]
+    for i in range(0, n, 7):        # slots overflow after a few rows
+        price[i] = int(r.integers(2**62, 2**63 - 1)) * (1 if i % 14 else -1)
+    for i in range(3, n, 11):       # values beyond 64 bits
+        price[i] = int(r.integers(-10**18, 10**18)) * 10**12
+    disc = [int(x) for x in r.integers(0, 11, n)]
+    tax = [int(x) for x in r.integers(0, 9, n)]
+    rf = r.choice(np.array([65, 78, 82], dtype=np.int16), n)
+    ls = r.choice(np.array([70, 79], dtype=np.int16), n)
+    ship = r.integers(8036, 10562, n).astype(np.int32)
+    pages = AL.encode_pages(U.Q1_D_SCHEMA, [(dec(qty), None), (dec(price), None), (dec(disc), None), (dec(tax), None),
+                                            (rf, None), (ls, None), (ship, None)])
+    scan = load(ctx, U.Q1_D_SCHEMA, pages)
+    res = U.gpu_q1_d(scan).run()
+    want, raw = U.oracle_q1_d(O.OTable.from_pages(pages, 65536, U.orc_cols(U.Q1_D_SCHEMA)))
+    assert res.rows_filtered == raw.rows_filtered and len(want) == 6
+    wrap = lambda v: ((v + 2**127) % 2**128) - 2**127    # wrapping i128 (DataFusion's Decimal128 sum wraps)
+    got = {k: tuple(v) for k, v in res.by_key().items()}
+    assert set(got) == set(want)
+    for k, w in want.items():
+        sums = tuple(wrap(x) for x in w[:4])
+        assert got[k][:4] == sums and got[k][7] == w[7], k
+    scan.release()

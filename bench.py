@@ -242,6 +242,114 @@ def sf100_measurements(ctx, pg, U, peak):
     return out
 
 
+def run_sf100(args):
+    """BASELINE.json configs[4]: the three shapes at SF100 with the pages sharded over the GPUs of
+    the box (strong scaling: 600 037 902 lineitem rows in total), partial aggregate states merged
+    over NCCL, broadcast joins and OR-merged Bloom filters for Q3.  Prints one JSON line; not the
+    driver's headline run (that is the default SF10 workload)."""
+    import torch
+
+    import pg_fusion_b200 as pg
+    from pg_fusion_b200 import multi_gpu as MG
+    from tests import util as U
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+    ctx = pg.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.compute_stream(), device=device)
+    peak, _ = measured_peak()
+    total = 10 * SF10_LINEITEM + 177_382
+    lo, hi = MG.shard_range(total, rank, world)
+    out = {"workload": "tpch_sf100_page_sharded", "n_gpus": world, "lineitem_rows": total, "steps": args.steps, "scaling": "strong"}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for name, table, make, bpr, sbytes in (("q6", pg.GenTable.LINEITEM_Q6, U.gpu_q6, Q6_BYTES_PER_ROW, 4096),
+                                           ("q1", pg.GenTable.LINEITEM_Q1, U.gpu_q1, Q1_BYTES_PER_ROW, 8192)):
+        scan = ctx.gen_scan(table, hi - lo, seed=42, first_row=lo)
+        plan = make(scan)
+        state = torch.zeros(sbytes, dtype=torch.uint8, device=device)
+        gathered = torch.zeros(world * sbytes, dtype=torch.uint8, device=device)
+
+        def step():
+            if world == 1:
+                return plan.run()
+            with torch.cuda.stream(stream):
+                plan.run_partial_async(state.data_ptr(), sbytes)
+                dist.all_gather_into_tensor(gathered, state)
+                return plan.merge_partials_bounded(gathered.data_ptr(), sbytes, world)
+        for _ in range(args.warmup):
+            res = step()
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        kms = []
+        for _ in range(args.steps):
+            res = step()
+            kms.append(res.kernel_ms)
+        ev1.record(stream)
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        k = max_over_ranks(statistics.mean(kms))
+        out[name] = {"rows_per_s": total / (ms / 1e3), "ms_per_step": ms, "kernel_ms_per_gpu": k,
+                     "per_gpu_achieved_GBps": (hi - lo) * bpr / (k / 1e3) / 1e9, "per_gpu_frac_of_measured_peak": (hi - lo) * bpr / (k / 1e3) / 1e9 / peak,
+                     "groups": len(res.keys)}
+        scan.release()
+    # Q3: customer 15 M, orders 150 M, lineitem 600 M rows; Bloom filters sized 16 bits per build key
+    ncust, nord = 15_000_000, 150_000_000
+    shards = []
+    for table, n, scale in ((pg.GenTable.CUSTOMER_Q3, ncust, 0), (pg.GenTable.ORDERS_Q3, nord, ncust), (pg.GenTable.LINEITEM_Q3, total, nord)):
+        a, b = MG.shard_range(n, rank, world)
+        shards.append(ctx.gen_scan(table, b - a, seed=42, first_row=a, scale_rows=scale))
+    for label, bp in (("q3_no_bloom", None), ("q3_bloom_16_bits_per_key", "sized")):
+        best, info = None, None
+        for _ in range(3):
+            params = None
+            if bp:
+                def pow2(n):
+                    b = 1
+                    while b < n:
+                        b <<= 1
+                    return b
+                params = (pg.BloomParams.new(pow2(16 * ncust // 5), 4, 7), pg.BloomParams.new(pow2(16 * nord // 10), 4, 7))
+            barrier()
+            t0 = time.perf_counter()
+            if world == 1:
+                res, st = U.gpu_q3(ctx, *shards, params, limit=10)
+            else:
+                res, st = U.gpu_q3_sharded(ctx, *shards, world, device, params, limit=10)
+            barrier()
+            dt = max_over_ranks(time.perf_counter() - t0)
+            if best is None or dt < best:
+                best = dt
+                info = {"rows_returned": len(res.keys), "joined_rows_this_rank": st["lineitem"].rows_out, "kernel_ms_per_gpu": {k: st[k].kernel_ms for k in ("customer", "orders", "lineitem")},
+                        "top1_orderkey": res.keys[0][0] if res.keys else None}
+        info.update({"lineitem_rows_per_s": total / best, "wall_ms": best * 1e3,
+                     "note": "wall clock of the whole query (ORDER BY revenue DESC, o_orderdate LIMIT 10): three fused pipelines, join-table "
+                             "export / all-gather / rebuild, Bloom OR-merge, partial -> final merge, device top-k"})
+        out[label] = info
+    if rank == 0:
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     """Reference arm: the reference's CPU path (DataFusion, single partition) cannot be built in
     this image (Rust); the oracle port of its semantics is timed on all host cores instead."""
@@ -290,9 +398,13 @@ def main():
     ap.add_argument("--rows", type=int, default=SF10_LINEITEM, help="lineitem rows per GPU")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-extras", action="store_true", help="skip the Q1 / Bloom side measurements")
+    ap.add_argument("--workload", default="sf10", choices=["sf10", "sf100"],
+                    help="sf10: the driver's headline run; sf100: BASELINE.json configs[4], page-sharded strong scaling")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "sf100":
+        return run_sf100(args)
 
     import numpy as np
     import torch

@@ -1412,7 +1412,23 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   const uint64_t ngroups = L.grouped ? h_header->used : 1;
   const uint64_t bytes = (1 + ngroups * ew) * 8;
   std::vector<uint64_t> h_state(1 + ngroups * ew);
-  if (ta.d_out) {
+  const bool topk = plan->nsort && plan->limit && plan->limit <= PGF_TOPK_DEVICE_MAX && ngroups > plan->limit;
+  uint32_t topk_launches = 0;
+  if (topk) {  // ORDER BY ... LIMIT k of the merged groups: select on the device, k rows leave the GPU
+    const uint64_t* d_entries = nullptr;
+    if (ta.d_out) {
+      d_entries = ta.d_out + 1;
+    } else {
+      PGF_TRY(grow(ctx, &ctx->d_out, &ctx->d_out_cap, bytes, "the result buffer"));
+      uint64_t* d_state = reinterpret_cast<uint64_t*>(ctx->d_out);
+      CU(ctx, cudaMemsetAsync(d_state, 0, 8, ctx->compute_stream));
+      PGF_TRY(extract_table(ctx, ta.t, capacity, plan->nexprs, L.grouped, d_state, ngroups));
+      d_entries = d_state + 1;
+    }
+    DevSort S;
+    PGF_TRY(lower_sort(ctx, plan, L, &S));
+    PGF_TRY(device_topk(ctx, S, d_entries, ngroups, uint32_t(plan->limit), &h_state, &topk_launches));
+  } else if (ta.d_out) {
     const uint64_t have = std::min<uint64_t>(ngroups, prefix_entries);
     std::memcpy(h_state.data(), h_out, (1 + have * ew) * 8);
     if (ngroups > have) {
@@ -1436,7 +1452,7 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
     return st;
   }
   sort_result(plan, res);  // ORDER BY / LIMIT of the final (merged) result
-  res->kernel_launches = nstates + 1;
+  res->kernel_launches = nstates + 1 + topk_launches;
   if (had_partial) {  // statistics of the asynchronous partial run that fed this merge
     const Counters& c = ph->counters;
     res->rows_in = c.rows_in;

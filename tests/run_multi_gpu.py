@@ -59,6 +59,12 @@ def main():
         joined = MG.all_gather_counts(st["lineitem"].rows_out, world, device)
         assert sum(joined) == st1["lineitem"].rows_out, (joined, st1["lineitem"].rows_out)
         assert U.top10(res)[0][0] == U.top10(single)[0][0]
+        # ORDER BY revenue DESC, o_orderdate LIMIT 10 on the merged groups (device top-k after the merge)
+        top, _ = U.gpu_q3_sharded(ctx, *shards, world, device, bp, limit=10)
+        want10 = U.top10(single)
+        assert [k[0] for k in top.keys] == [r[0] for r in want10]
+        for a, w in zip(top.aggs, want10):
+            U.assert_close(a[0], w[1], 1e-12, "revenue")
         for s in shards + wholes:
             s.release()
     dist.barrier()

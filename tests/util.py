@@ -124,8 +124,12 @@ LINEITEM_Q3_SCHEMA = [ColumnSpec(I32), ColumnSpec(F64), ColumnSpec(F64), ColumnS
 Q3_DATE = b"1995-03-15"
 
 
-def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDING"):
-    """Runs the three fused pipelines of the Q3 shape; returns (result, stats dict)."""
+Q3_ORDER = [("agg", 0, True), ("key", 1, False)]   # ORDER BY revenue DESC, o_orderdate (q03.sql)
+
+
+def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDING", limit=0):
+    """Runs the three fused pipelines of the Q3 shape; returns (result, stats dict).
+    limit > 0 adds ORDER BY revenue DESC, o_orderdate LIMIT n (device top-k)."""
     import pg_fusion_b200 as pg
     from pg_fusion_b200 import AggFunc, Cmp, Factor
     stats = {}
@@ -150,9 +154,12 @@ def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDIN
     p3 = lineitem.pipeline()
     if rf2 is not None:
         p3.bloom_probe(rf2, 0)
-    r3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(r2.join_table, 0)
+    p3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(r2.join_table, 0)
           .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
-                     expected_groups=max(1024, r2.rows_out)).run())
+                     expected_groups=max(1024, r2.rows_out)))
+    if limit:
+        p3.order_by(Q3_ORDER, limit=limit)
+    r3 = p3.run()
     ctx.destroy_join_table(r1.join_table)
     ctx.destroy_join_table(r2.join_table)
     stats.update(customer=r1, orders=r2, lineitem=r3, rf1=rf1, rf2=rf2)
@@ -175,7 +182,7 @@ def top10(res):
     return sorted(rows, key=lambda r: (-r[1], r[2]))[:10]
 
 
-def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=None, segment=b"BUILDING"):
+def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=None, segment=b"BUILDING", limit=0):
     """The Q3 shape with every scan sharded by pages over `world` ranks (one process per GPU):
     broadcast joins, OR-merged runtime filters, Partial -> Final aggregate."""
     from pg_fusion_b200 import AggFunc, Cmp, Factor
@@ -206,6 +213,8 @@ def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=
     p3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(t2, 0)
           .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
                      expected_groups=max(1024, total_orders)))
+    if limit:
+        p3.order_by(Q3_ORDER, limit=limit)   # applied to the merged (final) groups
     res, stats = MG.merge_partial_aggregate(p3, world, device, max_groups=max(1024, total_orders))
     ctx.destroy_join_table(t1)
     ctx.destroy_join_table(t2)

@@ -169,6 +169,7 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
     if (kv.second.d_words) cudaFree(kv.second.d_words);
   for (auto& kv : ctx->joins)
     if (kv.second.d_slots) cudaFree(kv.second.d_slots);
+  for (auto& c : ctx->join_cache) cudaFree(c.p);
   for (void* p : ctx->registered) cudaHostUnregister(p);
   for (int i = 0; i < 2; ++i) {
     if (ctx->staging[i]) cudaFreeHost(ctx->staging[i]);
@@ -798,7 +799,7 @@ pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
   if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)join_table);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->compute_stream);
-  cudaFree(it->second.d_slots);
+  ctx->join_free(it->second.d_slots, it->second.alloc_bytes);   // recycled by the next build of a similar size
   ctx->joins.erase(it);
   return PGF_OK;
 }

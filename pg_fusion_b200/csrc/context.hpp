@@ -49,6 +49,7 @@ struct BloomSlot {
 
 struct JoinTable {
   uint4* d_slots = nullptr;
+  size_t alloc_bytes = 0;   // size of the allocation behind d_slots (recycled through pgf_ctx::join_cache)
   uint32_t capacity = 0;
   uint32_t slot_u4 = 1;
   uint64_t rows = 0;
@@ -87,6 +88,39 @@ struct pgf_ctx {
   size_t d_topk_cap = 0;
   uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
   bool partial_pending = false;         // an asynchronous partial run awaits its merge
+  // Recycled join-table allocations: cudaMalloc / cudaFree of GB-sized tables cost 5-20 ms each
+  // (page-table work, implicit synchronisation), more than the join kernels themselves.
+  struct CachedBuf { void* p; size_t bytes; };
+  std::vector<CachedBuf> join_cache;
+  void* join_alloc(size_t bytes, size_t* got) {   // caller holds mu or is single threaded per the ABI contract
+    size_t best = join_cache.size();
+    for (size_t i = 0; i < join_cache.size(); ++i)
+      if (join_cache[i].bytes >= bytes && join_cache[i].bytes <= 2 * bytes + (1u << 20) &&
+          (best == join_cache.size() || join_cache[i].bytes < join_cache[best].bytes)) best = i;
+    if (best != join_cache.size()) {
+      void* p = join_cache[best].p;
+      *got = join_cache[best].bytes;
+      join_cache.erase(join_cache.begin() + long(best));
+      return p;
+    }
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+      cudaGetLastError();
+      for (auto& c : join_cache) cudaFree(c.p);   // give the cache back and retry once
+      join_cache.clear();
+      if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    }
+    *got = bytes;
+    return p;
+  }
+  void join_free(void* p, size_t bytes) {
+    if (!p) return;
+    if (join_cache.size() >= 4) {   // keep the four most recent
+      cudaFree(join_cache.front().p);
+      join_cache.erase(join_cache.begin());
+    }
+    join_cache.push_back(CachedBuf{p, bytes});
+  }
   std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;
   std::map<uint64_t, pgf::BloomSlot> blooms;
   std::map<uint64_t, pgf::JoinTable> joins;

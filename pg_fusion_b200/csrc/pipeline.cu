@@ -1,6 +1,9 @@
 // Host side of the fused pipelines: lowering of the C-ABI plan (pgf_pipeline) into the
 // device plan, eligibility rules, launch, and extraction of AggregateExec results.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "context.hpp"
@@ -16,6 +19,26 @@ cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t 
 
 namespace {
 
+// PGF_TRACE=1: synchronise at phase boundaries of pgf_pipeline_run and print the elapsed host time of
+// each phase to stderr (development aid; off by default, adds synchronisations when on).
+struct PhaseTrace {
+  bool on = false;
+  cudaStream_t stream;
+  std::chrono::steady_clock::time_point t;
+  explicit PhaseTrace(cudaStream_t s) : stream(s) {
+    const char* e = std::getenv("PGF_TRACE");
+    on = e && *e && *e != '0';
+    if (on) { cudaStreamSynchronize(stream); t = std::chrono::steady_clock::now(); }
+  }
+  void mark(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(stream);
+    const auto now = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[pgf trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
+};
+
 // ---- device helpers for the group table ------------------------------------------------
 // Partial-state entry: [kKeyWords key][1 null mask][nexprs * acc_words acc][nexprs + 1 counts]
 __host__ __device__ inline uint32_t entry_words(uint32_t nexprs, uint32_t acc_words) {
@@ -23,20 +46,59 @@ __host__ __device__ inline uint32_t entry_words(uint32_t nexprs, uint32_t acc_wo
 }
 
 // Compacts the occupied slots into out = [count][entries...]; out[0] must be zero on entry.
-// An aggregate without GROUP BY always has its single output row (slot 0).
-__global__ void table_extract_kernel(GroupTable t, uint32_t nexprs, bool grouped, uint64_t* out, uint64_t max_entries) {
+// An aggregate without GROUP BY always has its single output row (slot 0).  Every block owns a
+// contiguous segment of the table: it counts its occupied slots, reserves its output range with ONE
+// atomic (a per-slot atomic on the single counter serialises: 26 ms for 1.1 M groups) and writes
+// its entries at block-local prefix positions.
+constexpr uint32_t kExtractThreads = 256;
+__global__ void __launch_bounds__(kExtractThreads) table_extract_kernel(GroupTable t, uint32_t nexprs, bool grouped, uint64_t* out,
+                                                                       uint64_t max_entries) {
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_warp[kExtractThreads / 32];
   const uint32_t ew = entry_words(nexprs, t.acc_words);
   const uint64_t nslots = grouped ? uint64_t(t.mask) + 1 : 1;
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nslots; i += uint64_t(gridDim.x) * blockDim.x) {
-    const uint32_t s = t.state[i];
-    if (grouped && (s & 3u) != 2u) continue;
-    const unsigned long long pos = atomicAdd(reinterpret_cast<unsigned long long*>(out), 1ull);
-    if (pos >= max_entries) continue;
-    uint64_t* e = out + 1 + pos * ew;
-    for (uint32_t w = 0; w < kKeyWords; ++w) e[w] = t.keys[i * kKeyWords + w];
-    e[kKeyWords] = s >> 8;
-    for (uint32_t w = 0; w < nexprs * t.acc_words; ++w) e[kKeyWords + 1 + w] = t.acc[i * nexprs * t.acc_words + w];
-    for (uint32_t w = 0; w <= nexprs; ++w) e[kKeyWords + 1 + nexprs * t.acc_words + w] = t.cnt[i * (nexprs + 1) + w];
+  const uint64_t seg = ((nslots + gridDim.x - 1) / gridDim.x + kExtractThreads - 1) / kExtractThreads * kExtractThreads;
+  const uint64_t b0 = uint64_t(blockIdx.x) * seg, b1 = b0 + seg < nslots ? b0 + seg : nslots;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto occupied = [&](uint64_t i) { return i < b1 && (!grouped || (t.state[i] & 3u) == 2u); };
+  // pass 1: occupied slots of the segment
+  uint32_t mine = 0;
+  for (uint64_t i = b0 + threadIdx.x; i < b1; i += kExtractThreads) mine += occupied(i);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) s_warp[warp] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (uint32_t w = 0; w < kExtractThreads / 32; ++w) total += s_warp[w];
+    s_base = total ? atomicAdd(reinterpret_cast<unsigned long long*>(out), (unsigned long long)total) : 0ull;
+  }
+  __syncthreads();
+  unsigned long long pos_base = s_base;
+  // pass 2: write the entries at block-local prefix positions
+  for (uint64_t c0 = b0; c0 < b1; c0 += kExtractThreads) {
+    const uint64_t i = c0 + threadIdx.x;
+    const bool occ = occupied(i);
+    const uint32_t mask = __ballot_sync(0xffffffffu, occ);
+    __syncthreads();  // s_warp of the previous chunk has been read by everyone
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    uint32_t before = 0, chunk_total = 0;
+    for (uint32_t w = 0; w < kExtractThreads / 32; ++w) {
+      if (w < warp) before += s_warp[w];
+      chunk_total += s_warp[w];
+    }
+    if (occ) {
+      const unsigned long long pos = pos_base + before + __popc(mask & ((1u << lane) - 1u));
+      if (pos < max_entries) {
+        const uint32_t st = grouped ? t.state[i] : 0u;
+        uint64_t* e = out + 1 + pos * ew;
+        for (uint32_t w = 0; w < kKeyWords; ++w) e[w] = t.keys[i * kKeyWords + w];
+        e[kKeyWords] = st >> 8;
+        for (uint32_t w = 0; w < nexprs * t.acc_words; ++w) e[kKeyWords + 1 + w] = t.acc[i * nexprs * t.acc_words + w];
+        for (uint32_t w = 0; w <= nexprs; ++w) e[kKeyWords + 1 + nexprs * t.acc_words + w] = t.cnt[i * (nexprs + 1) + w];
+      }
+    }
+    pos_base += chunk_total;
   }
 }
 
@@ -1116,8 +1178,8 @@ pgf_status arena_table(pgf_ctx* ctx, uint64_t capacity, uint32_t nexprs, uint32_
 pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, uint32_t nexprs, bool grouped,
                          uint64_t* d_state, uint64_t max_entries) {
   const uint64_t nslots = grouped ? capacity : 1;
-  const uint32_t grid = uint32_t(std::min<uint64_t>((nslots + 255) / 256, uint64_t(ctx->sm_count) * 8));
-  table_extract_kernel<<<grid, 256, 0, ctx->compute_stream>>>(t, nexprs, grouped, d_state, max_entries);
+  const uint32_t grid = uint32_t(std::min<uint64_t>((nslots + kExtractThreads - 1) / kExtractThreads, uint64_t(ctx->sm_count) * 8));
+  table_extract_kernel<<<grid, kExtractThreads, 0, ctx->compute_stream>>>(t, nexprs, grouped, d_state, max_entries);
   CU(ctx, cudaGetLastError());
   return PGF_OK;
 }
@@ -1161,21 +1223,20 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     // slots followed by the one-byte tag directory
     const uint64_t slot_bytes = uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4);
     const uint64_t tag_bytes = uint64_t(jt.capacity) + 16;  // + mirror of the first tags (windows never wrap)
-    cudaError_t e = cudaMalloc(&jt.d_slots, slot_bytes + tag_bytes);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
-    }
+    jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
+    if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
     mem.ptrs.push_back(jt.d_slots);
     CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream));
     L.dev.build.slots = jt.d_slots;
     L.dev.build.tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
   }
 
+  PhaseTrace trace(ctx->compute_stream);
   for (int attempt = 0; attempt < 6; ++attempt) {
     TableAlloc ta;
     // header (+ group table + result entries) live in the arena; other sinks only use the header
     PGF_TRY(arena_table(ctx, agg ? capacity : 1, agg ? plan->nexprs : 0, aw, &ta));
+    trace.mark("arena + clear");
     L.dev.table = ta.t;
     L.dev.counters = &ta.d_header->counters;
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
@@ -1187,6 +1248,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
       ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
+    trace.mark("fused kernel");
     // small tables: extract right away so header and result travel with one synchronisation
     const bool inline_out = agg && !partial && ta.d_out != nullptr;
     uint64_t prefix_entries = 0;
@@ -1220,8 +1282,9 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
         *state_bytes = bytes;
         ++launches;
       } else {
-        std::vector<uint64_t> h_state(1 + ngroups * ew);
         const bool topk = plan->nsort && plan->limit && plan->limit <= PGF_TOPK_DEVICE_MAX && ngroups > plan->limit;
+        std::vector<uint64_t> h_state;
+        if (!topk) h_state.resize(1 + ngroups * ew);  // (an 80 MB host buffer at SF100: only when every group is returned)
         if (topk) {
           // TopK: only `limit` rows leave the GPU
           const uint64_t* d_entries = nullptr;
@@ -1235,9 +1298,11 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
             ++launches;
             d_entries = d_state + 1;
           }
+          trace.mark("extract groups");
           DevSort S;
           PGF_TRY(lower_sort(ctx, plan, L, &S));
           PGF_TRY(device_topk(ctx, S, d_entries, ngroups, uint32_t(plan->limit), &h_state, &launches));
+          trace.mark("device top-k");
           if (h_state[0] != plan->limit) return ctx->fail(PGF_ERR_STATE, "top-k selection returned %llu rows", (unsigned long long)h_state[0]);
         } else if (inline_out) {
           const uint64_t have = std::min<uint64_t>(ngroups, prefix_entries);
@@ -1269,6 +1334,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     break;
   }
 
+  trace.mark("result to host");
   const Counters& c = h_header->counters;
   res->rows_in = c.rows_in;
   res->rows_bloom = c.rows_bloom;
@@ -1411,8 +1477,9 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   if (h_header->overflow) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "final group table overflow");
   const uint64_t ngroups = L.grouped ? h_header->used : 1;
   const uint64_t bytes = (1 + ngroups * ew) * 8;
-  std::vector<uint64_t> h_state(1 + ngroups * ew);
   const bool topk = plan->nsort && plan->limit && plan->limit <= PGF_TOPK_DEVICE_MAX && ngroups > plan->limit;
+  std::vector<uint64_t> h_state;
+  if (!topk) h_state.resize(1 + ngroups * ew);
   uint32_t topk_launches = 0;
   if (topk) {  // ORDER BY ... LIMIT k of the merged groups: select on the device, k rows leave the GPU
     const uint64_t* d_entries = nullptr;
@@ -1504,10 +1571,8 @@ pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* 
   jt.capacity = uint32_t(cap);
   jt.rows = total;
   const uint64_t slot_bytes = cap * row_bytes, tag_bytes = cap + 16;
-  if (cudaMalloc(&jt.d_slots, slot_bytes + tag_bytes) != cudaSuccess) {
-    cudaGetLastError();
-    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
-  }
+  jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
+  if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
   cudaError_t e = cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream);
   uint8_t* tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
   for (uint32_t f = 0; f < nfragments && e == cudaSuccess; ++f) {

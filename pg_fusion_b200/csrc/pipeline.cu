@@ -104,15 +104,47 @@ __global__ void __launch_bounds__(kExtractThreads) table_extract_kernel(GroupTab
 
 // ---- broadcast-join exchange: a built table travels between GPUs as its occupied
 // slots.  Slots are self-contained records {key lo, key hi, occupancy/NULL flags, payload...}.
-__global__ void join_export_kernel(const uint4* slots, uint32_t capacity, uint32_t slot_u4, uint4* out,
-                                   unsigned long long max_rows, unsigned long long* count) {
-  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < capacity; i += uint64_t(gridDim.x) * blockDim.x) {
-    const uint4 s0 = slots[i * slot_u4];
-    if ((s0.z & 1u) == 0u) continue;
-    const unsigned long long pos = atomicAdd(count, 1ull);
-    if (pos >= max_rows) continue;
-    out[pos * slot_u4] = s0;
-    if (slot_u4 == 2) out[pos * 2 + 1] = slots[i * 2 + 1];
+// (block-aggregated like table_extract_kernel: one atomic per block reserves the output range)
+__global__ void __launch_bounds__(kExtractThreads) join_export_kernel(const uint4* slots, uint32_t capacity, uint32_t slot_u4, uint4* out,
+                                                                     unsigned long long max_rows, unsigned long long* count) {
+  __shared__ unsigned long long s_base;
+  __shared__ uint32_t s_warp[kExtractThreads / 32];
+  const uint64_t seg = ((uint64_t(capacity) + gridDim.x - 1) / gridDim.x + kExtractThreads - 1) / kExtractThreads * kExtractThreads;
+  const uint64_t b0 = uint64_t(blockIdx.x) * seg, b1 = b0 + seg < capacity ? b0 + seg : capacity;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto occupied = [&](uint64_t i) { return i < b1 && (reinterpret_cast<const uint32_t*>(slots + i * slot_u4)[2] & 1u); };
+  uint32_t mine = 0;
+  for (uint64_t i = b0 + threadIdx.x; i < b1; i += kExtractThreads) mine += occupied(i);
+  mine = __reduce_add_sync(0xffffffffu, mine);
+  if (lane == 0) s_warp[warp] = mine;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t total = 0;
+    for (uint32_t w = 0; w < kExtractThreads / 32; ++w) total += s_warp[w];
+    s_base = total ? atomicAdd(count, (unsigned long long)total) : 0ull;
+  }
+  __syncthreads();
+  unsigned long long pos_base = s_base;
+  for (uint64_t c0 = b0; c0 < b1; c0 += kExtractThreads) {
+    const uint64_t i = c0 + threadIdx.x;
+    const bool occ = occupied(i);
+    const uint32_t mask = __ballot_sync(0xffffffffu, occ);
+    __syncthreads();
+    if (lane == 0) s_warp[warp] = __popc(mask);
+    __syncthreads();
+    uint32_t before = 0, chunk_total = 0;
+    for (uint32_t w = 0; w < kExtractThreads / 32; ++w) {
+      if (w < warp) before += s_warp[w];
+      chunk_total += s_warp[w];
+    }
+    if (occ) {
+      const unsigned long long pos = pos_base + before + __popc(mask & ((1u << lane) - 1u));
+      if (pos < max_rows) {
+        out[pos * slot_u4] = slots[i * slot_u4];
+        if (slot_u4 == 2) out[pos * 2 + 1] = slots[i * 2 + 1];
+      }
+    }
+    pos_base += chunk_total;
   }
 }
 
@@ -1542,8 +1574,8 @@ pgf_status join_export(pgf_ctx* ctx, const JoinTable& jt, void* dev_rows_out, ui
   unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 4);
   unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 4);
   CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
-  const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(jt.capacity) + 255) / 256, uint64_t(ctx->sm_count) * 8));
-  join_export_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, jt.capacity, jt.slot_u4, static_cast<uint4*>(dev_rows_out),
+  const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(jt.capacity) + kExtractThreads - 1) / kExtractThreads, uint64_t(ctx->sm_count) * 8));
+  join_export_kernel<<<grid, kExtractThreads, 0, ctx->compute_stream>>>(jt.d_slots, jt.capacity, jt.slot_u4, static_cast<uint4*>(dev_rows_out),
                                                            capacity_rows, d_cnt);
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));

@@ -65,7 +65,7 @@ def broadcast_join_table(ctx, handle: int, world: int, device) -> int:
     info = ctx.join_table_info(handle)
     counts = all_gather_counts(info.rows, world, device)
     stride = max(1, max(counts)) * info.row_bytes
-    local = torch.zeros(stride, dtype=torch.uint8, device=device)
+    local = torch.empty(stride, dtype=torch.uint8, device=device)   # rows beyond the count are never read
     n = ctx.join_table_export(handle, local.data_ptr(), stride // info.row_bytes)
     assert n == info.rows
     gathered = all_gather_bytes(local, world)
@@ -90,7 +90,7 @@ def merge_partial_aggregate(plan, world: int, device, max_groups: int):
     all-gather the states (padded to the largest) and merge them in rank order on every rank."""
     import torch
     cap = plan.partial_state_bytes(max_groups)
-    state = torch.zeros(cap, dtype=torch.uint8, device=device)
+    state = torch.empty(cap, dtype=torch.uint8, device=device)      # the library writes count + entries
     nbytes, stats = plan.run_partial(state.data_ptr(), cap)
     sizes = all_gather_counts(nbytes, world, device)
     stride = (max(sizes) + 15) // 16 * 16

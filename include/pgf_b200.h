@@ -369,6 +369,7 @@ typedef struct {
    * after worker_runtime/src/result_pages.rs:201-249 normalize_result_transport_schema). */
   int32_t key_type[PGF_MAX_KEYS];
   int32_t agg_type[PGF_MAX_AGGS];
+  char variant[24];        /* which instantiation of the fused kernel ran: a registered shape or "generic" (EXPLAIN ANALYZE aid) */
 } pgf_result;
 
 pgf_status pgf_pipeline_check(pgf_ctx *ctx, const pgf_pipeline *plan); /* eligibility only */

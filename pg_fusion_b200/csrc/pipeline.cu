@@ -358,6 +358,7 @@ struct Lowered {
   uint32_t maxe = 2;
   size_t smem = 0;
   int32_t key_types[4] = {0, 0, 0, 0};
+  uint32_t expr_pos[kMaxExprs] = {0, 1, 2, 3, 4, 5, 6, 7};  // device position of the caller's expression e
   JoinTable build_table{};
   uint64_t table_capacity = 0;
 };
@@ -452,6 +453,24 @@ class Lowering {
       if (a.form == FORM_X_CMY && b.form == FORM_X_CMY_CPZ && a.f[0].ref.off == b.f[0].ref.off &&
           a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf && a.f[1].ci_lo == b.f[1].ci_lo && a.f[1].ci_hi == b.f[1].ci_hi)
         D.exprs[e].form = FORM_PREV_CPZ;
+    }
+    // The order of the conjuncts is irrelevant to the result: if some order of the range terms
+    // matches a registered shape, take it.
+    if (!pick_shape(*L_) && D.nterms >= 2 && D.nterms <= 4) {
+      bool plain = true;
+      for (uint32_t t = 0; t < D.nterms; ++t) plain &= D.terms[t].op == TERM_IN_RANGE;
+      if (plain) {
+        DevTerm orig[4];
+        uint32_t perm[4] = {0, 1, 2, 3};
+        for (uint32_t t = 0; t < D.nterms; ++t) orig[t] = D.terms[t];
+        bool found = false;
+        while (!found && std::next_permutation(perm, perm + D.nterms)) {
+          for (uint32_t t = 0; t < D.nterms; ++t) D.terms[t] = orig[perm[t]];
+          found = pick_shape(*L_) != nullptr;
+        }
+        if (!found)
+          for (uint32_t t = 0; t < D.nterms; ++t) D.terms[t] = orig[t];
+      }
     }
     PGF_TRY(layout_stage(s));
     fix_refs();
@@ -747,6 +766,21 @@ class Lowering {
     // an integer expression averaged as Float64 must not take the raw-f64 fast forms
     for (uint32_t e = 0; e < plan_->nexprs; ++e)
       if (expr_as_f64_[e]) D.exprs[e].form = FORM_GENERIC;
+    // Canonical argument order on the device: by form (x, x*y, x*(c-y), x*(c-y)*(c+z), generic), stable.
+    // The order aggregates are written in then no longer decides whether a registered shape matches,
+    // and x*(c-y)*(c+z) lands right behind its x*(c-y) for the common-subexpression rewrite.
+    {
+      auto rank = [](uint32_t form) { return form == FORM_GENERIC ? 99u : form; };
+      uint32_t order[kMaxExprs];
+      for (uint32_t e = 0; e < plan_->nexprs; ++e) order[e] = e;
+      std::stable_sort(order, order + plan_->nexprs, [&](uint32_t a, uint32_t b) { return rank(D.exprs[a].form) < rank(D.exprs[b].form); });
+      DevExpr tmp[kMaxExprs];
+      for (uint32_t e = 0; e < plan_->nexprs; ++e) tmp[e] = D.exprs[e];
+      for (uint32_t pos = 0; pos < plan_->nexprs; ++pos) {
+        D.exprs[pos] = tmp[order[pos]];
+        L_->expr_pos[order[pos]] = pos;
+      }
+    }
 
     uint32_t words = 0;
     for (uint32_t k = 0; k < plan_->nkeys; ++k) {
@@ -958,21 +992,22 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
       pgf_value& v = res->aggs[g * plan->naggs + a];
       const pgf_agg& ag = plan->aggs[a];
       if (ag.func == PGF_AGG_COUNT_STAR) { v.kind = PGF_V_I64; v.lo = int64_t(cnt[nexprs]); continue; }
-      const uint64_t c = cnt[ag.expr];
+      const uint32_t x = L.expr_pos[ag.expr];   // device position of the aggregate's argument
+      const uint64_t c = cnt[x];
       if (ag.func == PGF_AGG_COUNT) { v.kind = PGF_V_I64; v.lo = int64_t(c); continue; }
       if (c == 0) { v.kind = PGF_V_NULL; continue; }  // SUM / AVG over no rows is NULL
       if (L.acc_cls == CLS_F64) {
         double s;
-        std::memcpy(&s, acc + ag.expr, 8);
+        std::memcpy(&s, acc + x, 8);
         v.kind = PGF_V_F64;
         v.f64 = ag.func == PGF_AGG_AVG ? s / double(c) : s;  // f64 sum / (u64 count as f64)
       } else if (L.acc_cls == CLS_I64) {
         v.kind = PGF_V_I64;
-        v.lo = int64_t(acc[ag.expr]);
+        v.lo = int64_t(acc[x]);
         v.hi = v.lo < 0 ? -1 : 0;
         if (ag.func == PGF_AGG_AVG) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "integer AVG must be lowered to Float64");
       } else {
-        __int128 s = (__int128)(((unsigned __int128)acc[ag.expr * 2 + 1] << 64) | acc[ag.expr * 2]);
+        __int128 s = (__int128)(((unsigned __int128)acc[x * 2 + 1] << 64) | acc[x * 2]);
         if (ag.func == PGF_AGG_AVG) {
           // DecimalAverager: sum * 10^(s_out - s) / count with s_out = s + 4, truncating
           s = (s * 10000) / (__int128)c;
@@ -1030,8 +1065,8 @@ pgf_status lower_sort(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L, 
       if (sk.index < 0 || uint32_t(sk.index) >= plan->naggs) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "ORDER BY aggregate %d out of range", sk.index);
       const pgf_agg& ag = plan->aggs[sk.index];
       if (ag.func == PGF_AGG_COUNT_STAR) { d.kind = SK_COUNT; d.cnt_word = cnt0 + plan->nexprs; continue; }
-      d.word = acc0 + uint32_t(ag.expr) * aw;
-      d.cnt_word = cnt0 + uint32_t(ag.expr);
+      d.word = acc0 + L.expr_pos[ag.expr] * aw;
+      d.cnt_word = cnt0 + L.expr_pos[ag.expr];
       if (ag.func == PGF_AGG_COUNT) d.kind = SK_COUNT;
       else if (L.acc_cls == CLS_F64) d.kind = ag.func == PGF_AGG_AVG ? SK_F64_AVG : SK_F64_SUM;
       else if (L.acc_cls == CLS_I64) d.kind = SK_I64_SUM;
@@ -1376,6 +1411,10 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   res->kernel_ms = total_ms;
   ctx->last_kernel_ms = total_ms;
   res->kernel_launches = launches;
+  {
+    const ShapeEntry* se = pick_shape(L);
+    std::snprintf(res->variant, sizeof res->variant, "%s", se ? se->name : "generic");
+  }
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable jt = L.build_table;
     jt.rows = c.rows_out;

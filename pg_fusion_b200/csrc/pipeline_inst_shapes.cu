@@ -19,10 +19,11 @@ cudaError_t launch_shape(const DevPlan& plan, uint32_t grid, size_t smem, cudaSt
 // Q6: WHERE date-range AND f64-range AND f64-range ; SUM(x * y)
 using Q6Shape = ShapeT<false, IntList<LD_VIEW, LD_F64, LD_F64>, IntList<FORM_XY>, true>;
 // Q1 (standard, 8 aggregates -> 5 distinct arguments) and the reference's q01.sql (7 -> 4)
-// (the 4th argument price*(1-disc)*(1+tax) reuses the 3rd: FORM_PREV_CPZ; find_shape checks the operands match)
-using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true,
+// (arguments are in the canonical device order of lower_aggregate: by form; price*(1-disc)*(1+tax) reuses
+// price*(1-disc) right in front of it: FORM_PREV_CPZ, the lowering checks the operands match)
+using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ>, true,
                         IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
-using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_X>, true,
+using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY>, true,
                         IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
 // Q3 lineitem side: WHERE date-range ; join probe ; SUM(x * (1 - y)) GROUP BY ...
 // GROUP BY l_orderkey (scan), o_orderdate, o_shippriority (join payload)
@@ -31,21 +32,21 @@ using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true,
 
 // "D" variants: Decimal128 money, Date32 dates, Int16 flag codes; wrapping i128 arithmetic
 using Q6ShapeD = ShapeT<false, IntList<LD_I32, LD_DEC, LD_DEC>, IntList<FORM_XY>, true>;
-using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X>, true,
+using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ>, true,
                         IntList<key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1)>>;
 
 const ShapeEntry kShapes[] = {
     {{SINK_AGG, CLS_I128, 0, 0, 2, 3, {LD_I32, LD_DEC, LD_DEC, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_I128, false, 0, 2, Q6ShapeD>, "q6_decimal", 0},
-    {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1},
+    {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, -1, -1, -1},
       2, {key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1), 0, 0}},
      launch_shape<SINK_AGG, CLS_I128, true, 0, kAccI128MaxExprs, Q1ShapeD>, "q1_decimal_8aggs", 5},
     {{SINK_AGG, CLS_F64, 0, 0, 2, 3, {LD_VIEW, LD_F64, LD_F64, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>, "q6_f64", 0},
-    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, FORM_X, -1, -1, -1},
+    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, -1, -1, -1},
       2, {key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2), 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape8>, "q1_f64_8aggs", 5},
-    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X_CMY, FORM_X, -1, -1, -1, -1},
+    {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, -1, -1, -1, -1},
       2, {key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2), 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape7>, "q1_f64_7aggs", 4},
     {{SINK_AGG, CLS_F64, 1, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 1, {FORM_X_CMY, -1, -1, -1, -1, -1, -1, -1},

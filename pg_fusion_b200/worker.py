@@ -143,6 +143,7 @@ class PipelineResult:
     bloom_rows: int
     kernel_ms: float
     kernel_launches: int
+    variant: str = ""                                  # kernel instantiation that ran (registered shape or "generic")
     result_schema: Optional[List[ColumnSpec]] = None   # transport schema of the result pages
     result_pages: Optional[np.ndarray] = None          # [npages, page_size] uint8, reference page format
 
@@ -518,6 +519,7 @@ class Context:
             aggs = [tuple(_value_py(r.aggs[g * na + a]) for a in range(na)) for g in range(r.ngroups)]
             out = PipelineResult(r.rows_in, r.rows_bloom, r.rows_filtered, r.rows_out, keys, aggs, r.join_table,
                                  r.bloom_rows, r.kernel_ms, r.kernel_launches)
+            out.variant = bytes(r.variant).split(b"\0")[0].decode()
             if pages and (nk or na):
                 out.result_schema, out.result_pages = encode_result_pages(res, self.page_size)
             return out

@@ -367,3 +367,39 @@ def test_decimal_fast_group_by_is_exact_beyond_64_bits(ctx):
         sums = tuple(wrap(x) for x in w[:4])
         assert got[k][:4] == sums and got[k][7] == w[7], k
     scan.release()
+
+
+def test_registered_shapes_match_whatever_the_order_of_conjuncts_and_aggregates(ctx):
+    """Conjunct order and aggregate order are irrelevant to the result; they must not decide whether
+    the plan gets a specialised kernel either (pgf_result.variant names the instantiation)."""
+    import itertools
+    scan = ctx.gen_scan(pg.GenTable.LINEITEM_Q6, 200_000, seed=42)
+    base = U.gpu_q6(scan).run()
+    assert base.variant == "q6_f64"
+    conj = [(3, Cmp.GE, b"1994-01-01"), (3, Cmp.LT, b"1995-01-01"), (2, Cmp.GE, 0.05), (2, Cmp.LE, 0.07), (0, Cmp.LT, 24.0)]
+    for perm in list(itertools.permutations(conj))[::17]:
+        p = scan.pipeline()
+        for c in perm:
+            p.filter(*c)
+        r = p.aggregate([], [(AggFunc.COUNT_STAR, None), (AggFunc.SUM, [Factor.of(1), Factor.of(2)])]).run()
+        assert r.variant == "q6_f64"
+        assert r.aggs[0][0] == base.aggs[0][1] and r.rows_filtered == base.rows_filtered
+        U.assert_close(r.aggs[0][1], base.aggs[0][0], 1e-12, "revenue")
+    scan.release()
+    q1 = ctx.gen_scan(pg.GenTable.LINEITEM_Q1, 200_000, seed=42)
+    ref = U.gpu_q1(q1).run()
+    assert ref.variant == "q1_f64_8aggs"
+    q, pr, d, t, rf, ls, s = range(7)
+    disc_price = [Factor.of(pr), Factor.const_minus(1.0, d)]
+    charge = disc_price + [Factor.const_plus(1.0, t)]
+    aggs = [(AggFunc.AVG, [Factor.of(d)]), (AggFunc.SUM, charge), (AggFunc.COUNT_STAR, None), (AggFunc.SUM, [Factor.of(pr)]),
+            (AggFunc.AVG, [Factor.of(q)]), (AggFunc.SUM, disc_price), (AggFunc.SUM, [Factor.of(q)]), (AggFunc.AVG, [Factor.of(pr)])]
+    got = q1.pipeline().filter(s, Cmp.LE, b"1998-09-02").aggregate([rf, ls], aggs).order_by([("agg", 1, True)]).run()
+    assert got.variant == "q1_f64_8aggs"
+    back = [6, 3, 5, 1, 4, 7, 0, 2]   # position in `aggs` of each aggregate of U.gpu_q1's order
+    want = ref.by_key()
+    assert [a[1] for a in got.aggs] == sorted((a[1] for a in got.aggs), reverse=True)   # ORDER BY sum_charge DESC
+    for k, a in zip(got.keys, got.aggs):
+        for j in range(8):
+            U.assert_close(a[back[j]], want[k][j], 1e-12, f"group {k} agg {j}")
+    q1.release()

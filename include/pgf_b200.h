@@ -104,8 +104,15 @@ typedef struct {
   int32_t device;          /* CUDA device ordinal */
   uint32_t page_size;      /* 0 => 65536 */
   uint32_t staging_pages;  /* pinned staging ring for unregistered host pages; 0 => 512 */
-  uint32_t reserved;
+  uint32_t flags;          /* PGF_CFG_* */
 } pgf_config;
+/* A runtime filter is an optimisation only: rejecting early what a later join rejects anyway
+ * (runtime_filter/src/shared.rs:350-374 allows PassUnfiltered at any time).  By default the fused
+ * pipelines therefore drop a Bloom probe (a) when the same pipeline probes a join table on the same
+ * key column -- the table's tag directory already rejects misses at the same cost -- and (b) when
+ * the filter is saturated (expected pass rate of absent keys fill^k > 0.9).  This flag keeps every
+ * probe (tests of the fused probe itself, metrics parity with the backend-side probe counters). */
+#define PGF_CFG_KEEP_REDUNDANT_BLOOM_PROBES 1u
 
 /* ----------------------------------------------------------------- context */
 pgf_status pgf_device_count(int32_t *count_out);

@@ -23,7 +23,7 @@ P = C.POINTER
 
 
 class Config(C.Structure):
-    _fields_ = [("device", i32), ("page_size", u32), ("staging_pages", u32), ("reserved", u32)]
+    _fields_ = [("device", i32), ("page_size", u32), ("staging_pages", u32), ("flags", u32)]
 
 
 class ColumnSpec(C.Structure):

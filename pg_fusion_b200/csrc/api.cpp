@@ -130,6 +130,7 @@ pgf_status pgf_ctx_create(const pgf_config* config, pgf_ctx** ctx_out) {
   ctx->device = cfg.device;
   ctx->page_size = cfg.page_size ? cfg.page_size : 65536u;
   ctx->staging_pages = cfg.staging_pages ? cfg.staging_pages : 512u;
+  ctx->flags = cfg.flags;
   auto bail = [&](pgf_status st) {
     pgf_ctx_destroy(ctx);
     return st;
@@ -570,7 +571,7 @@ pgf_status pgf_bloom_publish_ready(pgf_ctx* ctx, uint64_t bloom) {
   BLOOM_OR_FAIL(ctx, bloom, b);
   // all inserts were queued on the compute stream; Ready is observable once they are done
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  PGF_TRY(bloom_count_bits(ctx, *b));   // synchronises; the fill decides whether fused probes are worth their cost
   return bloom_transition(ctx, b, PGF_RF_BUILDING, PGF_RF_READY);
 }
 pgf_status pgf_bloom_disable_build(pgf_ctx* ctx, uint64_t bloom) {

@@ -303,6 +303,13 @@ __global__ void bloom_or_kernel(uint64_t* dst, const uint64_t* src, uint64_t nwo
   }
 }
 
+__global__ void bloom_popcount_kernel(const uint64_t* words, uint64_t nwords, unsigned long long* out) {
+  unsigned long long mine = 0;
+  for (uint64_t i = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; i < nwords; i += uint64_t(gridDim.x) * blockDim.x) mine += __popcll(words[i]);
+  for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 int key_width_of(int type) {
   switch (type) {
     case PGF_T_INT16: return 2;
@@ -521,6 +528,21 @@ pgf_status bloom_probe_scan(pgf_ctx* ctx, BloomSlot& b, bool ready, Scan& s, uin
     CU(ctx, PGF_PROBE_DISPATCH(launch_probe_scan, smem, k, grid, bytes, ctx->compute_stream, b.dev, sk, ready, nwords, blocks_per_page, out));
     return PGF_OK;
   });
+}
+
+pgf_status bloom_count_bits(pgf_ctx* ctx, BloomSlot& b) {
+  CU(ctx, cudaSetDevice(ctx->device));
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 8);
+  unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 8);
+  CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
+  const uint64_t nwords = b.params.word_count;
+  const uint32_t grid = uint32_t((nwords + 255) / 256 < 1184 ? (nwords + 255) / 256 : 1184);
+  bloom_popcount_kernel<<<grid ? grid : 1, 256, 0, ctx->compute_stream>>>(b.d_words, nwords, d_cnt);
+  CU(ctx, cudaGetLastError());
+  CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  b.set_bits = *h_cnt;
+  return PGF_OK;
 }
 
 pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, uint64_t nwords, uint32_t narrays) {

@@ -44,6 +44,7 @@ struct BloomSlot {
   pgf_bloom_params params{};
   uint64_t* d_words = nullptr;
   uint64_t lifecycle = 0;  // (generation << 2) | state, runtime_filter/src/shared.rs:7-9
+  uint64_t set_bits = 0;   // popcount of the published bit array (saturation check of the fused probe)
   DevBloom dev{};
 };
 
@@ -65,6 +66,7 @@ struct pgf_ctx {
   int device = 0;
   uint32_t page_size = 65536;
   uint32_t staging_pages = 512;
+  uint32_t flags = 0;                   // PGF_CFG_*
   int sm_count = 148;
   cudaStream_t copy_stream = nullptr;
   cudaStream_t compute_stream = nullptr;
@@ -173,6 +175,7 @@ pgf_status bloom_probe_scan(pgf_ctx* ctx, BloomSlot& b, bool ready, Scan& s, uin
                             uint8_t* decisions, pgf_probe_stats* stats);
 pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, uint64_t nwords,
                            uint32_t narrays);
+pgf_status bloom_count_bits(pgf_ctx* ctx, BloomSlot& b);
 pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
                         uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out);
 pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out, uint64_t state_cap);

@@ -2,6 +2,7 @@
 // device plan, eligibility rules, launch, and extraction of AggregateExec results.
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -435,6 +436,16 @@ class Lowering {
       PGF_TRY(lower_ref(plan_->bloom[b].key, 0, &bp.key));
       if (bp.key.src != SRC_PAGE) return not_eligible("Bloom probe keys must be scan columns");
       if (!is_int_type(bp.key.type)) return not_eligible("runtime filter keys must be Int16/Int32/Int64");
+      if (!(ctx_->flags & PGF_CFG_KEEP_REDUNDANT_BLOOM_PROBES)) {
+        // (a) the same pipeline probes a join table on this key: its tag directory rejects misses just as cheaply
+        bool redundant = false;
+        for (uint32_t j = 0; j < D.njoins; ++j)
+          redundant |= D.joins[j].key.src == SRC_PAGE && D.joins[j].key.pcol == bp.key.pcol;
+        // (b) saturated filter: an absent key passes with probability fill^k; above 0.9 the probe costs more than it rejects
+        const double fill = double(bs.set_bits) / double(bs.params.bit_count);
+        redundant |= std::pow(fill, double(bs.params.hash_count)) > 0.9;
+        if (redundant) continue;   // PassUnfiltered for every row: the result is the same
+      }
       D.nbloom++;
     }
 

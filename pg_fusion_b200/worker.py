@@ -496,9 +496,12 @@ class RuntimeFilter:
 class Context:
     """One device context (one per GPU process)."""
 
-    def __init__(self, device: int = 0, page_size: int = 65536, staging_pages: int = 0):
+    def __init__(self, device: int = 0, page_size: int = 65536, staging_pages: int = 0,
+                 keep_redundant_bloom_probes: bool = False):
+        """keep_redundant_bloom_probes: PGF_CFG_KEEP_REDUNDANT_BLOOM_PROBES (by default a fused Bloom probe
+        is dropped when the same pipeline probes a join table on that key, or when the filter is saturated)."""
         self.h = C.c_void_p()
-        cfg = _lib.Config(device, page_size, staging_pages, 0)
+        cfg = _lib.Config(device, page_size, staging_pages, 1 if keep_redundant_bloom_probes else 0)
         rc = _lib.lib().pgf_ctx_create(C.byref(cfg), C.byref(self.h))
         if rc:
             self.h = None

@@ -16,7 +16,7 @@ E = O.Expr
 
 @pytest.fixture(scope="module")
 def ctx():
-    c = pg.Context()
+    c = pg.Context(keep_redundant_bloom_probes=True)   # these tests check the fused Bloom probe itself
     yield c
     c.close()
 
@@ -142,3 +142,30 @@ def test_q3_shape_matches_oracle(ctx, with_bloom):
         assert stats["lineitem"].rows_bloom < stats["lineitem"].rows_in   # the filter does reject rows
     for s in (customer, orders, lineitem):
         s.release()
+
+
+def test_redundant_and_saturated_bloom_probes_are_dropped_by_default():
+    """A runtime filter is an optimisation only.  By default a fused probe is dropped when the same
+    pipeline probes the join table on that key, or when the filter is saturated (fill^k > 0.9): the
+    result is identical, rows_bloom == rows_in shows that no row was probed."""
+    with pg.Context() as c:
+        r = np.random.default_rng(5)
+        bk = r.integers(0, 10**6, 20_000).astype(np.int32)
+        pk = r.integers(0, 10**6, 100_000).astype(np.int32)
+        build, bt = load(c, [ColumnSpec(TypeTag.Int32)], [(bk, None)])
+        probe, pt = load(c, [ColumnSpec(TypeTag.Int32)], [(pk, None)])
+        rf = c.runtime_filter(BloomParams.new(1 << 20, 4, 7))            # sparse: fill ~ 7 %
+        rf.try_acquire_builder()
+        b = build.pipeline().build_join(0, [], rf).run()
+        rf.publish_ready()
+        want = O.hash_join_pairs(bt, 0, pt, 0)[0].size
+        joined = probe.pipeline().bloom_probe(rf, 0).join(b.join_table, 0).count().run()
+        assert joined.rows_out == want and joined.rows_bloom == joined.rows_in      # (a) redundant next to the join probe
+        alone = probe.pipeline().bloom_probe(rf, 0).count().run()
+        assert alone.rows_bloom < alone.rows_in and alone.rows_out == alone.rows_bloom   # kept when it is the only filter
+        sat = c.runtime_filter(BloomParams.new(1 << 12, 4, 7))           # 20 000 keys in 4096 bits: saturated
+        sat.try_acquire_builder()
+        sat.insert_keys(bk)
+        sat.publish_ready()
+        dropped = probe.pipeline().bloom_probe(sat, 0).count().run()
+        assert dropped.rows_bloom == dropped.rows_in == dropped.rows_out                # (b) saturated

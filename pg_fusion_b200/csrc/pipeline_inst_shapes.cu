@@ -35,7 +35,14 @@ using Q6ShapeD = ShapeT<false, IntList<LD_I32, LD_DEC, LD_DEC>, IntList<FORM_XY>
 using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ>, true,
                         IntList<key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1)>>;
 
+// Q3 build sides: WHERE <string column range> [probe one join table] -> HashJoinExec build (+ Bloom)
+using BuildShape1V = ShapeT<false, IntList<LD_VIEW>, IntList<>, true>;
+
 const ShapeEntry kShapes[] = {
+    {{SINK_JOIN_BUILD, CLS_F64, 0, 0, 2, 1, {LD_VIEW, -1, -1, -1}, 0, {-1, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
+     launch_shape<SINK_JOIN_BUILD, CLS_I64, false, 0, 1, BuildShape1V>, "build_1_string_term", 0},
+    {{SINK_JOIN_BUILD, CLS_F64, 0, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 0, {-1, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
+     launch_shape<SINK_JOIN_BUILD, CLS_I64, false, 1, 1, BuildShape1V>, "probe_build_1_string_term", 0},
     {{SINK_AGG, CLS_I128, 0, 0, 2, 3, {LD_I32, LD_DEC, LD_DEC, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_I128, false, 0, 2, Q6ShapeD>, "q6_decimal", 0},
     {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, -1, -1, -1},

@@ -506,8 +506,8 @@ class Lowering {
       if (pt.cmp < PGF_CMP_LT || pt.cmp > PGF_CMP_NE) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad comparison operator");
       DevRef ref;
       PGF_TRY(lower_ref(pt.col, plan_->njoins, &ref));
-      int64_t k0;
-      uint64_t k1;
+      int64_t k0 = 0;
+      uint64_t k1 = 0;
       PGF_TRY(literal_key(pt.lit, ref.type, &k0, &k1));
       const bool wide = ref.ld == LD_VIEW || ref.ld == LD_DEC;
       const __int128 key = ((__int128)k0 << 64) | (__int128)k1;
@@ -946,8 +946,6 @@ class Lowering {
   int expr_cls_[kMaxExprs] = {0};
   bool expr_as_f64_[kMaxExprs] = {false};
 
- public:
-  bool expr_as_f64(uint32_t e) const { return expr_as_f64_[e]; }
 };
 
 // ---- result extraction ----------------------------------------------------------------

@@ -617,13 +617,6 @@ __device__ __forceinline__ bool dict_equal_fast(const BlockShared* sh, int g, co
   return g >= 0 && diff == 0;
 }
 
-__device__ __forceinline__ void pred_dadd(double& acc, double v, int g, int gg) {
-  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %2, %3;\n\t@p add.rn.f64 %0, %0, %1;\n\t}" : "+d"(acc) : "d"(v), "r"(g), "r"(gg));
-}
-__device__ __forceinline__ void pred_inc(uint32_t& n, int g, int gg) {
-  asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\t@p add.u32 %0, %0, 1;\n\t}" : "+r"(n) : "r"(g), "r"(gg));
-}
-
 // Float64 argument forms over NOT NULL scan columns (compile-time FORM)
 template <int FORM>
 __device__ __forceinline__ double eval_fast_f64(const DevExpr& e, const uint8_t* stage, uint32_t r, double prev) {

@@ -224,7 +224,7 @@ pgf_status pgf_bloom_disable_build(pgf_ctx *ctx, uint64_t bloom);  /* shared.rs:
 pgf_status pgf_bloom_retire_ready(pgf_ctx *ctx, uint64_t bloom);   /* shared.rs:244-260 */
 /* Word array exchange: read the bits (bit layout = bloom.rs:243-247: word = bit / 64,
  * mask = 1 << (bit % 64)), OR another array into them (multi-GPU merge / shm interop). */
-pgf_status pgf_bloom_read_words(pgf_ctx *ctx, uint64_t bloom, uint64_t *words_out, uint64_t nwords);
+pgf_status pgf_bloom_read_words(pgf_ctx *ctx, uint64_t bloom, uint64_t *words_out, uint64_t nwords); /* host or device buffer */
 pgf_status pgf_bloom_or_words(pgf_ctx *ctx, uint64_t bloom, const uint64_t *words, uint64_t nwords);
 /* device pointer to the words (for NCCL all-gather by the harness) */
 void *pgf_bloom_device_words(pgf_ctx *ctx, uint64_t bloom);

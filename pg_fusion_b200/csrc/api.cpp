@@ -609,7 +609,8 @@ pgf_status pgf_bloom_read_words(pgf_ctx* ctx, uint64_t bloom, uint64_t* words_ou
     return ctx->fail(PGF_ERR_BLOOM_INSUFFICIENT_WORDS, "bloom filter storage has %llu words, but %llu are required",
                      (unsigned long long)nwords, (unsigned long long)b->params.word_count);
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaMemcpyAsync(words_out, b->d_words, b->params.word_count * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  // cudaMemcpyDefault: words_out may be a host buffer or (for the multi-GPU OR-merge) a device buffer
+  CU(ctx, cudaMemcpyAsync(words_out, b->d_words, b->params.word_count * 8, cudaMemcpyDefault, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   return PGF_OK;
 }

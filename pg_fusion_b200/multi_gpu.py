@@ -79,7 +79,8 @@ def or_merge_filter(rf, world: int, device) -> None:
     """Bloom OR-merge: all-gather the word arrays of every rank's filter (still in
     Building state) and OR them into the local one; bit exact by idempotence."""
     import torch
-    words = torch.from_numpy(rf.words().view(np.uint8)).to(device)
+    words = torch.empty(rf.params.word_count * 8, dtype=torch.uint8, device=device)
+    rf.read_words_into(words.data_ptr())          # device to device: the bits never visit the host
     gathered = all_gather_bytes(words, world)
     torch.cuda.synchronize(device)
     rf.or_device_words(gathered.data_ptr(), world)

@@ -456,6 +456,10 @@ class RuntimeFilter:
         (runtime_filter/src/pool.rs: insert + publish_ready), so backends probe it unchanged."""
         self.ctx._check(_lib.lib().pgf_bloom_publish_to_pool(self.ctx.h, self.handle, base_ptr, length, slot_count, slot_index, generation))
 
+    def read_words_into(self, ptr: int) -> None:
+        """Copy the word array into a caller buffer (host or device pointer) of word_count * 8 bytes."""
+        self.ctx._check(_lib.lib().pgf_bloom_read_words(self.ctx.h, self.handle, C.c_void_p(ptr), self.params.word_count))
+
     def device_words_ptr(self) -> int:
         return _lib.lib().pgf_bloom_device_words(self.ctx.h, self.handle)
 

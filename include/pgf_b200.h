@@ -260,6 +260,18 @@ pgf_status pgf_shm_pool_disable_build(void *base, uint64_t len, uint32_t slot_co
                                       int32_t slot_index, uint64_t generation);
 pgf_status pgf_shm_pool_release_owner(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
                                       int32_t slot_index);
+/* Probe side of the same protocol (lookup_probes / decision_for_hash / handle drop, pool.rs:432-476 and
+ * shared.rs:350-374).  Backends run the reference's own code for this; it is exported so the pool
+ * implementation can be checked against the reference's pool tests. */
+typedef struct { int32_t slot_index; uint32_t key_type; uint64_t generation; uint32_t output_column, reserved; } pgf_pool_probe;
+pgf_status pgf_shm_pool_lookup_probes(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                      uint64_t session_epoch, uint64_t scan_id, pgf_pool_probe *out,
+                                      uint32_t max_probes, uint32_t *nprobes_out);
+pgf_status pgf_shm_pool_probe_decide(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                     int32_t slot_index, uint64_t generation, int32_t key_is_null, int64_t key,
+                                     int32_t *decision_out);
+pgf_status pgf_shm_pool_release_probe(void *base, uint64_t len, uint32_t slot_count, const pgf_bloom_params *params,
+                                      int32_t slot_index);
 /* Copy the words of a GPU-built filter (any lifecycle state) into the pool slot and publish it. */
 pgf_status pgf_bloom_publish_to_pool(pgf_ctx *ctx, uint64_t bloom, void *base, uint64_t len, uint32_t slot_count,
                                      int32_t slot_index, uint64_t generation);

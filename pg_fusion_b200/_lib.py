@@ -122,6 +122,10 @@ class RfTarget(C.Structure):
     _fields_ = [("session_epoch", u64), ("scan_id", u64), ("output_column", u32), ("key_type", u32)]
 
 
+class PoolProbe(C.Structure):
+    _fields_ = [("slot_index", i32), ("key_type", u32), ("generation", u64), ("output_column", u32), ("reserved", u32)]
+
+
 class JoinInfo(C.Structure):
     _fields_ = [("rows", u64), ("capacity", u32), ("row_bytes", u32), ("npayload", u32), ("reserved", u32)]
 
@@ -191,6 +195,9 @@ _SIGNATURES = {
     "pgf_shm_pool_disable_build": (i32, [vp, u64, u32, P(BloomParamsC), i32, u64]),
     "pgf_shm_pool_release_owner": (i32, [vp, u64, u32, P(BloomParamsC), i32]),
     "pgf_bloom_publish_to_pool": (i32, [vp, u64, vp, u64, u32, i32, u64]),
+    "pgf_shm_pool_lookup_probes": (i32, [vp, u64, u32, P(BloomParamsC), u64, u64, P(PoolProbe), u32, P(u32)]),
+    "pgf_shm_pool_probe_decide": (i32, [vp, u64, u32, P(BloomParamsC), i32, u64, i32, i64, P(i32)]),
+    "pgf_shm_pool_release_probe": (i32, [vp, u64, u32, P(BloomParamsC), i32]),
     "pgf_result_schema": (i32, [P(Result), P(ColumnSpec), P(u32)]),
     "pgf_result_encode_pages": (i32, [P(Result), u32, u64, vp, u64, P(u64), P(u64)]),
     "pgf_join_table_get_info": (i32, [vp, u64, P(JoinInfo)]),

@@ -18,7 +18,8 @@
 #include <atomic>
 #include <cstring>
 
-#include "context.hpp"
+#include "context.hpp"   // cuda_runtime.h first: bloom_device.cuh uses its __host__ __device__ markers
+#include "bloom_device.cuh"
 
 namespace {
 
@@ -210,6 +211,75 @@ pgf_status pgf_shm_pool_release_owner(void* base, uint64_t len, uint32_t slot_co
   if (slot_index < 0 || uint32_t(slot_index) >= slot_count) return PGF_ERR_INVALID_ARGUMENT;
   uint32_t expect = kSlotAllocated;  // release_owner (pool.rs:516-525)
   pool.slots[slot_index].state.compare_exchange_strong(expect, kSlotRetiring, std::memory_order_acq_rel, std::memory_order_acquire);
+  release_ref(pool, uint32_t(slot_index));
+  return PGF_OK;
+}
+
+/* ---- probe side (what a backend does; pool.rs:432-476, shared.rs:350-374).  The worker never needs it in
+ * production -- the backends run the reference's own code -- but it completes the protocol so the
+ * reference's pool tests can be replayed against this implementation. */
+pgf_status pgf_shm_pool_lookup_probes(void* base, uint64_t len, uint32_t slot_count, const pgf_bloom_params* params,
+                                      uint64_t session_epoch, uint64_t scan_id, pgf_pool_probe* out, uint32_t max_probes,
+                                      uint32_t* nprobes_out) {
+  if (!nprobes_out || (!out && max_probes)) return PGF_ERR_INVALID_ARGUMENT;
+  Pool pool;
+  PGF_TRY(open_pool(base, len, slot_count, params, true, &pool));
+  uint32_t n = 0;
+  for (uint32_t i = 0; i < slot_count && n < max_probes; ++i) {
+    PoolSlot& s = pool.slots[i];
+    if (s.state.load(std::memory_order_acquire) != kSlotAllocated) continue;
+    s.refs.fetch_add(1, std::memory_order_acq_rel);   // pin first, then re-check (the owner may be retiring)
+    const bool matches = s.state.load(std::memory_order_acquire) == kSlotAllocated &&
+                         s.session_epoch.load(std::memory_order_acquire) == session_epoch &&
+                         s.scan_id.load(std::memory_order_acquire) == scan_id;
+    const uint32_t kt = s.key_type.load(std::memory_order_acquire);
+    if (!matches || kt < 1 || kt > 3) {
+      release_ref(pool, i);
+      continue;
+    }
+    out[n++] = pgf_pool_probe{int32_t(i), kt, s.generation.load(std::memory_order_acquire),
+                              s.output_column.load(std::memory_order_acquire), 0};
+  }
+  *nprobes_out = n;
+  return PGF_OK;
+}
+
+pgf_status pgf_shm_pool_probe_decide(void* base, uint64_t len, uint32_t slot_count, const pgf_bloom_params* params,
+                                     int32_t slot_index, uint64_t generation, int32_t key_is_null, int64_t key,
+                                     int32_t* decision_out) {
+  if (!decision_out) return PGF_ERR_INVALID_ARGUMENT;
+  Pool pool;
+  PGF_TRY(open_pool(base, len, slot_count, params, true, &pool));
+  if (slot_index < 0 || uint32_t(slot_index) >= slot_count) return PGF_ERR_INVALID_ARGUMENT;
+  const uint64_t word = pool.slots[slot_index].lifecycle.load(std::memory_order_acquire);
+  if (word != ((generation << 2) | PGF_RF_READY)) {   // Free / Building / Disabled / another generation never reject
+    *decision_out = PGF_PASS_UNFILTERED;
+    return PGF_OK;
+  }
+  if (key_is_null) {                                   // decision_for_null: a NULL key cannot match an inner join
+    *decision_out = PGF_DEFINITELY_ABSENT;
+    return PGF_OK;
+  }
+  const std::atomic<uint64_t>* bits = pool.bits + uint64_t(slot_index) * pool.word_count;
+  const uint64_t h1 = pgf::splitmix64(uint64_t(key) ^ params->seed);           // bloom.rs:250-255
+  const uint64_t h2 = pgf::splitmix64(h1 ^ pgf::kBloomSalt) | 1ull;
+  uint64_t v = h1;
+  *decision_out = PGF_MAYBE_PRESENT;
+  for (uint64_t i = 0; i < params->hash_count; ++i, v += h2) {
+    const uint64_t bit = v % params->bit_count;
+    if (((bits[bit >> 6].load(std::memory_order_relaxed) >> (bit & 63)) & 1ull) == 0) {
+      *decision_out = PGF_DEFINITELY_ABSENT;
+      break;
+    }
+  }
+  return PGF_OK;
+}
+
+pgf_status pgf_shm_pool_release_probe(void* base, uint64_t len, uint32_t slot_count, const pgf_bloom_params* params,
+                                      int32_t slot_index) {
+  Pool pool;
+  PGF_TRY(open_pool(base, len, slot_count, params, true, &pool));
+  if (slot_index < 0 || uint32_t(slot_index) >= slot_count) return PGF_ERR_INVALID_ARGUMENT;
   release_ref(pool, uint32_t(slot_index));
   return PGF_OK;
 }

@@ -135,3 +135,83 @@ def test_release_waits_for_the_last_probe_reference():
     s = pool.slot(0)
     assert (s["state"], s["refs"]) == (SLOT_RETIRING, 1) and s["lifecycle"] == (gen << 2) | READY   # still probe-able
     assert pool.allocate(1, 3)[:2] == (0, -1)   # not reusable yet
+
+
+# ---- the reference's own pool tests, replayed against this implementation ------------------------
+def lookup(pool, epoch, scan):
+    out = (_lib.PoolProbe * 8)()
+    n = C.c_uint32()
+    assert pool.L.pgf_shm_pool_lookup_probes(pool.base, pool.len, pool.slots, C.byref(pool.p), epoch, scan, out, 8, C.byref(n)) == 0
+    return [out[i] for i in range(n.value)]
+
+
+def decide(pool, probe, key=None):
+    d = C.c_int32()
+    assert pool.L.pgf_shm_pool_probe_decide(pool.base, pool.len, pool.slots, C.byref(pool.p), probe.slot_index, probe.generation,
+                                            1 if key is None else 0, 0 if key is None else key, C.byref(d)) == 0
+    return d.value
+
+
+PASS_UNFILTERED, MAYBE_PRESENT, DEFINITELY_ABSENT = 0, 1, 2
+
+
+def words_for(p, keys):
+    b = O.Bloom(O.bloom_params(p.bit_count, p.hash_count, p.seed))
+    b.insert_keys(np.array(keys, dtype=np.int64))
+    return b.words
+
+
+def test_pool_publishes_filter_and_probe_rejects_absent_keys():
+    # runtime_filter/src/tests.rs:446-478
+    p = params(bits=1024, k=3, seed=17)
+    pool = Pool(1, p)
+    rc, slot, gen = pool.allocate(epoch=11, scan=22, col=3, key_type=3)
+    assert (rc, slot) == (0, 0)
+    building = lookup(pool, 11, 22)
+    assert len(building) == 1 and decide(pool, building[0], 42) == PASS_UNFILTERED      # Building never rejects
+    assert pool.L.pgf_shm_pool_release_probe(pool.base, pool.len, 1, C.byref(p), 0) == 0
+    assert pool.publish(slot, gen, words_for(p, [42])) == 0
+    probes = lookup(pool, 11, 22)
+    assert len(probes) == 1 and probes[0].output_column == 3 and probes[0].key_type == 3
+    assert decide(pool, probes[0], 42) == MAYBE_PRESENT
+    assert decide(pool, probes[0], 100_000) == DEFINITELY_ABSENT
+    assert decide(pool, probes[0], None) == DEFINITELY_ABSENT
+    assert lookup(pool, 11, 23) == [] and lookup(pool, 12, 22) == []                      # other targets find nothing
+    assert pool.slot(0)["refs"] == 2                                                       # owner + one probe
+
+
+def test_pool_does_not_reuse_storage_until_probes_are_dropped():
+    # runtime_filter/src/tests.rs:481-523
+    p = params(bits=1024, k=3, seed=17)
+    pool = Pool(1, p)
+    rc, slot, gen = pool.allocate(epoch=1, scan=2, col=0, key_type=2)
+    assert pool.publish(slot, gen, words_for(p, [7])) == 0
+    probes = lookup(pool, 1, 2)
+    assert len(probes) == 1
+    assert pool.release(slot) == 0                          # drop(build)
+    assert pool.allocate(3, 4, key_type=2)[:2] == (0, -1)   # allocate while the old probe exists: none
+    assert decide(pool, probes[0], 7) == MAYBE_PRESENT      # the old probe still reads consistent bits
+    assert pool.L.pgf_shm_pool_release_probe(pool.base, pool.len, 1, C.byref(p), probes[0].slot_index) == 0   # drop(probes)
+    rc, slot2, gen2 = pool.allocate(3, 4, key_type=2)
+    assert (rc, slot2, gen2) == (0, 0, gen + 1)
+    assert decide(pool, probes[0], 7) == PASS_UNFILTERED    # a stale generation never rejects
+
+
+def test_concurrent_allocation_hands_every_slot_out_once():
+    """allocate_build from several threads: the slot-state CAS gives every slot to exactly one builder."""
+    import threading
+    p = params(bits=4096, k=2, seed=1)
+    pool = Pool(16, p)
+    got, lock = [], threading.Lock()
+
+    def worker(tid):
+        for j in range(8):
+            rc, slot, gen = pool.allocate(tid, j)
+            assert rc == 0
+            if slot >= 0:
+                with lock:
+                    got.append(slot)
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert sorted(got) == list(range(16))

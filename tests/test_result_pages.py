@@ -93,3 +93,52 @@ def test_result_pages_decode_to_the_same_rows(page_size, n):
         assert (None if c1[g] is None else int(c1[g])) == ki
         assert (None if c2[g] is None else float(c2[g])) == sf
         assert int(c3[g]) == cnt
+
+
+def test_result_pages_with_integer_keys_and_decimal_sums():
+    """The D variant's output: Int16 / Int64 group keys, Decimal128 SUM / AVG (16-byte slots, the
+    extension tag 10), COUNT(*) -- every page passes the import checks and decodes to the same rows."""
+    T_I16, T_DEC = 2, 10
+    rng = np.random.default_rng(9)
+    n = 3000
+    keys = (_lib.Value * (2 * n + 1))()
+    aggs = (_lib.Value * (2 * n + 1))()
+    want = []
+    for g in range(n):
+        k16, k64 = int(rng.integers(-2**15, 2**15)), int(rng.integers(-2**62, 2**62))
+        dec = None if g % 53 == 0 else int(rng.integers(-10**18, 10**18)) * int(rng.integers(1, 10**15))
+        cnt = int(rng.integers(0, 2**50))
+        keys[2 * g].kind, keys[2 * g].lo, keys[2 * g].hi = V_I64, k16, -1 if k16 < 0 else 0
+        keys[2 * g + 1].kind, keys[2 * g + 1].lo, keys[2 * g + 1].hi = V_I64, k64, -1 if k64 < 0 else 0
+        if dec is None:
+            aggs[2 * g].kind = V_NULL
+        else:
+            u = dec & (2**128 - 1)
+            lo, hi = u & (2**64 - 1), u >> 64
+            aggs[2 * g].kind = V_I128
+            aggs[2 * g].lo = lo - 2**64 if lo >= 2**63 else lo
+            aggs[2 * g].hi = hi - 2**64 if hi >= 2**63 else hi
+        aggs[2 * g + 1].kind, aggs[2 * g + 1].lo = V_I64, cnt
+        want.append((k16, k64, dec, cnt))
+    r = _lib.Result()
+    r.ngroups, r.nkeys, r.naggs = n, 2, 2
+    r.keys, r.aggs = C.cast(keys, C.POINTER(_lib.Value)), C.cast(aggs, C.POINTER(_lib.Value))
+    r.key_type[0], r.key_type[1] = T_I16, T_I64
+    r.agg_type[0], r.agg_type[1] = T_DEC, T_I64
+    schema, pages = encode_result_pages(C.pointer(r), 65536)
+    cols = [(int(c.type_tag), bool(c.nullable)) for c in schema]
+    assert cols == [(T_I16, True), (T_I64, True), (T_DEC, True), (T_I64, False)]
+    for p in range(pages.shape[0]):
+        assert O.import_check(0x4152, 0, np.ascontiguousarray(pages[p, 20:]), cols) == 0
+    t = O.OTable.from_pages(pages, 65536, cols)
+    assert t.rows == n
+    k0, v0 = t.column(0)
+    k1, v1 = t.column(1)
+    raw, vd = t.column(2)
+    c3, _ = t.column(3)
+    for g, (k16, k64, dec, cnt) in enumerate(want):
+        assert int(k0[g]) == k16 and int(k1[g]) == k64 and int(c3[g]) == cnt
+        if dec is None:
+            assert vd is not None and not vd[g]
+        else:
+            assert (vd is None or vd[g]) and int.from_bytes(bytes(raw[g]), "little", signed=True) == dec

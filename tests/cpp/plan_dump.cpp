@@ -1,0 +1,135 @@
+// CPU test of the host-side planner (include/pgf_b200_plan.hpp): builds the Q6 / Q1 / Q3 physical
+// plans, runs install_runtime_filters + install_b200_operators without a device and prints, for
+// tests/test_cpp_host.py to check:
+//   TREE <name> / indented plan / END        the rewritten plan (DisplayAs)
+//   POD <name> <index> <hex of pgf_pipeline>  every lowered pipeline, build sides first
+//   CHECK <name> ok|FAILED                    host-side behaviours (errors, eligibility)
+#include <cstdio>
+#include <iostream>
+
+#include "plans.hpp"
+
+using namespace pgf_b200;
+
+namespace {
+
+int failures = 0;
+void check(const char* name, bool ok) {
+  std::printf("CHECK %s %s\n", name, ok ? "ok" : "FAILED");
+  if (!ok) ++failures;
+}
+
+// A pool that hands out fixed handles, so the lowering can be compared byte for byte.
+class FakePool final : public RuntimeFilterPool {
+ public:
+  explicit FakePool(uint32_t slots) : slots_(slots) {}
+  std::optional<RuntimeFilterBuildHandle> allocate_build(const RuntimeFilterTarget& t) override {
+    if (targets.size() >= slots_) return std::nullopt;
+    targets.push_back(t);
+    return RuntimeFilterBuildHandle{100 + targets.size(), 1};
+  }
+  std::vector<RuntimeFilterTarget> targets;
+
+ private:
+  uint32_t slots_;
+};
+
+void dump(const char* name, const PlanRef& plan) {
+  std::printf("TREE %s\n%sEND\n", name, display_indent(plan).c_str());
+  std::vector<const B200PipelineExec*> pods;
+  detail::collect_pods(plan, pods);
+  for (size_t i = 0; i < pods.size(); ++i) {
+    std::printf("POD %s %zu ", name, i);
+    const auto* bytes = reinterpret_cast<const unsigned char*>(&pods[i]->pod());
+    for (size_t b = 0; b < sizeof(pgf_pipeline); ++b) std::printf("%02x", bytes[b]);
+    std::printf("\n");
+  }
+}
+
+template <class F>
+bool throws(ErrorKind kind, F&& f) {
+  try {
+    f();
+  } catch (const DataFusionError& e) {
+    return e.kind() == kind;
+  } catch (...) {
+    return false;
+  }
+  return false;
+}
+
+}  // namespace
+
+int main() {
+  std::vector<std::string> skipped;
+  dump("q6", install_b200_operators(plans::q6(1), nullptr, &skipped));
+  dump("q1", install_b200_operators(plans::q1(2), nullptr, &skipped));
+  dump("q1_partial_final", install_b200_operators(plans::q1(2, true), nullptr, &skipped));
+  dump("q3", install_b200_operators(plans::q3(3, 4, 5), nullptr, &skipped));
+  {
+    FakePool pool(64);
+    PlanRef with_filters = install_runtime_filters(plans::q3(3, 4, 5), 7, pool);
+    std::printf("TREE q3_filters_before\n%sEND\n", display_indent(with_filters).c_str());
+    dump("q3_filters", install_b200_operators(with_filters, nullptr, &skipped));
+    // the inner join is visited first; targets name the probe-side scan and its key column
+    check("runtime_filter_targets", pool.targets.size() == 2 && pool.targets[0].scan_id == 4 && pool.targets[0].output_column == 1 &&
+                                        pool.targets[0].key_type == 2 && pool.targets[0].session_epoch == 7 &&
+                                        pool.targets[1].scan_id == 5 && pool.targets[1].output_column == 0);
+  }
+  {
+    FakePool pool(1);  // exhausted after the first join: a soft miss, the plan is still valid
+    PlanRef p = install_b200_operators(install_runtime_filters(plans::q3(3, 4, 5), 7, pool), nullptr, &skipped);
+    dump("q3_pool_exhausted", p);
+    check("pool_exhaustion_is_soft", pool.targets.size() == 1 && p->downcast<B200PipelineExec>() != nullptr);
+  }
+  check("everything_absorbed", skipped.empty());
+
+  // -- outside the grammar: the DataFusion node stays, with the reason recorded
+  {
+    PlanRef li = plans::scan(1, plans::lineitem_q6());
+    ExprRef disj = binary(binary(col("l_discount", 2), Operator::Lt, lit(0.05)), Operator::Or, binary(col("l_quantity", 0), Operator::Lt, lit(24.0)));
+    PlanRef agg = std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                                  std::vector<AggregateFunctionExpr>{count_star("n")}, plans::filter(disj, li));
+    std::vector<std::string> why;
+    PlanRef out = install_b200_operators(agg, nullptr, &why);
+    check("or_predicate_not_absorbed", out->downcast<AggregateExec>() != nullptr && why.size() == 1);
+    TaskContext tc(nullptr);
+    check("unabsorbed_node_has_no_cpu_operator", throws(ErrorKind::NotImplemented, [&] { out->execute(0, tc); }));
+  }
+  {
+    PlanRef c = plans::scan(3, plans::customer_q3()), o = plans::scan(4, plans::orders_q3());
+    PlanRef left_join = std::make_shared<HashJoinExec>(c, o, HashJoinExec::JoinOn{{col("c_custkey", 0), col("o_custkey", 1)}}, JoinType::Left);
+    PlanRef agg = std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                                  std::vector<AggregateFunctionExpr>{count_star("n")}, left_join);
+    FakePool pool(4);
+    std::vector<std::string> why;
+    PlanRef out = install_b200_operators(install_runtime_filters(agg, 1, pool), nullptr, &why);
+    check("outer_join_gets_no_filter_and_is_not_absorbed", pool.targets.empty() && out->downcast<AggregateExec>() != nullptr && why.size() == 1);
+    // a string join key is not eligible for a runtime filter (key_type_for), nor for the fused join
+    PlanRef sj = std::make_shared<HashJoinExec>(c, c, HashJoinExec::JoinOn{{col("c_mktsegment", 1), col("c_mktsegment", 1)}});
+    install_runtime_filters(sj, 1, pool);
+    check("string_key_gets_no_filter", pool.targets.empty());
+    // null_equals_null joins are skipped like in maybe_wrap_hash_join
+    PlanRef nn = std::make_shared<HashJoinExec>(c, o, HashJoinExec::JoinOn{{col("c_custkey", 0), col("o_custkey", 1)}}, JoinType::Inner,
+                                                PartitionMode::CollectLeft, true);
+    install_runtime_filters(nn, 1, pool);
+    check("null_equals_null_gets_no_filter", pool.targets.empty());
+  }
+  // -- the node surface
+  {
+    PlanRef p = install_b200_operators(plans::q6(1), nullptr);
+    TaskContext tc(nullptr);
+    check("one_partition", p->partition_count() == 1);
+    check("partition_1_is_a_plan_error", throws(ErrorKind::Plan, [&] { p->execute(1, tc); }));
+    check("no_device_is_an_execution_error", throws(ErrorKind::Execution, [&] { p->execute(0, tc); }));
+    check("with_new_children_arity", throws(ErrorKind::Plan, [&] { p->with_new_children({}); }));
+    PlanRef same = p->with_new_children(p->children());
+    check("with_new_children_roundtrip", same->downcast<B200PipelineExec>() &&
+                                             std::memcmp(&same->downcast<B200PipelineExec>()->pod(), &p->downcast<B200PipelineExec>()->pod(), sizeof(pgf_pipeline)) == 0);
+    int32_t devices = 0;
+    pgf_device_count(&devices);
+    if (devices == 0)  // the library refuses to create a context without a device: there is no CPU fallback
+      check("no_device_context", throws(ErrorKind::Execution, [] { B200Context ctx(0); (void)ctx; }));
+  }
+  return failures ? 1 : 0;
+}

@@ -1,0 +1,139 @@
+"""Host side above the C ABI in C++ (include/pgf_b200_plan.hpp): the plan-node surface, the
+install_runtime_filters / install_b200_operators rewrites and the lowering to pgf_pipeline.
+
+CPU part: tests/cpp/plan_dump.cpp is compiled with g++ -Werror, linked against libpgf_b200.so and
+run without a device; every pgf_pipeline it lowers from a DataFusion-shaped plan tree must be
+byte-identical to the one the ctypes PipelineBuilder produces for the same query (the builder is
+what the GPU parity tests run, so the two host layers are interchangeable)."""
+import ctypes as C
+import os
+import subprocess
+from types import SimpleNamespace
+
+import pytest
+
+from pg_fusion_b200 import AggFunc, Cmp, Factor, _lib
+from pg_fusion_b200.worker import PipelineBuilder
+
+from . import util as U
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_cpp(name: str, tmp: str) -> str:
+    exe = os.path.join(tmp, name)
+    lib = os.path.join(ROOT, "pg_fusion_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L", lib, "-lpgf_b200", f"-Wl,-rpath,{lib}", "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+@pytest.fixture(scope="module")
+def dump(tmp_path_factory):
+    exe = build_cpp("plan_dump", str(tmp_path_factory.mktemp("cpp")))
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    trees, pods, checks, cur = {}, {}, {}, None
+    for line in out.stdout.splitlines():
+        if line.startswith("TREE "):
+            cur = line[5:]
+            trees[cur] = []
+        elif line == "END":
+            cur = None
+        elif cur is not None:
+            trees[cur].append(line)
+        elif line.startswith("POD "):
+            _, name, idx, hexbytes = line.split()
+            pods.setdefault(name, {})[int(idx)] = bytes.fromhex(hexbytes)
+        elif line.startswith("CHECK "):
+            _, name, verdict = line.split()
+            checks[name] = verdict
+    return SimpleNamespace(rc=out.returncode, trees=trees, pods=pods, checks=checks, stderr=out.stderr)
+
+
+def fake_scan(scan_id, schema):
+    scan = SimpleNamespace(scan_id=scan_id, schema=list(schema))
+    scan.pipeline = lambda: PipelineBuilder(None, scan)
+    return scan
+
+
+def pod_bytes(builder) -> bytes:
+    return C.string_at(C.addressof(builder.p), C.sizeof(builder.p))
+
+
+def diff(a: bytes, b: bytes) -> str:
+    bad = [i for i in range(min(len(a), len(b))) if a[i] != b[i]]
+    return f"sizes {len(a)} / {len(b)}, first differing offsets {bad[:8]}"
+
+
+def test_host_checks_pass(dump):
+    assert dump.rc == 0, dump.stderr
+    assert dump.checks and all(v == "ok" for v in dump.checks.values()), dump.checks
+    for name in ("partition_1_is_a_plan_error", "unabsorbed_node_has_no_cpu_operator", "pool_exhaustion_is_soft",
+                 "or_predicate_not_absorbed", "runtime_filter_targets"):
+        assert name in dump.checks
+
+
+def test_struct_size_matches_the_ctypes_mirror(dump):
+    assert len(dump.pods["q6"][0]) == C.sizeof(_lib.Pipeline)
+
+
+def test_q6_plan_lowers_to_the_builder_pod(dump):
+    want = pod_bytes(U.gpu_q6(fake_scan(1, U.Q6_SCHEMA)))
+    assert dump.pods["q6"] == {0: want}, diff(dump.pods["q6"][0], want)
+    assert dump.trees["q6"][0].startswith("B200PipelineExec: scan_id=1") and "WorkerPgScanExec" in dump.trees["q6"][1]
+
+
+@pytest.mark.parametrize("name", ["q1", "q1_partial_final"])
+def test_q1_plan_with_cse_projection_and_sort_lowers_to_the_builder_pod(dump, name):
+    # the aggregate arguments go through DataFusion's common-subexpression projection; the SortExec
+    # above the aggregate is absorbed; Partial -> Final over one partition collapses to Single
+    want = pod_bytes(U.gpu_q1(fake_scan(2, U.Q1_SCHEMA)).order_by([("key", 0, False), ("key", 1, False)]))
+    assert dump.pods[name] == {0: want}, diff(dump.pods[name][0], want)
+
+
+def q3_builders(rf1=None, rf2=None, limit=10):
+    customer, orders, lineitem = fake_scan(3, U.CUSTOMER_SCHEMA), fake_scan(4, U.ORDERS_SCHEMA), fake_scan(5, U.LINEITEM_Q3_SCHEMA)
+    b1 = customer.pipeline().filter(1, Cmp.EQ, b"BUILDING").build_join(0, [], rf1)
+    b2 = orders.pipeline()
+    if rf1 is not None:
+        b2.bloom_probe(rf1, 1)
+    b2 = b2.filter(2, Cmp.LT, U.Q3_DATE).join(0, 1).build_join(0, [2, 3], rf2)
+    b3 = lineitem.pipeline()
+    if rf2 is not None:
+        b3.bloom_probe(rf2, 0)
+    b3 = (b3.filter(3, Cmp.GT, U.Q3_DATE).join(0, 0)
+          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])])
+          .order_by(U.Q3_ORDER, limit=limit))
+    return [b1, b2, b3]     # build sides before the pipeline that probes them
+
+
+def test_q3_plan_lowers_to_three_dependent_pipelines(dump):
+    want = [pod_bytes(b) for b in q3_builders()]
+    got = dump.pods["q3"]
+    assert sorted(got) == [0, 1, 2]
+    for i in range(3):
+        assert got[i] == want[i], f"pipeline {i}: " + diff(got[i], want[i])
+    tree = dump.trees["q3"]
+    assert [ln.strip().split(":")[0] for ln in tree] == ["B200PipelineExec", "B200PipelineExec", "B200PipelineExec",
+                                                         "WorkerPgScanExec", "WorkerPgScanExec", "WorkerPgScanExec"]
+
+
+def test_q3_runtime_filters_follow_the_reference_rewrite(dump):
+    # install_runtime_filters visits the inner join first (runtime_filter_plan.rs:27-48): filter 101 is built
+    # from c_custkey and probed on o_custkey, filter 102 from o_orderkey and probed on l_orderkey
+    rf1, rf2 = SimpleNamespace(handle=101, generation=1), SimpleNamespace(handle=102, generation=1)
+    want = [pod_bytes(b) for b in q3_builders(rf1, rf2)]
+    got = dump.pods["q3_filters"]
+    for i in range(3):
+        assert got[i] == want[i], f"pipeline {i}: " + diff(got[i], want[i])
+    before = "\n".join(dump.trees["q3_filters_before"])
+    assert before.count("RuntimeFilterBuildExec: key_index=0") == 2
+    assert "WorkerPgScanExec: scan_id=4, runtime_filter(col=1)" in before
+    assert "WorkerPgScanExec: scan_id=5, runtime_filter(col=0)" in before
+    # pool exhausted after one slot: only the customer -> orders filter exists
+    want = [pod_bytes(b) for b in q3_builders(rf1, None)]
+    got = dump.pods["q3_pool_exhausted"]
+    for i in range(3):
+        assert got[i] == want[i], f"pipeline {i}: " + diff(got[i], want[i])

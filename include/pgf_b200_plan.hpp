@@ -263,6 +263,36 @@ class DeviceRuntimeFilterPool final : public RuntimeFilterPool {
   std::vector<uint64_t> blooms_;
 };
 
+// The producer side of a scan: WorkerPgScanExec's scan thread receives transfer pages and hands
+// them on (worker_runtime/src/transport_scan_source.rs:251-426, one OS thread per scan); here the
+// pages go to HBM.  push_* of different scans may run concurrently; each call copies (or DMAs,
+// for registered memory) before it returns, so the caller can release the page immediately --
+// the deep copy PageMaterializeExec makes for retaining operators (page_materialize.rs:107-207).
+class ScanIngest {
+ public:
+  ScanIngest(B200Context& gpu, uint64_t scan_id, const Schema& schema, uint64_t expected_pages = 0) : gpu_(gpu), scan_id_(scan_id) {
+    std::vector<pgf_column_spec> specs;
+    for (const auto& f : schema.fields) specs.push_back(pgf_column_spec{uint16_t(f.type_tag), uint16_t(f.nullable ? 1 : 0)});
+    gpu_.check(pgf_scan_declare(gpu_.raw(), scan_id_, specs.data(), uint32_t(specs.size()), expected_pages));
+  }
+  void push_page(const uint8_t* page, uint32_t len) { gpu_.check(pgf_scan_push_page(gpu_.raw(), scan_id_, page, len)); }
+  void push_pages(const uint8_t* pages, uint64_t npages, uint64_t stride) {
+    gpu_.check(pgf_scan_push_pages(gpu_.raw(), scan_id_, pages, npages, stride));
+  }
+  // end of stream: waits for the copies, runs the row-level import checks on the device
+  void finish() { gpu_.check(pgf_scan_finish(gpu_.raw(), scan_id_)); }
+  pgf_scan_info info() const {
+    pgf_scan_info i;
+    gpu_.check(pgf_scan_get_info(gpu_.raw(), scan_id_, &i));
+    return i;
+  }
+  uint64_t scan_id() const { return scan_id_; }
+
+ private:
+  B200Context& gpu_;
+  uint64_t scan_id_;
+};
+
 // ------------------------------------------------------------------------------ RecordBatch
 struct PipelineMetrics {  // EXPLAIN ANALYZE counters of one fused pipeline
   std::string node;

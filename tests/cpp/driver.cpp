@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <string>
+#include <thread>
 
 #include "plans.hpp"
 
@@ -93,6 +94,46 @@ int main(int argc, char** argv) {
       gpu.check(pgf_bloom_params_new(1u << 20, 4, 0x7067667573696f6eull, &params));  // GUC defaults, pg/extension/src/guc.rs:41-46
       DeviceRuntimeFilterPool pool(gpu, params);
       run("q3_runtime_filters", gpu, plans::q3(3, 4, 5), &pool);
+    }
+    // "D" variants: exact Decimal128 sums
+    gen(gpu, 6, PGF_GEN_LINEITEM_Q6_D, q6_rows, 0);
+    gen(gpu, 7, PGF_GEN_LINEITEM_Q1_D, q1_rows, 0);
+    run("q6_decimal", gpu, plans::q6_d(6));
+    run("q1_decimal", gpu, plans::q1_d(7));
+    // Q3 again over scans that are fed page by page from one producer thread per scan, the way the
+    // worker's scan threads deliver transfer pages: declare -> push_page* (concurrently) -> finish
+    {
+      struct Feed { uint64_t from, to; Schema schema; std::vector<uint8_t> pages; pgf_scan_info info; };
+      Feed feeds[3] = {{3, 13, plans::customer_q3(), {}, {}}, {4, 14, plans::orders_q3(), {}, {}}, {5, 15, plans::lineitem_q3(), {}, {}}};
+      for (Feed& f : feeds) {
+        gpu.check(pgf_scan_get_info(gpu.raw(), f.from, &f.info));
+        f.pages.resize(size_t(f.info.pages) * gpu.page_size());
+        gpu.check(pgf_scan_read_pages(gpu.raw(), f.from, 0, f.info.pages, f.pages.data()));
+      }
+      // scans are declared when the plan is made; the producer threads only push (the one entry point
+      // the C ABI allows concurrently, one producer per scan); the consumer finishes each stream
+      std::vector<ScanIngest> ingests;
+      for (Feed& f : feeds) ingests.emplace_back(gpu, f.to, f.schema, f.info.pages);
+      std::vector<std::thread> producers;
+      std::string errors[3];
+      for (int i = 0; i < 3; ++i) {
+        producers.emplace_back([&, i] {
+          try {
+            const Feed& f = feeds[i];
+            for (uint64_t p = 0; p < f.info.pages; ++p) ingests[size_t(i)].push_page(f.pages.data() + p * gpu.page_size(), gpu.page_size());
+          } catch (const DataFusionError& e) {
+            errors[i] = e.what();
+          }
+        });
+      }
+      for (auto& t : producers) t.join();
+      for (const auto& e : errors)
+        if (!e.empty()) throw exec_err("streamed ingest: " + e);
+      for (int i = 0; i < 3; ++i) {
+        ingests[size_t(i)].finish();
+        if (ingests[size_t(i)].info().rows != feeds[i].info.rows) throw exec_err("streamed ingest: row count differs");
+      }
+      run("q3_streamed", gpu, plans::q3(13, 14, 15));
     }
     if (argc > 6) {  // ResultPageProducer: the Q1 rows as transfer pages
       uint64_t npages = 0;

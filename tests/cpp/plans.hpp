@@ -79,6 +79,46 @@ inline PlanRef q1(uint64_t scan_id, bool partial_final = false) {
   return std::make_shared<SortExec>(order, agg);
 }
 
+// ---- "D" variants: money Decimal128(15,2), dates Date32 (Int32 days), flags Int16 codes.
+// Literals are what DataFusion's type coercion leaves in the physical plan: unscaled Decimal128
+// values at the column's scale (0.05 -> 5, 24 -> 2400, 1 -> 100) and Date32 day numbers.
+inline Schema lineitem_q6_d() {
+  return schema_of({{"l_quantity", PGF_T_DECIMAL128}, {"l_extendedprice", PGF_T_DECIMAL128}, {"l_discount", PGF_T_DECIMAL128}, {"l_shipdate", PGF_T_INT32}});
+}
+inline Schema lineitem_q1_d() {
+  return schema_of({{"l_quantity", PGF_T_DECIMAL128}, {"l_extendedprice", PGF_T_DECIMAL128}, {"l_discount", PGF_T_DECIMAL128}, {"l_tax", PGF_T_DECIMAL128},
+                    {"l_returnflag", PGF_T_INT16}, {"l_linestatus", PGF_T_INT16}, {"l_shipdate", PGF_T_INT32}});
+}
+inline ExprRef dec(int64_t unscaled) { return lit(ScalarValue::decimal128(unscaled)); }
+
+inline PlanRef q6_d(uint64_t scan_id) {
+  PlanRef li = scan(scan_id, lineitem_q6_d());
+  ExprRef pred = and_(and_(and_(and_(binary(col("l_shipdate", 3), Operator::GtEq, lit(int64_t(8766))),    // 1994-01-01
+                                     binary(col("l_shipdate", 3), Operator::Lt, lit(int64_t(9131)))),     // 1995-01-01
+                                binary(col("l_discount", 2), Operator::GtEq, dec(5))),
+                           binary(col("l_discount", 2), Operator::LtEq, dec(7))),
+                      binary(col("l_quantity", 0), Operator::Lt, dec(2400)));
+  return std::make_shared<AggregateExec>(
+      AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+      std::vector<AggregateFunctionExpr>{sum(binary(col("l_extendedprice", 1), Operator::Multiply, col("l_discount", 2)), "revenue"),
+                                         count_star("count(*)")},
+      filter(pred, li));
+}
+
+inline PlanRef q1_d(uint64_t scan_id) {
+  PlanRef li = scan(scan_id, lineitem_q1_d());
+  PlanRef filtered = filter(binary(lit(int64_t(10471)), Operator::GtEq, col("l_shipdate", 6)), li);   // 1998-09-02 >= l_shipdate (flipped on purpose)
+  ExprRef disc_price = binary(col("l_extendedprice", 1), Operator::Multiply, binary(dec(100), Operator::Minus, col("l_discount", 2)));
+  std::vector<AggregateFunctionExpr> aggs{
+      sum(col("l_quantity", 0), "sum_qty"), sum(col("l_extendedprice", 1), "sum_base_price"), sum(disc_price, "sum_disc_price"),
+      sum(binary(disc_price, Operator::Multiply, binary(col("l_tax", 3), Operator::Plus, dec(100))), "sum_charge"),   // (x + c) form
+      avg(col("l_quantity", 0), "avg_qty"), avg(col("l_extendedprice", 1), "avg_price"), avg(col("l_discount", 2), "avg_disc"),
+      count_star("count_order")};
+  return std::make_shared<AggregateExec>(
+      AggregateMode::Single,
+      std::vector<std::pair<ExprRef, std::string>>{{col("l_returnflag", 4), "l_returnflag"}, {col("l_linestatus", 5), "l_linestatus"}}, aggs, filtered);
+}
+
 // q03.sql: customer(BUILDING) |><| orders(o_orderdate < d) |><| lineitem(l_shipdate > d),
 // group by l_orderkey, o_orderdate, o_shippriority order by revenue desc, o_orderdate limit 10
 inline PlanRef q3(uint64_t customer_id, uint64_t orders_id, uint64_t lineitem_id, uint64_t fetch = 10, const char* segment = "BUILDING") {

@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def build_cpp(name: str, tmp: str) -> str:
     exe = os.path.join(tmp, name)
     lib = os.path.join(ROOT, "pg_fusion_b200")
-    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+    cmd = ["g++", "-std=c++17", "-O1", "-pthread", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-L", lib, "-lpgf_b200", f"-Wl,-rpath,{lib}", "-o", exe]
     out = subprocess.run(cmd, capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
@@ -137,3 +137,12 @@ def test_q3_runtime_filters_follow_the_reference_rewrite(dump):
     got = dump.pods["q3_pool_exhausted"]
     for i in range(3):
         assert got[i] == want[i], f"pipeline {i}: " + diff(got[i], want[i])
+
+
+def test_decimal_plans_lower_to_the_builder_pods(dump):
+    # Decimal128 literals at the column's scale, Date32 day numbers, a flipped comparison
+    # (literal >= column) and the (x + c) spelling of a factor
+    want = pod_bytes(U.gpu_q6_d(fake_scan(6, U.Q6_D_SCHEMA)))
+    assert dump.pods["q6_decimal"] == {0: want}, diff(dump.pods["q6_decimal"][0], want)
+    want = pod_bytes(U.gpu_q1_d(fake_scan(7, U.Q1_D_SCHEMA)))
+    assert dump.pods["q1_decimal"] == {0: want}, diff(dump.pods["q1_decimal"][0], want)

@@ -86,7 +86,7 @@ def q3_oracle(ctx):
     return U.oracle_q3(ct, ot, lt)
 
 
-@pytest.mark.parametrize("name", ["q3", "q3_runtime_filters"])
+@pytest.mark.parametrize("name", ["q3", "q3_runtime_filters", "q3_streamed"])
 def test_q3_plan_top10(runs, ctx, name):
     want, wstats = q3_oracle(ctx)
     got = runs[name]
@@ -136,3 +136,21 @@ def test_q1_result_pages_from_the_cpp_layer(runs, ctx):
 def test_ineligible_plan_and_library_errors(runs):
     assert runs["ineligible"] == {"query": "ineligible", "kept": "AggregateExec", "reasons": 1, "not_implemented": True}
     assert runs["unknown_scan"]["status"] == 5               # PGF_ERR_UNKNOWN_HANDLE as DataFusionError::Execution
+
+
+def i128(v):
+    hi, lo = v
+    return (hi << 64) | lo
+
+
+def test_decimal_plans_are_exact(runs, ctx):
+    want = U.oracle_q6_d(table(ctx, GenTable.LINEITEM_Q6_D, Q6_ROWS, U.Q6_D_SCHEMA))
+    (revenue, count), = runs["q6_decimal"]["rows"]
+    assert i128(revenue) == want.aggs[0][0] and count == want.aggs[0][1]           # bit-exact i128 sum
+    assert runs["q6_decimal"]["pipelines"][0]["variant"] == "q6_decimal"
+    want, _ = U.oracle_q1_d(table(ctx, GenTable.LINEITEM_Q1_D, Q1_ROWS, U.Q1_D_SCHEMA))
+    got = runs["q1_decimal"]["rows"]
+    assert len(got) == len(want) == 4
+    for row in got:
+        w = want[(row[0], row[1])]
+        assert tuple(i128(v) for v in row[2:9]) == tuple(w[:7]) and row[9] == w[7]

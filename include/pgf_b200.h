@@ -13,9 +13,10 @@
  *     exits or throws across this boundary ("no panics in extension paths",
  *     ai/invariants.md:12-17).  CUDA errors are sticky per context.
  *   - host pointers are borrowed for the duration of the call unless stated otherwise.
- *   - a context is used by one thread at a time, except pgf_scan_push_* which may be
- *     called concurrently for different scans (one producer thread per scan, mirroring
- *     worker_runtime/src/transport_scan_source.rs:166-183).
+ *   - a context is used by one thread at a time, except pgf_scan_push_* and pgf_scan_finish,
+ *     which may be called concurrently for different scans (one producer thread per scan,
+ *     mirroring worker_runtime/src/transport_scan_source.rs:166-183), also while a pipeline
+ *     over other, finished scans runs.
  *   - there is no CPU fallback: without a CUDA device pgf_ctx_create fails.
  */
 #ifndef PGF_B200_H

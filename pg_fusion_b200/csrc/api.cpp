@@ -193,7 +193,14 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   delete ctx;
 }
 
-const char* pgf_last_error(const pgf_ctx* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+const char* pgf_last_error(const pgf_ctx* ctx) {
+  if (!ctx) return "null context";
+  // a per-thread copy: the message stays valid for the caller while other threads keep failing
+  thread_local std::string copy;
+  std::lock_guard<std::mutex> g(ctx->err_mu);
+  copy = ctx->last_error;
+  return copy.c_str();
+}
 
 pgf_status pgf_ctx_register_host_region(pgf_ctx* ctx, void* base, size_t len) {
   if (!ctx || !base || !len) return PGF_ERR_INVALID_ARGUMENT;
@@ -390,6 +397,10 @@ pgf_status pgf_scan_finish(pgf_ctx* ctx, uint64_t scan_id) {
   Scan& s = *sp;
   std::lock_guard<std::mutex> g(s.mu);
   if (s.finished) return PGF_OK;
+  // every scan thread ends its own stream (transport_scan_source.rs:251-426): the device-side
+  // checks share the context's event and error slot, so finishes of different scans serialise
+  // here (lock order: scan, then context -- the same as the staging path of push_pages)
+  std::lock_guard<std::mutex> gc(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   PGF_TRY(scan_sync_descs(ctx, s));
   // compute stream waits for the H2D copies; then the row-level import checks run on device

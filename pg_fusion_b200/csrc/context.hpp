@@ -129,6 +129,7 @@ struct pgf_ctx {
   uint64_t next_handle = 1;
   std::vector<void*> registered;
   std::mutex mu;
+  mutable std::mutex err_mu;    // scan producers of different scans may fail concurrently
   std::string last_error;
   pgf_status sticky = PGF_OK;
   float last_kernel_ms = 0.f;
@@ -139,6 +140,7 @@ struct pgf_ctx {
     va_start(ap, fmt);
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
+    std::lock_guard<std::mutex> g(err_mu);
     last_error = buf;
     return st;
   }

@@ -110,8 +110,8 @@ int main(int argc, char** argv) {
         f.pages.resize(size_t(f.info.pages) * gpu.page_size());
         gpu.check(pgf_scan_read_pages(gpu.raw(), f.from, 0, f.info.pages, f.pages.data()));
       }
-      // scans are declared when the plan is made; the producer threads only push (the one entry point
-      // the C ABI allows concurrently, one producer per scan); the consumer finishes each stream
+      // scans are declared when the plan is made; every producer thread pushes its pages and ends
+      // its own stream (push and finish of different scans may run concurrently)
       std::vector<ScanIngest> ingests;
       for (Feed& f : feeds) ingests.emplace_back(gpu, f.to, f.schema, f.info.pages);
       std::vector<std::thread> producers;
@@ -120,7 +120,10 @@ int main(int argc, char** argv) {
         producers.emplace_back([&, i] {
           try {
             const Feed& f = feeds[i];
-            for (uint64_t p = 0; p < f.info.pages; ++p) ingests[size_t(i)].push_page(f.pages.data() + p * gpu.page_size(), gpu.page_size());
+            ScanIngest& ingest = ingests[size_t(i)];
+            for (uint64_t p = 0; p < f.info.pages; ++p) ingest.push_page(f.pages.data() + p * gpu.page_size(), gpu.page_size());
+            ingest.finish();
+            if (ingest.info().rows != f.info.rows) errors[i] = "row count differs after ingest";
           } catch (const DataFusionError& e) {
             errors[i] = e.what();
           }
@@ -129,10 +132,6 @@ int main(int argc, char** argv) {
       for (auto& t : producers) t.join();
       for (const auto& e : errors)
         if (!e.empty()) throw exec_err("streamed ingest: " + e);
-      for (int i = 0; i < 3; ++i) {
-        ingests[size_t(i)].finish();
-        if (ingests[size_t(i)].info().rows != feeds[i].info.rows) throw exec_err("streamed ingest: row count differs");
-      }
       run("q3_streamed", gpu, plans::q3(13, 14, 15));
     }
     if (argc > 6) {  // ResultPageProducer: the Q1 rows as transfer pages

@@ -170,6 +170,30 @@ def cpu_q6(pages, nthreads, min_seconds=5.0):
             return rows_total / dt, passes, rows_in
 
 
+def acero_q6(pages, min_seconds=2.0):
+    """SURVEY 8d baseline (iii): the same Q6 shape in pyarrow / Acero (Arrow C++, NOT DataFusion) with its
+    default thread pool, over columns decoded from a bounded page sample.  Returns a dict for cpu_baseline."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from oracle import pyorc as O
+    from tests import util as U
+    t = O.OTable.from_pages(pages, PAGE, U.orc_cols(U.Q6_SCHEMA))
+    (q, _), (p, _), (d, _) = t.column(0), t.column(1), t.column(2)
+    tb = pa.table({"q": q, "p": p, "d": d, "s": pa.array(t.column(3), pa.binary()).cast(pa.string())})
+    f = pc.field
+    expr = (f("s") >= "1994-01-01") & (f("s") < "1995-01-01") & (f("d") >= 0.05) & (f("d") <= 0.07) & (f("q") < 24.0)
+    passes, t0 = 0, time.perf_counter()
+    while True:
+        r = tb.filter(expr)
+        value = pc.sum(pc.multiply(r["p"], r["d"])).as_py()
+        passes += 1
+        dt = time.perf_counter() - t0
+        if dt >= min_seconds:
+            break
+    return {"value": tb.num_rows * passes / dt, "unit": "rows/s", "threads": pa.cpu_count(), "engine": f"pyarrow {pa.__version__} (Acero)",
+            "sample": f"{tb.num_rows} rows decoded from the first {pages.shape[0]} pages, {passes} passes", "sum": value, "rows_out": r.num_rows}
+
+
 def side_measurements(ctx, pg, U, rows, peak, label="sf10", bloom=True):
     """Kernel-time throughput of the other BASELINE.json shapes (device events inside the library)."""
     extras = {}
@@ -577,10 +601,14 @@ def main():
             big = scan.read_pages(0, big_pages)
             vn, _, big_rows = cpu_q6(big, cores, min_seconds=3.0)
             del big
+            try:
+                acero = acero_q6(pages[:640])
+            except Exception as e:  # a baseline, never a reason to lose the bench line
+                acero = {"error": repr(e)[:200]}
             cpu = {"value": v1, "unit": "rows/s", "cores": 1, "kind": "port",
                    "sample": f"first {sample_pages} pages ({sample_rows} rows) of the same generated SF10 lineitem, {passes} passes; "
                              "1 thread mirrors the reference's single-partition execution (worker_runtime/src/runtime.rs:748-758)",
-                   "all_cores": {"value": vn, "cores": cores, "sample": f"first {big_pages} pages ({big_rows} rows, {big_pages * PAGE >> 20} MiB: larger than the host L3)"}}
+                   "acero": acero, "all_cores": {"value": vn, "cores": cores, "sample": f"first {big_pages} pages ({big_rows} rows, {big_pages * PAGE >> 20} MiB: larger than the host L3)"}}
         # DRAM traffic of one launch of the dominant kernel, from the committed ncu --set full capture of this workload
         traffic, traffic_src = None, None
         try:

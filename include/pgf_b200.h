@@ -390,6 +390,9 @@ typedef struct {
   int32_t key_type[PGF_MAX_KEYS];
   int32_t agg_type[PGF_MAX_AGGS];
   char variant[24];        /* which instantiation of the fused kernel ran: a registered shape or "generic" (EXPLAIN ANALYZE aid) */
+  /* PGF_AGG_* of every aggregate: decides the nullability of its result column (COUNT is NOT NULL,
+   * SUM / AVG are nullable whatever the data holds).  0 in a hand-built result = unknown. */
+  int32_t agg_func[PGF_MAX_AGGS];
 } pgf_result;
 
 pgf_status pgf_pipeline_check(pgf_ctx *ctx, const pgf_pipeline *plan); /* eligibility only */

@@ -115,7 +115,7 @@ class Result(C.Structure):
     _fields_ = [("rows_in", u64), ("rows_bloom", u64), ("rows_filtered", u64), ("rows_out", u64),
                 ("ngroups", u64), ("nkeys", u32), ("naggs", u32), ("keys", P(Value)), ("aggs", P(Value)),
                 ("join_table", u64), ("bloom_rows", u64), ("kernel_ms", C.c_float), ("kernel_launches", u32),
-                ("key_type", i32 * 4), ("agg_type", i32 * 16), ("variant", C.c_char * 24)]
+                ("key_type", i32 * 4), ("agg_type", i32 * 16), ("variant", C.c_char * 24), ("agg_func", i32 * 16)]
 
 
 class RfTarget(C.Structure):

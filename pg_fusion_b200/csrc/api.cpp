@@ -139,7 +139,7 @@ pgf_status pgf_ctx_create(const pgf_config* config, pgf_ctx** ctx_out) {
   if (cudaSetDevice(ctx->device) != cudaSuccess) return bail(PGF_ERR_CUDA);
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, ctx->device) != cudaSuccess) return bail(PGF_ERR_CUDA);
-  if (prop.major < 10) return bail(PGF_ERR_NO_DEVICE);  // kernels are built for sm_100a only
+  if (prop.major != 10 || prop.minor != 0) return bail(PGF_ERR_NO_DEVICE);  // the kernels are sm_100a code: only compute capability 10.0 runs them
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PGF_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(PGF_ERR_CUDA);
@@ -729,10 +729,16 @@ pgf_status pgf_result_schema(const pgf_result* r, pgf_column_spec* schema_out, u
   uint32_t n = 0;
   for (uint32_t k = 0; k < r->nkeys; ++k) schema_out[n++] = pgf_column_spec{uint16_t(r->key_type[k]), 1};
   for (uint32_t a = 0; a < r->naggs; ++a) {
-    // COUNT never yields NULL; SUM / AVG over no (non-null) rows do
-    bool nullable = false;
-    for (uint64_t g = 0; g < r->ngroups && !nullable; ++g) nullable = r->aggs[g * r->naggs + a].kind == PGF_V_NULL;
-    const bool is_count = r->agg_type[a] == PGF_T_INT64 && !nullable;
+    // COUNT never yields NULL; SUM / AVG over no (non-null) rows do, so their columns are nullable
+    // whatever this result happens to hold (the receiving schema is fixed by the plan)
+    bool is_count;
+    if (r->agg_func[a]) {
+      is_count = r->agg_func[a] == PGF_AGG_COUNT || r->agg_func[a] == PGF_AGG_COUNT_STAR;
+    } else {  // hand-built result without the function: an Int64 column without NULLs is taken for a count
+      bool has_null = false;
+      for (uint64_t g = 0; g < r->ngroups && !has_null; ++g) has_null = r->aggs[g * r->naggs + a].kind == PGF_V_NULL;
+      is_count = r->agg_type[a] == PGF_T_INT64 && !has_null;
+    }
     schema_out[n++] = pgf_column_spec{uint16_t(r->agg_type[a]), uint16_t(is_count ? 0 : 1)};
   }
   *ncols_out = n;

@@ -145,6 +145,10 @@ struct pgf_ctx {
     return st;
   }
   pgf_status cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaErrorMemoryAllocation) {  // recoverable: the context stays usable
+      cudaGetLastError();
+      return fail(PGF_ERR_OUT_OF_MEMORY, "out of device memory in %s at %s:%d", what, file, line);
+    }
     sticky = PGF_ERR_CUDA;
     return fail(PGF_ERR_CUDA, "CUDA error %d (%s) in %s at %s:%d", int(e), cudaGetErrorString(e), what, file, line);
   }

@@ -984,6 +984,7 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
   for (uint32_t k = 0; k < plan->nkeys; ++k) res->key_type[k] = L.key_types[k];
   for (uint32_t a = 0; a < plan->naggs; ++a) {
     const pgf_agg& ag = plan->aggs[a];
+    res->agg_func[a] = ag.func;
     if (ag.func == PGF_AGG_COUNT_STAR || ag.func == PGF_AGG_COUNT) res->agg_type[a] = PGF_T_INT64;
     else res->agg_type[a] = L.acc_cls == CLS_F64 ? PGF_T_FLOAT64 : L.acc_cls == CLS_I64 ? PGF_T_INT64 : PGF_T_DECIMAL128;
   }
@@ -1269,6 +1270,10 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   Lowered L;
   Lowering low(ctx, plan);
   PGF_TRY(low.run(&L));
+  if (plan->sink == PGF_SINK_AGGREGATE && plan->nsort) {  // ORDER BY terms are part of the eligibility check
+    DevSort S;
+    PGF_TRY(lower_sort(ctx, plan, L, &S));
+  }
   if (check_only) return PGF_OK;
   if (partial && plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
   PGF_TRY(scan_sync_descs(ctx, *L.scan));
@@ -1399,10 +1404,6 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
         }
         if (!topk && h_state[0] != ngroups) return ctx->fail(PGF_ERR_STATE, "group table extraction found %llu groups, expected %llu",
                                                              (unsigned long long)h_state[0], (unsigned long long)ngroups);
-        if (plan->nsort) {  // validates the ORDER BY terms even when the host orders the rows
-          DevSort S;
-          PGF_TRY(lower_sort(ctx, plan, L, &S));
-        }
         PGF_TRY(build_result(ctx, plan, L, h_state, res));
         sort_result(plan, res);
       }
@@ -1487,6 +1488,10 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   Lowered L;
   Lowering low(ctx, plan);
   PGF_TRY(low.run(&L));
+  if (plan->nsort) {  // validate the ORDER BY terms before anything is ordered by them
+    DevSort S;
+    PGF_TRY(lower_sort(ctx, plan, L, &S));
+  }
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
   if (stride < (1 + uint64_t(ew)) * 8) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state stride too small");

@@ -138,8 +138,10 @@ def test_reference_smoke_values(ctx):
     schema = [ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Utf8View)]
     pages = AL.encode_pages(schema, [(ids, None), (AL.inline_views([b"payload"] * 5000), None)])
     scan = load(ctx, schema, pages)
-    res = scan.pipeline().aggregate([], [(AggFunc.COUNT, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(0)])]).run()
+    res = scan.pipeline().aggregate([], [(AggFunc.COUNT, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(0)])]).run(pages=True)
     assert res.aggs[0] == (5000, 12502500)                  # smoke_tests.rs:228-251
+    # transport schema: COUNT is NOT NULL, SUM(Int64) is a nullable Int64 although this result holds no NULL
+    assert [(int(c.type_tag), bool(c.nullable)) for c in res.result_schema] == [(4, False), (4, True)]
     res = scan.pipeline().filter(0, Cmp.GE, 10).filter(0, Cmp.LE, 20).aggregate([], [(AggFunc.SUM, [Factor.of(0)])]).run()
     assert res.aggs[0] == (sum(range(10, 21)),)             # smoke_tests.rs:382-471 (BETWEEN)
     scan.release()

@@ -107,3 +107,20 @@ def test_order_by_with_null_keys_ties_and_integer_sums(ctx, limit):
         want = py_order(rows, terms, limit)
         assert list(zip(got.keys, got.aggs)) == want   # integer sums and counts: exact, total order given all keys
     scan.release()
+
+
+def test_order_by_terms_are_validated_by_the_eligibility_check(ctx):
+    """A malformed ORDER BY (index outside the output columns, too many terms) is an argument error of
+    pgf_pipeline_check and of every run / merge entry point -- never an out-of-bounds read."""
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q1, 10_000, seed=1)
+    for terms in ([("key", 2, False)], [("agg", 8, True)], [("key", -1, False)]):
+        p = U.gpu_q1(scan).order_by(terms)
+        assert p.check() == 1                      # PGF_ERR_INVALID_ARGUMENT
+        with pytest.raises(pg.PgfError) as e:
+            p.run()
+        assert e.value.code == 1
+    p = U.gpu_q1(scan).order_by([("key", 0, False)])
+    p.p.nsort = 5                                  # > PGF_MAX_SORT
+    assert p.check() == 1
+    assert U.gpu_q1(scan).order_by([("key", 1, True), ("agg", 7, False)]).check() == 0
+    scan.release()

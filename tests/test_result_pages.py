@@ -142,3 +142,21 @@ def test_result_pages_with_integer_keys_and_decimal_sums():
             assert vd is not None and not vd[g]
         else:
             assert (vd is None or vd[g]) and int.from_bytes(bytes(raw[g]), "little", signed=True) == dec
+
+
+def test_nullability_follows_the_aggregate_function_not_the_data():
+    """The receiving schema is fixed by the plan (page/import/src/lib.rs:150-180 rejects a nullability
+    mismatch): SUM(Int64) is nullable even when this result holds no NULL, COUNT never is."""
+    rows = [(b"a", 1, 1.5, 10), (b"b", 2, 2.5, 20)]
+    r, keep = make_result(rows)
+    r.agg_type[0], r.agg_type[1] = T_I64, T_I64
+    for g in range(2):
+        r.aggs[2 * g].kind, r.aggs[2 * g].lo = V_I64, 100 + g
+    r.agg_func[0], r.agg_func[1] = 1, 3                      # SUM, COUNT(*)
+    schema, pages = encode_result_pages(C.pointer(r), 65536)
+    assert [(int(c.type_tag), c.nullable) for c in schema] == [(T_VIEW, True), (T_I32, True), (T_I64, True), (T_I64, False)]
+    cols = [(int(c.type_tag), bool(c.nullable)) for c in schema]
+    assert O.import_check(0x4152, 0, np.ascontiguousarray(pages[0][20:]), cols) == 0
+    r.agg_func[0], r.agg_func[1] = 4, 2                      # COUNT(x), AVG
+    schema, _ = encode_result_pages(C.pointer(r), 65536)
+    assert [c.nullable for c in schema[2:]] == [False, True]

@@ -892,7 +892,7 @@ inline pgf_literal make_literal(const ScalarValue& v, int32_t col_tag) {
       l.hi = v.hi;
       break;
     case ScalarValue::Utf8:
-      if (v.str.size() > sizeof l.str) throw NotEligible{"string literal longer than 16 bytes"};
+      if (v.str.size() > 12) throw NotEligible{"string literal longer than 12 bytes (needs the out-of-line view path)"};
       l.type_tag = PGF_T_UTF8VIEW;
       l.slen = int32_t(v.str.size());
       std::memcpy(l.str, v.str.data(), v.str.size());
@@ -901,6 +901,17 @@ inline pgf_literal make_literal(const ScalarValue& v, int32_t col_tag) {
       throw NotEligible{"NULL literal"};
   }
   return l;
+}
+
+constexpr uint32_t kMaxFusedJoinProbes = 1;
+
+inline uint32_t value_words(int32_t type_tag) {  // 32-bit words of a value in a join-table slot
+  switch (type_tag) {
+    case PGF_T_INT16: case PGF_T_INT32: case PGF_T_FLOAT32: return 1;
+    case PGF_T_INT64: case PGF_T_FLOAT64: return 2;
+    case PGF_T_UTF8VIEW: case PGF_T_BINARYVIEW: case PGF_T_DECIMAL128: return 4;
+    default: return 0;
+  }
 }
 
 struct BuildSpec {
@@ -944,7 +955,9 @@ class Lowering {
       if (j->on().size() != 1 || !j->on()[0].first->downcast<Column>() || !j->on()[0].second->downcast<Column>())
         throw NotEligible{"join needs exactly one (column, column) key pair"};
       walk(j->right());
-      if (pod.njoins >= PGF_MAX_JOINS) throw NotEligible{"too many joins in one pipeline"};
+      // the fused kernel probes one join table per pipeline in this build (libpgf_b200 answers
+      // PGF_ERR_NOT_ELIGIBLE for more): a second probe on the same stream keeps its DataFusion node
+      if (pod.njoins >= kMaxFusedJoinProbes) throw NotEligible{"more than one join probe on one scan stream"};
       const uint32_t slot = pod.njoins++;
       builds.push_back(BuildSpec{j, {}});
       const Bound key = bind(j->right(), j->on()[0].second->downcast<Column>()->index());
@@ -1033,6 +1046,7 @@ class Lowering {
       cmp = flipped[cmp];
     }
     if (!column || !literal) throw NotEligible{"comparison is not <column> <cmp> <literal>"};
+    if (column->bound().ref.source != 0) throw NotEligible{"predicate on a build-side column (predicates are evaluated on scan columns)"};
     if (pod.nterms >= PGF_MAX_TERMS) throw NotEligible{"too many predicate terms"};
     pgf_pred_term& t = pod.terms[pod.nterms++];
     t.col = column->bound().ref;
@@ -1067,10 +1081,33 @@ class Lowering {
     throw NotEligible{"aggregate argument outside the x, (c - x), (c + x) product grammar"};
   }
 
+  static void collect_types(const ExprRef& e, std::vector<int32_t>& out) {
+    if (auto c = e->downcast<BoundColumn>()) out.push_back(c->bound().type_tag);
+    if (auto b = e->downcast<BinaryExpr>()) {
+      collect_types(b->left(), out);
+      collect_types(b->right(), out);
+    }
+  }
+
   int32_t value_expr(const ExprRef& e) {
     pgf_value_expr v;
     std::memset(&v, 0, sizeof v);
+    std::vector<int32_t> types;
+    collect_types(e, types);
     factors(e, v);
+    // one arithmetic class per expression (Float64, Decimal128 or integers); narrow integers wrap at
+    // their own width in arrow, so only a plain column or all-Int64 arithmetic is computed exactly
+    int cls = -1;
+    bool all_i64 = true;
+    for (int32_t t : types) {
+      const int c = t == PGF_T_FLOAT64 ? 0 : t == PGF_T_DECIMAL128 ? 1 : key_type_for(t) ? 2 : -1;
+      if (c < 0) throw NotEligible{"aggregate argument of a type the fused kernels do not compute"};
+      if (cls >= 0 && cls != c) throw NotEligible{"mixed-type arithmetic in one aggregate argument"};
+      cls = c;
+      all_i64 = all_i64 && t == PGF_T_INT64;
+    }
+    if (cls == 2 && !all_i64 && !(v.nfactors == 1 && v.factors[0].kind == PGF_FACTOR_COL))
+      throw NotEligible{"arithmetic on Int16/Int32 columns"};
     for (uint32_t i = 0; i < pod.nexprs; ++i)  // SUM(x) and AVG(x) share one accumulator
       if (std::memcmp(&pod.exprs[i], &v, sizeof v) == 0) return int32_t(i);
     if (pod.nexprs >= PGF_MAX_EXPRS) throw NotEligible{"too many distinct aggregate arguments"};
@@ -1105,9 +1142,12 @@ inline PlanRef lower_build(const HashJoinExec& join, const std::vector<size_t>& 
   l.pod.build_key = key.ref;
   Schema schema;
   schema.fields.push_back(left->schema().field(key_index));
+  uint32_t payload_words = 0;  // 32-bit words carried next to the key: at most 5 (a 32-byte slot)
   for (size_t c : payload) {
     const Bound b = l.bind(left, c);
     if (b.ref.source != 0) throw NotEligible{"payload column does not come from the build-side scan"};
+    payload_words += value_words(b.type_tag);
+    if (value_words(b.type_tag) == 0 || payload_words > 5) throw NotEligible{"build-side columns used above the join are wider than 20 bytes"};
     l.pod.payload[l.pod.npayload++] = b.ref;
     schema.fields.push_back(left->schema().field(c));
   }
@@ -1134,6 +1174,7 @@ inline PlanRef lower_aggregate(const AggregateExec& agg) {
   if (agg.group_expr().size() > PGF_MAX_KEYS) throw NotEligible{"too many group keys"};
   if (agg.aggr_expr().size() > PGF_MAX_AGGS) throw NotEligible{"too many aggregates"};
   int64_t groups_join = -1;
+  uint32_t key_words = 0;
   std::vector<B200PipelineExec::Output> outputs;
   for (const auto& g : agg.group_expr()) {
     auto c = l.rebase(input, g.first)->downcast<BoundColumn>();
@@ -1141,6 +1182,11 @@ inline PlanRef lower_aggregate(const AggregateExec& agg) {
     const pgf_colref ref = c->bound().ref;
     for (uint32_t j = 0; j < l.pod.njoins; ++j)
       if (l.pod.joins[j].probe_key.source == ref.source && l.pod.joins[j].probe_key.col == ref.col) groups_join = int64_t(j);
+    // group keys are hashed as 64-bit words: integers one, inline views / Decimal128 two, 32 bytes in all
+    const int32_t kt = c->bound().type_tag;
+    const uint32_t kw = key_type_for(kt) ? 1u : (kt == PGF_T_UTF8VIEW || kt == PGF_T_BINARYVIEW || kt == PGF_T_DECIMAL128) ? 2u : 0u;
+    key_words += kw;
+    if (kw == 0 || key_words > 4) throw NotEligible{"group key of an unsupported type or wider than 32 bytes"};
     outputs.push_back({false, l.pod.nkeys});
     l.pod.keys[l.pod.nkeys++] = ref;
   }

@@ -142,8 +142,8 @@ int main(int argc, char** argv) {
       std::fclose(f);
       std::printf("{\"query\": \"q1_result_pages\", \"pages\": %" PRIu64 "}\n", npages);
     }
-    // the library's own eligibility check runs at plan time: a 15-byte string literal needs the
-    // out-of-line view path, so the aggregate stays a DataFusion node and has no operator here
+    // outside the fused grammar (a 15-byte string literal needs the out-of-line view path): the
+    // aggregate stays a DataFusion node and has no operator here
     {
       PlanRef li = plans::scan(1, plans::lineitem_q6());
       PlanRef agg = std::make_shared<AggregateExec>(

@@ -117,6 +117,62 @@ int main() {
     install_runtime_filters(nn, 1, pool);
     check("null_equals_null_gets_no_filter", pool.targets.empty());
   }
+  {
+    // right-deep chain: lineitem probes orders and then customer-like table on one stream -> two probes
+    PlanRef c = plans::scan(3, plans::customer_q3()), o = plans::scan(4, plans::orders_q3()), l = plans::scan(5, plans::lineitem_q3());
+    PlanRef inner = std::make_shared<HashJoinExec>(o, l, HashJoinExec::JoinOn{{col("o_orderkey", 0), col("l_orderkey", 0)}});
+    PlanRef outer = std::make_shared<HashJoinExec>(c, inner, HashJoinExec::JoinOn{{col("c_custkey", 0), col("o_custkey", 1)}});
+    PlanRef agg = std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                                  std::vector<AggregateFunctionExpr>{count_star("n")}, outer);
+    std::vector<std::string> why;
+    PlanRef out = install_b200_operators(agg, nullptr, &why);
+    check("two_probes_on_one_stream_stay_datafusion", out->downcast<AggregateExec>() != nullptr && why.size() == 1);
+  }
+  {
+    // limits of the fused kernels that the grammar mirrors, so that joined pipelines (which the library
+    // can only check once their tables exist) are decided at plan time too
+    auto count_over = [](PlanRef in) {
+      return PlanRef(std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                                     std::vector<AggregateFunctionExpr>{count_star("n")}, std::move(in)));
+    };
+    std::vector<std::string> why;
+    PlanRef li = plans::scan(1, plans::lineitem_q6());
+    PlanRef long_lit = count_over(plans::filter(binary(col("l_shipdate", 3), Operator::Lt, lit("1995-01-01 00:00")), li));
+    check("long_string_literal_not_absorbed", install_b200_operators(long_lit, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    // predicate on a build-side column above the join
+    PlanRef c = plans::scan(3, plans::customer_q3()), o = plans::scan(4, plans::orders_q3());
+    PlanRef join = std::make_shared<HashJoinExec>(c, o, HashJoinExec::JoinOn{{col("c_custkey", 0), col("o_custkey", 1)}});
+    PlanRef build_pred = count_over(plans::filter(binary(col("c_mktsegment", 1), Operator::Eq, lit("BUILDING")), join));
+    check("predicate_on_build_column_not_absorbed", install_b200_operators(build_pred, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    // build-side columns above the join wider than a slot: two views = 32 bytes > 20
+    Schema wide = plans::schema_of({{"k", PGF_T_INT32}, {"a", PGF_T_UTF8VIEW}, {"b", PGF_T_UTF8VIEW}});
+    PlanRef wj = std::make_shared<HashJoinExec>(plans::scan(8, wide), o, HashJoinExec::JoinOn{{col("k", 0), col("o_custkey", 3 - 2)}});
+    PlanRef wagg = std::make_shared<AggregateExec>(
+        AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{{col("a", 1), "a"}, {col("b", 2), "b"}},
+        std::vector<AggregateFunctionExpr>{count_star("n")}, wj);
+    check("wide_payload_not_absorbed", install_b200_operators(wagg, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    // group key wider than 32 bytes: three views
+    Schema three = plans::schema_of({{"a", PGF_T_UTF8VIEW}, {"b", PGF_T_UTF8VIEW}, {"c", PGF_T_UTF8VIEW}});
+    PlanRef kagg = std::make_shared<AggregateExec>(
+        AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{{col("a", 0), "a"}, {col("b", 1), "b"}, {col("c", 2), "c"}},
+        std::vector<AggregateFunctionExpr>{count_star("n")}, plans::scan(9, three));
+    check("wide_group_key_not_absorbed", install_b200_operators(kagg, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    // arithmetic on narrow integers wraps at their own width in arrow: not computed here
+    PlanRef l3 = plans::scan(5, plans::lineitem_q3());
+    PlanRef narrow = std::make_shared<AggregateExec>(
+        AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+        std::vector<AggregateFunctionExpr>{sum(binary(col("l_orderkey", 0), Operator::Multiply, col("l_orderkey", 0)), "s")}, l3);
+    check("int32_arithmetic_not_absorbed", install_b200_operators(narrow, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    PlanRef mixed = std::make_shared<AggregateExec>(
+        AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+        std::vector<AggregateFunctionExpr>{sum(binary(col("l_orderkey", 0), Operator::Multiply, col("l_discount", 2)), "s")}, l3);
+    check("mixed_type_arithmetic_not_absorbed", install_b200_operators(mixed, nullptr, &why)->downcast<AggregateExec>() != nullptr);
+    PlanRef plain = std::make_shared<AggregateExec>(
+        AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+        std::vector<AggregateFunctionExpr>{sum(col("l_orderkey", 0), "s")}, l3);
+    check("plain_int32_sum_is_absorbed", install_b200_operators(plain, nullptr, &why)->downcast<B200PipelineExec>() != nullptr);
+    check("limits_record_their_reasons", why.size() == 6);
+  }
   // -- the node surface
   {
     PlanRef p = install_b200_operators(plans::q6(1), nullptr);

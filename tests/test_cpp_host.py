@@ -71,7 +71,7 @@ def test_host_checks_pass(dump):
     assert dump.rc == 0, dump.stderr
     assert dump.checks and all(v == "ok" for v in dump.checks.values()), dump.checks
     for name in ("partition_1_is_a_plan_error", "unabsorbed_node_has_no_cpu_operator", "pool_exhaustion_is_soft",
-                 "or_predicate_not_absorbed", "runtime_filter_targets"):
+                 "or_predicate_not_absorbed", "runtime_filter_targets", "two_probes_on_one_stream_stay_datafusion"):
         assert name in dump.checks
 
 

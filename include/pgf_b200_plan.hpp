@@ -850,6 +850,57 @@ inline std::vector<uint8_t> encode_result_pages(const RecordBatch& batch, uint32
   return pages;
 }
 
+// ResultPageProducer::next_step as a state machine (result_pages.rs:118-148): one call produces at
+// most one outbound page; after the last row one CloseFrame step; std::nullopt only after the close
+// step has been handed out.  Empty results go straight to the close step (empty batches are
+// skipped, result_pages.rs:137).
+struct ResultPageStep {
+  enum Kind { OutboundPage, CloseFrame } kind = CloseFrame;
+  std::vector<uint8_t> page;  // OutboundPage: one transfer page (20-byte header + arrow_layout block)
+  uint64_t rows = 0;          // rows carried by this page
+};
+
+class ResultPageProducer {
+ public:
+  ResultPageProducer(RecordBatch batch, uint32_t page_size) : batch_(std::move(batch)), page_size_(page_size) {
+    if (!batch_.raw) throw exec_err("ResultPageProducer: the batch does not come from a B200PipelineExec");
+    pgf_column_spec schema[PGF_MAX_KEYS + PGF_MAX_AGGS];
+    uint32_t ncols = 0;
+    pgf_status st = pgf_result_schema(batch_.raw.get(), schema, &ncols);
+    if (st != PGF_OK) throw exec_err("ResultPageProducer: the result has no transport schema", st);
+    specs_.assign(schema, schema + ncols);
+    st = pgf_layout_fixed_row_cap(schema, ncols, page_size_ - PGF_PAGE_HEADER_LEN, &rows_per_page_);
+    if (st != PGF_OK || rows_per_page_ == 0) throw exec_err("ResultPageProducer: one result row does not fit a page", st);
+  }
+  // normalize_result_transport_schema applied to the aggregate's output (result_pages.rs:201-249)
+  const std::vector<pgf_column_spec>& transport_schema() const { return specs_; }
+  uint32_t rows_per_page() const { return rows_per_page_; }
+
+  std::optional<ResultPageStep> next_step() {
+    if (pending_row_ < batch_.raw->ngroups) {
+      ResultPageStep step;
+      step.kind = ResultPageStep::OutboundPage;
+      step.page.resize(page_size_);
+      uint64_t npages = 0;
+      const pgf_status st = pgf_result_encode_pages(batch_.raw.get(), page_size_, pending_row_, step.page.data(), 1, &npages, &step.rows);
+      if (st != PGF_OK || npages != 1 || step.rows == 0) throw exec_err("pgf_result_encode_pages failed", st);
+      pending_row_ += step.rows;
+      return step;
+    }
+    if (close_emitted_) return std::nullopt;
+    close_emitted_ = true;
+    return ResultPageStep{};
+  }
+
+ private:
+  RecordBatch batch_;
+  uint32_t page_size_;
+  std::vector<pgf_column_spec> specs_;
+  uint32_t rows_per_page_ = 0;
+  uint64_t pending_row_ = 0;
+  bool close_emitted_ = false;
+};
+
 // ------------------------------------------------------------------ lowering (lower_to_pod)
 namespace detail {
 

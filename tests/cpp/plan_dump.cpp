@@ -173,6 +173,56 @@ int main() {
     check("plain_int32_sum_is_absorbed", install_b200_operators(plain, nullptr, &why)->downcast<B200PipelineExec>() != nullptr);
     check("limits_record_their_reasons", why.size() == 6);
   }
+  {
+    // ResultPageProducer over a hand-built aggregate result: 10 000 rows of (Int64 key, nullable Float64 sum,
+    // count) leave as pages of the fixed row cap, then one close step, then nothing
+    const uint64_t n = 10000;
+    auto* r = new pgf_result();
+    r->ngroups = n; r->nkeys = 1; r->naggs = 2;
+    r->keys = new pgf_value[n + 1]();
+    r->aggs = new pgf_value[2 * n + 1]();
+    r->key_type[0] = PGF_T_INT64; r->agg_type[0] = PGF_T_FLOAT64; r->agg_type[1] = PGF_T_INT64;
+    r->agg_func[0] = PGF_AGG_SUM; r->agg_func[1] = PGF_AGG_COUNT_STAR;
+    for (uint64_t g = 0; g < n; ++g) {
+      r->keys[g].kind = PGF_V_I64; r->keys[g].lo = int64_t(g) - 5000;
+      if (g % 7 == 3) r->aggs[2 * g].kind = PGF_V_NULL;
+      else { r->aggs[2 * g].kind = PGF_V_F64; r->aggs[2 * g].f64 = double(g) * 0.5; }
+      r->aggs[2 * g + 1].kind = PGF_V_I64; r->aggs[2 * g + 1].lo = int64_t(g);
+    }
+    RecordBatch batch;
+    batch.num_rows = n;
+    batch.raw = std::shared_ptr<pgf_result>(r, [](pgf_result* p) { pgf_result_free(p); });
+    ResultPageProducer producer(batch, 65536);
+    const auto& schema = producer.transport_schema();
+    check("transport_schema", schema.size() == 3 && schema[0].type_tag == PGF_T_INT64 && schema[0].nullable == 1 &&
+                                  schema[1].type_tag == PGF_T_FLOAT64 && schema[1].nullable == 1 && schema[2].nullable == 0);
+    uint64_t pages = 0, rows = 0;
+    bool pages_ok = true, closed = false;
+    while (auto step = producer.next_step()) {
+      if (step->kind == ResultPageStep::CloseFrame) { closed = true; continue; }
+      pages_ok = pages_ok && !closed && step->rows <= producer.rows_per_page();
+      uint16_t kind = 0, flags = 0;
+      uint32_t len = 0;
+      pages_ok = pages_ok && pgf_page_header_decode(step->page.data(), &kind, &flags, &len) == PGF_OK && kind == PGF_ARROW_LAYOUT_BATCH_KIND;
+      pages_ok = pages_ok && pgf_block_import_check(kind, flags, step->page.data() + PGF_PAGE_HEADER_LEN, len, schema.data(), 3) == PGF_OK;
+      ++pages;
+      rows += step->rows;
+    }
+    const uint64_t cap = producer.rows_per_page();
+    check("result_pages_one_per_step", pages_ok && closed && rows == n && pages == (n + cap - 1) / cap && pages > 1);
+    check("nothing_after_the_close_step", !producer.next_step() && !producer.next_step());
+    RecordBatch empty;
+    auto* e = new pgf_result();
+    e->nkeys = 1; e->key_type[0] = PGF_T_INT64;
+    e->keys = new pgf_value[1]();
+    e->aggs = new pgf_value[1]();
+    empty.raw = std::shared_ptr<pgf_result>(e, [](pgf_result* p) { pgf_result_free(p); });
+    ResultPageProducer none(empty, 65536);
+    auto first = none.next_step();
+    check("empty_result_goes_straight_to_close", first && first->kind == ResultPageStep::CloseFrame && !none.next_step());
+    RecordBatch foreign;
+    check("producer_needs_a_pipeline_result", throws(ErrorKind::Execution, [&] { ResultPageProducer p(foreign, 65536); }));
+  }
   // -- the node surface
   {
     PlanRef p = install_b200_operators(plans::q6(1), nullptr);

@@ -71,7 +71,8 @@ def test_host_checks_pass(dump):
     assert dump.rc == 0, dump.stderr
     assert dump.checks and all(v == "ok" for v in dump.checks.values()), dump.checks
     for name in ("partition_1_is_a_plan_error", "unabsorbed_node_has_no_cpu_operator", "pool_exhaustion_is_soft",
-                 "or_predicate_not_absorbed", "runtime_filter_targets", "two_probes_on_one_stream_stay_datafusion"):
+                 "or_predicate_not_absorbed", "runtime_filter_targets", "two_probes_on_one_stream_stay_datafusion",
+                 "result_pages_one_per_step", "nothing_after_the_close_step", "limits_record_their_reasons"):
         assert name in dump.checks
 
 

@@ -147,3 +147,107 @@ def test_decimal_plans_lower_to_the_builder_pods(dump):
     assert dump.pods["q6_decimal"] == {0: want}, diff(dump.pods["q6_decimal"][0], want)
     want = pod_bytes(U.gpu_q1_d(fake_scan(7, U.Q1_D_SCHEMA)))
     assert dump.pods["q1_decimal"] == {0: want}, diff(dump.pods["q1_decimal"][0], want)
+
+
+# ---- randomly generated plans: the C++ lowering and the Python builder must agree byte for byte ----
+T_I16, T_I32, T_I64, T_F64, T_VIEW, T_DEC = 2, 3, 4, 6, 8, 10
+OPS = {"lt": Cmp.LT, "le": Cmp.LE, "gt": Cmp.GT, "ge": Cmp.GE, "eq": Cmp.EQ, "ne": Cmp.NE}
+
+
+def random_plan(rng, scan_id):
+    """Returns (spec lines for tests/cpp/plan_from_spec.cpp, the equivalent PipelineBuilder)."""
+    from pg_fusion_b200 import ColumnSpec, TypeTag
+    cls = rng.choice([T_F64, T_DEC, T_I64])                       # arithmetic class of the aggregates
+    ncols = rng.randint(2, 8)
+    types = [rng.choice([cls, cls, T_VIEW, T_I32, T_I16, T_I64]) for _ in range(ncols)]
+    types[0] = cls
+    schema = [ColumnSpec(TypeTag(t)) for t in types]
+    lines = [f"scan {scan_id} {ncols} " + " ".join(str(t) for t in types)]
+    b = fake_scan(scan_id, schema).pipeline()
+
+    def lit_for(t):
+        if t == T_F64:
+            v = rng.choice([0.05, 24.0, -1.5, 1e9, 0.07, rng.uniform(-1e6, 1e6)])
+            return "f", repr(v), v
+        if t == T_VIEW:
+            s = "".join(rng.choice("ABCXYZ0123456789-") for _ in range(rng.randint(1, 12)))
+            return "s", s, s.encode()
+        if t == T_DEC:
+            v = rng.choice([5, 7, 2400, -100, rng.randint(-2**62, 2**62)])
+            return "d", str(v), v
+        v = rng.choice([0, 1, -1, 10471, rng.randint(-2**31, 2**31 - 1)]) if t != T_I64 else rng.randint(-2**62, 2**62)
+        return "i", str(v), v
+
+    for _ in range(rng.randint(0, 6)):
+        c = rng.randrange(ncols)
+        op = rng.choice(list(OPS))
+        kind, text, value = lit_for(types[c])
+        flip = rng.random() < 0.3
+        # written flipped in the plan (<literal> <op'> <column>): the lowering must turn it back
+        lines.append(f"term {c} {op} {kind} {text}" + (" flip" if flip else ""))
+        b.filter(c, OPS[op], value)
+    keyable = [c for c in range(ncols) if types[c] != T_F64]
+    keys, words = [], 0
+    for c in rng.sample(keyable, min(len(keyable), rng.randint(0, 3))):
+        w = 1 if types[c] in (T_I16, T_I32, T_I64) else 2
+        if words + w <= 4:
+            keys.append(c)
+            words += w
+            lines.append(f"key {c}")
+    cls_cols = [c for c in range(ncols) if types[c] == cls]
+    aggs = []
+    for _ in range(rng.randint(1, 6)):
+        func = rng.choice(["sum", "avg", "count", "countstar"] if cls != T_I64 else ["sum", "count", "countstar"])
+        if func == "countstar":
+            lines.append("agg countstar 0")
+            aggs.append((AggFunc.COUNT_STAR, None))
+            continue
+        nf = rng.randint(1, 3)
+        factors, parts = [], []
+        for f in range(nf):
+            c = rng.choice(cls_cols)
+            kind = rng.choice([0, 0, 1, 2])
+            if kind == 0:
+                parts.append(f"0 {c} i 0")
+                factors.append(Factor.of(c))
+            else:
+                k, text, value = lit_for(cls)
+                parts.append(f"{kind} {c} {k} {text}")
+                factors.append(Factor.const_minus(value, c) if kind == 1 else Factor.const_plus(value, c))
+        lines.append(f"agg {func} {nf} " + " ".join(parts))
+        aggs.append(({"sum": AggFunc.SUM, "avg": AggFunc.AVG, "count": AggFunc.COUNT}[func], factors))
+    b.aggregate(keys, aggs)
+    order = []
+    for _ in range(rng.randint(0, 2)):
+        is_agg = rng.random() < 0.5 or not keys
+        index = rng.randrange(len(aggs)) if is_agg else rng.randrange(len(keys))
+        desc, nulls_first = rng.random() < 0.5, rng.random() < 0.5
+        lines.append(f"sort {int(is_agg)} {index} {int(desc)} {int(nulls_first)}")
+        order.append(("agg" if is_agg else "key", index, desc, nulls_first))
+    limit = rng.choice([0, 10, 64, 1000]) if order else 0
+    if order:
+        if limit:
+            lines.append(f"limit {limit}")
+        b.order_by(order, limit=limit)
+    lines.append("end")
+    return lines, b
+
+
+def test_random_plans_lower_identically_in_both_host_layers(tmp_path):
+    import random
+    exe = build_cpp("plan_from_spec", str(tmp_path))
+    rng = random.Random(20240611)
+    specs, builders = [], []
+    for i in range(400):
+        lines, b = random_plan(rng, 100 + i)
+        specs.extend(lines)
+        builders.append((lines, b))
+    out = subprocess.run([exe], input="\n".join(specs) + "\n", capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = out.stdout.splitlines()
+    assert len(got) == len(builders)
+    for line, (spec, b) in zip(got, builders):
+        assert line.startswith("POD "), (line, spec)
+        want = pod_bytes(b)
+        have = bytes.fromhex(line[4:])
+        assert have == want, (diff(have, want), spec)

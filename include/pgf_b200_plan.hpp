@@ -1228,7 +1228,8 @@ inline PlanRef lower_aggregate(const AggregateExec& agg) {
   uint32_t key_words = 0;
   std::vector<B200PipelineExec::Output> outputs;
   for (const auto& g : agg.group_expr()) {
-    auto c = l.rebase(input, g.first)->downcast<BoundColumn>();
+    const ExprRef bound = l.rebase(input, g.first);  // keeps the BoundColumn alive
+    auto c = bound->downcast<BoundColumn>();
     if (!c) throw NotEligible{"group key is not a column"};
     const pgf_colref ref = c->bound().ref;
     for (uint32_t j = 0; j < l.pod.njoins; ++j)

@@ -251,3 +251,24 @@ def test_random_plans_lower_identically_in_both_host_layers(tmp_path):
         want = pod_bytes(b)
         have = bytes.fromhex(line[4:])
         assert have == want, (diff(have, want), spec)
+
+
+def test_planner_is_clean_under_address_and_ub_sanitizers(tmp_path):
+    """plan_dump and 100 random plans again, built with -fsanitize=address,undefined (leak check on):
+    the lowering juggles short-lived expression trees and must not read freed nodes."""
+    import random
+    lib = os.path.join(ROOT, "pg_fusion_b200")
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1:protect_shadow_gap=0", UBSAN_OPTIONS="halt_on_error=1")
+    rng = random.Random(7)
+    spec = "\n".join("\n".join(random_plan(rng, 500 + i)[0]) for i in range(100)) + "\n"
+    for name, stdin in (("plan_dump", ""), ("plan_from_spec", spec)):
+        exe = os.path.join(str(tmp_path), name + "_asan")
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-pthread",
+               "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", name + ".cpp"),
+               "-L", lib, "-lpgf_b200", f"-Wl,-rpath,{lib}", "-o", exe]
+        built = subprocess.run(cmd, capture_output=True, text=True)
+        if built.returncode != 0 and "asan" in built.stderr.lower():
+            pytest.skip("sanitizer runtime not available")
+        assert built.returncode == 0, built.stderr
+        out = subprocess.run([exe], input=stdin, capture_output=True, text=True, timeout=300, env=env)
+        assert out.returncode == 0 and "ERROR" not in out.stderr and "runtime error" not in out.stderr, out.stderr[-3000:]

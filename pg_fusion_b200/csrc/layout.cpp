@@ -190,32 +190,54 @@ pgf_status validate_block(const uint8_t* block, size_t len) {
   return PGF_OK;
 }
 
-pgf_status check_block_structure(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
-                                 const pgf_column_spec* schema, uint32_t ncols) {
+namespace {
+
+// kind / flags, BlockRef::open, validate_schema: everything import_owned checks before it touches a column
+pgf_status check_block_schema(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
+                              const pgf_column_spec* schema, uint32_t ncols) {
   if (kind != PGF_ARROW_LAYOUT_BATCH_KIND) return PGF_ERR_IMPORT_WRONG_KIND;    // import/src/lib.rs:121-126
   if (flags != 0) return PGF_ERR_IMPORT_UNSUPPORTED_FLAGS;                      // :127-131
   if (pgf_status st = validate_block(block, len)) return st;
   const BlockHeader h = load_header(block);
   if (h.col_count != ncols) return PGF_ERR_IMPORT_SCHEMA_COLUMN_COUNT_MISMATCH; // :209-214
+  // validate_schema runs over every column before any column is imported (:134-138, :208-234)
   for (uint32_t c = 0; c < ncols; ++c) {
     const ColumnDesc d = load_desc(block, c);
     if (d.type_tag != schema[c].type_tag) return PGF_ERR_IMPORT_SCHEMA_TYPE_MISMATCH;
     const bool nullable = (d.flags & kFlagNullable) != 0;
     if (nullable != (schema[c].nullable != 0)) return PGF_ERR_IMPORT_SCHEMA_NULLABILITY_MISMATCH;
-    // import_nulls bounds (:245-262)
-    if (!nullable ? d.null_count != 0 : d.null_count > h.row_count) return PGF_ERR_IMPORT_INVALID_NULL_COUNT;
   }
+  return PGF_OK;
+}
+
+// import_nulls bounds (:245-262)
+pgf_status check_null_count_bounds(const BlockHeader& h, const ColumnDesc& d) {
+  const bool nullable = (d.flags & kFlagNullable) != 0;
+  if (!nullable ? d.null_count != 0 : d.null_count > h.row_count) return PGF_ERR_IMPORT_INVALID_NULL_COUNT;
+  return PGF_OK;
+}
+
+}  // namespace
+
+pgf_status check_block_structure(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
+                                 const pgf_column_spec* schema, uint32_t ncols) {
+  if (pgf_status st = check_block_schema(kind, flags, block, len, schema, ncols)) return st;
+  const BlockHeader h = load_header(block);
+  for (uint32_t c = 0; c < ncols; ++c)
+    if (pgf_status st = check_null_count_bounds(h, load_desc(block, c))) return st;
   return PGF_OK;
 }
 
 pgf_status check_block_full(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
                             const pgf_column_spec* schema, uint32_t ncols) {
-  if (pgf_status st = check_block_structure(kind, flags, block, len, schema, ncols)) return st;
+  if (pgf_status st = check_block_schema(kind, flags, block, len, schema, ncols)) return st;
   const BlockHeader h = load_header(block);
   const uint32_t pool_capacity = h.block_size - h.pool_base;
   const uint32_t tail_start = h.tail_cursor - h.pool_base;  // access.rs:88-93
+  // columns are imported one after the other: the first failing column decides the error (:160-203)
   for (uint32_t c = 0; c < ncols; ++c) {
     const ColumnDesc d = load_desc(block, c);
+    if (pgf_status st = check_null_count_bounds(h, d)) return st;
     const bool nullable = (d.flags & kFlagNullable) != 0;
     const uint8_t* validity = block + d.validity_off;
     if (nullable) {  // import/src/lib.rs:264-289

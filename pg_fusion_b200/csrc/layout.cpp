@@ -28,7 +28,8 @@ inline std::optional<uint32_t> round_up_biased(uint64_t v, uint32_t a, uint32_t 
   return *up - delta;
 }
 
-inline uint32_t bitmap_len(uint32_t rows) { return (rows + 7) / 8; }  // bitmap.rs:4-6
+// bitmap.rs:4-6 (div_ceil: `(rows + 7) / 8` would wrap for rows > 2^32 - 8 and let a crafted max_rows through)
+inline uint32_t bitmap_len(uint32_t rows) { return rows / 8 + (rows % 8 != 0); }
 
 inline std::optional<uint32_t> reserved_values(int type, uint32_t max_rows) {  // types.rs:152-162
   if (type == PGF_T_BOOLEAN) return round_up(bitmap_len(max_rows), kAlign);

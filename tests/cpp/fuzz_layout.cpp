@@ -141,6 +141,8 @@ int main(int argc, char** argv) {
       {{{PGF_T_BOOLEAN, 1}, {PGF_T_INT16, 0}, {PGF_T_INT32, 1}, {PGF_T_INT64, 1}, {PGF_T_FLOAT32, 0}, {PGF_T_FLOAT64, 1},
         {PGF_T_UUID, 0}, {PGF_T_UTF8VIEW, 1}, {PGF_T_BINARYVIEW, 0}}},
       {{{PGF_T_DECIMAL128, 1}, {PGF_T_INT32, 0}, {PGF_T_UTF8VIEW, 1}}},
+      {{{PGF_T_BOOLEAN, 1}}},                       // bitmaps only: the one layout where a huge max_rows does not overflow the values
+      {{{PGF_T_BOOLEAN, 0}, {PGF_T_BOOLEAN, 1}}},
       {{}},
   };
   uint64_t disagreements = 0, accepted = 0, rejected = 0;
@@ -193,6 +195,75 @@ int main(int argc, char** argv) {
     }
     std::free(exact);
   }
+  // ---- planner: LayoutPlan::new and the fixed row cap for random schemas, row counts (up to overflow) and block sizes
+  uint64_t plans = 0;
+  for (uint64_t it = 0; it < iterations; ++it) {
+    const uint32_t ncols = uint32_t(pick(3) ? pick(12) : pick(70));
+    std::vector<pgf_column_spec> ps(ncols);
+    std::vector<orc_column_spec> os(ncols);
+    for (uint32_t c = 0; c < ncols; ++c) {
+      // (a ColumnSpec of the reference holds a TypeTag enum: unknown tags are rejected when the spec is made,
+      // before any planning -- so they are exercised alone, without a competing overflow, further down)
+      ps[c] = {uint16_t(1 + pick(10)), uint16_t(pick(2))};
+      os[c] = {ps[c].type_tag, ps[c].nullable};
+    }
+    const uint32_t block_size = pick(5) ? uint32_t(pick(70000)) : interesting(65516, 65516);
+    uint32_t max_rows = pick(4) ? uint32_t(pick(10000)) : interesting(1000, block_size);
+    if (ncols && ncols <= 64 && pick(50) == 0) {  // one unknown tag, modest row count: InvalidTypeTag on both sides
+      const uint32_t c = uint32_t(pick(ncols));
+      ps[c].type_tag = os[c].type_tag = uint16_t(pick(2) ? 0 : 11 + pick(1000));
+      max_rows = uint32_t(pick(1000));
+    }
+    pgf_layout_plan pp;
+    orc_layout_plan op;
+    std::memset(&pp, 0, sizeof pp);
+    std::memset(&op, 0, sizeof op);
+    const int a = pgf::plan_layout(ps.data(), ncols, max_rows, block_size, &pp);
+    const int b = orc_layout_plan_new(os.data(), ncols, max_rows, block_size, &op);
+    bool same = a == b;
+    if (same && a == PGF_OK) {
+      same = pp.block_size == op.block_size && pp.max_rows == op.max_rows && pp.front_base == op.front_base && pp.pool_base == op.pool_base && pp.ncols == op.ncols;
+      for (uint32_t c = 0; same && c < ncols; ++c)
+        same = pp.cols[c].type_tag == op.cols[c].type_tag && pp.cols[c].flags == op.cols[c].flags && pp.cols[c].validity_off == op.cols[c].validity_off &&
+               pp.cols[c].values_off == op.cols[c].values_off && pp.cols[c].validity_len == op.cols[c].validity_len && pp.cols[c].values_len == op.cols[c].values_len;
+    }
+    uint32_t cap_p = 0, cap_o = 0;
+    if (it % 16 == 0) {  // the cap search plans ~20 times: sample it
+      const int ca = pgf::fixed_row_cap(ps.data(), ncols, block_size, &cap_p);
+      const int cb = orc_fixed_row_cap(os.data(), ncols, block_size, &cap_o);
+      same = same && ca == cb && (ca != PGF_OK || cap_p == cap_o);
+    }
+    if (!same) {
+      if (disagreements < 10) std::printf("PLAN DISAGREE ncols=%u max_rows=%u block_size=%u status %d/%d cap %u/%u\n", ncols, max_rows, block_size, a, b, cap_p, cap_o);
+      ++disagreements;
+    }
+    ++plans;
+  }
+  // ---- transfer page header: decode of arbitrary 20 bytes, and encode/decode round trips
+  uint64_t headers = 0;
+  for (uint64_t it = 0; it < iterations; ++it) {
+    uint8_t h[20];
+    const uint16_t kind = uint16_t(rng()), flags = uint16_t(rng());
+    const uint32_t payload = uint32_t(rng());
+    pgf::encode_page_header(kind, flags, payload, h);
+    uint8_t ho[20];
+    orc_page_header_encode(kind, flags, payload, ho);
+    bool same = std::memcmp(h, ho, 20) == 0;
+    const uint64_t nmut = pick(3);
+    for (uint64_t k = 0; k < nmut; ++k) h[pick(20)] = pick(2) ? uint8_t(rng()) : uint8_t(h[pick(20)] ^ (1u << pick(8)));
+    uint16_t k1 = 0, f1 = 0, k2 = 0, f2 = 0;
+    uint32_t p1 = 0, p2 = 0;
+    const int a = pgf::decode_page_header(h, &k1, &f1, &p1);
+    const int b = orc_page_header_decode(h, &k2, &f2, &p2);
+    same = same && a == b && (a != PGF_OK || (k1 == k2 && f1 == f2 && p1 == p2));
+    if (nmut == 0) same = same && a == PGF_OK && k1 == kind && f1 == flags && p1 == payload;
+    if (!same) {
+      if (disagreements < 10) std::printf("HEADER DISAGREE status %d/%d\n", a, b);
+      ++disagreements;
+    }
+    ++headers;
+  }
+  std::printf("plans %llu headers %llu\n", (unsigned long long)plans, (unsigned long long)headers);
   std::printf("codes");
   for (int c = 0; c < 256; ++c)
     if (histogram[c]) std::printf(" %d:%llu", c, (unsigned long long)histogram[c]);

@@ -151,7 +151,11 @@ pgf_status pgf_shm_pool_allocate_build(void* base, uint64_t len, uint32_t slot_c
     PoolSlot& s = pool.slots[i];
     uint32_t expect = kSlotFree;
     if (!s.state.compare_exchange_strong(expect, kSlotAllocated, std::memory_order_acq_rel, std::memory_order_acquire)) continue;
-    s.refs.store(1, std::memory_order_release);
+    // The owner's reference.  The reference stores 1 here (pool.rs:401); a backend whose lookup_probes pinned
+    // the slot between the CAS above and this line would lose its pin to that store and later drive the
+    // count below the owner's.  An increment keeps such a transient pin (a Free slot has refs == 0, so the
+    // result is the same 1 when nobody interferes) and is indistinguishable on the wire.
+    s.refs.fetch_add(1, std::memory_order_acq_rel);
     s.session_epoch.store(target->session_epoch, std::memory_order_release);
     s.scan_id.store(target->scan_id, std::memory_order_release);
     s.output_column.store(target->output_column, std::memory_order_release);
@@ -164,7 +168,7 @@ pgf_status pgf_shm_pool_allocate_build(void* base, uint64_t len, uint32_t slot_c
       if (state == PGF_RF_BUILDING || state == PGF_RF_READY) err = PGF_ERR_LIFECYCLE_BUSY;
       else if (generation + 1 > kMaxGeneration) err = PGF_ERR_LIFECYCLE_GENERATION_EXHAUSTED;
       if (err) {
-        s.refs.store(0, std::memory_order_release);
+        s.refs.fetch_sub(1, std::memory_order_acq_rel);  // (the reference stores 0, pool.rs:423; see above)
         s.state.store(kSlotFree, std::memory_order_release);
         return err;
       }

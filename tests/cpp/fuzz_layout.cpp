@@ -62,6 +62,46 @@ std::vector<uint8_t> make_block(const Schema& s, uint32_t block_size, uint32_t m
   return block;
 }
 
+// The same kind of block through the oracle's row-at-a-time writer (access.rs:316-457), which also
+// emits out-of-line views: strings longer than 12 bytes live in the tail arena that grows down from
+// block_size, the slot carries {len, 4-byte prefix, buffer 0, offset from pool_base}.
+std::vector<uint8_t> make_block_rowwise(const Schema& s, uint32_t block_size, uint32_t max_rows, uint32_t rows) {
+  std::vector<orc_column_spec> os;
+  for (const auto& c : s.cols) os.push_back({c.type_tag, c.nullable});
+  orc_layout_plan plan;
+  if (orc_layout_plan_new(os.data(), uint32_t(os.size()), max_rows, block_size, &plan) != 0) return {};
+  std::vector<uint8_t> block(block_size, 0);
+  if (orc_init_block(block.data(), block.size(), &plan) != 0) return {};
+  for (uint32_t r = 0; r < rows; ++r) {
+    for (uint32_t c = 0; c < s.cols.size(); ++c) {
+      const int type = s.cols[c].type_tag;
+      if (s.cols[c].nullable && pick(4) == 0) {
+        if (orc_block_write_null(block.data(), block.size(), c, r) != 0) return {};
+        continue;
+      }
+      int rc = 0;
+      if (type == PGF_T_BOOLEAN) {
+        rc = orc_block_write_bool(block.data(), block.size(), c, r, int(pick(2)));
+      } else if (pgf::is_view(type)) {
+        uint8_t text[64];
+        const uint32_t n = uint32_t(pick(3) ? pick(13) : 13 + pick(40));
+        for (uint32_t i = 0; i < n; ++i) text[i] = uint8_t('a' + pick(26));
+        rc = orc_block_write_view_bytes(block.data(), block.size(), c, r, text, n);
+        if (rc != 0) rc = orc_block_write_view_bytes(block.data(), block.size(), c, r, text, 3);  // arena full: a short one
+      } else {
+        uint8_t v[16];
+        const uint32_t w = pgf::row_width(type);
+        for (uint32_t i = 0; i < w; ++i) v[i] = uint8_t(rng());
+        if (type == PGF_T_FLOAT32 || type == PGF_T_FLOAT64) v[w - 1] &= 0x3F;
+        rc = orc_block_write_fixed(block.data(), block.size(), c, r, v, w);
+      }
+      if (rc != 0) return {};
+    }
+    if (orc_block_commit_current_row(block.data(), block.size()) != 0) return {};
+  }
+  return block;
+}
+
 uint32_t interesting(uint32_t original, uint32_t len) {
   switch (pick(12)) {
     case 0: return 0;
@@ -147,6 +187,7 @@ int main(int argc, char** argv) {
   };
   uint64_t disagreements = 0, accepted = 0, rejected = 0;
   uint64_t histogram[256] = {0};
+  uint64_t rowwise_blocks = 0;
   for (uint64_t it = 0; it < iterations; ++it) {
     const Schema& s = schemas[pick(schemas.size())];
     const uint32_t block_size = uint32_t(1024 + 16 * pick(200));
@@ -155,7 +196,9 @@ int main(int argc, char** argv) {
     const uint32_t max_rows = s.cols.empty() ? uint32_t(pick(100)) : uint32_t(1 + pick(cap ? cap : 1));
     if (!s.cols.empty() && cap == 0) continue;
     const uint32_t rows = uint32_t(pick(max_rows + 1));
-    std::vector<uint8_t> valid = make_block(s, block_size, max_rows, rows);
+    const bool rowwise = pick(3) == 0;
+    std::vector<uint8_t> valid = rowwise ? make_block_rowwise(s, block_size, max_rows, rows) : make_block(s, block_size, max_rows, rows);
+    if (rowwise && !valid.empty()) ++rowwise_blocks;
     if (valid.empty()) continue;
     std::vector<uint8_t> m = valid;
     const uint64_t nmut = pick(4);  // 0 = the valid block itself
@@ -263,7 +306,7 @@ int main(int argc, char** argv) {
     }
     ++headers;
   }
-  std::printf("plans %llu headers %llu\n", (unsigned long long)plans, (unsigned long long)headers);
+  std::printf("plans %llu headers %llu rowwise_blocks %llu\n", (unsigned long long)plans, (unsigned long long)headers, (unsigned long long)rowwise_blocks);
   std::printf("codes");
   for (int c = 0; c < 256; ++c)
     if (histogram[c]) std::printf(" %d:%llu", c, (unsigned long long)histogram[c]);

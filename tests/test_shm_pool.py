@@ -245,3 +245,39 @@ def test_pool_protocol_under_thread_sanitizer(tmp_path):
                 pytest.skip(run.stderr.splitlines()[0])
             assert run.returncode == 0 and "WARNING: ThreadSanitizer" not in run.stderr, run.stdout[-500:] + run.stderr[-3000:]
             assert "false_negatives 0 " in run.stdout and "reusable_slots 3/3" in run.stdout
+
+
+def test_parameters_and_decisions_match_the_oracle_on_random_inputs():
+    """Differential check of the host-side Bloom arithmetic: BloomParams::new / for_expected_items (the
+    floating-point sizing formula, bloom.rs:52-79) and the pool's probe decisions (splitmix64 double hashing,
+    modulo for arbitrary bit counts) against the oracle, on random parameters, seeds and keys."""
+    rng = np.random.default_rng(11)
+    L = _lib.lib()
+    for _ in range(3000):
+        n = int(rng.choice([0, 1, 2, 1000, 10**6, int(rng.integers(1, 2**40)), int(rng.integers(1, 2**63))]))
+        fpr = float(rng.choice([0.0, 1.0, -0.1, 1e-12, 0.01, 0.5, 0.999999, float(rng.random()), float("nan"), float("inf")]))
+        seed = int(rng.integers(0, 2**63)) * 2 + int(rng.integers(0, 2))
+        got = _lib.BloomParamsC()
+        rc = L.pgf_bloom_params_for_expected_items(n, fpr, seed, C.byref(got))
+        try:
+            want = O.bloom_params_for_expected_items(n, fpr, seed)
+            assert rc == 0 and (got.bit_count, got.word_count, got.hash_count, got.seed) == \
+                (want.bit_count, want.word_count, want.hash_count, want.seed), (n, fpr)
+        except O.OracleError as e:
+            assert rc == 19 + e.code, (n, fpr, rc, e.code)   # PGF_ERR_BLOOM_* = 20.. in BloomParamError's order (oracle: 1..)
+    for _ in range(40):
+        bits = int(rng.choice([1, 2, 63, 64, 65, 4096, 4099, int(rng.integers(1, 1 << 16))]))
+        k = int(rng.integers(1, 17))
+        seed = int(rng.integers(0, 2**63)) * 2 + 1
+        p = params(bits, k, seed)
+        pool = Pool(2, p)
+        keys = rng.integers(-2**63, 2**63 - 1, 200, dtype=np.int64)
+        ob = O.Bloom(O.bloom_params(bits, k, seed))
+        ob.insert_keys(keys[:100])
+        rc, slot, gen = pool.allocate(5, 9)
+        assert rc == 0 and pool.publish(slot, gen, ob.words) == 0
+        (probe,) = lookup(pool, 5, 9)
+        for key in keys:
+            want = MAYBE_PRESENT if ob.might_contain_u64(int(key)) else DEFINITELY_ABSENT
+            assert decide(pool, probe, int(key)) == want, (bits, k, seed, int(key))
+        assert all(decide(pool, probe, int(key)) == MAYBE_PRESENT for key in keys[:100])   # no false negatives

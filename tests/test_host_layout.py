@@ -179,3 +179,39 @@ def test_validators_agree_with_the_oracle_on_mutated_blocks_under_sanitizers(tmp
         # every rejection reason of the validator and the import list has been exercised
         assert {101, 102, 103, 105, 106, 107, 108, 109, 110, 111, 112, 117, 118, 119, 120,
                 201, 202, 203, 204, 205, 206, 207, 208, 210} <= codes, sorted(codes)
+
+
+def test_row_estimator_fixed_width_cases_in_the_product():
+    """The same cases as tests/test_oracle_layout.py::test_row_estimator_fixed_width_cases through the C ABI, and
+    what the result encoder makes of them: no column -> no transport schema, no row fits -> DoesNotFit."""
+    import ctypes as C
+    from pg_fusion_b200 import _lib
+    schema = [ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Boolean, True)]
+    cap = AL.fixed_row_cap(schema, 256)
+    assert cap == O.fixed_row_cap(U.orc_cols(schema), 256) > 0
+    AL.LayoutPlan(schema, cap, 256)
+    with pytest.raises(pg.PgfError):
+        AL.LayoutPlan(schema, cap + 1, 256)
+    one = [ColumnSpec(TypeTag.Int64)]
+    sizes = [c for c in range(1, 512) if _fits(one, 0, c) and O.fixed_row_cap(U.orc_cols(one), c) == 0]
+    assert sizes and all(AL.fixed_row_cap(one, c) == 0 for c in sizes)
+    L = _lib.lib()
+    r = _lib.Result()                                   # an aggregate result without any column
+    n = C.c_uint32()
+    assert L.pgf_result_schema(C.byref(r), (_lib.ColumnSpec * 20)(), C.byref(n)) == 1   # PGF_ERR_INVALID_ARGUMENT
+    keys = (_lib.Value * 2)()
+    keys[0].kind, keys[0].lo = 2, 7
+    r.ngroups, r.nkeys, r.keys, r.aggs = 1, 1, C.cast(keys, C.POINTER(_lib.Value)), C.cast(keys, C.POINTER(_lib.Value))
+    r.key_type[0] = int(TypeTag.Int64)
+    got, rows = C.c_uint64(), C.c_uint64()
+    buf = (C.c_uint8 * 4096)()
+    page_size = sizes[0] + 20                           # holds the block header of the layout, but not one row
+    assert L.pgf_result_encode_pages(C.byref(r), page_size, 0, buf, 1, C.byref(got), C.byref(rows)) in (1, 113)
+
+
+def _fits(schema, rows, size):
+    try:
+        AL.LayoutPlan(schema, rows, size)
+        return True
+    except pg.PgfError:
+        return False

@@ -242,3 +242,25 @@ def test_fixed_row_cap_matches_survey_table(cols, cap):
     O.layout_plan(cols, cap, 65516)
     with pytest.raises(O.OracleError):
         O.layout_plan(cols, cap + 1, 65516)
+
+
+def test_row_estimator_fixed_width_cases():
+    """page/row_estimator/src/tests.rs:21-65 for fixed-width shapes (the only ones the result encoder emits):
+    the cap is exact (cap rows fit, cap + 1 do not), and a block that holds the header of a one-column layout
+    but not one row has cap 0 (LayoutCannotFitAnyRows)."""
+    cols = [(O.T_INT64, False), (O.T_BOOLEAN, True)]
+    cap = O.fixed_row_cap(cols, 256)
+    assert cap > 0
+    O.layout_plan(cols, cap, 256)
+    with pytest.raises(O.OracleError):
+        O.layout_plan(cols, cap + 1, 256)
+    one = [(O.T_INT64, False)]
+
+    def fits(rows, size):
+        try:
+            O.layout_plan(one, rows, size)
+            return True
+        except O.OracleError:
+            return False
+    block_size = next(c for c in range(1, 512) if fits(0, c) and not fits(1, c))
+    assert O.fixed_row_cap(one, block_size) == 0

@@ -160,3 +160,35 @@ def test_nullability_follows_the_aggregate_function_not_the_data():
     r.agg_func[0], r.agg_func[1] = 4, 2                      # COUNT(x), AVG
     schema, _ = encode_result_pages(C.pointer(r), 65536)
     assert [c.nullable for c in schema[2:]] == [False, True]
+
+
+def test_encoding_can_continue_from_a_start_row():
+    """page/batch_encoder/src/tests.rs:476-530 (append_batch_can_continue_from_start_row) through
+    pgf_result_encode_pages(first_row, max_pages): pages produced one call at a time carry exactly the rows of
+    a single call over the whole result, and a call that starts at the end produces nothing."""
+    rows = sample_rows(5000, seed=9)
+    r, keep = make_result(rows)
+    schema, all_pages = encode_result_pages(C.pointer(r), 4096)
+    cols = [(int(c.type_tag), bool(c.nullable)) for c in schema]
+    cap = O.fixed_row_cap(cols, 4096 - 20)
+    L = _lib.lib()
+    first, stepped = 0, []
+    while True:
+        page = np.zeros(4096, dtype=np.uint8)
+        got, done = C.c_uint64(), C.c_uint64()
+        assert L.pgf_result_encode_pages(C.pointer(r), 4096, first, page.ctypes.data_as(C.c_void_p), 1, C.byref(got), C.byref(done)) == 0
+        if got.value == 0:
+            assert done.value == 0 and first == len(rows)
+            break
+        assert got.value == 1 and done.value == min(cap, len(rows) - first)     # full pages until the last one
+        stepped.append(page)
+        first += done.value
+    assert len(stepped) == all_pages.shape[0] and all((a == b).all() for a, b in zip(stepped, all_pages))
+    # starting in the middle of a page boundary-free position: rows [7, 7 + cap) land in one page
+    page = np.zeros(4096, dtype=np.uint8)
+    got, done = C.c_uint64(), C.c_uint64()
+    assert L.pgf_result_encode_pages(C.pointer(r), 4096, 7, page.ctypes.data_as(C.c_void_p), 1, C.byref(got), C.byref(done)) == 0
+    t = O.OTable.from_pages(page.reshape(1, 4096), 4096, cols)
+    assert t.rows == cap and [int(c) for c in t.column(3)[0]] == [row[3] for row in rows[7:7 + cap]]
+    # a start row beyond the result is an argument error
+    assert L.pgf_result_encode_pages(C.pointer(r), 4096, len(rows) + 1, page.ctypes.data_as(C.c_void_p), 1, C.byref(got), C.byref(done)) == 1

@@ -1,0 +1,65 @@
+"""What the compiled library contains, checked without a GPU (nvcc cross-compiles here):
+every device image is sm_100a, the fused pipeline kernels move their tiles with bulk asynchronous
+copies completed on mbarriers (the SASS the TMA path compiles to, /opt/skills/guides/B200_PROFILING.md
+"SASS mnemonics"), and the registered Float64 shapes -- the kernels the headline numbers are measured
+on -- do not spill registers."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "pg_fusion_b200", "libpgf_b200.so")
+BUILD = os.path.join(ROOT, "pg_fusion_b200", "csrc", "build")
+CUOBJDUMP = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+
+pytestmark = pytest.mark.skipif(not os.path.exists(CUOBJDUMP), reason="cuobjdump not installed")
+
+
+def test_every_device_image_is_sm_100a():
+    out = subprocess.run([CUOBJDUMP, "-lelf", LIB], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    images = re.findall(r"ELF file\s+\d+:\s+(\S+)", out.stdout)
+    assert len(images) >= 8 and all(name.endswith(".sm_100a.cubin") for name in images), images
+    ptx = subprocess.run([CUOBJDUMP, "-lptx", LIB], capture_output=True, text=True, timeout=120)
+    assert "sm_" not in ptx.stdout.replace("sm_100a", ""), ptx.stdout     # no PTX for other targets (no JIT fallback path)
+
+
+@pytest.fixture(scope="module")
+def shapes_sass(tmp_path_factory):
+    cubin_dir = tmp_path_factory.mktemp("cubin")
+    out = subprocess.run([CUOBJDUMP, "-xelf", "pipeline_inst_shapes", LIB], capture_output=True, text=True, timeout=120, cwd=cubin_dir)
+    assert out.returncode == 0, out.stderr
+    cubins = [f for f in os.listdir(cubin_dir) if f.endswith(".cubin")]
+    assert len(cubins) == 1, cubins
+    sass = subprocess.run([CUOBJDUMP, "-sass", os.path.join(cubin_dir, cubins[0])], capture_output=True, text=True, timeout=600)
+    assert sass.returncode == 0, sass.stderr
+    return sass.stdout
+
+
+def test_pipeline_kernels_stage_tiles_with_bulk_copies_on_mbarriers(shapes_sass):
+    kernels = re.split(r"\n\s*Function : ", shapes_sass)[1:]
+    pipelines = [k for k in kernels if k.startswith("_ZN3pgf15pipeline_kernel")]
+    assert len(pipelines) >= 8, [k.split("\n")[0][:60] for k in kernels]
+    for k in pipelines:
+        name = k.split("\n")[0]
+        assert "UBLKCP" in k, f"{name}: no bulk asynchronous copy (cp.async.bulk) in the SASS"
+        assert "SYNCS" in k, f"{name}: no mbarrier instructions in the SASS"
+
+
+def test_registered_float64_shapes_do_not_spill():
+    log = open(os.path.join(BUILD, "pipeline_inst_shapes.ptxas.log")).read()
+    entries = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                         r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", log)
+    assert len(entries) >= 8
+    # template arguments <SINK, ACC, GROUPED, NJ, MAXE, Shape>: ACC 0 = Float64 accumulators (Lj1ELj0E...)
+    f64 = [e for e in entries if re.match(r"_ZN3pgf15pipeline_kernelILj1ELj0E", e[0])]
+    assert len(f64) >= 4          # Q6, Q1 with 8 and 7 aggregates, Q3 lineitem
+    for name, stack, st, ld, regs in f64:
+        assert int(st) == 0 and int(ld) == 0, f"{name[:80]} spills {st}/{ld} bytes"
+        assert int(regs) <= 128
+    # the budget the launch bounds allow: 16 consumer warps + producer on one SM need <= 96 registers ... 128 for 14 warps
+    worst = max(int(e[4]) for e in entries)
+    assert worst <= 128, worst

@@ -111,7 +111,23 @@ struct DevJoin {
   uint32_t mask;         // capacity - 1
   uint32_t slot_u4;      // 1 (16-byte slot) or 2 (32-byte slot)
   DevRef key;
+  uint32_t shift;        // 64 - log2(capacity): home bucket = (join_hash(key) >> shift) & ~7
+  uint32_t pad;
 };
+
+// Join tables hash the sign-extended key with one 32 x 64-bit multiply (Fibonacci hashing): the top
+// log2(capacity) bits pick the slot, rounded down to an 8-slot bucket whose tags are one aligned
+// 8-byte word; the three dropped bits and the five below them make the tag byte (never 0 = empty).
+constexpr uint32_t kJoinBucket = 8;
+__host__ __device__ __forceinline__ uint64_t join_hash(int64_t key) {
+  const uint32_t lo = uint32_t(uint64_t(key)), hi = uint32_t(uint64_t(key) >> 32);
+  return uint64_t(lo ^ (hi * 0x85EBCA6Bu)) * 0x9E3779B97F4A7C15ull;
+}
+__host__ __device__ __forceinline__ uint32_t join_home(uint64_t h, uint32_t shift) { return uint32_t(h >> shift) & ~(kJoinBucket - 1u); }
+__host__ __device__ __forceinline__ uint32_t join_tag8(uint64_t h, uint32_t shift) {
+  const uint32_t b = uint32_t(h >> (shift - 5u)) & 0xFFu;
+  return b ? b : 1u;
+}
 
 struct DevBloomProbe {
   DevBloom bloom;
@@ -132,10 +148,10 @@ struct GroupTable {
 };
 
 struct JoinBuild {
-  uint4* slots;
-  uint8_t* tags;
-  uint32_t mask;
+  uint4* rows;             // dense build rows {key lo, key hi, occupancy/NULL flags, payload...}, slot_u4 x uint4 each
+  uint64_t rows_cap;       // room in `rows`; the row count lives in the arena header (`used`)
   uint32_t slot_u4;
+  uint32_t pad0;
   DevRef key;
   uint32_t npayload;
   DevRef payload[4];
@@ -176,6 +192,11 @@ struct DevPlan {
   DevBloom build_bloom;
   uint32_t has_build_bloom;
   uint32_t pad;
+  unsigned long long* build_count;  // rows appended to build.rows so far (arena header)
+  // Float64 aggregate sinks of the streaming kernel: per-CTA sums [grid][kRegGroups][2 + nexprs] and the
+  // arrival counter of the fixed-order cross-CTA reduction
+  uint64_t* cta_rec;
+  uint32_t* cta_done;
 
   Counters* counters;
 };

@@ -11,12 +11,15 @@
 #include "layout.hpp"
 #include "pipeline_kernel.cuh"
 #include "pipeline_shapes.hpp"
+#include "probe_kernel.cuh"
 
 namespace pgf {
 
 // implemented in pipeline_inst_*.cu (explicit instantiations split for parallel builds)
 cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t nj, uint32_t maxe,
                             const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
+// implemented in pipeline_inst_probe.cu: the compaction pipeline (joins, build sinks)
+cudaError_t launch_probe(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
 
 namespace {
 
@@ -149,17 +152,18 @@ __global__ void __launch_bounds__(kExtractThreads) join_export_kernel(const uint
   }
 }
 
-__global__ void join_import_kernel(uint4* slots, uint8_t* tags, uint32_t mask, uint32_t slot_u4, const uint4* rows, uint64_t nrows) {
+// Builds the table from dense build rows (the output of a build-sink pipeline, or the fragments of a
+// broadcast / partitioned exchange): linear probing from the key's home bucket, CAS on the occupancy
+// word, then tag byte + slot.  capacity >= 2 x rows, so an empty slot always exists.
+__global__ void join_build_kernel(uint4* slots, uint8_t* tags, uint32_t mask, uint32_t shift, uint32_t slot_u4, const uint4* rows, uint64_t nrows) {
   for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < nrows; r += uint64_t(gridDim.x) * blockDim.x) {
     const uint4 s0 = rows[r * slot_u4];
-    const uint64_t key = (uint64_t(s0.y) << 32) | s0.x;
-    const uint64_t hk = mix64(key);
-    uint32_t i = uint32_t(hk) & mask;
-    for (;;) {  // capacity >= 2 x rows: an empty slot always exists
+    const uint64_t hk = join_hash(int64_t((uint64_t(s0.y) << 32) | s0.x));
+    uint32_t i = join_home(hk, shift);
+    for (;;) {
       uint32_t* slot = reinterpret_cast<uint32_t*>(slots + uint64_t(i) * slot_u4);
       if (atomicCAS(slot + 2, 0u, s0.z) == 0u) {
-        tags[i] = uint8_t(join_tag(hk));
-        if (i < 4u) tags[mask + 1u + i] = uint8_t(join_tag(hk));
+        tags[i] = uint8_t(join_tag8(hk, shift));
         slot[0] = s0.x;
         slot[1] = s0.y;
         slot[3] = s0.w;
@@ -358,6 +362,8 @@ struct Lowered {
   uint32_t nj = 0;
   uint32_t maxe = 2;
   size_t smem = 0;
+  bool probe = false;       // runs the compaction pipeline (probe_kernel.cuh): joins and build sinks
+  int t0 = -1;              // its predicate specialisation (LD_* of the single plain range term), -1 = generic
   int32_t key_types[4] = {0, 0, 0, 0};
   uint32_t expr_pos[kMaxExprs] = {0, 1, 2, 3, 4, 5, 6, 7};  // device position of the caller's expression e
   JoinTable build_table{};
@@ -404,7 +410,11 @@ class Lowering {
     if (plan_->nbloom > kMaxBlooms || plan_->nterms > kMaxTerms || plan_->njoins > kMaxJoins ||
         plan_->nkeys > 4 || plan_->nexprs > kMaxExprs || plan_->naggs > PGF_MAX_AGGS || plan_->npayload > PGF_MAX_PAYLOAD)
       return not_eligible("plan exceeds the fixed operator limits");
-    if (plan_->njoins > 1) return not_eligible("at most one HashJoinExec probe per pipeline in this build");
+    // Pipelines with a join probe or a build sink run the compaction kernel: only the predicate
+    // columns, the Bloom keys and the first probe key are staged; everything a surviving row needs
+    // later is read from the page in HBM (late refs).
+    probe_ = plan_->njoins > 0 || plan_->sink == PGF_SINK_JOIN_BUILD;
+    L_->probe = probe_;
 
     // joins first: payload refs need the tables
     for (uint32_t j = 0; j < plan_->njoins; ++j) {
@@ -418,7 +428,9 @@ class Lowering {
       dj.tags = reinterpret_cast<const uint8_t*>(jtables_[j]->d_slots) + uint64_t(jtables_[j]->capacity) * jtables_[j]->slot_u4 * sizeof(uint4);
       dj.mask = jtables_[j]->capacity - 1;
       dj.slot_u4 = jtables_[j]->slot_u4;
-      PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key));
+      dj.shift = 64;
+      for (uint32_t c = jtables_[j]->capacity; c > 1; c >>= 1) dj.shift--;
+      PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key, /*late=*/j > 0));
       if (!is_int_type(dj.key.type)) return not_eligible("join keys must be Int16/Int32/Int64");
     }
     D.njoins = plan_->njoins;
@@ -459,7 +471,7 @@ class Lowering {
     }
     // common subexpression: x*(c-y)*(c2+z) right after x*(c-y) reuses the previous value
     // (ref.off still holds the stage slot of the column here: equal slots <=> equal columns)
-    for (uint32_t e = 1; e < D.nexprs; ++e) {
+    for (uint32_t e = 1; e < D.nexprs && !probe_; ++e) {
       const DevExpr &a = D.exprs[e - 1], &b = D.exprs[e];
       if (a.form == FORM_X_CMY && b.form == FORM_X_CMY_CPZ && a.f[0].ref.off == b.f[0].ref.off &&
           a.f[1].ref.off == b.f[1].ref.off && a.f[1].cf == b.f[1].cf && a.f[1].ci_lo == b.f[1].ci_lo && a.f[1].ci_hi == b.f[1].ci_hi)
@@ -467,7 +479,7 @@ class Lowering {
     }
     // The order of the conjuncts is irrelevant to the result: if some order of the range terms
     // matches a registered shape, take it.
-    if (!pick_shape(*L_) && D.nterms >= 2 && D.nterms <= 4) {
+    if (!probe_ && !pick_shape(*L_) && D.nterms >= 2 && D.nterms <= 4) {
       bool plain = true;
       for (uint32_t t = 0; t < D.nterms; ++t) plain &= D.terms[t].op == TERM_IN_RANGE;
       if (plain) {
@@ -483,7 +495,12 @@ class Lowering {
           for (uint32_t t = 0; t < D.nterms; ++t) D.terms[t] = orig[t];
       }
     }
-    PGF_TRY(layout_stage(s));
+    if (probe_) {
+      PGF_TRY(layout_stage_probe(s));
+      if (D.nterms == 1 && D.terms[0].op == TERM_IN_RANGE && D.used_null_mask == 0 && D.terms[0].ref.ld == LD_VIEW) L_->t0 = LD_VIEW;
+    } else {
+      PGF_TRY(layout_stage(s));
+    }
     fix_refs();
     return PGF_OK;
   }
@@ -588,13 +605,25 @@ class Lowering {
   // Resolve a column reference; scan columns get a stage slot.  For scan columns `off`
   // temporarily holds the slot; fix_ref() turns it into shared-memory offsets once the
   // stage layout is known.
-  pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out) {
+  static constexpr uint32_t kLateRef = 0xFFFFFFFEu;  // `off` of a page column that is not staged (read from HBM by stage C)
+  pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out, bool late = false) {
     Scan& s = *L_->scan;
     DevPlan& D = L_->dev;
     if (r.source == 0) {
       if (r.col < 0 || size_t(r.col) >= s.schema.size()) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "column %d out of range", r.col);
       const int type = s.schema[r.col].type_tag;
       if (row_width(type) == 0 || type == PGF_T_UUID) return not_eligible("Boolean / Uuid columns are not evaluated on the GPU path");
+      if (late && probe_) {
+        out->src = SRC_PAGE;
+        out->ld = ld_kind(type);
+        out->type = uint8_t(type);
+        out->pcol = uint8_t(r.col);
+        out->off = kLateRef;
+        out->valid_off = s.schema[r.col].nullable ? 0u : kNoValidity;
+        if (s.schema[r.col].nullable) D.used_null_mask |= 1u << r.col;
+        if (is_view(type)) D.view_mask |= 1u << r.col;
+        return PGF_OK;
+      }
       uint32_t slot = 0;
       for (; slot < D.nstage_cols; ++slot)
         if (D.scol[slot].page_col == r.col) break;
@@ -630,6 +659,7 @@ class Lowering {
 
   void fix_ref(DevRef* ref) {
     if (ref->src != SRC_PAGE) return;
+    if (ref->off == kLateRef) { ref->off = 0; return; }
     const DevStageCol& sc = L_->dev.scol[ref->off];
     ref->valid_off = sc.nullable ? sc.valid_off : kNoValidity;
     ref->off = sc.smem_off;
@@ -706,7 +736,7 @@ class Lowering {
       bool all_i64 = true;
       for (uint32_t f = 0; f < x.nfactors; ++f) {
         DevFactor& df = dx.f[f];
-        PGF_TRY(lower_ref(x.factors[f].col, plan_->njoins, &df.ref));
+        PGF_TRY(lower_ref(x.factors[f].col, plan_->njoins, &df.ref, /*late=*/true));
         df.kind = uint32_t(x.factors[f].kind);
         if (df.kind > PGF_FACTOR_CONST_PLUS_COL) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad factor kind");
         int fcls;
@@ -796,7 +826,7 @@ class Lowering {
     uint32_t words = 0;
     for (uint32_t k = 0; k < plan_->nkeys; ++k) {
       DevKeyPart& kp = D.keys[k];
-      PGF_TRY(lower_ref(plan_->keys[k], plan_->njoins, &kp.ref));
+      PGF_TRY(lower_ref(plan_->keys[k], plan_->njoins, &kp.ref, /*late=*/true));
       const int t = kp.ref.type;
       if (is_int_type(t)) kp.nwords = 1;
       else if (is_view(t) || t == PGF_T_DECIMAL128) kp.nwords = 2;
@@ -825,14 +855,14 @@ class Lowering {
     DevPlan& D = L_->dev;
     D.sink = SINK_JOIN_BUILD;
     JoinBuild& jb = D.build;
-    PGF_TRY(lower_ref(plan_->build_key, plan_->njoins, &jb.key));
+    PGF_TRY(lower_ref(plan_->build_key, plan_->njoins, &jb.key, /*late=*/true));
     if (!is_int_type(jb.key.type)) return not_eligible("join keys must be Int16/Int32/Int64");
     JoinTable& jt = L_->build_table;
     jt.key_type = jb.key.type;
     jt.npayload = plan_->npayload;
     uint32_t words = 0;
     for (uint32_t p = 0; p < plan_->npayload; ++p) {
-      PGF_TRY(lower_ref(plan_->payload[p], plan_->njoins, &jb.payload[p]));
+      PGF_TRY(lower_ref(plan_->payload[p], plan_->njoins, &jb.payload[p], /*late=*/true));
       const uint32_t w = type_u32_words(jb.payload[p].type);
       if (!w) return not_eligible("join payload column type");
       jb.payload_word[p] = uint16_t(words);
@@ -845,11 +875,6 @@ class Lowering {
     jb.npayload = plan_->npayload;
     jb.slot_u4 = words > 1 ? 2 : 1;
     jt.slot_u4 = jb.slot_u4;
-    uint64_t cap = 1024;
-    while (cap < L_->scan->rows * 2) cap <<= 1;
-    if (cap > (1ull << 31)) return not_eligible("join build side too large for one table");
-    jt.capacity = uint32_t(cap);
-    jb.mask = jt.capacity - 1;
     if (plan_->build_bloom) {
       auto bt = ctx_->blooms.find(plan_->build_bloom);
       if (bt == ctx_->blooms.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown bloom filter %llu", (unsigned long long)plan_->build_bloom);
@@ -939,8 +964,55 @@ class Lowering {
     return PGF_OK;
   }
 
+  // Stage ring of the compaction pipeline: whole pages when three of them fit next to the per-warp
+  // queues, else row tiles; as deep as shared memory allows (up to kPMaxStages).
+  pgf_status layout_stage_probe(Scan& s) {
+    DevPlan& D = L_->dev;
+    const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
+    const uint32_t budget = 227u * 1024u - probe_shared_bytes() - uint32_t(kPConsumerWarps) * kPQueueBytesPerWarp;
+    uint32_t gran = 16;
+    for (uint32_t c = 0; c < D.nstage_cols; ++c)
+      if (D.scol[c].nullable) gran = 128;
+    auto shape = [&](uint32_t ntiles, uint32_t* tile_rows_out, uint32_t* stage_bytes_out) {
+      const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + gran - 1) / gran * gran;
+      uint32_t stage_bytes = 0;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += tile_rows * D.scol[c].width + (D.scol[c].nullable ? tile_rows / 8 : 0u);
+      *tile_rows_out = tile_rows;
+      *stage_bytes_out = std::max(128u, (stage_bytes + 127u) & ~127u);
+    };
+    uint32_t tile_rows = 0, stage_bytes = 0, ntiles = 1;
+    for (;; ++ntiles) {
+      shape(ntiles, &tile_rows, &stage_bytes);
+      if (stage_bytes * 3u <= budget) break;
+      if (tile_rows <= gran) return not_eligible("row too wide for the shared-memory stages");
+    }
+    uint32_t off = 0;
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+      D.scol[c].smem_off = off;
+      off += tile_rows * D.scol[c].width;
+    }
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) {
+      D.scol[c].valid_off = off;
+      if (D.scol[c].nullable) off += tile_rows / 8;
+    }
+    D.nstages = std::min<uint32_t>(kPMaxStages, budget / stage_bytes);
+    D.tile_rows = tile_rows;
+    D.tiles_per_page = (max_rows + tile_rows - 1) / tile_rows;
+    D.stage_bytes = stage_bytes;
+    D.npages = uint32_t(s.npages);
+    if (s.npages * uint64_t(D.tiles_per_page) > 0xFFFFFFF0ull) return not_eligible("scan too large for 32-bit tile ids");
+    D.nitems = uint32_t(s.npages) * D.tiles_per_page;
+    D.pages = s.d_pages;
+    D.descs = s.d_descs;
+    D.classes = s.d_classes;
+    D.page_stride = ctx_->page_size;
+    L_->smem = probe_shared_bytes() + size_t(D.nstages) * D.stage_bytes + size_t(kPConsumerWarps) * kPQueueBytesPerWarp;
+    return PGF_OK;
+  }
+
   pgf_ctx* ctx_;
   const pgf_pipeline* plan_;
+  bool probe_ = false;
   Lowered* L_ = nullptr;
   JoinTable* jtables_[kMaxJoins] = {nullptr, nullptr};
   int expr_cls_[kMaxExprs] = {0};
@@ -1200,14 +1272,17 @@ const ShapeEntry* pick_shape(const Lowered& L) {
 // Device header at the start of the arena (one memset clears header + table).
 struct ArenaHeader {
   Counters counters;         // 48 bytes
-  uint32_t overflow, used;   // group-table overflow flag, occupied slots
-  uint64_t pad;
+  uint32_t overflow, used;   // group-table (or build-row buffer) overflow flag, occupied slots
+  unsigned long long build_rows;  // rows a build sink appended (may exceed the buffer when `overflow` is set)
+  uint32_t cta_done;         // CTAs that finished (fixed-order Float64 reduction of the streaming kernel)
+  uint32_t pad[15];
 };
-static_assert(sizeof(ArenaHeader) == 64, "arena header layout");
+static_assert(sizeof(ArenaHeader) == 128, "arena header layout");
 constexpr uint64_t kSmallTable = 1ull << 16;   // tables up to this many slots keep their result entries in the arena
 constexpr size_t kHostArena = 64 * 1024;       // pinned mirror: header + first result entries
 
 struct TableAlloc {
+  uint64_t* d_cta_rec = nullptr;  // per-CTA Float64 sums (zeroed with the table)
   GroupTable t{};
   uint64_t capacity = 0;
   ArenaHeader* d_header = nullptr;
@@ -1226,6 +1301,7 @@ pgf_status arena_table(pgf_ctx* ctx, uint64_t capacity, uint32_t nexprs, uint32_
   const size_t o_keys = off;  off += capacity * kKeyWords * 8;
   const size_t o_acc = off;   off += capacity * ne * acc_words * 8;
   const size_t o_cnt = off;   off += capacity * (nexprs + 1) * 8;
+  const size_t o_rec = off;   off += size_t(ctx->sm_count) * kRegGroups * (2 + nexprs) * 8;
   out->zero_bytes = off;
   const bool small = capacity <= kSmallTable;
   const size_t o_out = off = align_up(off, 16);
@@ -1243,6 +1319,7 @@ pgf_status arena_table(pgf_ctx* ctx, uint64_t capacity, uint32_t nexprs, uint32_
   t.acc_words = acc_words;
   t.overflow = &out->d_header->overflow;
   t.used = &out->d_header->used;
+  out->d_cta_rec = reinterpret_cast<uint64_t*>(base + o_rec);
   out->d_out = small ? reinterpret_cast<uint64_t*>(base + o_out) : nullptr;
   out->out_entries = small ? capacity : 0;
   CU(ctx, cudaMemsetAsync(base, 0, out->zero_bytes, ctx->compute_stream));
@@ -1259,6 +1336,19 @@ pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, u
   table_extract_kernel<<<grid, kExtractThreads, 0, ctx->compute_stream>>>(t, nexprs, grouped, d_state, max_entries);
   CU(ctx, cudaGetLastError());
   return PGF_OK;
+}
+
+// Launch the fused kernel the lowering chose: the compaction pipeline, a registered shape, or the generic
+// streaming instantiation.
+cudaError_t launch_fused(const Lowered& L, uint32_t grid, cudaStream_t stream) {
+  if (L.probe) return launch_probe(L.acc_cls, L.t0, L.dev, grid, L.smem, stream);
+  if (const ShapeEntry* se = pick_shape(L)) return se->fn(L.dev, grid, L.smem, stream);
+  return launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, stream);
+}
+const char* variant_name(const Lowered& L) {
+  if (L.probe) return L.t0 == LD_VIEW ? "compact_1_string_term" : "compact_generic";
+  const ShapeEntry* se = pick_shape(L);
+  return se ? se->name : "generic";
 }
 
 }  // namespace
@@ -1299,17 +1389,20 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   uint64_t* h_out = reinterpret_cast<uint64_t*>(ctx->h_arena + sizeof(ArenaHeader));
   const uint64_t h_out_entries = (kHostArena / 2 - sizeof(ArenaHeader) - 8) / (uint64_t(ew) * 8);
 
+  // HashJoinExec build side: the fused kernel appends the build rows to a dense buffer; the table is
+  // built from them afterwards, sized by the rows that actually arrived (not by the rows scanned), so
+  // its tag directory is as small -- as L2 resident -- as the join allows.
+  struct RowBuf {
+    pgf_ctx* ctx;
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~RowBuf() { if (p) ctx->join_free(p, bytes); }
+  } rowbuf{ctx};
+  uint64_t rows_cap = 0;
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
-    JoinTable& jt = L.build_table;
-    // slots followed by the one-byte tag directory
-    const uint64_t slot_bytes = uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4);
-    const uint64_t tag_bytes = uint64_t(jt.capacity) + 16;  // + mirror of the first tags (windows never wrap)
-    jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
-    if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
-    mem.ptrs.push_back(jt.d_slots);
-    CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream));
-    L.dev.build.slots = jt.d_slots;
-    L.dev.build.tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
+    rows_cap = plan->expected_groups ? plan->expected_groups : std::max<uint64_t>(L.scan->rows, 1);
+    rowbuf.p = ctx->join_alloc(rows_cap * L.build_table.slot_u4 * sizeof(uint4), &rowbuf.bytes);
+    if (!rowbuf.p) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a build-row buffer of %llu rows", (unsigned long long)rows_cap);
   }
 
   PhaseTrace trace(ctx->compute_stream);
@@ -1320,12 +1413,14 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     trace.mark("arena + clear");
     L.dev.table = ta.t;
     L.dev.counters = &ta.d_header->counters;
+    L.dev.build_count = &ta.d_header->build_rows;
+    L.dev.cta_rec = ta.d_cta_rec;
+    L.dev.cta_done = &ta.d_header->cta_done;
+    L.dev.build.rows = static_cast<uint4*>(rowbuf.p);
+    L.dev.build.rows_cap = rows_cap;
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
     if (L.dev.nitems) {
-      if (const ShapeEntry* se = pick_shape(L))
-        CU(ctx, se->fn(L.dev, grid, L.smem, ctx->compute_stream));
-      else
-        CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
+      CU(ctx, launch_fused(L, grid, ctx->compute_stream));
       ++launches;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
@@ -1351,6 +1446,44 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
       capacity *= 16;
       if (capacity > (1ull << 30)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "group table would exceed 2^30 slots");
       continue;
+    }
+    if (plan->sink == PGF_SINK_JOIN_BUILD) {
+      const uint64_t nrows = h_header->build_rows;
+      if (h_header->overflow) {  // more build rows than the buffer holds (a hint that was too small, or a join that multiplies rows)
+        ctx->join_free(rowbuf.p, rowbuf.bytes);
+        rowbuf.p = nullptr;
+        rows_cap = nrows + nrows / 8 + 1024;  // the kernel counted every row it wanted to append
+        rowbuf.p = ctx->join_alloc(rows_cap * L.build_table.slot_u4 * sizeof(uint4), &rowbuf.bytes);
+        if (!rowbuf.p) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a build-row buffer of %llu rows", (unsigned long long)rows_cap);
+        continue;
+      }
+      JoinTable& jt = L.build_table;
+      uint64_t cap = 1024;
+      while (cap < nrows * 2) cap <<= 1;
+      if (cap > (1ull << 31)) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "join build side too large for one table");
+      jt.capacity = uint32_t(cap);
+      jt.rows = nrows;
+      // slots followed by the one-byte tag directory
+      const uint64_t slot_bytes = cap * jt.slot_u4 * sizeof(uint4), tag_bytes = cap + 16;
+      jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
+      if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
+      mem.ptrs.push_back(jt.d_slots);
+      CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
+      CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream));
+      if (nrows) {
+        uint32_t shift = 64;
+        for (uint64_t c = cap; c > 1; c >>= 1) shift--;
+        const uint32_t bgrid = uint32_t(std::min<uint64_t>((nrows + 255) / 256, uint64_t(ctx->sm_count) * 8));
+        join_build_kernel<<<bgrid, 256, 0, ctx->compute_stream>>>(jt.d_slots, reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes, jt.capacity - 1,
+                                                                  shift, jt.slot_u4, static_cast<const uint4*>(rowbuf.p), nrows);
+        CU(ctx, cudaGetLastError());
+        ++launches;
+      }
+      CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
+      CU(ctx, cudaEventSynchronize(ctx->ev_b));
+      CU(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+      total_ms += ms;  // clearing + filling the table is part of the build side's device time
+      trace.mark("join table from rows");
     }
     if (agg) {
       const uint64_t ngroups = L.grouped ? h_header->used : 1;
@@ -1421,13 +1554,9 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   res->kernel_ms = total_ms;
   ctx->last_kernel_ms = total_ms;
   res->kernel_launches = launches;
-  {
-    const ShapeEntry* se = pick_shape(L);
-    std::snprintf(res->variant, sizeof res->variant, "%s", se ? se->name : "generic");
-  }
+  std::snprintf(res->variant, sizeof res->variant, "%s", variant_name(L));
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable jt = L.build_table;
-    jt.rows = c.rows_out;
     mem.release(jt.d_slots);
     const uint64_t id = ctx->next_handle++;
     ctx->joins[id] = jt;
@@ -1465,13 +1594,11 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
   L.dev.table = ta.t;
   L.dev.counters = &ta.d_header->counters;
   const uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
+  L.dev.build_count = &ta.d_header->build_rows;
+  L.dev.cta_rec = ta.d_cta_rec;
+  L.dev.cta_done = &ta.d_header->cta_done;
   CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
-  if (L.dev.nitems) {
-    if (const ShapeEntry* se = pick_shape(L))
-      CU(ctx, se->fn(L.dev, grid, L.smem, ctx->compute_stream));
-    else
-      CU(ctx, launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, ctx->compute_stream));
-  }
+  if (L.dev.nitems) CU(ctx, launch_fused(L, grid, ctx->compute_stream));
   CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
   CU(ctx, cudaMemsetAsync(dev_state_out, 0, 8, ctx->compute_stream));
   PGF_TRY(extract_table(ctx, ta.t, L.table_capacity, plan->nexprs, L.grouped, static_cast<uint64_t*>(dev_state_out), max_entries));
@@ -1664,7 +1791,9 @@ pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* 
     if (!counts[f]) continue;
     const uint4* rows = reinterpret_cast<const uint4*>(static_cast<const uint8_t*>(dev_rows) + f * stride_bytes);
     const uint32_t grid = uint32_t(std::min<uint64_t>((counts[f] + 255) / 256, uint64_t(ctx->sm_count) * 8));
-    join_import_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, tags, jt.capacity - 1, jt.slot_u4, rows, counts[f]);
+    uint32_t shift = 64;
+    for (uint64_t c = cap; c > 1; c >>= 1) shift--;
+    join_build_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, tags, jt.capacity - 1, shift, jt.slot_u4, rows, counts[f]);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->compute_stream);

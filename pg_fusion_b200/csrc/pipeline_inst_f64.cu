@@ -13,12 +13,8 @@ static cudaError_t launch_one(const DevPlan& plan, uint32_t grid, size_t smem, c
 }
 
 cudaError_t launch_agg_f64(bool grouped, uint32_t nj, uint32_t maxe, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
-  if (grouped == true && nj == 1 && maxe == 2) return launch_one<SINK_AGG, CLS_F64, true, 1, 2>(plan, grid, smem, stream);
-  if (grouped == true && nj == 1 && maxe == 8) return launch_one<SINK_AGG, CLS_F64, true, 1, 8>(plan, grid, smem, stream);
   if (grouped == true && nj == 0 && maxe == 2) return launch_one<SINK_AGG, CLS_F64, true, 0, 2>(plan, grid, smem, stream);
   if (grouped == true && nj == 0 && maxe == 8) return launch_one<SINK_AGG, CLS_F64, true, 0, 8>(plan, grid, smem, stream);
-  if (grouped == false && nj == 1 && maxe == 2) return launch_one<SINK_AGG, CLS_F64, false, 1, 2>(plan, grid, smem, stream);
-  if (grouped == false && nj == 1 && maxe == 8) return launch_one<SINK_AGG, CLS_F64, false, 1, 8>(plan, grid, smem, stream);
   if (grouped == false && nj == 0 && maxe == 2) return launch_one<SINK_AGG, CLS_F64, false, 0, 2>(plan, grid, smem, stream);
   if (grouped == false && nj == 0 && maxe == 8) return launch_one<SINK_AGG, CLS_F64, false, 0, 8>(plan, grid, smem, stream);
   return cudaErrorInvalidValue;

@@ -1,4 +1,5 @@
-// Explicit instantiations of the fused pipeline kernel: HashJoinExec build sink and the counting sink.
+// Explicit instantiation of the streaming pipeline kernel with the counting sink (plans with a join or a
+// build sink run the compaction pipeline, probe_kernel.cuh).
 #include "pipeline_kernel.cuh"
 
 namespace pgf {
@@ -14,11 +15,8 @@ static cudaError_t launch_one(const DevPlan& plan, uint32_t grid, size_t smem, c
 
 cudaError_t launch_build_or_count(bool grouped, uint32_t nj, uint32_t maxe, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
   (void)maxe;
-  if (grouped)  // "grouped" selects the join-build sink here
-    return nj ? launch_one<SINK_JOIN_BUILD, CLS_I64, false, 1, 1>(plan, grid, smem, stream)
-              : launch_one<SINK_JOIN_BUILD, CLS_I64, false, 0, 1>(plan, grid, smem, stream);
-  return nj ? launch_one<SINK_COUNT, CLS_I64, false, 1, 1>(plan, grid, smem, stream)
-            : launch_one<SINK_COUNT, CLS_I64, false, 0, 1>(plan, grid, smem, stream);
+  if (grouped || nj) return cudaErrorInvalidValue;  // build sinks and join probes never reach the streaming kernel
+  return launch_one<SINK_COUNT, CLS_I64, false, 0, 1>(plan, grid, smem, stream);
 }
 
 }  // namespace pgf

@@ -1,0 +1,25 @@
+// Explicit instantiations of the compaction pipeline (probe_kernel.cuh): one per accumulator class, generic
+// predicate or the single-string-range specialisation of the TPC-H Q3 pipelines.
+#include "probe_kernel.cuh"
+
+namespace pgf {
+
+template <uint32_t ACC, int T0>
+static cudaError_t launch_one(const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
+  auto kernel = probe_pipeline_kernel<ACC, T0>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, kPThreads, smem, stream>>>(plan);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_probe(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
+  const bool view1 = t0 == int(LD_VIEW);
+  switch (acc) {
+    case CLS_F64: return view1 ? launch_one<CLS_F64, LD_VIEW>(plan, grid, smem, stream) : launch_one<CLS_F64, -1>(plan, grid, smem, stream);
+    case CLS_I64: return view1 ? launch_one<CLS_I64, LD_VIEW>(plan, grid, smem, stream) : launch_one<CLS_I64, -1>(plan, grid, smem, stream);
+    default: return view1 ? launch_one<CLS_I128, LD_VIEW>(plan, grid, smem, stream) : launch_one<CLS_I128, -1>(plan, grid, smem, stream);
+  }
+}
+
+}  // namespace pgf

@@ -1,5 +1,5 @@
 // Specialised instantiations of the fused pipeline kernel for the headline plan shapes
-// (TPC-H Q6 / Q1 / Q3 over the reference's Float64 + Utf8View schema).
+// (TPC-H Q6 / Q1 over the reference's Float64 + Utf8View schema).
 #include "pipeline_kernel.cuh"
 #include "pipeline_shapes.hpp"
 
@@ -25,24 +25,13 @@ using Q1Shape8 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X,
                         IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
 using Q1Shape7 = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY>, true,
                         IntList<key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2)>>;
-// Q3 lineitem side: WHERE date-range ; join probe ; SUM(x * (1 - y)) GROUP BY ...
-// GROUP BY l_orderkey (scan), o_orderdate, o_shippriority (join payload)
-using Q3Shape = ShapeT<false, IntList<LD_VIEW>, IntList<FORM_X_CMY>, true,
-                       IntList<key_enc(LD_I32, false, 0), key_enc(LD_VIEW, true, 1), key_enc(LD_I32, true, 3)>>;
 
 // "D" variants: Decimal128 money, Date32 dates, Int16 flag codes; wrapping i128 arithmetic
 using Q6ShapeD = ShapeT<false, IntList<LD_I32, LD_DEC, LD_DEC>, IntList<FORM_XY>, true>;
 using Q1ShapeD = ShapeT<false, IntList<LD_I32>, IntList<FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ>, true,
                         IntList<key_enc(LD_I16, false, 0), key_enc(LD_I16, false, 1)>>;
 
-// Q3 build sides: WHERE <string column range> [probe one join table] -> HashJoinExec build (+ Bloom)
-using BuildShape1V = ShapeT<false, IntList<LD_VIEW>, IntList<>, true>;
-
 const ShapeEntry kShapes[] = {
-    {{SINK_JOIN_BUILD, CLS_F64, 0, 0, 2, 1, {LD_VIEW, -1, -1, -1}, 0, {-1, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
-     launch_shape<SINK_JOIN_BUILD, CLS_I64, false, 0, 1, BuildShape1V>, "build_1_string_term", 0},
-    {{SINK_JOIN_BUILD, CLS_F64, 0, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 0, {-1, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
-     launch_shape<SINK_JOIN_BUILD, CLS_I64, false, 1, 1, BuildShape1V>, "probe_build_1_string_term", 0},
     {{SINK_AGG, CLS_I128, 0, 0, 2, 3, {LD_I32, LD_DEC, LD_DEC, -1}, 1, {FORM_XY, -1, -1, -1, -1, -1, -1, -1}, 0, {0, 0, 0, 0}},
      launch_shape<SINK_AGG, CLS_I128, false, 0, 2, Q6ShapeD>, "q6_decimal", 0},
     {{SINK_AGG, CLS_I128, 1, 0, kAccI128MaxExprs, 1, {LD_I32, -1, -1, -1}, 5, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, FORM_PREV_CPZ, -1, -1, -1},
@@ -56,9 +45,6 @@ const ShapeEntry kShapes[] = {
     {{SINK_AGG, CLS_F64, 1, 0, 8, 1, {LD_VIEW, -1, -1, -1}, 4, {FORM_X, FORM_X, FORM_X, FORM_X_CMY, -1, -1, -1, -1},
       2, {key_enc(LD_VIEW, false, 0), key_enc(LD_VIEW, false, 2), 0, 0}},
      launch_shape<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape7>, "q1_f64_7aggs", 4},
-    {{SINK_AGG, CLS_F64, 1, 1, 2, 1, {LD_VIEW, -1, -1, -1}, 1, {FORM_X_CMY, -1, -1, -1, -1, -1, -1, -1},
-      3, {key_enc(LD_I32, false, 0), key_enc(LD_VIEW, true, 1), key_enc(LD_I32, true, 3), 0}},
-     launch_shape<SINK_AGG, CLS_F64, true, 1, 2, Q3Shape>, "q3_lineitem_f64", 0},
 };
 
 bool same(const ShapeSig& a, const ShapeSig& b) {

@@ -6,11 +6,10 @@
 // row and entirely in registers:
 //   runtime Bloom probe(s)  -> K2  (pg/backend_service/src/source.rs:496-532)
 //   FilterExec predicate     -> K3  (conjunction of <column> <cmp> <literal>)
-//   HashJoinExec probe(s)    -> K6  (CollectLeft, Inner; duplicates multiply)
 //   ProjectionExec exprs     -> K4  (products of x, (c - x), (c + x))
 //   sink: AggregateExec      -> K5  (no-group / register pre-aggregated / global hash)
-//         HashJoinExec build [+ RuntimeFilterBuildExec]  -> K6 / K1
-// so every page byte is read from HBM exactly once and nothing is materialised.
+// so every page byte is read from HBM exactly once and nothing is materialised.  Plans with a
+// HashJoinExec probe or a build sink (K6 / K1) run the compaction pipeline in probe_kernel.cuh.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -130,8 +129,6 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return x;
 }
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
-// Join tables: slot = low hash bits, directory tag = top hash byte | 1 (never 0 = empty).
-__device__ __forceinline__ uint32_t join_tag(uint64_t h) { return uint32_t(h >> 56) | 1u; }
 
 struct I128 {
   uint64_t lo, hi;
@@ -499,6 +496,7 @@ struct BlockShared {
   uint64_t red[kMaxConsumerWarps][2];
   // per-warp deferred-sink queues (entries live behind the stage ring)
   uint32_t qcount[kMaxConsumerWarps];
+  uint32_t last_cta;  // this CTA was the last to finish: it runs the fixed-order Float64 reduction
 };
 
 __device__ __forceinline__ bool dict_entry_equals(const BlockShared* sh, uint32_t g, const uint64_t* key, uint32_t nwords, uint32_t knull) {
@@ -1004,90 +1002,18 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
           }
           continue;
         }
-        // HashJoinExec probe, batched over the R rows of this thread so the memory round trips
-        // overlap: (A) hash every row and fetch a window of four directory tags starting at its
-        // home slot, (B) scan the windows (SIMD-in-register byte compares) for the first tag hit
-        // and the end of the probe chain, (C) fetch the heads of the candidate slots.  Only rows
-        // with a tag hit or a chain longer than the window enter the per-row loop below (a bit
-        // mask per thread), so the common miss costs no control flow.  NULL keys never match.
-        constexpr uint32_t kNone = 0xFFFFFFFFu;
-        uint32_t ji[R], jtag[R], jcand[R], jres[R];
-        int64_t jkey[R];
-        uint4 js0[R];
-        uint32_t pending = 0;  // bit h: row h needs the per-row loop
-        if constexpr (NJ == 0) {
+        // (plans with a HashJoinExec probe or a build sink run the compaction pipeline, probe_kernel.cuh)
+        static_assert(NJ == 0 && SINK != SINK_JOIN_BUILD, "the streaming kernel has no join stages");
+        uint32_t pending = 0;  // bit h: row h reaches the sink
 #pragma unroll
-          for (uint32_t h = 0; h < R; ++h) {
-            ji[h] = 0; jtag[h] = 0; jcand[h] = kNone; jres[h] = kNone; jkey[h] = 0; js0[h] = make_uint4(0, 0, 0, 0);
-            pending |= uint32_t(keep[h]) << h;
-          }
-        } else {
-          const DevJoin& j = P.joins[0];
-          // keys of all rows with one dispatch on the key width
-          {
-            const uint8_t* kp = stage + j.key.off;
-            if (j.key.ld == LD_I32) {
-#pragma unroll
-              for (uint32_t h = 0; h < R; ++h) jkey[h] = int64_t(reinterpret_cast<const int32_t*>(kp)[rr[h]]);
-            } else if (j.key.ld == LD_I64) {
-#pragma unroll
-              for (uint32_t h = 0; h < R; ++h) jkey[h] = reinterpret_cast<const int64_t*>(kp)[rr[h]];
-            } else {
-#pragma unroll
-              for (uint32_t h = 0; h < R; ++h) jkey[h] = int64_t(reinterpret_cast<const int16_t*>(kp)[rr[h]]);
-            }
-          }
-#pragma unroll
-          for (uint32_t h = 0; h < R; ++h) {
-            bool live = keep[h];
-            if constexpr (!SHAPE::no_nulls) live = live && ref_valid(j.key, Row{stage, rr[h], tile_nulls, nullptr, 0});
-            const uint64_t hk = mix64(uint64_t(jkey[h]));
-            ji[h] = uint32_t(hk) & j.mask;
-            jtag[h] = live ? join_tag(hk) : 0u;
-          }
-          // the loads of all rows sit in one straight-line block (no control flow in between)
-          uint32_t wlo[R], whi[R];
-#pragma unroll
-          for (uint32_t h = 0; h < R; ++h) {
-            const uint32_t* w32 = reinterpret_cast<const uint32_t*>(j.tags + (ji[h] & ~3u));
-            wlo[h] = ldg_u32_if(w32, jtag[h] != 0u, 0u);
-            whi[h] = ldg_u32_if(w32 + 1, jtag[h] != 0u, 0u);
-          }
-#pragma unroll
-          for (uint32_t h = 0; h < R; ++h) {
-            const uint32_t win = __funnelshift_r(wlo[h], whi[h], (ji[h] & 3u) * 8u);  // tags[i .. i+3]
-            // 0x80 in every byte of the window that is zero (end of chain) / equals the tag: exact
-            // zero-byte detection, no carries between bytes
-            const uint32_t x = win ^ (jtag[h] * 0x01010101u);
-            const uint32_t mz = ~(((win & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | win | 0x7F7F7F7Fu);
-            const uint32_t mt = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-            const uint32_t below_end = mz ? ((mz & (0u - mz)) - 1u) : 0xFFFFFFFFu;  // bytes before the first zero tag
-            uint32_t hits = mt & below_end;
-            jcand[h] = kNone;
-            jres[h] = kNone;
-            if (jtag[h] != 0u) {
-              if (hits) {
-                jcand[h] = (ji[h] + ((31u - __clz(hits & (0u - hits))) >> 3)) & j.mask;
-                hits &= hits - 1u;
-                if (hits) jres[h] = (ji[h] + ((31u - __clz(hits & (0u - hits))) >> 3)) & j.mask;  // second hit: walk from there
-              }
-              if (jres[h] == kNone && mz == 0u) jres[h] = (ji[h] + 4u) & j.mask;  // chain continues past the window
-              pending |= uint32_t(jcand[h] != kNone || jres[h] != kNone) << h;
-            }
-          }
-#pragma unroll
-          for (uint32_t h = 0; h < R; ++h)
-            js0[h] = ldg_u128_if(j.slots + uint64_t(jcand[h] != kNone ? jcand[h] : 0u) * j.slot_u4, jcand[h] != kNone);
-        }
+        for (uint32_t h = 0; h < R; ++h) pending |= uint32_t(keep[h]) << h;
         while (pending) {
           const uint32_t half = 31u - __clz(pending & (0u - pending));
           pending &= pending - 1u;
-          uint32_t rsel = rr[0], tagsel = jtag[0], candsel = jcand[0], ressel = jres[0];
-          int64_t keysel = jkey[0];
-          uint4 s0sel = js0[0];
+          uint32_t rsel = rr[0];
 #pragma unroll
           for (uint32_t h = 1; h < R; ++h)
-            if (half == h) { rsel = rr[h]; tagsel = jtag[h]; candsel = jcand[h]; ressel = jres[h]; keysel = jkey[h]; s0sel = js0[h]; }
+            if (half == h) rsel = rr[h];
           Row row{stage, rsel, tile_nulls, nullptr, 0};
 
           // -- sink (optionally behind one HashJoinExec probe)
@@ -1228,85 +1154,10 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
                 }
                 if (!queued) global_accumulate<ACC, MAXE>(P, GROUPED, key, knull, valid_mask, v);
               }
-            } else if constexpr (SINK == SINK_JOIN_BUILD) {
-              const JoinBuild& jb = P.build;
-              if (ref_valid(jb.key, rc)) {  // NULL keys never match: not inserted
-                const int64_t key = load_i64(jb.key, rc);
-                uint32_t pay[5] = {0, 0, 0, 0, 0};
-                uint32_t occ = 1u;
-#pragma unroll
-                for (uint32_t p = 0; p < 4; ++p) {
-                  if (p >= jb.npayload) continue;
-                  if (!ref_valid(jb.payload[p], rc)) { occ |= 2u << p; continue; }
-                  const uint32_t w = jb.payload_word[p], nw = jb.payload_nwords[p];
-                  uint4 raw = make_uint4(0, 0, 0, 0);
-                  if (nw == 4) raw = load_u128(jb.payload[p], rc);
-                  else {
-                    const int64_t x = jb.payload[p].ld == LD_F64 ? __double_as_longlong(load_f64(jb.payload[p], rc))
-                                    : jb.payload[p].ld == LD_F32 ? int64_t(__float_as_uint(float(load_f64(jb.payload[p], rc))))
-                                                                 : load_i64(jb.payload[p], rc);
-                    raw.x = uint32_t(uint64_t(x));
-                    raw.y = uint32_t(uint64_t(x) >> 32);
-                  }
-#pragma unroll
-                  for (uint32_t q = 0; q < 5; ++q) {  // static indices keep pay[] in registers
-                    if (q == w) pay[q] = raw.x;
-                    if (nw >= 2 && q == w + 1) pay[q] = raw.y;
-                    if (nw == 4 && q == w + 2) pay[q] = raw.z;
-                    if (nw == 4 && q == w + 3) pay[q] = raw.w;
-                  }
-                }
-                const uint64_t hk = mix64(uint64_t(key));
-                uint32_t i = uint32_t(hk) & jb.mask;
-                for (;;) {  // capacity >= 2 x rows: an empty slot always exists
-                  uint32_t* slot = reinterpret_cast<uint32_t*>(jb.slots + uint64_t(i) * jb.slot_u4);
-                  if (atomicCAS(slot + 2, 0u, occ) == 0u) {
-                    jb.tags[i] = uint8_t(join_tag(hk));
-                    if (i < 4u) jb.tags[jb.mask + 1u + i] = uint8_t(join_tag(hk));  // mirror: tag windows never wrap
-                    slot[0] = uint32_t(uint64_t(key));
-                    slot[1] = uint32_t(uint64_t(key) >> 32);
-                    slot[3] = pay[0];
-                    if (jb.slot_u4 == 2) { slot[4] = pay[1]; slot[5] = pay[2]; slot[6] = pay[3]; slot[7] = pay[4]; }
-                    break;
-                  }
-                  i = (i + 1) & jb.mask;
-                }
-                if (P.has_build_bloom) { bloom_insert(P.build_bloom, uint64_t(key)); ++n_bloom_ins; }
-              }
             }
           };
 
-          if constexpr (NJ == 0) {
-            sink(row);
-          } else {
-            const DevJoin& j = P.joins[0];
-            const uint32_t tag = tagsel;
-            if (!tag) continue;  // NULL key
-            const int64_t key = keysel;
-            const uint32_t klo = uint32_t(uint64_t(key)), khi = uint32_t(uint64_t(key) >> 32);
-            if (candsel != kNone && s0sel.x == klo && s0sel.y == khi) {
-              row.pay = reinterpret_cast<const uint32_t*>(j.slots + uint64_t(candsel) * j.slot_u4);
-              row.occ = s0sel.z;
-              sink(row);
-            }
-            if (ressel != kNone) {  // rest of the chain, one tag at a time
-              uint32_t i = ressel;
-              uint32_t t = __ldg(j.tags + i);
-              while (t != 0u) {
-                if (t == tag) {
-                  const uint4* slot = j.slots + uint64_t(i) * j.slot_u4;
-                  const uint4 s0 = __ldg(slot);
-                  if (s0.x == klo && s0.y == khi) {
-                    row.pay = reinterpret_cast<const uint32_t*>(slot);
-                    row.occ = s0.z;
-                    sink(row);
-                  }
-                }
-                i = (i + 1) & j.mask;
-                t = __ldg(j.tags + i);
-              }
-            }
-          }
+          sink(row);
         }
         if constexpr (SINK == SINK_AGG && GROUPED) {
           __syncwarp();
@@ -1367,7 +1218,13 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
           if (e < P.nexprs) {
             AccT t = Ops::zero();
             for (int w = 0; w < kConsumerWarps; ++w) t = Ops::add(t, *reinterpret_cast<AccT*>(&sh->red[w][0]));
-            Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, t);
+            if constexpr (ACC == CLS_F64) {
+              // Float64: the CTA's sum goes to its record; the last CTA to finish adds the records in CTA
+              // order (below), so the result does not depend on which CTA finishes first
+              P.cta_rec[(uint64_t(blockIdx.x) * kRegGroups + g) * (2u + P.nexprs) + 2u + e] = uint64_t(__double_as_longlong(t));
+            } else {
+              Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, t);
+            }
           } else {
             uint64_t t = 0;
             for (int w = 0; w < kConsumerWarps; ++w) t += sh->red[w][0];
@@ -1379,6 +1236,50 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
           }
         }
         __syncthreads();
+      }
+      if constexpr (ACC == CLS_F64) {
+        if (threadIdx.x == 32) P.cta_rec[(uint64_t(blockIdx.x) * kRegGroups + g) * (2u + P.nexprs)] = uint64_t(slot) + 1ull;  // 0 = no record
+      }
+    }
+    if constexpr (ACC == CLS_F64) {
+      // ===== fixed-order cross-CTA reduction (threadfence reduction: the last CTA to arrive does it) =====
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) sh->last_cta = atomicAdd(P.cta_done, 1u) == gridDim.x - 1u;
+      __syncthreads();
+      if (sh->last_cta) {
+        __threadfence();
+        const uint32_t rw = 2u + P.nexprs;                 // record: [slot + 1][unused][sum per argument]
+        const uint32_t nrec = gridDim.x * kRegGroups;
+        // (staged in the idle stage ring when it is large enough, else read from L2)
+        const bool fits = uint64_t(nrec) * rw * 8u <= uint64_t(kNumStages) * P.stage_bytes;
+        const uint64_t* recs = fits ? reinterpret_cast<const uint64_t*>(stages) : P.cta_rec;
+        if (fits)
+          for (uint32_t i = threadIdx.x; i < nrec * rw; i += blockDim.x)
+            reinterpret_cast<uint64_t*>(stages)[i] = *reinterpret_cast<volatile uint64_t*>(P.cta_rec + i);
+        __syncthreads();
+        // a record leads its group if no earlier record names the same slot; (leader, argument) pairs are
+        // dealt to the threads, each adds the records of its slot in CTA order
+        for (uint32_t r = threadIdx.x / 16u; r < nrec; r += blockDim.x / 16u) {
+          const uint32_t e = threadIdx.x % 16u;
+          const uint64_t tag = recs[uint64_t(r) * rw];
+          if (tag == 0ull || e >= P.nexprs) continue;
+          bool leader = true;
+          for (uint32_t q = 0; q < r; ++q) leader &= recs[uint64_t(q) * rw] != tag;
+          if (!leader) continue;
+          double sum = 0.0;
+          bool first = true;
+          for (uint32_t q = r; q < nrec; ++q) {
+            if (recs[uint64_t(q) * rw] != tag) continue;
+            const double v = __longlong_as_double((long long)recs[uint64_t(q) * rw + 2u + e]);
+            sum = first ? v : __dadd_rn(sum, v);
+            first = false;
+          }
+          // what the table already holds came from the rows of the slow path (NULL inputs, more than
+          // kRegGroups groups per CTA); every CTA finished those before it took its ticket
+          double* dst = reinterpret_cast<double*>(P.table.acc + (tag - 1ull) * P.nexprs + e);
+          *dst = __dadd_rn(*dst, sum);
+        }
       }
     }
   }

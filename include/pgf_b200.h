@@ -40,6 +40,7 @@ enum {
   PGF_ERR_NOT_ELIGIBLE = 6,    /* plan outside the supported grammar: keep the DataFusion node */
   PGF_ERR_STATE = 7,           /* call not valid in the object's current state */
   PGF_ERR_UNSUPPORTED_DATA = 8,/* e.g. out-of-line (> 12 byte) view in a predicate/key column */
+  PGF_ERR_COMM = 9,            /* NCCL / communicator error */
   /* BloomParamError / BloomAttachError (runtime_filter/src/bloom.rs:103-137) */
   PGF_ERR_BLOOM_ZERO_BIT_COUNT = 20,
   PGF_ERR_BLOOM_ZERO_HASH_COUNT = 21,
@@ -347,7 +348,7 @@ typedef struct {
   uint32_t nkeys;   pgf_colref keys[PGF_MAX_KEYS];
   uint32_t nexprs;  pgf_value_expr exprs[PGF_MAX_EXPRS];
   uint32_t naggs;   pgf_agg aggs[PGF_MAX_AGGS];
-  uint64_t expected_groups;       /* sizing hint for the group table; 0 = unknown */
+  uint64_t expected_groups;       /* sizing hint: groups of an aggregate sink / build rows of a build sink; 0 = unknown */
   /* PGF_SINK_JOIN_BUILD: key must be Int16/Int32/Int64; payload columns are carried in the
    * table and addressed by later pipelines as pgf_colref{source = join index + 1, col = i} */
   pgf_colref build_key;
@@ -359,7 +360,16 @@ typedef struct {
    * and only `limit` rows leave the GPU.  DataFusion defaults: ASC NULLS LAST, DESC NULLS FIRST. */
   uint32_t nsort;  pgf_sort_key sort[PGF_MAX_SORT];
   uint64_t limit;                 /* 0 = no limit */
+  /* PGF_SINK_JOIN_BUILD: PGF_BUILD_ROWS_ONLY keeps the build rows as a dense ROW SET and builds no hash table
+   * (result.join_table is then a row-set handle: input of pgf_join_table_exchange or of a row-set scan). */
+  uint32_t build_flags;
+  uint32_t reserved0;
+  /* != 0: the pipeline scans this row set instead of scan_id (the probe side of a hash-partitioned join
+   * after the exchange).  Column 0 of source 0 is the row's key, column i + 1 its payload i; no Bloom probes
+   * and no predicate terms. */
+  uint64_t scan_row_set;
 } pgf_pipeline;
+#define PGF_BUILD_ROWS_ONLY 1u
 
 /* Result values */
 enum { PGF_V_NULL = 0, PGF_V_F64 = 1, PGF_V_I64 = 2, PGF_V_I128 = 3, PGF_V_STR = 4 };
@@ -372,8 +382,9 @@ typedef struct {
 
 typedef struct {
   uint64_t rows_in;        /* rows scanned */
-  uint64_t rows_bloom;     /* rows surviving the Bloom probes */
-  uint64_t rows_filtered;  /* rows surviving the predicate */
+  uint64_t rows_bloom;     /* rows_in minus the rows a runtime filter rejected (RuntimeFilterProbeRowsRejectedTotal);
+                            * pipelines with joins / build sinks probe only rows the predicate kept */
+  uint64_t rows_filtered;  /* rows surviving the runtime filters and the predicate */
   uint64_t rows_out;       /* rows reaching the sink (after joins) */
   uint64_t ngroups;        /* PGF_SINK_AGGREGATE: output rows */
   uint32_t nkeys, naggs;
@@ -393,6 +404,11 @@ typedef struct {
   /* PGF_AGG_* of every aggregate: decides the nullability of its result column (COUNT is NOT NULL,
    * SUM / AVG are nullable whatever the data holds).  0 in a hand-built result = unknown. */
   int32_t agg_func[PGF_MAX_AGGS];
+  /* 1: group key k comes from a NOT NULL column (of the scan, or of a join build side), so its output
+   * field is non-nullable -- exactly what DataFusion's AggregateExec derives from the input schema and
+   * what ArrowPageDecoder::validate_schema compares (page/import/src/lib.rs:208-235; a nullability
+   * mismatch is SchemaNullabilityMismatch).  0: nullable, or unknown in a hand-built result. */
+  int32_t key_not_null[PGF_MAX_KEYS];
 } pgf_result;
 
 pgf_status pgf_pipeline_check(pgf_ctx *ctx, const pgf_pipeline *plan); /* eligibility only */
@@ -403,8 +419,9 @@ void pgf_result_free(pgf_result *result);
  * (worker_runtime/src/result_pages.rs:150-196; page/batch_encoder/src/encoder.rs:49-298) for
  * the aggregate output of a pipeline: rows are encoded into transfer pages (20-byte header, kind
  * 0x4152, payload = one arrow_layout block of page_size - 20 bytes with max_rows = the fixed row
- * cap of the schema) that slot_import / ArrowPageDecoder consume unchanged.  Keys are nullable
- * columns; SUM / AVG are nullable, COUNT is not.  Strings are inline views (<= 12 bytes).
+ * cap of the schema) that slot_import / ArrowPageDecoder consume unchanged.  A group key column is
+ * nullable iff its source column is (key_not_null); SUM / AVG are nullable, COUNT is not -- the output
+ * schema DataFusion derives for AggregateExec.  Strings are inline views (<= 12 bytes).
  * `first_row` / `max_pages` allow page-at-a-time production like next_step(); *rows_done is the
  * number of rows encoded by this call. */
 pgf_status pgf_result_schema(const pgf_result *result, pgf_column_spec *schema_out, uint32_t *ncols_out);
@@ -450,6 +467,40 @@ pgf_status pgf_pipeline_run_partial_async(pgf_ctx *ctx, const pgf_pipeline *plan
 pgf_status pgf_pipeline_merge_partials_bounded(pgf_ctx *ctx, const pgf_pipeline *plan,
                                                const void *dev_states, uint64_t state_stride_bytes,
                                                uint32_t nstates, pgf_result **result_out);
+
+/* ------------------------------------------------------------ multi-GPU (one process per GPU)
+ * The reference runs every operator in one partition (worker_runtime/src/runtime.rs:748-758) and moves pages
+ * between processes through shared memory only; across the GPUs of one box this library shards every scan by
+ * pages (the analogue of the reference's CTID-range scan producers, ai/architecture.md:119-133) and runs the
+ * exchange steps itself, with NCCL over NVLink / NVSwitch (libnccl.so.2 is loaded on first use; a single-GPU host
+ * never needs it).  One context per process and GPU; rank 0 creates the id and hands it to the other ranks out
+ * of band (shared memory in the worker, a file or torch.distributed in the tests). */
+#define PGF_COMM_ID_BYTES 128
+pgf_status pgf_comm_unique_id(uint8_t id_out[PGF_COMM_ID_BYTES]);
+pgf_status pgf_comm_init(pgf_ctx *ctx, const uint8_t id[PGF_COMM_ID_BYTES], int32_t rank, int32_t world);
+pgf_status pgf_comm_destroy(pgf_ctx *ctx);
+pgf_status pgf_comm_info(pgf_ctx *ctx, int32_t *rank_out, int32_t *world_out);
+/* all-gather of `bytes` device bytes per rank on the context's compute stream (stream ordered, not synchronised) */
+pgf_status pgf_comm_all_gather(pgf_ctx *ctx, const void *dev_send, void *dev_recv, uint64_t bytes);
+/* AggregateExec Partial -> exchange -> Final in one call: the fused kernel over this rank's pages, extraction of
+ * the partial state (sized for max_groups groups: 72 bytes for Q6), all-gather of the states, fixed-order merge
+ * (rank order: every rank gets the same bits; exact for Int64 / Decimal128) and one synchronisation for the result. */
+pgf_status pgf_pipeline_run_sharded(pgf_ctx *ctx, const pgf_pipeline *plan, uint64_t max_groups, pgf_result **result_out);
+/* Bloom OR-merge: all-gather of the word arrays of every rank's filter (Building state) + bitwise OR;
+ * bit exact whatever the order.  Stream ordered. */
+pgf_status pgf_bloom_or_all_reduce(pgf_ctx *ctx, uint64_t bloom);
+/* Join exchange.  Input: a join table or a row set built from this rank's pages.
+ * PGF_XCHG_BROADCAST: every rank receives every row (all-gather) -- small build sides.
+ * PGF_XCHG_PARTITION: row r goes to rank hash(key) % world (all-to-all, grouped ncclSend / ncclRecv) -- large build
+ *   sides, and the probe side of a partitioned join.  Rows with equal keys meet on one rank, so a GROUP BY that
+ *   contains the join key needs no further merge.
+ * PGF_XCHG_ROWS_ONLY: the output is a row set (no hash table): the input of a row-set scan.
+ * The input handle stays valid.  nvlink_bytes_out (optional): bytes this rank sent over NVLink. */
+enum { PGF_XCHG_BROADCAST = 0, PGF_XCHG_PARTITION = 1, PGF_XCHG_ROWS_ONLY = 4 };
+pgf_status pgf_join_table_exchange(pgf_ctx *ctx, uint64_t table_or_rows, uint32_t mode, uint64_t *out_handle,
+                                   uint64_t *nvlink_bytes_out);
+/* rank that owns a key under PGF_XCHG_PARTITION (for tests) */
+uint32_t pgf_partition_of_key(int64_t key, uint32_t world);
 
 /* -------------------------------------------------- synthetic TPC-H-shaped data
  * Counter-based generator (row id -> values) writing reference-format pages directly in

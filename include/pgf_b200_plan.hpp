@@ -485,7 +485,12 @@ class AggregateExec final : public ExecutionPlan {
                 std::vector<AggregateFunctionExpr> aggr_expr, PlanRef input)
       : mode_(mode), group_by_(std::move(group_by)), aggr_(std::move(aggr_expr)), input_(std::move(input)) {
     const Schema& in = input_->schema();
-    for (const auto& g : group_by_) schema_.fields.push_back(Field{g.second, g.first->data_type(in), true});
+    for (const auto& g : group_by_) {
+      // a group field keeps the nullability of its input field (DataFusion derives it with PhysicalExpr::nullable)
+      Field f{g.second, g.first->data_type(in), true};
+      if (auto c = g.first->downcast<Column>()) f.nullable = in.field(c->index()).nullable;
+      schema_.fields.push_back(f);
+    }
     for (const auto& a : aggr_) {
       int32_t t = PGF_T_INT64;
       if (a.fun != AggregateFunction::Count) {

@@ -415,4 +415,18 @@ int orc_q1_pages(const uint8_t *pages, uint64_t npages, uint64_t page_stride, in
 #ifdef __cplusplus
 }
 #endif
+
+/* ---- orc_q3.c: TPC-H Q3 shape, page-sharded, fed shard by shard (test / bench baseline only) ---- */
+typedef struct orc_q3 orc_q3;
+orc_q3 *orc_q3_new(const char *segment, const char *date);
+void orc_q3_free(orc_q3 *q);
+int orc_q3_customer(orc_q3 *q, const uint8_t *pages, uint64_t npages, uint64_t stride, int nthreads);
+int orc_q3_customer_finish(orc_q3 *q);
+int orc_q3_orders(orc_q3 *q, const uint8_t *pages, uint64_t npages, uint64_t stride, int nthreads);
+int orc_q3_orders_finish(orc_q3 *q, int nthreads);
+int orc_q3_lineitem(orc_q3 *q, const uint8_t *pages, uint64_t npages, uint64_t stride, int nthreads);
+int orc_q3_stats(const orc_q3 *q, uint64_t out[6]);
+uint64_t orc_q3_groups(const orc_q3 *q, int32_t *keys, uint8_t *dates12, int32_t *datelens, int32_t *prios, double *sums,
+                       uint64_t *counts, uint64_t cap);
+
 #endif

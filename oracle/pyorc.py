@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(_DIR, "liborc.so")
 
 def build(force: bool = False) -> str:
     """Compile oracle/liborc.so with gcc (plain C, no GPU)."""
-    srcs = [os.path.join(_DIR, f) for f in ("orc_bloom.c", "orc_layout.c", "orc_ops.c", "orc_fast.c", "orc.h")]
+    srcs = [os.path.join(_DIR, f) for f in ("orc_bloom.c", "orc_layout.c", "orc_ops.c", "orc_fast.c", "orc_q3.c", "orc.h")]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
@@ -177,6 +177,17 @@ def lib():
         L.orc_q6_pages.argtypes = [vp, u64, u64, C.c_int, P(i32), C.c_char_p, C.c_char_p, C.c_double,
                                    C.c_double, C.c_double, P(Q6Result)]
         L.orc_q1_pages.argtypes = [vp, u64, u64, C.c_int, P(i32), C.c_char_p, C.c_int, P(Q1Result)]
+        L.orc_q3_new.restype = vp
+        L.orc_q3_new.argtypes = [C.c_char_p, C.c_char_p]
+        L.orc_q3_free.restype = None
+        L.orc_q3_free.argtypes = [vp]
+        for fn in (L.orc_q3_customer, L.orc_q3_orders, L.orc_q3_lineitem):
+            fn.argtypes = [vp, vp, u64, u64, C.c_int]
+        L.orc_q3_customer_finish.argtypes = [vp]
+        L.orc_q3_orders_finish.argtypes = [vp, C.c_int]
+        L.orc_q3_stats.argtypes = [vp, P(u64)]
+        L.orc_q3_groups.restype = u64
+        L.orc_q3_groups.argtypes = [vp, vp, vp, vp, vp, vp, vp, u64]
         _lib = L
     return _lib
 
@@ -621,3 +632,75 @@ def q1_pages(pages: np.ndarray, page_stride: int, nthreads: int, cols=(0, 1, 2, 
                                                    sum_disc_price=gr.sum_disc_price, sum_charge=gr.sum_charge,
                                                    sum_disc=gr.sum_disc, count=gr.count)
     return out, res.rows_in
+
+
+class Q3Stream:
+    """The TPC-H Q3 shape fed shard by shard (orc_q3.c): customer pages, then orders pages, then lineitem
+    pages, each in any number of calls; SF100 never has to exist on the host at once."""
+
+    def __init__(self, segment: bytes = b"BUILDING", date: bytes = b"1995-03-15", nthreads: int = 1):
+        self.h = lib().orc_q3_new(segment, date)
+        if not self.h:
+            raise OracleError(-1, "orc_q3_new")
+        self.nthreads = nthreads
+        self._stage = 0
+
+    def _pages(self, fn, pages, stride, what):
+        pages = np.ascontiguousarray(pages).reshape(-1)
+        rc = fn(self.h, _ptr(pages), pages.size // stride, stride, self.nthreads)
+        if rc:
+            raise OracleError(rc, what)
+
+    def customer(self, pages, stride=65536):
+        assert self._stage == 0
+        self._pages(lib().orc_q3_customer, pages, stride, "q3 customer")
+
+    def orders(self, pages, stride=65536):
+        if self._stage == 0:
+            if lib().orc_q3_customer_finish(self.h):
+                raise OracleError(-1, "q3 customer_finish")
+            self._stage = 1
+        assert self._stage == 1
+        self._pages(lib().orc_q3_orders, pages, stride, "q3 orders")
+
+    def lineitem(self, pages, stride=65536):
+        if self._stage == 0:
+            self.orders(np.zeros(0, dtype=np.uint8))
+        if self._stage == 1:
+            if lib().orc_q3_orders_finish(self.h, self.nthreads):
+                raise OracleError(-1, "q3 orders_finish")
+            self._stage = 2
+        self._pages(lib().orc_q3_lineitem, pages, stride, "q3 lineitem")
+
+    def stats(self):
+        out = (C.c_uint64 * 6)()
+        lib().orc_q3_stats(self.h, out)
+        return dict(customers=out[0], orders=out[1], lineitem_rows=out[2], filtered=out[3], joined=out[4], matched_orders=out[5])
+
+    def groups(self):
+        """{(l_orderkey, o_orderdate bytes, o_shippriority): (revenue, rows)}"""
+        n = self.stats()["matched_orders"]
+        keys = np.zeros(n, dtype=np.int32)
+        dates = np.zeros((n, 12), dtype=np.uint8)
+        lens = np.zeros(n, dtype=np.int32)
+        prios = np.zeros(n, dtype=np.int32)
+        sums = np.zeros(n, dtype=np.float64)
+        cnts = np.zeros(n, dtype=np.uint64)
+        got = lib().orc_q3_groups(self.h, _ptr(keys), _ptr(dates), _ptr(lens), _ptr(prios), _ptr(sums), _ptr(cnts), n)
+        assert got == n
+        out = {}
+        for i in range(n):
+            k = (int(keys[i]), bytes(dates[i, : lens[i]]), int(prios[i]))
+            if k in out:   # build rows with equal (key, date, priority) are one group
+                out[k] = (out[k][0] + float(sums[i]), out[k][1] + int(cnts[i]))
+            else:
+                out[k] = (float(sums[i]), int(cnts[i]))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().orc_q3_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()

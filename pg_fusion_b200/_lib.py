@@ -104,6 +104,8 @@ class Pipeline(C.Structure):
         ("build_bloom", u64),
         ("nsort", u32), ("sort", SortKey * 4),
         ("limit", u64),
+        ("build_flags", u32), ("reserved0", u32),
+        ("scan_row_set", u64),
     ]
 
 
@@ -115,7 +117,8 @@ class Result(C.Structure):
     _fields_ = [("rows_in", u64), ("rows_bloom", u64), ("rows_filtered", u64), ("rows_out", u64),
                 ("ngroups", u64), ("nkeys", u32), ("naggs", u32), ("keys", P(Value)), ("aggs", P(Value)),
                 ("join_table", u64), ("bloom_rows", u64), ("kernel_ms", C.c_float), ("kernel_launches", u32),
-                ("key_type", i32 * 4), ("agg_type", i32 * 16), ("variant", C.c_char * 24), ("agg_func", i32 * 16)]
+                ("key_type", i32 * 4), ("agg_type", i32 * 16), ("variant", C.c_char * 24), ("agg_func", i32 * 16),
+                ("key_not_null", i32 * 4)]
 
 
 class RfTarget(C.Structure):
@@ -204,6 +207,15 @@ _SIGNATURES = {
     "pgf_join_table_export": (i32, [vp, u64, vp, u64, P(u64)]),
     "pgf_join_table_from_fragments": (i32, [vp, u64, vp, u64, P(u64), u32, P(u64)]),
     "pgf_pipeline_run_partial_async": (i32, [vp, P(Pipeline), vp, u64]),
+    "pgf_comm_unique_id": (i32, [vp]),
+    "pgf_comm_init": (i32, [vp, vp, i32, i32]),
+    "pgf_comm_destroy": (i32, [vp]),
+    "pgf_comm_info": (i32, [vp, P(i32), P(i32)]),
+    "pgf_comm_all_gather": (i32, [vp, vp, vp, u64]),
+    "pgf_pipeline_run_sharded": (i32, [vp, P(Pipeline), u64, P(P(Result))]),
+    "pgf_bloom_or_all_reduce": (i32, [vp, u64]),
+    "pgf_join_table_exchange": (i32, [vp, u64, u32, P(u64), P(u64)]),
+    "pgf_partition_of_key": (u32, [i64, u32]),
     "pgf_pipeline_merge_partials_bounded": (i32, [vp, P(Pipeline), vp, u64, u32, P(P(Result))]),
     "pgf_gen_scan": (i32, [vp, u64, P(GenSpec)]),
     "pgf_gen_schema": (i32, [i32, P(ColumnSpec), P(u32)]),

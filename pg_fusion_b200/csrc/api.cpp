@@ -168,8 +168,12 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   }
   for (auto& kv : ctx->blooms)
     if (kv.second.d_words) cudaFree(kv.second.d_words);
-  for (auto& kv : ctx->joins)
+  comm_release(ctx);
+  if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+  for (auto& kv : ctx->joins) {
     if (kv.second.d_slots) cudaFree(kv.second.d_slots);
+    if (kv.second.d_rows) cudaFree(kv.second.d_rows);
+  }
   for (auto& c : ctx->join_cache) cudaFree(c.p);
   for (void* p : ctx->registered) cudaHostUnregister(p);
   for (int i = 0; i < 2; ++i) {
@@ -656,6 +660,26 @@ pgf_status pgf_bloom_or_device_words(pgf_ctx* ctx, uint64_t bloom, const void* d
   return bloom_or_device(ctx, *b, dev_words, nwords, narrays);
 }
 
+pgf_status pgf_bloom_or_all_reduce(pgf_ctx* ctx, uint64_t bloom) {
+  BLOOM_OR_FAIL(ctx, bloom, b);
+  if (ctx->comm_world == 1) return PGF_OK;
+  // all-gather of the word arrays + OR of every array into the local one (NCCL has no bitwise-OR reduction)
+  const uint64_t bytes = b->params.word_count * 8;
+  CU(ctx, cudaSetDevice(ctx->device));
+  if (ctx->d_xchg_cap < bytes * uint64_t(ctx->comm_world)) {
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+    ctx->d_xchg = nullptr;
+    ctx->d_xchg_cap = 0;
+    void* p = nullptr;
+    if (cudaMalloc(&p, bytes * uint64_t(ctx->comm_world)) != cudaSuccess) { cudaGetLastError(); return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange scratch"); }
+    ctx->d_xchg = static_cast<uint8_t*>(p);
+    ctx->d_xchg_cap = bytes * uint64_t(ctx->comm_world);
+  }
+  PGF_TRY(comm_all_gather(ctx, b->d_words, ctx->d_xchg, bytes));
+  return bloom_or_device(ctx, *b, ctx->d_xchg, b->params.word_count, uint32_t(ctx->comm_world));
+}
+
 pgf_status pgf_bloom_probe_keys(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_generation, const void* keys,
                                 int32_t key_width, const uint8_t* validity, uint64_t n, uint8_t* decisions_out,
                                 pgf_probe_stats* stats) {
@@ -727,7 +751,9 @@ void pgf_result_free(pgf_result* r) {
 pgf_status pgf_result_schema(const pgf_result* r, pgf_column_spec* schema_out, uint32_t* ncols_out) {
   if (!r || !schema_out || !ncols_out) return PGF_ERR_INVALID_ARGUMENT;
   uint32_t n = 0;
-  for (uint32_t k = 0; k < r->nkeys; ++k) schema_out[n++] = pgf_column_spec{uint16_t(r->key_type[k]), 1};
+  // a group key is nullable iff its source column is (DataFusion: the AggregateExec output field of a
+  // group expression keeps the nullability of its input field)
+  for (uint32_t k = 0; k < r->nkeys; ++k) schema_out[n++] = pgf_column_spec{uint16_t(r->key_type[k]), uint16_t(r->key_not_null[k] ? 0 : 1)};
   for (uint32_t a = 0; a < r->naggs; ++a) {
     // COUNT never yields NULL; SUM / AVG over no (non-null) rows do, so their columns are nullable
     // whatever this result happens to hold (the receiving schema is fixed by the plan)
@@ -795,6 +821,7 @@ pgf_status pgf_result_encode_pages(const pgf_result* r, uint32_t page_size, uint
       for (uint32_t i = 0; i < n; ++i) {
         const pgf_value& v = c < r->nkeys ? r->keys[(row + i) * r->nkeys + c] : r->aggs[(row + i) * r->naggs + (c - r->nkeys)];
         if (v.kind == PGF_V_NULL) {
+          if (!schema[c].nullable) return PGF_ERR_INVALID_ARGUMENT;   // a NULL in a column declared NOT NULL
           std::memset(values.data() + size_t(i) * w, 0, w);
         } else {
           validity[i >> 3] |= uint8_t(1u << (i & 7));
@@ -812,6 +839,8 @@ pgf_status pgf_result_encode_pages(const pgf_result* r, uint32_t page_size, uint
   return PGF_OK;
 }
 
+uint32_t pgf_partition_of_key(int64_t key, uint32_t world) { return world ? join_partition(key, world) : 0u; }
+
 pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
   if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
   auto it = ctx->joins.find(join_table);
@@ -819,6 +848,7 @@ pgf_status pgf_join_table_destroy(pgf_ctx* ctx, uint64_t join_table) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->compute_stream);
   ctx->join_free(it->second.d_slots, it->second.alloc_bytes);   // recycled by the next build of a similar size
+  ctx->join_free(it->second.d_rows, it->second.rows_alloc_bytes);
   ctx->joins.erase(it);
   return PGF_OK;
 }

@@ -49,6 +49,8 @@ struct BloomSlot {
 };
 
 struct JoinTable {
+  uint4* d_rows = nullptr;  // dense build rows (row sets: PGF_BUILD_ROWS_ONLY / PGF_XCHG_ROWS_ONLY); d_slots is null then
+  size_t rows_alloc_bytes = 0;
   uint4* d_slots = nullptr;
   size_t alloc_bytes = 0;   // size of the allocation behind d_slots (recycled through pgf_ctx::join_cache)
   uint32_t capacity = 0;
@@ -57,6 +59,7 @@ struct JoinTable {
   int32_t key_type = 0;
   uint32_t npayload = 0;
   int32_t payload_type[4] = {0, 0, 0, 0};
+  uint8_t payload_nullable[4] = {1, 1, 1, 1};   // nullability of the build-side column behind each payload
   uint16_t payload_word[4] = {0, 0, 0, 0};
 };
 
@@ -123,6 +126,11 @@ struct pgf_ctx {
     }
     join_cache.push_back(CachedBuf{p, bytes});
   }
+  // multi-GPU: NCCL communicator of this rank (comm.cpp) and grow-only exchange scratch
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+  uint8_t* d_xchg = nullptr;
+  size_t d_xchg_cap = 0;
   std::map<uint64_t, std::unique_ptr<pgf::Scan>> scans;
   std::map<uint64_t, pgf::BloomSlot> blooms;
   std::map<uint64_t, pgf::JoinTable> joins;
@@ -190,6 +198,12 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
 pgf_status join_export(pgf_ctx* ctx, const JoinTable& jt, void* dev_rows_out, uint64_t capacity_rows, uint64_t* rows_out);
 pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* dev_rows, uint64_t stride_bytes,
                                const uint64_t* counts, uint32_t nfragments, uint64_t* table_out);
+pgf_status pipeline_run_sharded(pgf_ctx* ctx, const pgf_pipeline* plan, uint64_t max_groups, pgf_result** out);
+pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t* out_handle, uint64_t* nvlink_bytes);
+pgf_status comm_all_gather(pgf_ctx* ctx, const void* send, void* recv, uint64_t bytes);   // compute stream, not synchronised
+pgf_status comm_all_to_all_v(pgf_ctx* ctx, const void* send, const uint64_t* send_off, const uint64_t* send_bytes, void* recv,
+                             const uint64_t* recv_off, const uint64_t* recv_bytes);
+void comm_release(pgf_ctx* ctx);
 pgf_status gen_scan(pgf_ctx* ctx, uint64_t scan_id, const pgf_gen_spec* spec);
 pgf_status gen_schema(int32_t table, pgf_column_spec* schema, uint32_t* ncols);
 }  // namespace pgf

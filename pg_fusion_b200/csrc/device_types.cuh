@@ -39,7 +39,7 @@ struct DevBloom {
 };
 
 // ---- pipeline plan -----------------------------------------------------------------
-enum : uint8_t { SRC_PAGE = 0 };  // 1.. = payload of join (src - 1)
+enum : uint8_t { SRC_PAGE = 0, kSrcRecord = 3 };  // 1, 2 = payload of join (src - 1); 3 = the scanned row of a row-set scan
 enum : uint8_t { CLS_F64 = 0, CLS_I64 = 1, CLS_I128 = 2 };
 
 struct DevStageCol {
@@ -123,6 +123,15 @@ __host__ __device__ __forceinline__ uint64_t join_hash(int64_t key) {
   const uint32_t lo = uint32_t(uint64_t(key)), hi = uint32_t(uint64_t(key) >> 32);
   return uint64_t(lo ^ (hi * 0x85EBCA6Bu)) * 0x9E3779B97F4A7C15ull;
 }
+// owner rank of a key in a hash-partitioned exchange: bits of a second multiplicative hash, independent of the
+// bits that place the key inside its owner's table
+__host__ __device__ __forceinline__ uint32_t join_partition(int64_t key, uint32_t world) {
+  const uint32_t lo = uint32_t(uint64_t(key)), hi = uint32_t(uint64_t(key) >> 32);
+  uint64_t h = uint64_t(lo ^ (hi * 0x85EBCA6Bu)) * 0xD6E8FEB86659FD93ull;
+  h ^= h >> 32;
+  h *= 0xD6E8FEB86659FD93ull;
+  return uint32_t(h >> 40) % world;
+}
 __host__ __device__ __forceinline__ uint32_t join_home(uint64_t h, uint32_t shift) { return uint32_t(h >> shift) & ~(kJoinBucket - 1u); }
 __host__ __device__ __forceinline__ uint32_t join_tag8(uint64_t h, uint32_t shift) {
   const uint32_t b = uint32_t(h >> (shift - 5u)) & 0xFFu;
@@ -178,6 +187,9 @@ struct DevPlan {
   DevStageCol scol[kMaxStageCols];
 
   uint32_t nbloom, nterms, njoins, sink;
+  // compaction pipeline: 1 = bloom[0] is keyed on the column the queue entries carry (the first probe key, or its
+  // own key when there is no join) and is probed AFTER the predicate, on dense lanes (stage B)
+  uint32_t bloom_dense, pad2;
   DevBloomProbe bloom[kMaxBlooms];
   DevTerm terms[kMaxTerms];
   DevJoin joins[kMaxJoins];
@@ -197,6 +209,10 @@ struct DevPlan {
   // arrival counter of the fixed-order cross-CTA reduction
   uint64_t* cta_rec;
   uint32_t* cta_done;
+  // row-set scans (rows_pipeline_kernel): dense rows in build-row format instead of pages
+  const uint4* row_src;
+  uint64_t row_count;
+  uint32_t row_u4, pad1;
 
   Counters* counters;
 };

@@ -20,6 +20,7 @@ cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t 
                             const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
 // implemented in pipeline_inst_probe.cu: the compaction pipeline (joins, build sinks)
 cudaError_t launch_probe(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_rows(uint32_t acc, const DevPlan& plan, uint32_t grid, cudaStream_t stream);
 
 namespace {
 
@@ -172,6 +173,48 @@ __global__ void join_build_kernel(uint4* slots, uint8_t* tags, uint32_t mask, ui
       }
       i = (i + 1) & mask;
     }
+  }
+}
+
+// ---- hash-partitioned exchange: rows grouped by owner rank = join_partition(key) --------
+// pass 1 counts the rows of every destination, pass 2 scatters them behind per-destination cursors (block-local
+// counts first, one atomic per block and destination).
+constexpr uint32_t kMaxRanks = 16;
+__global__ void partition_count_kernel(const uint4* rows, uint64_t nrows, uint32_t row_u4, uint32_t world, unsigned long long* counts) {
+  __shared__ uint32_t s_cnt[kMaxRanks];
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < nrows; r += uint64_t(gridDim.x) * blockDim.x) {
+    const uint4 s0 = rows[r * row_u4];
+    atomicAdd(&s_cnt[join_partition(int64_t((uint64_t(s0.y) << 32) | s0.x), world)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < world && s_cnt[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]);
+}
+__global__ void partition_scatter_kernel(const uint4* rows, uint64_t nrows, uint32_t row_u4, uint32_t world, unsigned long long* cursors,
+                                         uint4* out) {
+  __shared__ uint32_t s_cnt[kMaxRanks];
+  __shared__ unsigned long long s_base[kMaxRanks];
+  const uint64_t per_block = (nrows + gridDim.x - 1) / gridDim.x;
+  const uint64_t b0 = blockIdx.x * per_block, b1 = b0 + per_block < nrows ? b0 + per_block : nrows;
+  if (threadIdx.x < kMaxRanks) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (uint64_t r = b0 + threadIdx.x; r < b1; r += blockDim.x) {
+    const uint4 s0 = rows[r * row_u4];
+    atomicAdd(&s_cnt[join_partition(int64_t((uint64_t(s0.y) << 32) | s0.x), world)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < world) {
+    s_base[threadIdx.x] = s_cnt[threadIdx.x] ? atomicAdd(cursors + threadIdx.x, (unsigned long long)s_cnt[threadIdx.x]) : 0ull;
+    s_cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  for (uint64_t r = b0 + threadIdx.x; r < b1; r += blockDim.x) {
+    const uint4 s0 = rows[r * row_u4];
+    const uint32_t d = join_partition(int64_t((uint64_t(s0.y) << 32) | s0.x), world);
+    const unsigned long long pos = s_base[d] + atomicAdd(&s_cnt[d], 1u);
+    out[pos * row_u4] = s0;
+    if (row_u4 == 2) out[pos * 2 + 1] = rows[r * 2 + 1];
   }
 }
 
@@ -362,9 +405,12 @@ struct Lowered {
   uint32_t nj = 0;
   uint32_t maxe = 2;
   size_t smem = 0;
+  bool rowscan = false;     // scans a row set (rows_pipeline_kernel) instead of pages
+  Scan row_scan;            // its stand-in scan: schema = [key, payload...], rows = rows of the set
   bool probe = false;       // runs the compaction pipeline (probe_kernel.cuh): joins and build sinks
   int t0 = -1;              // its predicate specialisation (LD_* of the single plain range term), -1 = generic
   int32_t key_types[4] = {0, 0, 0, 0};
+  bool key_not_null[4] = {false, false, false, false};
   uint32_t expr_pos[kMaxExprs] = {0, 1, 2, 3, 4, 5, 6, 7};  // device position of the caller's expression e
   JoinTable build_table{};
   uint64_t table_capacity = 0;
@@ -401,9 +447,26 @@ class Lowering {
 
   pgf_status run(Lowered* out) {
     L_ = out;
+    if (plan_->scan_row_set) {
+      // the pipeline reads a row set (the output of a build sink with PGF_BUILD_ROWS_ONLY or of an exchange):
+      // column 0 is the key, column i + 1 payload i
+      auto rt = ctx_->joins.find(plan_->scan_row_set);
+      if (rt == ctx_->joins.end() || !rt->second.d_rows) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown row set %llu", (unsigned long long)plan_->scan_row_set);
+      if (plan_->nterms || plan_->nbloom) return not_eligible("row-set scans carry no predicate terms or Bloom probes");
+      const JoinTable& rs = rt->second;
+      rowset_ = &rs;
+      L_->rowscan = true;
+      L_->row_scan.schema.push_back(pgf_column_spec{uint16_t(rs.key_type), 0});
+      for (uint32_t p = 0; p < rs.npayload; ++p) L_->row_scan.schema.push_back(pgf_column_spec{uint16_t(rs.payload_type[p]), rs.payload_nullable[p]});
+      L_->row_scan.rows = rs.rows;
+      L_->row_scan.finished = true;
+      L_->dev.row_src = rs.d_rows;
+      L_->dev.row_count = rs.rows;
+      L_->dev.row_u4 = rs.slot_u4;
+    }
     auto it = ctx_->scans.find(plan_->scan_id);
-    if (it == ctx_->scans.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)plan_->scan_id);
-    Scan& s = *it->second;
+    if (!L_->rowscan && it == ctx_->scans.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)plan_->scan_id);
+    Scan& s = L_->rowscan ? L_->row_scan : *it->second;
     if (!s.finished) return ctx_->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)plan_->scan_id);
     L_->scan = &s;
     DevPlan& D = L_->dev;
@@ -413,7 +476,7 @@ class Lowering {
     // Pipelines with a join probe or a build sink run the compaction kernel: only the predicate
     // columns, the Bloom keys and the first probe key are staged; everything a surviving row needs
     // later is read from the page in HBM (late refs).
-    probe_ = plan_->njoins > 0 || plan_->sink == PGF_SINK_JOIN_BUILD;
+    probe_ = plan_->njoins > 0 || plan_->sink == PGF_SINK_JOIN_BUILD || L_->rowscan;
     L_->probe = probe_;
 
     // joins first: payload refs need the tables
@@ -421,6 +484,7 @@ class Lowering {
       auto jt = ctx_->joins.find(plan_->joins[j].join_table);
       if (jt == ctx_->joins.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table %llu", (unsigned long long)plan_->joins[j].join_table);
       jtables_[j] = &jt->second;
+      if (!jt->second.d_slots) return ctx_->fail(PGF_ERR_STATE, "join input %llu is a row set: it has no hash table to probe", (unsigned long long)plan_->joins[j].join_table);
     }
     for (uint32_t j = 0; j < plan_->njoins; ++j) {
       DevJoin& dj = D.joins[j];
@@ -430,7 +494,7 @@ class Lowering {
       dj.slot_u4 = jtables_[j]->slot_u4;
       dj.shift = 64;
       for (uint32_t c = jtables_[j]->capacity; c > 1; c >>= 1) dj.shift--;
-      PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key, /*late=*/j > 0));
+      PGF_TRY(lower_ref(plan_->joins[j].probe_key, j, &dj.key, /*late=*/j > 0 || L_->rowscan));
       if (!is_int_type(dj.key.type)) return not_eligible("join keys must be Int16/Int32/Int64");
     }
     D.njoins = plan_->njoins;
@@ -495,7 +559,21 @@ class Lowering {
           for (uint32_t t = 0; t < D.nterms; ++t) D.terms[t] = orig[t];
       }
     }
-    if (probe_) {
+    if (probe_ && !L_->rowscan && D.nbloom) {
+      // A runtime filter keyed on the column the compacted entries carry is probed after the predicate, on dense
+      // lanes: a Bloom probe costs ~120 instructions, so it should only see rows the predicate kept.  Put it first.
+      const int want = D.njoins ? int(D.joins[0].key.pcol) : -1;
+      for (uint32_t b = 0; b < D.nbloom; ++b) {
+        if (want < 0 || int(D.bloom[b].key.pcol) == want) {
+          std::swap(D.bloom[0], D.bloom[b]);
+          D.bloom_dense = 1;
+          break;
+        }
+      }
+    }
+    if (L_->rowscan) {
+      D.nitems = s.rows ? 1 : 0;
+    } else if (probe_) {
       PGF_TRY(layout_stage_probe(s));
       if (D.nterms == 1 && D.terms[0].op == TERM_IN_RANGE && D.used_null_mask == 0 && D.terms[0].ref.ld == LD_VIEW) L_->t0 = LD_VIEW;
     } else {
@@ -613,6 +691,15 @@ class Lowering {
       if (r.col < 0 || size_t(r.col) >= s.schema.size()) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "column %d out of range", r.col);
       const int type = s.schema[r.col].type_tag;
       if (row_width(type) == 0 || type == PGF_T_UUID) return not_eligible("Boolean / Uuid columns are not evaluated on the GPU path");
+      if (L_->rowscan) {  // a column of the scanned row: word 0..1 = key, 3 + payload word = payload (GRow::rec)
+        out->src = kSrcRecord;
+        out->ld = ld_kind(type);
+        out->type = uint8_t(type);
+        out->pcol = uint8_t(r.col == 0 ? 30 : r.col - 1);   // bit 1 + pcol of the row's flag word says NULL; the key never is
+        out->off = r.col == 0 ? 0u : 3u + rowset_->payload_word[r.col - 1];
+        out->valid_off = kNoValidity;
+        return PGF_OK;
+      }
       if (late && probe_) {
         out->src = SRC_PAGE;
         out->ld = ld_kind(type);
@@ -655,6 +742,12 @@ class Lowering {
     out->off = jt.payload_word[r.col];
     out->valid_off = kNoValidity;
     return PGF_OK;
+  }
+
+  // Is the value behind a column reference declared NOT NULL?  (scan column, or build-side column of a join)
+  bool ref_not_null(const pgf_colref& r) const {
+    if (r.source == 0) return !L_->scan->schema[r.col].nullable;
+    return !jtables_[r.source - 1]->payload_nullable[r.col];
   }
 
   void fix_ref(DevRef* ref) {
@@ -834,6 +927,7 @@ class Lowering {
       kp.word = uint16_t(words);
       words += kp.nwords;
       L_->key_types[k] = t;
+      L_->key_not_null[k] = ref_not_null(plan_->keys[k]);
     }
     if (words > kKeyWords) return not_eligible("group key wider than 32 bytes");
     D.nkeys = plan_->nkeys;
@@ -868,6 +962,7 @@ class Lowering {
       jb.payload_word[p] = uint16_t(words);
       jb.payload_nwords[p] = uint16_t(w);
       jt.payload_type[p] = jb.payload[p].type;
+      jt.payload_nullable[p] = ref_not_null(plan_->payload[p]) ? 0 : 1;
       jt.payload_word[p] = uint16_t(words);
       words += w;
     }
@@ -964,28 +1059,32 @@ class Lowering {
     return PGF_OK;
   }
 
-  // Stage ring of the compaction pipeline: whole pages when three of them fit next to the per-warp
-  // queues, else row tiles; as deep as shared memory allows (up to kPMaxStages).
+  // Per-warp tile rings of the compaction pipeline: tiles of 128 rows (fewer when the staged row is
+  // wide), as deep as the warp's share of shared memory allows (2 .. kPMaxDepth tiles in flight).
   pgf_status layout_stage_probe(Scan& s) {
     DevPlan& D = L_->dev;
     const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
-    const uint32_t budget = 227u * 1024u - probe_shared_bytes() - uint32_t(kPConsumerWarps) * kPQueueBytesPerWarp;
-    uint32_t gran = 16;
-    for (uint32_t c = 0; c < D.nstage_cols; ++c)
-      if (D.scol[c].nullable) gran = 128;
-    auto shape = [&](uint32_t ntiles, uint32_t* tile_rows_out, uint32_t* stage_bytes_out) {
-      const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + gran - 1) / gran * gran;
-      uint32_t stage_bytes = 0;
-      for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += tile_rows * D.scol[c].width + (D.scol[c].nullable ? tile_rows / 8 : 0u);
-      *tile_rows_out = tile_rows;
-      *stage_bytes_out = std::max(128u, (stage_bytes + 127u) & ~127u);
+    const uint32_t budget = ((227u * 1024u - probe_shared_bytes()) / uint32_t(kPConsumerWarps) - kPQueueBytesPerWarp) & ~127u;
+    bool nullable = false;
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) nullable |= D.scol[c].nullable != 0;
+    auto stage_bytes_for = [&](uint32_t tile_rows) {
+      uint32_t b = 0;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) b += tile_rows * D.scol[c].width + (D.scol[c].nullable ? tile_rows / 8 : 0u);
+      return std::max(128u, (b + 127u) & ~127u);
     };
-    uint32_t tile_rows = 0, stage_bytes = 0, ntiles = 1;
-    for (;; ++ntiles) {
-      shape(ntiles, &tile_rows, &stage_bytes);
-      if (stage_bytes * 3u <= budget) break;
-      if (tile_rows <= gran) return not_eligible("row too wide for the shared-memory stages");
+    // Tile = the largest multiple of 32 rows (of 128 with a staged validity bitmap: its slices must start 16-byte
+    // aligned) up to 256 of which two stages fit the warp's share: the per-tile work (barrier, descriptor, bulk-copy
+    // issue) is amortised over more rows, and two tiles in flight per warp x 16-20 warps cover the HBM latency.
+    const uint32_t step = nullable ? 128u : 32u;
+    uint32_t tile_rows = 256;
+    if (const char* e = std::getenv("PGF_PROBE_TILE_ROWS")) tile_rows = std::max<uint32_t>(step, uint32_t(std::atoi(e)) / step * step);   // experiments
+    while (tile_rows > step && stage_bytes_for(tile_rows) * 2u > budget) tile_rows -= step;
+    if (stage_bytes_for(tile_rows) * 2u > budget) {
+      if (nullable) return not_eligible("row too wide for the shared-memory stages");
+      tile_rows = 16;
+      if (stage_bytes_for(tile_rows) * 2u > budget) return not_eligible("row too wide for the shared-memory stages");
     }
+    const uint32_t stage_bytes = stage_bytes_for(tile_rows);
     uint32_t off = 0;
     for (uint32_t c = 0; c < D.nstage_cols; ++c) {
       D.scol[c].smem_off = off;
@@ -995,7 +1094,8 @@ class Lowering {
       D.scol[c].valid_off = off;
       if (D.scol[c].nullable) off += tile_rows / 8;
     }
-    D.nstages = std::min<uint32_t>(kPMaxStages, budget / stage_bytes);
+    D.nstages = std::min<uint32_t>(kPMaxDepth, budget / stage_bytes);
+    if (const char* e = std::getenv("PGF_PROBE_DEPTH")) D.nstages = std::min<uint32_t>(D.nstages, std::max(2, std::atoi(e)));
     D.tile_rows = tile_rows;
     D.tiles_per_page = (max_rows + tile_rows - 1) / tile_rows;
     D.stage_bytes = stage_bytes;
@@ -1006,13 +1106,14 @@ class Lowering {
     D.descs = s.d_descs;
     D.classes = s.d_classes;
     D.page_stride = ctx_->page_size;
-    L_->smem = probe_shared_bytes() + size_t(D.nstages) * D.stage_bytes + size_t(kPConsumerWarps) * kPQueueBytesPerWarp;
+    L_->smem = probe_shared_bytes() + size_t(kPConsumerWarps) * (size_t(D.nstages) * D.stage_bytes + kPQueueBytesPerWarp);
     return PGF_OK;
   }
 
   pgf_ctx* ctx_;
   const pgf_pipeline* plan_;
   bool probe_ = false;
+  const JoinTable* rowset_ = nullptr;
   Lowered* L_ = nullptr;
   JoinTable* jtables_[kMaxJoins] = {nullptr, nullptr};
   int expr_cls_[kMaxExprs] = {0};
@@ -1053,7 +1154,10 @@ pgf_status build_result(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L
   res->ngroups = n;
   res->nkeys = plan->nkeys;
   res->naggs = plan->naggs;
-  for (uint32_t k = 0; k < plan->nkeys; ++k) res->key_type[k] = L.key_types[k];
+  for (uint32_t k = 0; k < plan->nkeys; ++k) {
+    res->key_type[k] = L.key_types[k];
+    res->key_not_null[k] = L.key_not_null[k] ? 1 : 0;
+  }
   for (uint32_t a = 0; a < plan->naggs; ++a) {
     const pgf_agg& ag = plan->aggs[a];
     res->agg_func[a] = ag.func;
@@ -1341,11 +1445,13 @@ pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, u
 // Launch the fused kernel the lowering chose: the compaction pipeline, a registered shape, or the generic
 // streaming instantiation.
 cudaError_t launch_fused(const Lowered& L, uint32_t grid, cudaStream_t stream) {
+  if (L.rowscan) return launch_rows(L.acc_cls, L.dev, grid, stream);
   if (L.probe) return launch_probe(L.acc_cls, L.t0, L.dev, grid, L.smem, stream);
   if (const ShapeEntry* se = pick_shape(L)) return se->fn(L.dev, grid, L.smem, stream);
   return launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, stream);
 }
 const char* variant_name(const Lowered& L) {
+  if (L.rowscan) return "row_set_scan";
   if (L.probe) return L.t0 == LD_VIEW ? "compact_1_string_term" : "compact_generic";
   const ShapeEntry* se = pick_shape(L);
   return se ? se->name : "generic";
@@ -1366,9 +1472,11 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   }
   if (check_only) return PGF_OK;
   if (partial && plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
-  PGF_TRY(scan_sync_descs(ctx, *L.scan));
-  L.dev.descs = L.scan->d_descs;
-  L.dev.classes = L.scan->d_classes;
+  if (!L.rowscan) {
+    PGF_TRY(scan_sync_descs(ctx, *L.scan));
+    L.dev.descs = L.scan->d_descs;
+    L.dev.classes = L.scan->d_classes;
+  }
 
   pgf_result* res = new (std::nothrow) pgf_result();
   if (!res) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "result allocation failed");
@@ -1382,6 +1490,9 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
   uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
+  if (L.probe)  // the compaction pipeline deals tiles to warps: one CTA per SM while every warp has a tile
+    grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((uint64_t(L.dev.nitems) + kPConsumerWarps - 1) / kPConsumerWarps, 1), uint64_t(ctx->sm_count)));
+  if (L.rowscan) grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((L.dev.row_count + 255) / 256, 1), uint64_t(ctx->sm_count) * 8));
   uint64_t capacity = L.table_capacity;
   float total_ms = 0.f;
   uint32_t launches = 0;
@@ -1458,6 +1569,14 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
         continue;
       }
       JoinTable& jt = L.build_table;
+      jt.rows = nrows;
+      if (plan->build_flags & PGF_BUILD_ROWS_ONLY) {  // the row set is the result: no hash table
+        jt.d_rows = static_cast<uint4*>(rowbuf.p);
+        jt.rows_alloc_bytes = rowbuf.bytes;
+        rowbuf.p = nullptr;
+        jt.capacity = 0;
+        break;
+      }
       uint64_t cap = 1024;
       while (cap < nrows * 2) cap <<= 1;
       if (cap > (1ull << 31)) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "join build side too large for one table");
@@ -1557,7 +1676,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   std::snprintf(res->variant, sizeof res->variant, "%s", variant_name(L));
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     JoinTable jt = L.build_table;
-    mem.release(jt.d_slots);
+    if (jt.d_slots) mem.release(jt.d_slots);
     const uint64_t id = ctx->next_handle++;
     ctx->joins[id] = jt;
     res->join_table = id;
@@ -1582,9 +1701,11 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
   Lowered L;
   Lowering low(ctx, plan);
   PGF_TRY(low.run(&L));
-  PGF_TRY(scan_sync_descs(ctx, *L.scan));
-  L.dev.descs = L.scan->d_descs;
-  L.dev.classes = L.scan->d_classes;
+  if (!L.rowscan) {
+    PGF_TRY(scan_sync_descs(ctx, *L.scan));
+    L.dev.descs = L.scan->d_descs;
+    L.dev.classes = L.scan->d_classes;
+  }
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
   if (state_cap < (1 + uint64_t(ew)) * 8) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial state buffer too small");
@@ -1593,7 +1714,10 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
   PGF_TRY(arena_table(ctx, L.table_capacity, plan->nexprs, aw, &ta));
   L.dev.table = ta.t;
   L.dev.counters = &ta.d_header->counters;
-  const uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
+  uint32_t grid = uint32_t(std::min<uint64_t>(L.dev.npages ? L.dev.npages : 1, uint64_t(ctx->sm_count)));  // CTAs take whole pages
+  if (L.probe)
+    grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((uint64_t(L.dev.nitems) + kPConsumerWarps - 1) / kPConsumerWarps, 1), uint64_t(ctx->sm_count)));
+  if (L.rowscan) grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((L.dev.row_count + 255) / 256, 1), uint64_t(ctx->sm_count) * 8));
   L.dev.build_count = &ta.d_header->build_rows;
   L.dev.cta_rec = ta.d_cta_rec;
   L.dev.cta_done = &ta.d_header->cta_done;
@@ -1804,6 +1928,193 @@ pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* 
   const uint64_t id = ctx->next_handle++;
   ctx->joins[id] = jt;
   *table_out = id;
+  return PGF_OK;
+}
+
+namespace {
+pgf_status xchg_reserve(pgf_ctx* ctx, size_t bytes) {
+  if (ctx->d_xchg_cap >= bytes) return PGF_OK;
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+  ctx->d_xchg = nullptr;
+  ctx->d_xchg_cap = 0;
+  const size_t want = align_up(bytes + bytes / 4, 1 << 16);
+  void* p = nullptr;
+  if (cudaMalloc(&p, want) != cudaSuccess) {
+    cudaGetLastError();
+    return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate %zu bytes of exchange scratch", want);
+  }
+  ctx->d_xchg = static_cast<uint8_t*>(p);
+  ctx->d_xchg_cap = want;
+  return PGF_OK;
+}
+
+// hash table over dense rows (caller holds ctx->mu); `rows` may be freed once the stream has passed the build
+pgf_status table_from_rows(pgf_ctx* ctx, const JoinTable& like, const uint4* rows, uint64_t nrows, JoinTable* out) {
+  uint64_t cap = 1024;
+  while (cap < nrows * 2) cap <<= 1;
+  if (cap > (1ull << 31)) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "join build side too large for one table");
+  JoinTable jt = like;
+  jt.d_rows = nullptr;
+  jt.rows_alloc_bytes = 0;
+  jt.capacity = uint32_t(cap);
+  jt.rows = nrows;
+  const uint64_t slot_bytes = cap * jt.slot_u4 * sizeof(uint4), tag_bytes = cap + 16;
+  jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
+  if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
+  cudaError_t e = cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream);
+  if (e == cudaSuccess && nrows) {
+    uint32_t shift = 64;
+    for (uint64_t c = cap; c > 1; c >>= 1) shift--;
+    const uint32_t grid = uint32_t(std::min<uint64_t>((nrows + 255) / 256, uint64_t(ctx->sm_count) * 8));
+    join_build_kernel<<<grid, 256, 0, ctx->compute_stream>>>(jt.d_slots, reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes, jt.capacity - 1, shift,
+                                                              jt.slot_u4, rows, nrows);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    ctx->join_free(jt.d_slots, jt.alloc_bytes);
+    return ctx->cuda_fail(e, "table_from_rows", __FILE__, __LINE__);
+  }
+  *out = jt;
+  return PGF_OK;
+}
+}  // namespace
+
+// AggregateExec Partial -> all-gather -> Final in one call (the collectives stay behind the C ABI).
+pgf_status pipeline_run_sharded(pgf_ctx* ctx, const pgf_pipeline* plan, uint64_t max_groups, pgf_result** out) {
+  if (ctx->comm_world == 1) return pipeline_run(ctx, plan, false, nullptr, 0, nullptr, false, out);
+  if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "pgf_pipeline_run_sharded runs aggregate sinks");
+  uint64_t state_bytes = 0;
+  PGF_TRY(pgf_partial_state_bytes(plan, max_groups ? max_groups : 1, &state_bytes));
+  state_bytes = align_up(state_bytes, 16);
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    CU(ctx, cudaSetDevice(ctx->device));
+    PGF_TRY(xchg_reserve(ctx, state_bytes * (size_t(ctx->comm_world) + 1)));
+  }
+  uint8_t* mine = ctx->d_xchg;
+  uint8_t* all = ctx->d_xchg + state_bytes;
+  PGF_TRY(pipeline_run_partial_async(ctx, plan, mine, state_bytes));
+  {
+    std::lock_guard<std::mutex> g(ctx->mu);
+    PGF_TRY(comm_all_gather(ctx, mine, all, state_bytes));
+  }
+  return pipeline_merge(ctx, plan, all, state_bytes, uint32_t(ctx->comm_world), true, out);
+}
+
+// Join exchange over NCCL: broadcast (all-gather of every rank's rows) or hash partition (all-to-all).
+pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t* out_handle, uint64_t* nvlink_bytes) {
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  auto it = ctx->joins.find(handle);
+  if (it == ctx->joins.end()) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown join table / row set %llu", (unsigned long long)handle);
+  const JoinTable src = it->second;
+  const uint32_t world = uint32_t(ctx->comm_world), rank = uint32_t(ctx->comm_rank);
+  if (world > kMaxRanks) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "at most %u ranks", kMaxRanks);
+  const bool partition = (mode & 3u) == PGF_XCHG_PARTITION, rows_only = (mode & PGF_XCHG_ROWS_ONLY) != 0;
+  const uint64_t row_bytes = uint64_t(src.slot_u4) * sizeof(uint4);
+  cudaStream_t st = ctx->compute_stream;
+  struct Buf {
+    pgf_ctx* ctx;
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~Buf() { if (p) ctx->join_free(p, bytes); }
+    bool alloc(size_t n) { p = ctx->join_alloc(n ? n : 16, &bytes); return p != nullptr; }
+    void* release() { void* q = p; p = nullptr; return q; }
+  };
+  // 1. this rank's rows, dense
+  Buf exported{ctx};
+  const uint4* rows = src.d_rows;
+  uint64_t nrows = src.rows;
+  unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(ctx->d_flags + 4);   // [kMaxRanks] counters / cursors
+  unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 4);
+  if (!rows) {
+    if (!exported.alloc(nrows * row_bytes)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: row buffer");
+    CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, st));
+    const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(src.capacity) + kExtractThreads - 1) / kExtractThreads, uint64_t(ctx->sm_count) * 8));
+    join_export_kernel<<<grid, kExtractThreads, 0, st>>>(src.d_slots, src.capacity, src.slot_u4, static_cast<uint4*>(exported.p), nrows, d_cnt);
+    CU(ctx, cudaGetLastError());
+    rows = static_cast<const uint4*>(exported.p);
+  }
+  uint64_t sent = 0;
+  Buf recv{ctx};
+  uint64_t total = 0;
+  if (world == 1) {
+    if (!recv.alloc(nrows * row_bytes)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: row buffer");
+    CU(ctx, cudaMemcpyAsync(recv.p, rows, nrows * row_bytes, cudaMemcpyDeviceToDevice, st));
+    total = nrows;
+  } else if (!partition) {
+    // ---- broadcast: every rank's row count, then an all-gather of fragments padded to the largest
+    PGF_TRY(xchg_reserve(ctx, 8 * (size_t(world) + 1)));
+    CU(ctx, cudaMemcpyAsync(ctx->d_xchg, &nrows, 8, cudaMemcpyHostToDevice, st));
+    PGF_TRY(comm_all_gather(ctx, ctx->d_xchg, ctx->d_xchg + 8, 8));
+    std::vector<uint64_t> counts(world);
+    CU(ctx, cudaMemcpyAsync(counts.data(), ctx->d_xchg + 8, 8 * world, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    uint64_t mx = 0;
+    for (uint64_t c : counts) { mx = std::max(mx, c); total += c; }
+    Buf padded{ctx}, gathered{ctx};
+    if (!padded.alloc(mx * row_bytes) || !gathered.alloc(mx * row_bytes * world) || !recv.alloc(total * row_bytes))
+      return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: broadcast buffers");
+    CU(ctx, cudaMemcpyAsync(padded.p, rows, nrows * row_bytes, cudaMemcpyDeviceToDevice, st));
+    PGF_TRY(comm_all_gather(ctx, padded.p, gathered.p, mx * row_bytes));
+    uint64_t off = 0;
+    for (uint32_t r = 0; r < world; ++r) {   // compact the fragments (rank order)
+      if (counts[r]) CU(ctx, cudaMemcpyAsync(static_cast<uint8_t*>(recv.p) + off, static_cast<uint8_t*>(gathered.p) + uint64_t(r) * mx * row_bytes,
+                                             counts[r] * row_bytes, cudaMemcpyDeviceToDevice, st));
+      off += counts[r] * row_bytes;
+    }
+    sent = mx * row_bytes * (world - 1);
+    CU(ctx, cudaStreamSynchronize(st));   // padded / gathered go back to the cache
+  } else {
+    // ---- hash partition: count per owner, scatter into owner order, all-to-all
+    CU(ctx, cudaMemsetAsync(d_cnt, 0, 8 * kMaxRanks, st));
+    const uint32_t grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((nrows + 255) / 256, 1), uint64_t(ctx->sm_count) * 4));
+    if (nrows) partition_count_kernel<<<grid, 256, 0, st>>>(rows, nrows, src.slot_u4, world, d_cnt);
+    CU(ctx, cudaGetLastError());
+    PGF_TRY(xchg_reserve(ctx, 8 * kMaxRanks * (size_t(world) + 1)));
+    CU(ctx, cudaMemcpyAsync(ctx->d_xchg, d_cnt, 8 * kMaxRanks, cudaMemcpyDeviceToDevice, st));
+    PGF_TRY(comm_all_gather(ctx, ctx->d_xchg, ctx->d_xchg + 8 * kMaxRanks, 8 * kMaxRanks));
+    std::vector<uint64_t> matrix(size_t(world) * kMaxRanks);   // matrix[src][dst]
+    CU(ctx, cudaMemcpyAsync(matrix.data(), ctx->d_xchg + 8 * kMaxRanks, 8 * kMaxRanks * world, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    std::vector<uint64_t> soff(world), sbytes(world), roff(world), rbytes(world);
+    uint64_t so = 0, ro = 0;
+    for (uint32_t p = 0; p < world; ++p) {
+      soff[p] = so; sbytes[p] = matrix[size_t(rank) * kMaxRanks + p] * row_bytes; so += sbytes[p];
+      roff[p] = ro; rbytes[p] = matrix[size_t(p) * kMaxRanks + rank] * row_bytes; ro += rbytes[p];
+      if (p != rank) sent += sbytes[p];
+    }
+    total = ro / row_bytes;
+    Buf sendbuf{ctx};
+    if (!sendbuf.alloc(so) || !recv.alloc(ro)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: partition buffers");
+    for (uint32_t p = 0; p < world; ++p) h_cnt[p] = soff[p] / row_bytes;   // cursors start at the owners' offsets
+    CU(ctx, cudaMemcpyAsync(d_cnt, h_cnt, 8 * world, cudaMemcpyHostToDevice, st));
+    if (nrows) partition_scatter_kernel<<<grid, 256, 0, st>>>(rows, nrows, src.slot_u4, world, d_cnt, static_cast<uint4*>(sendbuf.p));
+    CU(ctx, cudaGetLastError());
+    PGF_TRY(comm_all_to_all_v(ctx, sendbuf.p, soff.data(), sbytes.data(), recv.p, roff.data(), rbytes.data()));
+    CU(ctx, cudaStreamSynchronize(st));   // the send buffer goes back to the cache
+  }
+  // 2. the output: a row set, or a hash table over the received rows
+  JoinTable outjt = src;
+  outjt.d_slots = nullptr;
+  outjt.alloc_bytes = 0;
+  outjt.capacity = 0;
+  outjt.d_rows = nullptr;
+  outjt.rows_alloc_bytes = 0;
+  outjt.rows = total;
+  if (rows_only) {
+    outjt.rows_alloc_bytes = recv.bytes;
+    outjt.d_rows = static_cast<uint4*>(recv.release());
+  } else {
+    PGF_TRY(table_from_rows(ctx, src, static_cast<const uint4*>(recv.p), total, &outjt));
+    CU(ctx, cudaStreamSynchronize(st));   // recv goes back to the cache
+  }
+  CU(ctx, cudaStreamSynchronize(st));   // every temporary of the exchange is idle before it returns to the cache
+  const uint64_t id = ctx->next_handle++;
+  ctx->joins[id] = outjt;
+  *out_handle = id;
+  if (nvlink_bytes) *nvlink_bytes = sent;
   return PGF_OK;
 }
 

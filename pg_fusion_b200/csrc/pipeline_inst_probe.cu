@@ -22,4 +22,13 @@ cudaError_t launch_probe(uint32_t acc, int t0, const DevPlan& plan, uint32_t gri
   }
 }
 
+cudaError_t launch_rows(uint32_t acc, const DevPlan& plan, uint32_t grid, cudaStream_t stream) {
+  switch (acc) {
+    case CLS_F64: rows_pipeline_kernel<CLS_F64><<<grid, 256, 0, stream>>>(plan); break;
+    case CLS_I64: rows_pipeline_kernel<CLS_I64><<<grid, 256, 0, stream>>>(plan); break;
+    default: rows_pipeline_kernel<CLS_I128><<<grid, 256, 0, stream>>>(plan); break;
+  }
+  return cudaGetLastError();
+}
+
 }  // namespace pgf

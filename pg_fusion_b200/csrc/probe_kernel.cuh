@@ -1,31 +1,34 @@
 // The fused scan pipeline for selective plans: anything with a HashJoinExec probe or a
 // HashJoinExec build sink (sm_100a).
 //
-// Same front end as pipeline_kernel.cuh (one persistent CTA per SM, one producer warp feeding a
-// shared-memory ring with TMA bulk copies + mbarrier transaction counts), but the consumer side is
-// organised around *selection-vector compaction* instead of per-thread predication:
+// One persistent CTA per SM, and inside it every warp is its own pipeline: it owns a private ring of
+// row tiles in shared memory which it fills itself with TMA bulk copies (cp.async.bulk + mbarrier
+// transaction counts, marked evict_first in L2) a few tiles ahead of where it reads.  There is no
+// producer warp and no CTA-wide barrier, so a warp that is busy in the rare, latency-heavy stage C
+// below never holds up the others.  The work of a warp is organised around *selection-vector
+// compaction* instead of per-thread predication:
 //
-//   stage A  filter      28 warps walk the staged tile 32 rows at a time: runtime Bloom probes and the
-//                        FilterExec conjuncts in registers, then ballot + prefix-popcount compaction of
-//                        the surviving (page, row, join key) triples into a per-warp queue in shared
-//                        memory.  Only the predicate columns and the probe key are staged at all.
-//   stage B  tag probe   whenever a warp's queue holds 32 survivors it pops them onto DENSE lanes,
-//                        hashes the keys and issues one aligned 8-byte load of the home bucket's tag
-//                        bytes (L2 resident directory, evict_last).  The loads stay in flight while
-//                        the warp goes back to stage A; they are resolved (SIMD-in-register byte
-//                        compares) just before the next batch is issued.  Tag hits are compacted into
-//                        a second per-warp queue.
-//   stage C  match+sink  32 tag hits at a time, again on dense lanes: walk the probe chain, compare
-//                        the slot keys (duplicates multiply, NULL keys never match), optionally probe
-//                        a second join table, and feed the sink.  Columns that only matched rows need
+//   stage A  filter      32 rows at a time from the staged tile: runtime Bloom probes and the FilterExec
+//                        conjuncts in registers, then ballot + prefix-popcount compaction of the surviving
+//                        (page, row, join key) triples into a per-warp queue in shared memory.  Only the
+//                        predicate columns and the probe key are staged at all.
+//   stage B  tag probe   whenever the queue holds 32 survivors they are popped onto DENSE lanes, hashed,
+//                        and one aligned 8-byte load of the home bucket's tag bytes is issued per lane (L2
+//                        resident directory, evict_last).  The loads stay in flight while the warp goes
+//                        back to stage A; they are resolved (SIMD-in-register byte compares) just before
+//                        the next batch is issued.  Tag hits are compacted into a second queue.
+//   stage C  match+sink  32 tag hits at a time, again on dense lanes: walk the probe chain, compare the
+//                        slot keys (duplicates multiply, NULL keys never match), optionally probe a
+//                        second join table, and feed the sink.  Columns that only matched rows need
 //                        (aggregate arguments, group keys, build payloads) are read straight from the
 //                        page in HBM here -- late materialisation: for TPC-H Q3's lineitem side that is
 //                        1 % of the rows, so 16 of the 36 algorithmic bytes per row never leave DRAM.
 //
-// Sinks: AggregateExec into the global group table (grouped) or warp-reduced into slot 0 (no GROUP
-// BY); HashJoinExec build side as a dense array of build rows (warp-aggregated append; the table is
-// built from the rows afterwards at exactly the capacity the row count asks for, see
-// join_build_kernel in pipeline.cu) [+ RuntimeFilterBuildExec]; row count.
+// Sinks: AggregateExec into the global group table (rows of one group inside a warp elect a leader with
+// match.any, so a group is looked up once per warp and batch) or warp-reduced into slot 0 (no GROUP BY);
+// HashJoinExec build side as a dense array of build rows (warp-aggregated append; the table is built
+// from the rows afterwards at exactly the capacity the row count asks for, see join_build_kernel in
+// pipeline.cu) [+ RuntimeFilterBuildExec]; row count.
 #pragma once
 #include "pipeline_kernel.cuh"
 
@@ -35,20 +38,21 @@ namespace pgf {
 #define PGF_PROBE_WARPS 20
 #endif
 constexpr int kPConsumerWarps = PGF_PROBE_WARPS;
-constexpr int kPThreads = (kPConsumerWarps + 1) * 32;
-constexpr uint32_t kPMaxStages = 6;
+constexpr int kPThreads = kPConsumerWarps * 32;
+constexpr uint32_t kPMaxDepth = 4;                                   // tiles in flight per warp
 constexpr uint32_t kPQueueEntries = 64;                              // per warp and queue; drained 32 at a time
 constexpr uint32_t kPQueueBytesPerWarp = 2u * kPQueueEntries * 16u;  // survivors + tag hits
 
 struct PStageMeta {
   uint32_t nrows, null_mask, page, r0;
 };
-struct ProbeShared {
-  uint64_t full[kPMaxStages];
-  uint64_t empty[kPMaxStages];
-  PStageMeta meta[kPMaxStages];
+struct PWarpCtl {  // one per warp
+  uint64_t full[kPMaxDepth];
+  PStageMeta meta[kPMaxDepth];
+  uint8_t pad[128 - kPMaxDepth * (8 + sizeof(PStageMeta))];
 };
-__host__ __device__ constexpr uint32_t probe_shared_bytes() { return uint32_t((sizeof(ProbeShared) + 127) & ~size_t(127)); }
+static_assert(sizeof(PWarpCtl) == 128, "per-warp control block");
+__host__ __device__ constexpr uint32_t probe_shared_bytes() { return uint32_t(kPConsumerWarps) * uint32_t(sizeof(PWarpCtl)); }
 
 // ---- L2 residency control: the page stream is read once (evict_first), the tag directories and the
 // group table are what should stay (evict_last)
@@ -96,6 +100,16 @@ __device__ __forceinline__ TagWindow scan_tags(uint2 w, uint32_t tag) {
   return r;
 }
 
+// Stage B only needs to know whether the window is worth a visit by stage C: some tag before the first empty one
+// equals `tag`, or the window holds no empty tag at all (the chain goes on in the next bucket).
+__device__ __forceinline__ bool window_may_match(uint2 w, uint32_t tag) {
+  const uint32_t t4 = tag * 0x01010101u;
+  const uint32_t z0 = zero_bytes(w.x), z1 = zero_bytes(w.y), m0 = zero_bytes(w.x ^ t4), m1 = zero_bytes(w.y ^ t4);
+  const uint32_t before0 = z0 ? (z0 & (0u - z0)) - 1u : 0xFFFFFFFFu;   // bytes of the low word before its first empty tag
+  const uint32_t before1 = z0 ? 0u : (z1 ? (z1 & (0u - z1)) - 1u : 0xFFFFFFFFu);
+  return ((m0 & before0) | (m1 & before1) | uint32_t((z0 | z1) == 0u)) != 0u;
+}
+
 // ---- a row of a page in HBM (stage C reads what it needs from there) ----------------------
 struct GRow {
   const uint8_t* page;
@@ -103,9 +117,10 @@ struct GRow {
   uint32_t r;
   uint32_t nulls;                  // page columns with nulls in this page (already masked by use)
   const uint32_t *pay0, *pay1;     // matched join slots (u32 words: key lo, key hi, occ, payload...)
-  uint32_t occ0, occ1;
-  __device__ __forceinline__ const uint32_t* pay(uint32_t src) const { return src == 1 ? pay0 : pay1; }
-  __device__ __forceinline__ uint32_t occ(uint32_t src) const { return src == 1 ? occ0 : occ1; }
+  const uint32_t* rec;             // row-set scans: the scanned row itself, same record format (source kSrcRecord)
+  uint32_t occ0, occ1, occr;
+  __device__ __forceinline__ const uint32_t* pay(uint32_t src) const { return src == 1 ? pay0 : (src == 2 ? pay1 : rec); }
+  __device__ __forceinline__ uint32_t occ(uint32_t src) const { return src == 1 ? occ0 : (src == 2 ? occ1 : occr); }
 };
 
 __device__ __forceinline__ bool g_valid(const DevRef& ref, const GRow& g) {
@@ -124,7 +139,7 @@ __device__ __forceinline__ int64_t g_i64(const DevRef& ref, const GRow& g) {
       default: return reinterpret_cast<const int64_t*>(p)[g.r];
     }
   }
-  const uint32_t* p = g.pay(ref.src) + 3 + ref.off;
+  const uint32_t* p = (ref.src == kSrcRecord ? g.rec + ref.off : g.pay(ref.src) + 3 + ref.off);
   switch (ref.ld) {
     case LD_I16: return int64_t(int16_t(__ldg(p)));
     case LD_I32: return int64_t(int32_t(__ldg(p)));
@@ -133,7 +148,7 @@ __device__ __forceinline__ int64_t g_i64(const DevRef& ref, const GRow& g) {
 }
 __device__ __forceinline__ uint4 g_u128(const DevRef& ref, const GRow& g) {
   if (ref.src == SRC_PAGE) return reinterpret_cast<const uint4*>(g.page + g.lc->values_off[ref.pcol])[g.r];
-  const uint32_t* p = g.pay(ref.src) + 3 + ref.off;
+  const uint32_t* p = (ref.src == kSrcRecord ? g.rec + ref.off : g.pay(ref.src) + 3 + ref.off);
   return make_uint4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
 }
 __device__ __forceinline__ double g_f64(const DevRef& ref, const GRow& g) {
@@ -143,7 +158,7 @@ __device__ __forceinline__ double g_f64(const DevRef& ref, const GRow& g) {
     if (ref.ld == LD_F32) return double(reinterpret_cast<const float*>(p)[g.r]);
     return double(g_i64(ref, g));  // AVG over integers runs on the Float64 cast
   }
-  const uint32_t* p = g.pay(ref.src) + 3 + ref.off;
+  const uint32_t* p = (ref.src == kSrcRecord ? g.rec + ref.off : g.pay(ref.src) + 3 + ref.off);
   if (ref.ld == LD_F64) return __longlong_as_double((long long)((uint64_t(__ldg(p + 1)) << 32) | __ldg(p)));
   if (ref.ld == LD_F32) return double(__uint_as_float(__ldg(p)));
   return double(g_i64(ref, g));
@@ -256,37 +271,92 @@ struct JoinIter {
 };
 
 // ---- sinks (stage C, dense lanes) -----------------------------------------------------------
+// group_slot() without waiting: -2 when the probe runs into a slot another thread is publishing.  The
+// caller retries from a converged point, so lanes of one warp never spin on each other.
+__device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uint64_t* key, uint32_t nwords, uint32_t knull, uint64_t h) {
+  uint32_t i = uint32_t(h) & t.mask;
+  const uint32_t ready = 2u | (knull << 8);
+  for (uint32_t probes = 0; probes <= t.mask; ++probes, i = (i + 1) & t.mask) {
+    uint32_t s = *reinterpret_cast<volatile uint32_t*>(t.state + i);
+    if (s == 0) {
+      const uint32_t old = atomicCAS(t.state + i, 0u, 1u);
+      if (old == 0) {
+#pragma unroll
+        for (uint32_t w = 0; w < kKeyWords; ++w)
+          if (w < nwords) t.keys[uint64_t(i) * kKeyWords + w] = key[w];
+        __threadfence();
+        atomicExch(t.state + i, ready);
+        atomicAdd(t.used, 1u);
+        return i;
+      }
+      s = old;
+    }
+    if ((s & 3u) == 1u) return -2;
+    if (s == ready) {
+      __threadfence();
+      bool same = true;
+#pragma unroll
+      for (uint32_t w = 0; w < kKeyWords; ++w)
+        if (w < nwords) same &= *reinterpret_cast<volatile uint64_t*>(t.keys + uint64_t(i) * kKeyWords + w) == key[w];
+      if (same) return i;
+    }
+  }
+  atomicExch(t.overflow, 1u);
+  return -1;
+}
+
+// Called by all 32 lanes; `found` lanes carry a row.  Rows of one group that meet in a batch (the
+// lineitems of an order are neighbours) elect a leader with match.any: one table lookup per group, warp
+// and batch, and no two lanes of a warp ever insert the same key.
 template <uint32_t ACC>
-__device__ __forceinline__ void sink_agg_grouped(const DevPlan& P, const GRow& g, uint32_t& bad) {
+__device__ __forceinline__ void sink_agg_grouped(const DevPlan& P, const GRow& g, bool found, uint32_t lane, uint32_t& bad) {
   using Ops = AccOps<ACC>;
   uint64_t key[kKeyWords] = {0, 0, 0, 0};
   uint32_t knull = 0;
+  if (found) {
 #pragma unroll
-  for (uint32_t kp = 0; kp < 4; ++kp) {
-    if (kp < P.nkeys) {
-      const DevKeyPart& part = P.keys[kp];
-      if (!g_valid(part.ref, g)) {
-        knull |= 1u << kp;  // NULL keys form one group; words stay zero
-      } else {
-        uint64_t w0, w1 = 0;
-        if (part.nwords == 1) {
-          w0 = uint64_t(g_i64(part.ref, g));
+    for (uint32_t kp = 0; kp < 4; ++kp) {
+      if (kp < P.nkeys) {
+        const DevKeyPart& part = P.keys[kp];
+        if (!g_valid(part.ref, g)) {
+          knull |= 1u << kp;  // NULL keys form one group; words stay zero
         } else {
-          const uint4 raw = g_u128(part.ref, g);
-          if (part.ref.ld == LD_VIEW && raw.x > 12u) ++bad;
-          w0 = (uint64_t(raw.y) << 32) | raw.x;
-          w1 = (uint64_t(raw.w) << 32) | raw.z;
-        }
+          uint64_t w0, w1 = 0;
+          if (part.nwords == 1) {
+            w0 = uint64_t(g_i64(part.ref, g));
+          } else {
+            const uint4 raw = g_u128(part.ref, g);
+            if (part.ref.ld == LD_VIEW && raw.x > 12u) ++bad;
+            w0 = (uint64_t(raw.y) << 32) | raw.x;
+            w1 = (uint64_t(raw.w) << 32) | raw.z;
+          }
 #pragma unroll
-        for (uint32_t w = 0; w < kKeyWords; ++w) {
-          if (w == part.word) key[w] = w0;
-          if (part.nwords == 2 && w == part.word + 1u) key[w] = w1;
+          for (uint32_t w = 0; w < kKeyWords; ++w) {
+            if (w == part.word) key[w] = w0;
+            if (part.nwords == 2 && w == part.word + 1u) key[w] = w1;
+          }
         }
       }
     }
   }
-  const int64_t slot = group_slot(P.table, key, P.nkeywords, knull);
-  if (slot < 0) return;
+  const uint64_t h = found ? key_hash(key, P.nkeywords, knull) : (0xFFFFFFFF00000000ull | lane);
+  const uint32_t peers = __match_any_sync(0xffffffffu, h);
+  const uint32_t leader = uint32_t(__ffs(int(peers))) - 1u;
+  bool same = __shfl_sync(0xffffffffu, knull, leader) == knull;
+#pragma unroll
+  for (uint32_t w = 0; w < kKeyWords; ++w) same &= __shfl_sync(0xffffffffu, key[w], leader) == key[w];
+  const bool own = found && (lane == leader || !same);  // (a hash collision inside the warp: that lane looks up its own key)
+  int64_t slot = -1;
+  bool todo = own;
+  while (__any_sync(0xffffffffu, todo)) {
+    if (todo) {
+      const int64_t s = group_slot_try(P.table, key, P.nkeywords, knull, h);
+      if (s != -2) { slot = s; todo = false; }
+    }
+  }
+  const int64_t lslot = __shfl_sync(0xffffffffu, slot, leader);
+  if (found && !own) slot = lslot;
+  if (!found || slot < 0) return;
   for (uint32_t e = 0; e < P.nexprs; ++e) {
     if (g_expr_valid(P.exprs[e], g)) {
       Ops::atomic_add(P.table.acc + (uint64_t(slot) * P.nexprs + e) * P.table.acc_words, g_eval<ACC>(P.exprs[e], g));
@@ -365,28 +435,41 @@ __device__ __forceinline__ void sink_build(const DevPlan& P, const GRow& g, bool
 // ---- stage C: n entries on dense lanes: probe chains, second join, sink ---------------------
 // (inlined at its single call site: an ABI call in the consumer loop makes ptxas keep the loop state on
 // the stack)
-template <uint32_t ACC>
-__device__ __forceinline__ void stage_c(const DevPlan& P, const uint4* q, uint32_t n, uint32_t lane, uint32_t& n_out, uint32_t& n_bad,
+// e: {page, row, key lo, key hi} of a page scan, or {row index lo, hi, key lo, key hi} of a row-set scan (ROWS).
+template <uint32_t ACC, bool ROWS = false>
+__device__ __forceinline__ void stage_c(const DevPlan& P, uint4 e, bool act, uint32_t lane, uint32_t& n_out, uint32_t& n_bad,
                                         uint32_t& n_bloom_ins) {
-  const bool act = lane < n;
-  uint4 e = make_uint4(0, 0, 0, 0);
-  if (act) e = q[lane];
-  __syncwarp();
   GRow g;
-  g.page = P.pages + uint64_t(e.x) * P.page_stride;
-  PageDesc d{};
-  if (act) d = P.descs[e.x];
-  g.lc = P.classes + d.layout_class;
-  g.r = e.y;
-  g.nulls = d.null_mask & P.used_null_mask;
-  g.pay0 = g.pay1 = nullptr;
-  g.occ0 = g.occ1 = 0;
+  g.pay0 = g.pay1 = g.rec = nullptr;
+  g.occ0 = g.occ1 = g.occr = 0;
+  if constexpr (ROWS) {
+    g.page = nullptr;
+    g.lc = nullptr;
+    g.r = 0;
+    g.nulls = 0;
+    g.rec = reinterpret_cast<const uint32_t*>(P.row_src + ((uint64_t(e.y) << 32) | e.x) * P.row_u4);
+    if (act) g.occr = __ldg(g.rec + 2);
+  } else {
+    g.page = P.pages + uint64_t(e.x) * P.page_stride;
+    PageDesc d{};
+    if (act) d = P.descs[e.x];
+    g.lc = P.classes + d.layout_class;
+    g.r = e.y;
+    g.nulls = d.null_mask & P.used_null_mask;
+  }
   JoinIter it0, it1;
   it0.cand = it1.cand = 0;
   it0.ended = it1.ended = true;
   it0.base = it0.tag = it0.klo = it0.khi = it1.base = it1.tag = it1.klo = it1.khi = 0;
   bool have0 = false;
-  if (P.njoins) it0.init(P.joins[0], int64_t((uint64_t(e.w) << 32) | e.z), act);
+  if (P.njoins) {
+    int64_t k0 = int64_t((uint64_t(e.w) << 32) | e.z);
+    bool v0 = act;
+    if constexpr (ROWS) {  // any column of the scanned row may be the probe key
+      if (act) { k0 = g_i64(P.joins[0].key, g); v0 = g_valid(P.joins[0].key, g); }
+    }
+    it0.init(P.joins[0], k0, v0);
+  }
   bool fresh = act;  // no join at all: every entry is emitted exactly once
   for (;;) {
     bool found = false;
@@ -415,13 +498,31 @@ __device__ __forceinline__ void stage_c(const DevPlan& P, const uint4* q, uint32
     if (!m) break;
     n_out += __popc(m);
     if (P.sink == SINK_AGG) {
-      if (P.nkeys) { if (found) sink_agg_grouped<ACC>(P, g, n_bad); }
+      if (P.nkeys) sink_agg_grouped<ACC>(P, g, found, lane, n_bad);
       else sink_agg_single<ACC>(P, g, found, lane);
     } else if (P.sink == SINK_JOIN_BUILD) {
       sink_build(P, g, found, lane, n_bloom_ins);
     }
     __syncwarp();
   }
+}
+
+// Inline view in range, the way view_in_range() defines it -- the key is the 128-bit number (big-endian bytes 0..3,
+// 4..7, 8..11, length) and the test is (key - lo) <= span, unsigned -- with explicit 32-bit carry chains: 3 byte
+// permutes + 9 integer instructions, against ~45 for the compiler's generic 128-bit arithmetic.
+__device__ __forceinline__ bool view_in_range_fast(const uint4 v, const DevTerm& T, uint32_t& bad) {
+  bad += v.x > 12u;  // out-of-line views are not compared by this kernel
+  const uint32_t w0 = bswap32(v.y), w1 = bswap32(v.z), w2 = bswap32(v.w), w3 = v.x;
+  const uint32_t l0 = uint32_t(uint64_t(T.lo0) >> 32), l1 = uint32_t(uint64_t(T.lo0)), l2 = uint32_t(T.lo1 >> 32), l3 = uint32_t(T.lo1);
+  const uint32_t s0 = uint32_t(uint64_t(T.hi0) >> 32), s1 = uint32_t(uint64_t(T.hi0)), s2 = uint32_t(T.hi1 >> 32), s3 = uint32_t(T.hi1);
+  uint32_t borrow;
+  asm("{\n\t.reg .u32 d0, d1, d2, d3, t;\n\t"
+      "sub.cc.u32 d3, %1, %5;\n\tsubc.cc.u32 d2, %2, %6;\n\tsubc.cc.u32 d1, %3, %7;\n\tsubc.u32 d0, %4, %8;\n\t"       // d = key - lo
+      "sub.cc.u32 t, %9, d3;\n\tsubc.cc.u32 t, %10, d2;\n\tsubc.cc.u32 t, %11, d1;\n\tsubc.cc.u32 t, %12, d0;\n\t"   // span - d
+      "subc.u32 %0, 0, 0;\n\t}"                                                                                    // 0 or 0xFFFFFFFF = borrow
+      : "=r"(borrow)
+      : "r"(w3), "r"(w2), "r"(w1), "r"(w0), "r"(l3), "r"(l2), "r"(l1), "r"(l0), "r"(s3), "r"(s2), "r"(s1), "r"(s0));
+  return borrow == 0u;
 }
 
 // FilterExec conjunct for one row of the staged tile (see term_pass2)
@@ -432,7 +533,7 @@ __device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stag
   const uint32_t ld = LD >= 0 ? uint32_t(LD) : uint32_t(T.ref.ld);
   switch (ld) {
     case LD_F64: a = in_range1(f64_key(reinterpret_cast<const int64_t*>(p)[r]), T); break;
-    case LD_VIEW: a = view_in_range(reinterpret_cast<const uint4*>(p)[r], T, bad); break;
+    case LD_VIEW: a = view_in_range_fast(reinterpret_cast<const uint4*>(p)[r], T, bad); break;
     case LD_I32: a = in_range1(reinterpret_cast<const int32_t*>(p)[r], T); break;
     case LD_I64: a = in_range1(reinterpret_cast<const int64_t*>(p)[r], T); break;
     case LD_I16: a = in_range1(reinterpret_cast<const int16_t*>(p)[r], T); break;
@@ -460,75 +561,79 @@ template <uint32_t ACC, int T0>
 __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr bool kNoNull = T0 >= 0;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  ProbeShared* sh = reinterpret_cast<ProbeShared*>(smem_raw);
-  uint8_t* stages = smem_raw + probe_shared_bytes();
-  const uint32_t kNumStages = P.nstages;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) {
-    for (uint32_t s = 0; s < kPMaxStages; ++s) {
-      mbar_init(&sh->full[s], 1);
-      mbar_init(&sh->empty[s], kPConsumerWarps);
-    }
+  const uint32_t D = P.nstages;  // tiles in flight per warp
+  PWarpCtl* ctl = reinterpret_cast<PWarpCtl*>(smem_raw) + warp;
+  uint8_t* stages = smem_raw + probe_shared_bytes() + size_t(warp) * D * P.stage_bytes;
+  uint4* q1 = reinterpret_cast<uint4*>(smem_raw + probe_shared_bytes() + size_t(kPConsumerWarps) * D * P.stage_bytes) + size_t(warp) * (2u * kPQueueEntries);
+  uint4* q2 = q1 + kPQueueEntries;
+  if (lane == 0) {
+    for (uint32_t s = 0; s < kPMaxDepth; ++s) mbar_init(&ctl->full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  __syncthreads();
+  __syncwarp();
 
-  uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0;
+  uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0, n_bloom_rej = 0;
 
-  if (warp == 0) {
-    // ===== producer (see pipeline_kernel.cuh): lanes 0..15 copy the values slice of staged column `lane`,
-    // lanes 16..31 its validity slice; the page stream is marked evict_first in L2
-    const uint64_t pol = l2_policy_evict_first();
-    uint32_t ps = 0, pphase = 0;
-    const uint32_t mycol = lane & 15u;
-    const bool is_validity = lane >= 16;
-    const bool has_col = mycol < P.nstage_cols;
-    DevStageCol sc{};
-    if (has_col) sc = P.scol[mycol];
-    const bool want = has_col && (!is_validity || sc.nullable);
-    const uint32_t width = is_validity ? 0u : uint32_t(sc.width);
-    const uint32_t smem_off = is_validity ? sc.valid_off : sc.smem_off;
-    uint32_t cur_class = 0xFFFFFFFFu, col_off = 0;
-    uint32_t page = blockIdx.x;
-    PageDesc d_next{};
-    if (page < P.npages) d_next = P.descs[page];
-    for (; page < P.npages; page += gridDim.x) {
-      const PageDesc d = d_next;
-      if (page + gridDim.x < P.npages) d_next = P.descs[page + gridDim.x];
-      if (d.layout_class != cur_class) {
-        cur_class = d.layout_class;
-        const LayoutClass* lc = P.classes + cur_class;
-        col_off = want ? (is_validity ? lc->validity_off[sc.page_col] : lc->values_off[sc.page_col]) : 0u;
-      }
-      const uint8_t* col_base = P.pages + uint64_t(page) * P.page_stride + col_off;
-      const uint32_t null_mask = d.null_mask & P.used_null_mask;
-      const bool active = want && (!is_validity || ((null_mask >> sc.page_col) & 1u));
-      for (uint32_t tile = 0, r0 = 0; tile < P.tiles_per_page; ++tile, r0 += P.tile_rows) {
-        const uint32_t s = ps;
-        const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
-        uint32_t bytes = 0;
-        if (active && n) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * width + 15u) & ~15u);
-        const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-        mbar_wait(&sh->empty[s], pphase ^ 1u);
-        if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
-        if (lane == 0) {
-          sh->meta[s] = PStageMeta{n, null_mask, page, r0};
-          mbar_arrive_expect_tx(&sh->full[s], total);
-        }
-        __syncwarp();
-        if (bytes)
-          tma_load_1d_hint(stages + size_t(s) * P.stage_bytes + smem_off, col_base + (is_validity ? (r0 >> 3) : r0 * width), bytes, &sh->full[s], pol);
-      }
+  // ---- this warp's tile stream: tiles wg, wg + nw, wg + 2 nw, ... of the scan (tile = tile_rows rows of a page)
+  const uint32_t wg = blockIdx.x * kPConsumerWarps + warp, nw = gridDim.x * kPConsumerWarps;
+  const uint64_t total_tiles = uint64_t(P.npages) * P.tiles_per_page;
+  const uint32_t my_tiles = total_tiles > wg ? uint32_t((total_tiles - wg + nw - 1) / nw) : 0u;
+  uint32_t ipage = wg / P.tiles_per_page, itip = wg % P.tiles_per_page;  // issue cursor
+  const uint32_t dq = nw / P.tiles_per_page, dr = nw % P.tiles_per_page;
+  uint32_t issued = 0, is = 0;
+  // lanes 0..15 copy the values slice of staged column `lane`, lanes 16..31 its validity slice
+  const uint64_t pol_stream = l2_policy_evict_first();
+  const uint32_t mycol = lane & 15u;
+  const bool is_validity = lane >= 16;
+  bool want = false;
+  uint32_t my_width = 0, my_soff = 0, my_pcol = 0, my_coff = 0, cur_class = 0xFFFFFFFFu;
+  if (mycol < P.nstage_cols) {
+    const DevStageCol sc = P.scol[mycol];
+    want = !is_validity || sc.nullable;
+    my_width = is_validity ? 0u : uint32_t(sc.width);
+    my_soff = is_validity ? sc.valid_off : sc.smem_off;
+    my_pcol = sc.page_col;
+  }
+  PageDesc dnext{};  // descriptor of the page of the next tile to issue, loaded one tile ahead
+  if (my_tiles) dnext = P.descs[ipage];
+  auto issue_next = [&]() {
+    if (issued >= my_tiles) return;
+    const PageDesc d = dnext;
+    if (d.layout_class != cur_class) {  // rare: pages of one scan share their layout class
+      cur_class = d.layout_class;
+      const LayoutClass* lc = P.classes + cur_class;
+      my_coff = want ? (is_validity ? lc->validity_off[my_pcol] : lc->values_off[my_pcol]) : 0u;
     }
-  } else {
-    // ===== consumers =====
-    // Stages A, B and C each appear exactly once, inlined, in one loop: per 32-row chunk stage A runs, then
-    // stage B if 32 survivors are queued, then stage C if 32 tag hits are queued.  After the last tile the
-    // same loop keeps turning with no chunk until both queues and the pending batch are drained.
-    uint4* q1 = reinterpret_cast<uint4*>(stages + size_t(kNumStages) * P.stage_bytes) + size_t(warp - 1) * (2u * kPQueueEntries);
-    uint4* q2 = q1 + kPQueueEntries;
-    uint4* qa = P.njoins ? q1 : q2;             // without a join the survivors go straight to stage C
+    const uint32_t r0 = itip * P.tile_rows;
+    const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
+    const uint32_t null_mask = d.null_mask & P.used_null_mask;
+    const bool active = want && n && (!is_validity || ((null_mask >> my_pcol) & 1u));
+    uint32_t bytes = 0;
+    if (active) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * my_width + 15u) & ~15u);
+    const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
+    if (lane == 0) {
+      ctl->meta[is] = PStageMeta{n, null_mask, ipage, r0};
+      mbar_arrive_expect_tx(&ctl->full[is], total);
+    }
+    __syncwarp();
+    if (bytes)
+      tma_load_1d_hint(stages + size_t(is) * P.stage_bytes + my_soff,
+                       P.pages + uint64_t(ipage) * P.page_stride + my_coff + (is_validity ? (r0 >> 3) : r0 * my_width), bytes, &ctl->full[is], pol_stream);
+    ipage += dq;
+    itip += dr;
+    if (itip >= P.tiles_per_page) { itip -= P.tiles_per_page; ++ipage; }
+    ++issued;
+    if (++is == D) is = 0;
+    if (issued < my_tiles) dnext = P.descs[ipage];  // in flight while the warp works on its next tile
+  };
+  for (uint32_t i = 0; i < D; ++i) issue_next();
+
+  // Per 32-row chunk: stage A, then stage B once 32 survivors are queued, then stage C once 32 tag hits are
+  // queued.  The hot loop carries no drain logic; what is left in the queues after the last tile is drained by
+  // the same (out-of-line copies of the) stages below.
+  {
     uint32_t q1n = 0, q2n = 0;                  // warp-uniform fill levels
     const uint32_t lt = (1u << lane) - 1u;
     const uint64_t pol_keep = l2_policy_evict_last();
@@ -538,40 +643,68 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     uint2 pw = make_uint2(0, 0);
     uint32_t ptag = 0;
 
-    uint32_t cs = 0, cphase = 0, cb = 0;  // ring stage / phase; chunks dealt so far modulo the warp count
-    const uint32_t my_pages = P.npages > blockIdx.x ? (P.npages - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-    const uint32_t my_items = my_pages * P.tiles_per_page;
-    for (uint32_t item = 0; item <= my_items; ++item) {
-      const bool last = item == my_items;  // the drain turn
-      uint32_t s = 0, nchunks = 0, c = 0;
-      PStageMeta meta{0, 0, 0, 0};
-      const uint8_t* stage = stages;
-      if (!last) {
-        s = cs;
-        mbar_wait(&sh->full[s], cphase);
-        if (++cs == kNumStages) { cs = 0; cphase ^= 1u; }
-        meta = sh->meta[s];
-        stage = stages + size_t(s) * P.stage_bytes;
-        nchunks = (meta.nrows + 31u) >> 5;
-        // 32-row chunks are dealt to the warps round-robin ACROSS tiles, so the load stays balanced
-        // whatever the tile size; the ring lets a warp run ahead of the others by its depth
-        c = warp - 1u >= cb ? warp - 1u - cb : warp - 1u + kPConsumerWarps - cb;
-        cb = (cb + nchunks) % kPConsumerWarps;
+    // -- stage C: n tag hits (32, or what is left when draining) on dense lanes
+    auto run_c = [&](uint32_t n) {
+      q2n -= n;
+      uint4 e = make_uint4(0, 0, 0, 0);
+      if (lane < n) e = q2[q2n + lane];
+      __syncwarp();
+      stage_c<ACC>(P, e, lane < n, lane, n_out, n_bad, n_bloom_ins);
+    };
+    // -- stage B: resolve the tag loads of the pending batch (SIMD-in-register byte compares), compact its hits
+    // into q2; then pop n survivors onto dense lanes, hash them and issue their tag loads
+    auto run_b = [&](uint32_t n) {
+      if (pend) {
+        pend = false;
+        const bool hit = pact && window_may_match(pw, ptag);
+        const uint32_t m = __ballot_sync(0xffffffffu, hit);
+        if (m) {
+          if (hit) q2[q2n + __popc(m & lt)] = pe;
+          q2n += __popc(m);
+          __syncwarp();
+        }
       }
-      for (;;) {
-        const bool have = c < nchunks;
-        if (!have && !(last && (q1n | q2n | uint32_t(pend)))) break;
-        if (have) {
-          // -- stage A: runtime Bloom probes (NULL key => DefinitelyAbsent, shared.rs:367-374), conjuncts,
-          // compaction of the survivors
-          const uint32_t r = c * 32u + lane;
-          const bool has = r < meta.nrows;
-          const uint32_t rr = has ? r : 0u;  // row 0 of a tile always exists
-          const uint32_t nhere = min(32u, meta.nrows - c * 32u);
-          c += kPConsumerWarps;
-          bool keep = has;
-          n_in += nhere;
-          for (uint32_t b = 0; b < P.nbloom; ++b) {
+      if (n) {
+        q1n -= n;
+        pact = lane < n;
+        if (pact) pe = q1[q1n + lane];
+        __syncwarp();
+        if (P.bloom_dense) {  // the runtime filter on the entry key, probed on dense lanes
+          const bool alive = pact && bloom_contains(P.bloom[0].bloom, (uint64_t(pe.w) << 32) | pe.z);
+          n_bloom_rej += __popc(__ballot_sync(0xffffffffu, pact && !alive));
+          pact = alive;
+        }
+        if (P.njoins) {
+          const DevJoin& j = P.joins[0];
+          const uint64_t h = join_hash(int64_t((uint64_t(pe.w) << 32) | pe.z));
+          ptag = join_tag8(h, j.shift);
+          pw = ldg_tags8(j.tags + join_home(h, j.shift), pact, pol_keep);
+          pend = true;
+        } else {   // no join: the survivors are the sink's rows
+          const uint32_t m = __ballot_sync(0xffffffffu, pact);
+          if (pact) q2[q2n + __popc(m & lt)] = pe;
+          q2n += __popc(m);
+          __syncwarp();
+        }
+      }
+    };
+
+    uint32_t cs = 0, cphase = 0;  // ring stage / mbarrier phase of the tile being read
+    for (uint32_t k = 0; k < my_tiles; ++k) {
+      mbar_wait(&ctl->full[cs], cphase);
+      const PStageMeta meta = ctl->meta[cs];
+      const uint8_t* stage = stages + size_t(cs) * P.stage_bytes;
+      if (++cs == D) { cs = 0; cphase ^= 1u; }
+      n_in += meta.nrows;
+      for (uint32_t r0 = 0; r0 < meta.nrows; r0 += 32u) {
+        // -- stage A: runtime Bloom probes (NULL key => DefinitelyAbsent, shared.rs:367-374), conjuncts,
+        // compaction of the survivors
+        const uint32_t r = r0 + lane;
+        const bool has = r < meta.nrows;
+        const uint32_t rr = has ? r : 0u;  // row 0 of a tile always exists
+        bool keep = has;
+        if (P.nbloom > P.bloom_dense) {
+          for (uint32_t b = P.bloom_dense; b < P.nbloom; ++b) {
             const DevBloomProbe& bp = P.bloom[b];
             const Row rq{stage, rr, meta.null_mask, nullptr, 0};
             bool k1[1] = {keep && ref_valid(bp.key, rq)};
@@ -579,82 +712,69 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
             bloom_contains_n<1>(bp.bloom, bk, k1);
             keep = k1[0];
           }
-          if (P.nbloom) n_bloom += __popc(__ballot_sync(0xffffffffu, keep));
-          else n_bloom += nhere;
-          if constexpr (T0 >= 0) {
-            keep = keep && term_pass1<T0, true>(P.terms[0], stage, rr, 0u, n_bad);
-          } else {
-            for (uint32_t t = 0; t < P.nterms; ++t) {
-              if (!__any_sync(0xffffffffu, keep)) break;
-              keep = keep && term_pass1<-1, false>(P.terms[t], stage, rr, meta.null_mask, n_bad);
-            }
-          }
-          uint32_t m = __ballot_sync(0xffffffffu, keep);
-          n_filt += __popc(m);
-          int64_t key = 0;
-          if (P.njoins) {
-            const DevJoin& j = P.joins[0];
-            const Row rq{stage, rr, meta.null_mask, nullptr, 0};
-            key = load_i64(j.key, rq);
-            if constexpr (!kNoNull) {
-              keep = keep && ref_valid(j.key, rq);  // NULL keys never match: an inner join drops the row
-              m = __ballot_sync(0xffffffffu, keep);
-            }
-          }
-          if (m) {
-            const uint32_t qn = P.njoins ? q1n : q2n;
-            if (keep) qa[qn + __popc(m & lt)] = make_uint4(meta.page, meta.r0 + rr, uint32_t(uint64_t(key)), uint32_t(uint64_t(key) >> 32));
-            if (P.njoins) q1n += __popc(m);
-            else q2n += __popc(m);
-            __syncwarp();
+          n_bloom += __popc(__ballot_sync(0xffffffffu, keep));
+        }
+        if constexpr (T0 >= 0) {
+          keep = keep && term_pass1<T0, true>(P.terms[0], stage, rr, 0u, n_bad);
+        } else {
+          for (uint32_t t = 0; t < P.nterms; ++t) {
+            if (!__any_sync(0xffffffffu, keep)) break;
+            keep = keep && term_pass1<-1, false>(P.terms[t], stage, rr, meta.null_mask, n_bad);
           }
         }
-        // -- stage B: resolve the tag loads of the pending batch (SIMD-in-register byte compares) and compact
-        // the hits into q2; then pop the next batch of survivors onto dense lanes, hash, issue its tag loads
-        if (q1n >= 32u || (!have && (q1n | uint32_t(pend)))) {
-          if (pend) {
-            pend = false;
-            const TagWindow tw = scan_tags(pw, ptag);
-            const bool hit = pact && (tw.cand != 0ull || !tw.ended);
-            const uint32_t m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-              if (hit) q2[q2n + __popc(m & lt)] = pe;
-              q2n += __popc(m);
-              __syncwarp();
-            }
+        uint32_t m = __ballot_sync(0xffffffffu, keep);
+        n_filt += __popc(m);
+        int64_t key = 0;
+        if (P.njoins) {
+          const DevJoin& j = P.joins[0];
+          const Row rq{stage, rr, meta.null_mask, nullptr, 0};
+          key = load_i64(j.key, rq);
+          if constexpr (!kNoNull) {
+            const bool valid = ref_valid(j.key, rq);  // NULL keys never match: an inner join drops the row
+            if (P.bloom_dense) n_bloom_rej += __popc(__ballot_sync(0xffffffffu, keep && !valid));   // ... and DefinitelyAbsent
+            keep = keep && valid;
+            m = __ballot_sync(0xffffffffu, keep);
           }
-          const uint32_t n = min(q1n, 32u);
-          if (n) {
-            q1n -= n;
-            pact = lane < n;
-            if (pact) pe = q1[q1n + lane];
-            __syncwarp();
-            const DevJoin& j = P.joins[0];
-            const uint64_t h = join_hash(int64_t((uint64_t(pe.w) << 32) | pe.z));
-            ptag = join_tag8(h, j.shift);
-            pw = ldg_tags8(j.tags + join_home(h, j.shift), pact, pol_keep);
-            pend = true;
+        } else if (P.bloom_dense) {  // no join: the entry carries the runtime filter's key
+          const DevBloomProbe& bp = P.bloom[0];
+          const Row rq{stage, rr, meta.null_mask, nullptr, 0};
+          key = load_i64(bp.key, rq);
+          if constexpr (!kNoNull) {
+            const bool valid = ref_valid(bp.key, rq);  // NULL key => DefinitelyAbsent (shared.rs:367-374)
+            n_bloom_rej += __popc(__ballot_sync(0xffffffffu, keep && !valid));
+            keep = keep && valid;
+            m = __ballot_sync(0xffffffffu, keep);
           }
         }
-        // -- stage C: 32 tag hits (all that is left on the drain turn) on dense lanes
-        if (q2n >= 32u || (!have && q2n && !pend && !q1n)) {
-          const uint32_t n = min(q2n, 32u);
-          q2n -= n;
-          stage_c<ACC>(P, q2 + q2n, n, lane, n_out, n_bad, n_bloom_ins);
+        if (m) {
+          if (keep) q1[q1n + __popc(m & lt)] = make_uint4(meta.page, meta.r0 + rr, uint32_t(uint64_t(key)), uint32_t(uint64_t(key) >> 32));
+          q1n += __popc(m);
+          __syncwarp();
+          if (q1n >= 32u) {
+            run_b(32u);
+            if (q2n >= 32u) run_c(32u);
+          }
         }
       }
-      if (!last) {
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->empty[s]);
-      }
+      __syncwarp();   // every lane is done reading the stage: refill it with the tile D ahead
+      issue_next();
     }
+    // drain: the rest of q1 goes through stage B, the last pending batch is resolved, the rest of q2 through stage C
+    while (q1n | uint32_t(pend)) {
+      run_b(min(q1n, 32u));
+      if (q2n >= 32u) run_c(32u);
+    }
+    while (q2n) run_c(min(q2n, 32u));
+    if (P.nbloom == P.bloom_dense) n_bloom = n_in;   // no probe ran in stage A
+    n_bloom -= n_bloom_rej;                          // rows_bloom = rows the runtime filters did not reject
+    n_filt -= n_bloom_rej;                           // rows_filtered = rows past the filters AND the predicate
   }
 
   // counters (RuntimeFilter*/Worker* style metrics).  n_in .. n_out are warp-uniform in the consumer
   // warps (ballot popcounts): one lane adds them; n_bad and n_bloom_ins are per lane.
   {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.counters);
-    if (lane == 0 && warp > 0) {
+    if (lane == 0) {
       if (n_in) atomicAdd(dst + 0, (unsigned long long)n_in);
       if (n_bloom) atomicAdd(dst + 1, (unsigned long long)n_bloom);
       if (n_filt) atomicAdd(dst + 2, (unsigned long long)n_filt);
@@ -668,6 +788,43 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == 0 && v) atomicAdd(dst + 4 + q, (unsigned long long)v);
     }
+  }
+}
+
+// ---- row-set scans ------------------------------------------------------------------------------
+// The input is a dense array of rows in build-row format {key lo, key hi, occupancy / NULL flags, payload...}
+// -- what a build sink emits and what a hash-partitioned exchange delivers -- instead of pages: every warp takes
+// 32 rows at a time straight into stage C (probe chains, sink).  Column 0 of the scan is the key, column i + 1
+// payload i (DevRef.src == kSrcRecord).
+template <uint32_t ACC>
+__global__ void __launch_bounds__(256) rows_pipeline_kernel(const __grid_constant__ DevPlan P) {
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t n_out = 0, n_bad = 0, n_bloom_ins = 0, n_in = 0;
+  const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5), w0 = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (uint64_t base = w0 * 32u; base < P.row_count; base += nwarps * 32u) {
+    const uint64_t i = base + lane;
+    const bool act = i < P.row_count;
+    uint4 e = make_uint4(uint32_t(i), uint32_t(i >> 32), 0u, 0u);
+    if (act) {
+      const uint4 head = __ldg(P.row_src + i * P.row_u4);
+      e.z = head.x;
+      e.w = head.y;
+    }
+    n_in += __popc(__ballot_sync(0xffffffffu, act));
+    stage_c<ACC, true>(P, e, act, lane, n_out, n_bad, n_bloom_ins);
+  }
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.counters);
+  if (lane == 0) {
+    if (n_in) { atomicAdd(dst + 0, (unsigned long long)n_in); atomicAdd(dst + 1, (unsigned long long)n_in); atomicAdd(dst + 2, (unsigned long long)n_in); }
+    if (n_out) atomicAdd(dst + 3, (unsigned long long)n_out);
+  }
+  uint32_t vals[2] = {n_bloom_ins, n_bad};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t v = vals[q];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) atomicAdd(dst + 4 + q, (unsigned long long)v);
   }
 }
 

@@ -294,8 +294,12 @@ class PipelineBuilder:
         return self
 
     def build_join(self, key: ColRefLike, payload: Sequence[ColRefLike] = (),
-                   bloom: Optional["RuntimeFilter"] = None) -> "PipelineBuilder":
+                   bloom: Optional["RuntimeFilter"] = None, expected_rows: int = 0, rows_only: bool = False) -> "PipelineBuilder":
+        """expected_rows: sizing hint for the build-row buffer (0: as many rows as the scan holds); a hint that
+        turns out too small costs one more pass, never a wrong result."""
         self.p.sink = 2
+        self.p.expected_groups = expected_rows
+        self.p.build_flags = 1 if rows_only else 0
         self.p.build_key = _colref(key)
         self.p.npayload = len(payload)
         for i, c in enumerate(payload):
@@ -327,6 +331,12 @@ class PipelineBuilder:
         n = C.c_uint64()
         self.ctx._check(_lib.lib().pgf_partial_state_bytes(C.byref(self.p), max_groups, C.byref(n)))
         return n.value
+
+    def run_sharded(self, max_groups: int = 1) -> PipelineResult:
+        """AggregateExec Partial -> all-gather -> Final inside the library (pgf_pipeline_run_sharded)."""
+        res = C.POINTER(_lib.Result)()
+        self.ctx._check(_lib.lib().pgf_pipeline_run_sharded(self.ctx.h, C.byref(self.p), max_groups, C.byref(res)))
+        return self.ctx._take_result(res)
 
     def run_partial_async(self, dev_ptr: int, capacity_bytes: int) -> None:
         """Enqueue kernel + partial-state extraction on the compute stream; no synchronisation."""
@@ -463,6 +473,10 @@ class RuntimeFilter:
     def device_words_ptr(self) -> int:
         return _lib.lib().pgf_bloom_device_words(self.ctx.h, self.handle)
 
+    def or_all_reduce(self) -> None:
+        """Bloom OR-merge over the context's communicator (pgf_bloom_or_all_reduce)."""
+        self.ctx._check(_lib.lib().pgf_bloom_or_all_reduce(self.ctx.h, self.handle))
+
     def or_device_words(self, dev_ptr: int, narrays: int) -> None:
         self.ctx._check(_lib.lib().pgf_bloom_or_device_words(self.ctx.h, self.handle, dev_ptr, self.params.word_count, narrays))
 
@@ -582,6 +596,47 @@ class Context:
 
     def destroy_join_table(self, handle: int) -> None:
         self._check(_lib.lib().pgf_join_table_destroy(self.h, handle))
+
+    # ---- multi-GPU: one process per GPU, the collectives run inside the library (NCCL over NVLink) ----
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = _lib.lib().pgf_comm_unique_id(buf)
+        if rc:
+            raise PgfError(rc, "pgf_comm_unique_id")
+        return bytes(buf)
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int) -> None:
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._check(_lib.lib().pgf_comm_init(self.h, buf, rank, world))
+
+    def comm_info(self) -> Tuple[int, int]:
+        r, w = C.c_int32(), C.c_int32()
+        self._check(_lib.lib().pgf_comm_info(self.h, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def comm_destroy(self) -> None:
+        self._check(_lib.lib().pgf_comm_destroy(self.h))
+
+    def comm_all_gather(self, send_ptr: int, recv_ptr: int, nbytes: int) -> None:
+        self._check(_lib.lib().pgf_comm_all_gather(self.h, send_ptr, recv_ptr, nbytes))
+
+    def exchange(self, handle: int, partition: bool, rows_only: bool = False) -> Tuple[int, int]:
+        """pgf_join_table_exchange: (new handle, bytes this rank sent over NVLink)."""
+        out, sent = C.c_uint64(), C.c_uint64()
+        mode = (1 if partition else 0) | (4 if rows_only else 0)
+        self._check(_lib.lib().pgf_join_table_exchange(self.h, handle, mode, C.byref(out), C.byref(sent)))
+        return out.value, sent.value
+
+    def row_set_pipeline(self, row_set: int, schema) -> "PipelineBuilder":
+        """A pipeline that scans a row set (column 0 = key, column i + 1 = payload i) instead of pages."""
+        class _RowScan:
+            scan_id = 0
+        rs = _RowScan()
+        rs.schema = schema
+        pb = PipelineBuilder(self, rs)
+        pb.p.scan_row_set = row_set
+        return pb
 
     def synchronize(self) -> None:
         self._check(_lib.lib().pgf_ctx_synchronize(self.h))

@@ -121,8 +121,11 @@ def test_q1_result_pages_from_the_cpp_layer(runs, ctx):
     got = runs["q1"]
     npages = runs["q1_result_pages"]["pages"]
     pages = np.fromfile(runs["_pages_file"], dtype=np.uint8).reshape(npages, 65536)
-    cols = [(O.T_UTF8VIEW, True)] * 2 + [(O.T_FLOAT64, True)] * 7 + [(O.T_INT64, False)]
+    # the receiving schema is the PLAN's: l_returnflag / l_linestatus are NOT NULL columns, so DataFusion's
+    # AggregateExec output fields for them are non-nullable; SUM / AVG nullable, COUNT(*) not
+    cols = [(O.T_UTF8VIEW, False)] * 2 + [(O.T_FLOAT64, True)] * 7 + [(O.T_INT64, False)]
     t = O.OTable.from_pages(pages, 65536, cols)               # runs the reference's import checks on every page
+    assert O.import_check(0x4152, 0, np.ascontiguousarray(pages[0, 20:]), [(O.T_UTF8VIEW, True)] * 2 + cols[2:]) != 0
     assert t.rows == 4
     # result pages carry the pod's column order (keys, then aggregates), which is also Q1's output order
     flags = t.column(0)                                       # view columns decode to a list of bytes

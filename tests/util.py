@@ -57,6 +57,7 @@ def q1_pages(li, page_size=65536, rows_per_page=None) -> np.ndarray:
 
 
 E = O.Expr
+from pg_fusion_b200.tpch import gpu_q1, gpu_q1_d, gpu_q3, gpu_q3_sharded, gpu_q6, gpu_q6_d  # noqa: E402,F401  (the plans live in the package)
 
 
 def oracle_q6(table: O.OTable, cols=(0, 1, 2, 3), sum_lanes=0) -> O.AggOut:
@@ -74,26 +75,6 @@ def oracle_q1(table: O.OTable) -> O.AggOut:
     aggs = [(O.AGG_SUM, E.col(q)), (O.AGG_SUM, E.col(p)), (O.AGG_SUM, disc_price), (O.AGG_SUM, charge),
             (O.AGG_AVG, E.col(q)), (O.AGG_AVG, E.col(p)), (O.AGG_AVG, E.col(d)), (O.AGG_COUNT_STAR, None)]
     return O.aggregate(table, filt, [E.col(rf), E.col(ls)], aggs)
-
-
-def gpu_q6(scan, cols=(0, 1, 2, 3)):
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    q, p, d, s = cols
-    return (scan.pipeline()
-            .filter(s, Cmp.GE, b"1994-01-01").filter(s, Cmp.LT, b"1995-01-01")
-            .filter(d, Cmp.GE, 0.05).filter(d, Cmp.LE, 0.07).filter(q, Cmp.LT, 24.0)
-            .aggregate([], [(AggFunc.SUM, [Factor.of(p), Factor.of(d)]), (AggFunc.COUNT_STAR, None)]))
-
-
-def gpu_q1(scan):
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    q, p, d, t, rf, ls, s = range(7)
-    disc_price = [Factor.of(p), Factor.const_minus(1.0, d)]
-    charge = disc_price + [Factor.const_plus(1.0, t)]
-    aggs = [(AggFunc.SUM, [Factor.of(q)]), (AggFunc.SUM, [Factor.of(p)]), (AggFunc.SUM, disc_price),
-            (AggFunc.SUM, charge), (AggFunc.AVG, [Factor.of(q)]), (AggFunc.AVG, [Factor.of(p)]),
-            (AggFunc.AVG, [Factor.of(d)]), (AggFunc.COUNT_STAR, None)]
-    return scan.pipeline().filter(s, Cmp.LE, b"1998-09-02").aggregate([rf, ls], aggs)
 
 
 def assert_close(a, b, rel=1e-12, what=""):
@@ -127,45 +108,6 @@ Q3_DATE = b"1995-03-15"
 Q3_ORDER = [("agg", 0, True), ("key", 1, False)]   # ORDER BY revenue DESC, o_orderdate (q03.sql)
 
 
-def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDING", limit=0):
-    """Runs the three fused pipelines of the Q3 shape; returns (result, stats dict).
-    limit > 0 adds ORDER BY revenue DESC, o_orderdate LIMIT n (device top-k)."""
-    import pg_fusion_b200 as pg
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    stats = {}
-    rf1 = rf2 = None
-    if bloom_params is not None:
-        rf1 = ctx.runtime_filter(bloom_params[0])
-        rf1.try_acquire_builder()
-    # customer(BUILDING) -> join table T1 keyed by c_custkey (+ Bloom for the orders scan)
-    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1).run()
-    if rf1 is not None:
-        rf1.publish_ready()
-    # orders: [Bloom probe] -> o_orderdate < date -> probe T1 -> T2 keyed by o_orderkey with payload
-    p2 = orders.pipeline()
-    if rf1 is not None:
-        p2.bloom_probe(rf1, 1)
-        rf2 = ctx.runtime_filter(bloom_params[1])
-        rf2.try_acquire_builder()
-    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(r1.join_table, 1).build_join(0, [2, 3], rf2).run()
-    if rf2 is not None:
-        rf2.publish_ready()
-    # lineitem: [Bloom probe] -> l_shipdate > date -> probe T2 -> GROUP BY l_orderkey, o_orderdate, o_shippriority
-    p3 = lineitem.pipeline()
-    if rf2 is not None:
-        p3.bloom_probe(rf2, 0)
-    p3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(r2.join_table, 0)
-          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
-                     expected_groups=max(1024, r2.rows_out)))
-    if limit:
-        p3.order_by(Q3_ORDER, limit=limit)
-    r3 = p3.run()
-    ctx.destroy_join_table(r1.join_table)
-    ctx.destroy_join_table(r2.join_table)
-    stats.update(customer=r1, orders=r2, lineitem=r3, rf1=rf1, rf2=rf2)
-    return r3, stats
-
-
 def oracle_q3(customer_t, orders_t, lineitem_t, segment=b"BUILDING"):
     cust_f = customer_t.select(O.filter_rows(customer_t, E.col(1).eq(E.s(segment))))
     ord_f = orders_t.select(O.filter_rows(orders_t, E.col(2).lt(E.s(Q3_DATE))))
@@ -182,45 +124,6 @@ def top10(res):
     return sorted(rows, key=lambda r: (-r[1], r[2]))[:10]
 
 
-def gpu_q3_sharded(ctx, customer, orders, lineitem, world, device, bloom_params=None, segment=b"BUILDING", limit=0):
-    """The Q3 shape with every scan sharded by pages over `world` ranks (one process per GPU):
-    broadcast joins, OR-merged runtime filters, Partial -> Final aggregate."""
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    from pg_fusion_b200 import multi_gpu as MG
-    rf1 = rf2 = None
-    if bloom_params is not None:
-        rf1 = ctx.runtime_filter(bloom_params[0])
-        rf1.try_acquire_builder()
-    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1).run()
-    t1 = MG.broadcast_join_table(ctx, r1.join_table, world, device)
-    if rf1 is not None:
-        MG.or_merge_filter(rf1, world, device)
-        rf1.publish_ready()
-    p2 = orders.pipeline()
-    if rf1 is not None:
-        p2.bloom_probe(rf1, 1)
-        rf2 = ctx.runtime_filter(bloom_params[1])
-        rf2.try_acquire_builder()
-    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(t1, 1).build_join(0, [2, 3], rf2).run()
-    t2 = MG.broadcast_join_table(ctx, r2.join_table, world, device)
-    if rf2 is not None:
-        MG.or_merge_filter(rf2, world, device)
-        rf2.publish_ready()
-    p3 = lineitem.pipeline()
-    if rf2 is not None:
-        p3.bloom_probe(rf2, 0)
-    total_orders = ctx.join_table_info(t2).rows
-    p3 = (p3.filter(3, Cmp.GT, Q3_DATE).join(t2, 0)
-          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
-                     expected_groups=max(1024, total_orders)))
-    if limit:
-        p3.order_by(Q3_ORDER, limit=limit)   # applied to the merged (final) groups
-    res, stats = MG.merge_partial_aggregate(p3, world, device, max_groups=max(1024, total_orders))
-    ctx.destroy_join_table(t1)
-    ctx.destroy_join_table(t2)
-    return res, dict(customer=r1, orders=r2, lineitem=stats)
-
-
 # ---- "D" schema variants (SURVEY 8d): money Decimal128(15,2) as unscaled hundredths in 16-byte slots,
 # dates Date32 (Int32 days since 1970-01-01), flags Int16 character codes.  Decimal arithmetic follows
 # DataFusion's type rules: 1 - disc -> (100 - disc) at scale 2, products are plain i128 products.
@@ -230,26 +133,10 @@ Q1_D_SCHEMA = [ColumnSpec(DEC)] * 4 + [ColumnSpec(I16), ColumnSpec(I16), ColumnS
 D_1994, D_1995, D_1998_09_02 = 8766, 9131, 10471   # days since 1970-01-01
 
 
-def gpu_q6_d(scan):
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    return (scan.pipeline().filter(3, Cmp.GE, D_1994).filter(3, Cmp.LT, D_1995)
-            .filter(2, Cmp.GE, 5).filter(2, Cmp.LE, 7).filter(0, Cmp.LT, 2400)
-            .aggregate([], [(AggFunc.SUM, [Factor.of(1), Factor.of(2)]), (AggFunc.COUNT_STAR, None)]))
-
-
 def oracle_q6_d(table: O.OTable) -> O.AggOut:
     filt = (E.col(3).ge(E.i64(D_1994))).and_(E.col(3).lt(E.i64(D_1995))) \
         .and_(E.col(2).ge(E.i128(5))).and_(E.col(2).le(E.i128(7))).and_(E.col(0).lt(E.i128(2400)))
     return O.aggregate(table, filt, [], [(O.AGG_SUM, E.col(1) * E.col(2)), (O.AGG_COUNT_STAR, None)])
-
-
-def gpu_q1_d(scan):
-    from pg_fusion_b200 import AggFunc, Cmp, Factor
-    disc_price = [Factor.of(1), Factor.const_minus(100, 2)]
-    charge = disc_price + [Factor.const_plus(100, 3)]
-    aggs = [(AggFunc.SUM, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(1)]), (AggFunc.SUM, disc_price), (AggFunc.SUM, charge),
-            (AggFunc.AVG, [Factor.of(0)]), (AggFunc.AVG, [Factor.of(1)]), (AggFunc.AVG, [Factor.of(2)]), (AggFunc.COUNT_STAR, None)]
-    return scan.pipeline().filter(6, Cmp.LE, D_1998_09_02).aggregate([4, 5], aggs)
 
 
 def oracle_q1_d(table: O.OTable):
@@ -264,3 +151,35 @@ def oracle_q1_d(table: O.OTable):
         avg = lambda s: (abs(s * 10000) // cnt) * (1 if s >= 0 else -1)
         out[k] = (sq, sp, sdp, sch, avg(sq), avg(sp), avg(sd), cnt)
     return out, res
+
+
+def q3_host_tables(ncust: int, nord: int, nli: int, seed: int, dup_keys: bool = False, rows_per_page=None):
+    """Small Q3-shaped tables fabricated on the host (numpy): pages + oracle tables.  dup_keys: customer and
+    order keys repeat, so both joins multiply rows (HashJoinExec keeps every pair)."""
+    r = np.random.default_rng(seed)
+    segs = [b"AUTOMOBILE", b"BUILDING", b"FURNITURE", b"MACHINERY", b"HOUSEHOLD"]
+    ckey = (r.integers(1, max(2, ncust // 2), ncust) if dup_keys else np.arange(1, ncust + 1)).astype(np.int32)
+    cseg = [segs[i] for i in r.integers(0, 5, ncust)]
+    okey = (r.integers(1, max(2, nord // 2), nord) if dup_keys else np.arange(1, nord + 1) * 4).astype(np.int32)
+    ocust = r.integers(1, ncust + 1, nord).astype(np.int32)
+    odate = dates_from_days(r.integers(1, 2400, nord))
+    oprio = r.integers(0, 3, nord).astype(np.int32)
+    lkey = okey[r.integers(0, nord, nli)].astype(np.int32)
+    lkey[r.random(nli) < 0.1] = -7                      # keys without a partner
+    lprice = r.integers(90000, 10_000_000, nli) / 100.0
+    ldisc = r.integers(0, 11, nli) / 100.0
+    ldate = dates_from_days(r.integers(1, 2527, nli))
+    pages = [AL.encode_pages(CUSTOMER_SCHEMA, [(ckey, None), (AL.inline_views(cseg), None)], 65536, rows_per_page),
+             AL.encode_pages(ORDERS_SCHEMA, [(okey, None), (ocust, None), (AL.inline_views(odate), None), (oprio, None)], 65536, rows_per_page),
+             AL.encode_pages(LINEITEM_Q3_SCHEMA, [(lkey, None), (lprice, None), (ldisc, None), (AL.inline_views(ldate), None)], 65536, rows_per_page)]
+    tables = [O.OTable.from_pages(p, 65536, orc_cols(s)) for p, s in zip(pages, (CUSTOMER_SCHEMA, ORDERS_SCHEMA, LINEITEM_Q3_SCHEMA))]
+    return pages, tables
+
+
+def assert_q3_stream_equals(res, groups: dict, rel=1e-12):
+    """res: pipeline result or oracle AggOut keyed (l_orderkey, o_orderdate, o_shippriority) -> (revenue,);
+    groups: O.Q3Stream.groups()."""
+    got = res.by_key()
+    assert set(got) == set(groups), f"{len(got)} vs {len(groups)} groups"
+    for k, (s, _) in groups.items():
+        assert_close(got[k][0], s, rel, f"group {k}")

@@ -260,6 +260,15 @@ class Comm:
             dist.init_process_group("nccl", device_id=self.device)
             self.dist = dist
 
+    def attach(self, ctx, pg):
+        """Give the library its own communicator: rank 0's id travels over torch.distributed, every collective of the
+        data path (partial-state all-gather, Bloom OR, join exchanges) then runs inside libpgf_b200 (pgf_comm_*)."""
+        if self.world == 1:
+            return
+        ids = [pg.Context.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(ids, src=0)
+        ctx.comm_init(ids[0], self.rank, self.world)
+
     def barrier(self):
         if self.dist:
             self.dist.barrier()
@@ -315,21 +324,18 @@ class Shapes:
         return out
 
     def agg(self, name):
-        plan, c = self.plans[name], self.comm
-        if c.world == 1:
-            return plan.run()
-        st, ga = self.state[name], self.gathered[name]
-        with c.torch.cuda.stream(self.stream):
-            plan.run_partial_async(st.data_ptr(), st.numel())
-            c.dist.all_gather_into_tensor(ga, st)
-            return plan.merge_partials_bounded(ga.data_ptr(), st.numel(), c.world)
+        # one library call: fused kernel -> partial state -> NCCL all-gather -> fixed-order merge -> result
+        return self.plans[name].run_sharded(max_groups=1 if name == "q6" else 16)
 
     def q3(self, bloom=False):
+        """-> (top-10 rows [(l_orderkey, revenue, o_orderdate, o_shippriority)], stats)"""
         s, c = self.scans, self.comm
-        bp = q3_bloom_params(self.pg, self.ncust, self.nord) if bloom else None
         if c.world == 1:
-            return self.T.gpu_q3(self.ctx, s["customer"], s["orders"], s["lineitem"], bp, limit=10)
-        return self.T.gpu_q3_sharded(self.ctx, s["customer"], s["orders"], s["lineitem"], c.world, c.device, bp, limit=10)
+            bp = q3_bloom_params(self.pg, self.ncust, self.nord) if bloom else None
+            res, st = self.T.gpu_q3(self.ctx, s["customer"], s["orders"], s["lineitem"], bp, limit=10)
+            return [(int(k[0]), float(a[0]), bytes(k[1]), int(k[2])) for k, a in zip(res.keys, res.aggs)], st
+        # hash-partitioned joins and GROUP BY (SURVEY 8e rows 4-5); the runtime filter is part of the plan
+        return self.T.gpu_q3_partitioned(self.ctx, s["customer"], s["orders"], s["lineitem"], nord_total=self.nord, limit=10)
 
     def release(self):
         for s in self.scans.values():
@@ -340,7 +346,7 @@ def result_digest(r6, r1, r3, st3):
     """What a run computed, in a JSON-friendly form (counts exact, Float64 sums to compare at 1e-12)."""
     q1 = {"|".join(x.decode() for x in k): [float(v) if isinstance(v, float) else int(v) for v in a] for k, a in sorted(r1.by_key().items())}
     return {"q6": {"revenue": r6.aggs[0][0], "rows_kept": int(r6.aggs[0][1])}, "q1": q1,
-            "q3": {"top10": [[int(k[0]), float(a[0]), k[1].decode(), int(k[2])] for k, a in zip(r3.keys, r3.aggs)]}}
+            "q3": {"top10": [[int(k), float(v), d.decode(), int(p)] for k, v, d, p in r3]}}
 
 
 def compare_digest(got, want, rel=1e-12):
@@ -373,6 +379,7 @@ def run_ours(args):
     numa = bind_to_gpu_numa_node(local)   # pinned host pages must live on the GPU's own socket
     peak, peak_src = measured_peak()
     ctx = pg.Context(local)
+    comm.attach(ctx, pg)
     sf = args.sf
     free_b, _ = torch.cuda.mem_get_info()
     need = {100: 112, 10: 13, 1: 2}[sf] * (1 << 30) // world
@@ -409,8 +416,9 @@ def run_ours(args):
                 t_shape[name].append(ev[i].elapsed_time(ev[i + 1]))
             k_ms["q6"].append(r6.kernel_ms); k_ms["q1"].append(r1.kernel_ms)
             for name in ("customer", "orders", "lineitem"):
-                k_ms["q3_" + name].append(st3[name].kernel_ms)
-            launches += r6.kernel_launches + r1.kernel_launches + sum(st3[n].kernel_launches for n in ("customer", "orders", "lineitem"))
+                k_ms["q3_" + name].append(st3[name].kernel_ms + (st3["final"].kernel_ms if name == "lineitem" and "final" in st3 else 0.0))
+            launches += r6.kernel_launches + r1.kernel_launches + sum(st3[n].kernel_launches for n in ("customer", "orders", "lineitem", "final") if n in st3)
+            nvlink = st3.get("nvlink_bytes", 0)
         comm.barrier()
         wall = time.perf_counter() - t0
     ms = {k: comm.max(statistics.mean(v)) for k, v in t_shape.items()}     # device time, max over ranks
@@ -450,7 +458,7 @@ def run_ours(args):
         e1.record(sh.stream)
         torch.cuda.synchronize()
         q3_bloom_ms = comm.max(e0.elapsed_time(e1))
-        assert [k[0] for k in rb.keys] == [k[0] for k in r3.keys], "runtime filters changed the result"
+        assert [r[0] for r in rb] == [r[0] for r in r3], "runtime filters changed the result"
 
     # ---- end to end through the C ABI from pinned host pages (H2D inside the timed region), on an SF10 window:
     # every rank pushes its shard of the window from pinned host memory through its own PCIe link
@@ -469,7 +477,11 @@ def run_ours(args):
         shapes["q3"].update({"kernel_ms_by_pipeline": {"customer_build": kms["q3_customer"], "orders_probe_build": kms["q3_orders"], "lineitem_probe_aggregate": kms["q3_lineitem"]},
                              "all_scans_achieved_GBps": scanned / (k3 / 1e3) / 1e9, "all_scans_frac": scanned / (k3 / 1e3) / 1e9 / peak,
                              "ms_per_pass_with_runtime_filters": q3_bloom_ms,
-                             "rows": {"orders_build": int(st3["orders"].rows_out), "after_filter": int(st3["lineitem"].rows_filtered), "joined": int(st3["lineitem"].rows_out)}})
+                             "nvlink_bytes_sent_per_pass_rank0": int(nvlink),
+                             "plan": ("hash-partitioned: customer broadcast, orders and the Bloom-filtered lineitem rows routed by hash(orderkey) over NVLink, "
+                                      "groups complete on their owner, top-10 merged" if world > 1 else "three fused pipelines + device top-10"),
+                             "rows": {"orders_build": int(st3["orders"].rows_out), "after_filter": int(st3["lineitem"].rows_filtered),
+                                      "joined": int(st3["final"].rows_out if "final" in st3 else st3["lineitem"].rows_out)}})
         worst = min(("q6", "q1", "q3"), key=lambda n: shapes[n]["frac"])
         kernel_names = {"q6": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>", "q1": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape8>",
                         "q3": "pgf::probe_pipeline_kernel<CLS_F64, LD_VIEW> (lineitem: filter + join probe + GROUP BY)"}
@@ -495,7 +507,8 @@ def run_ours(args):
             "config": {"workload": f"tpch_q6_q1_q3_sf{sf}_F_schema", "lineitem_rows": nli, "orders_rows": sh.nord, "customer_rows": sh.ncust,
                        "page_size": PAGE, "bytes_per_row_algorithmic": BYTES_PER_ROW,
                        "l2_policy": "inputs (24 / 49 / 26 GB per shape at SF100, divided by the GPU count) are far larger than the 126 MB L2",
-                       "parallelism": (f"tables page-sharded over {world} GPUs; partial aggregate states merged and join build sides exchanged over NCCL" if world > 1 else "1 GPU"),
+                       "parallelism": (f"tables page-sharded over {world} GPUs; every collective inside the library (pgf_comm_*, NCCL over NVLink): partial aggregate "
+                                       "states all-gathered and merged in rank order, join sides hash-partitioned with an all-to-all" if world > 1 else "1 GPU"),
                        "step": "one pass of each shape: Q6, Q1, Q3 (three pipelines + device top-10)"},
             "shapes": shapes,
             "roofline": {"bound": "hbm", "achieved": shapes[worst]["achieved_GBps"], "peak": peak, "unit": "GB/s", "frac": shapes[worst]["frac"],
@@ -519,6 +532,8 @@ def run_ours(args):
         out["other_workloads"] = side_measurements(ctx, pg, peak)
     if rank == 0:
         print(json.dumps(out))
+    if world > 1:
+        ctx.comm_destroy()
     ctx.close()
     comm.close()
 

@@ -482,6 +482,8 @@ pgf_status pgf_comm_destroy(pgf_ctx *ctx);
 pgf_status pgf_comm_info(pgf_ctx *ctx, int32_t *rank_out, int32_t *world_out);
 /* all-gather of `bytes` device bytes per rank on the context's compute stream (stream ordered, not synchronised) */
 pgf_status pgf_comm_all_gather(pgf_ctx *ctx, const void *dev_send, void *dev_recv, uint64_t bytes);
+/* the same for small host buffers (row counts, the top-k rows of every rank): staged through the device, synchronous */
+pgf_status pgf_comm_all_gather_host(pgf_ctx *ctx, const void *host_send, void *host_recv, uint64_t bytes);
 /* AggregateExec Partial -> exchange -> Final in one call: the fused kernel over this rank's pages, extraction of
  * the partial state (sized for max_groups groups: 72 bytes for Q6), all-gather of the states, fixed-order merge
  * (rank order: every rank gets the same bits; exact for Int64 / Decimal128) and one synchronisation for the result. */
@@ -497,6 +499,9 @@ pgf_status pgf_bloom_or_all_reduce(pgf_ctx *ctx, uint64_t bloom);
  * PGF_XCHG_ROWS_ONLY: the output is a row set (no hash table): the input of a row-set scan.
  * The input handle stays valid.  nvlink_bytes_out (optional): bytes this rank sent over NVLink. */
 enum { PGF_XCHG_BROADCAST = 0, PGF_XCHG_PARTITION = 1, PGF_XCHG_ROWS_ONLY = 4 };
+/* Tests on one GPU: a context WITHOUT a communicator plays rank r of a w-way partition of its own rows (the same
+ * count / scatter kernels; the output holds the rows rank r owns). */
+#define PGF_XCHG_EMULATE(w, r) ((((uint32_t)(w)) & 0xFFu) << 8 | (((uint32_t)(r)) & 0xFFu) << 16)
 pgf_status pgf_join_table_exchange(pgf_ctx *ctx, uint64_t table_or_rows, uint32_t mode, uint64_t *out_handle,
                                    uint64_t *nvlink_bytes_out);
 /* rank that owns a key under PGF_XCHG_PARTITION (for tests) */

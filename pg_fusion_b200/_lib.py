@@ -212,6 +212,7 @@ _SIGNATURES = {
     "pgf_comm_destroy": (i32, [vp]),
     "pgf_comm_info": (i32, [vp, P(i32), P(i32)]),
     "pgf_comm_all_gather": (i32, [vp, vp, vp, u64]),
+    "pgf_comm_all_gather_host": (i32, [vp, vp, vp, u64]),
     "pgf_pipeline_run_sharded": (i32, [vp, P(Pipeline), u64, P(P(Result))]),
     "pgf_bloom_or_all_reduce": (i32, [vp, u64]),
     "pgf_join_table_exchange": (i32, [vp, u64, u32, P(u64), P(u64)]),

@@ -307,6 +307,7 @@ pgf_status pgf_scan_declare(pgf_ctx* ctx, uint64_t scan_id, const pgf_column_spe
 
 pgf_status pgf_scan_push_pages(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pages, uint64_t npages,
                                uint64_t stride) {
+  NvtxRange nvtx_("pgf:scan_push_pages");
   if (!ctx || (!pages && npages)) return PGF_ERR_INVALID_ARGUMENT;
   if (ctx->sticky) return ctx->sticky;
   Scan* sp = find_scan(ctx, scan_id);
@@ -394,6 +395,7 @@ pgf_status pgf_scan_push_page(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pag
 }
 
 pgf_status pgf_scan_finish(pgf_ctx* ctx, uint64_t scan_id) {
+  NvtxRange nvtx_("pgf:scan_finish");
   if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
   if (ctx->sticky) return ctx->sticky;
   Scan* sp = find_scan(ctx, scan_id);

@@ -153,6 +153,34 @@ pgf_status pgf_comm_all_gather(pgf_ctx* ctx, const void* dev_send, void* dev_rec
   return comm_all_gather(ctx, dev_send, dev_recv, bytes);
 }
 
+pgf_status pgf_comm_all_gather_host(pgf_ctx* ctx, const void* host_send, void* host_recv, uint64_t bytes) {
+  if (!ctx || !host_send || !host_recv) return PGF_ERR_INVALID_ARGUMENT;
+  if (ctx->sticky) return ctx->sticky;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  CU(ctx, cudaSetDevice(ctx->device));
+  const uint64_t world = uint64_t(ctx->comm_world);
+  if (world == 1) {
+    std::memcpy(host_recv, host_send, bytes);
+    return PGF_OK;
+  }
+  const size_t need = bytes * (world + 1);
+  if (ctx->d_xchg_cap < need) {
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+    if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+    ctx->d_xchg = nullptr;
+    ctx->d_xchg_cap = 0;
+    void* p = nullptr;
+    if (cudaMalloc(&p, need) != cudaSuccess) { cudaGetLastError(); return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange scratch"); }
+    ctx->d_xchg = static_cast<uint8_t*>(p);
+    ctx->d_xchg_cap = need;
+  }
+  CU(ctx, cudaMemcpyAsync(ctx->d_xchg, host_send, bytes, cudaMemcpyHostToDevice, ctx->compute_stream));
+  PGF_TRY(comm_all_gather(ctx, ctx->d_xchg, ctx->d_xchg + bytes, bytes));
+  CU(ctx, cudaMemcpyAsync(host_recv, ctx->d_xchg + bytes, bytes * world, cudaMemcpyDeviceToHost, ctx->compute_stream));
+  CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+  return PGF_OK;
+}
+
 pgf_status pgf_pipeline_run_sharded(pgf_ctx* ctx, const pgf_pipeline* plan, uint64_t max_groups, pgf_result** result_out) {
   if (!ctx || !plan || !result_out) return PGF_ERR_INVALID_ARGUMENT;
   if (ctx->sticky) return ctx->sticky;

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only: ranges cost nothing unless a tool (nsys, ncu --nvtx) is attached
 
 #include <cstdarg>
 #include <cstdio>
@@ -19,6 +20,15 @@
 struct pgf_ctx;
 
 namespace pgf {
+
+// NVTX range over a scope (the reference traces planning / execution with `tracing`; here the phases of
+// the hot path show up as named ranges in nsys / ncu timelines): ingest, fused pipelines, merges, exchanges.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct Scan {
   uint64_t id = 0;

@@ -189,7 +189,11 @@ struct DevPlan {
   uint32_t nbloom, nterms, njoins, sink;
   // compaction pipeline: 1 = bloom[0] is keyed on the column the queue entries carry (the first probe key, or its
   // own key when there is no join) and is probed AFTER the predicate, on dense lanes (stage B)
-  uint32_t bloom_dense, pad2;
+  uint32_t bloom_dense;
+  // 1: every page of the scan has layout class 0, whose offsets travel in the plan itself (class0): stage C then
+  // reads column offsets from the constant bank instead of chasing descs[page] -> classes[class] through HBM
+  uint32_t single_class;
+  LayoutClass class0;
   DevBloomProbe bloom[kMaxBlooms];
   DevTerm terms[kMaxTerms];
   DevJoin joins[kMaxJoins];

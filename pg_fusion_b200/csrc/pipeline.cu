@@ -110,14 +110,14 @@ __global__ void __launch_bounds__(kExtractThreads) table_extract_kernel(GroupTab
 // ---- broadcast-join exchange: a built table travels between GPUs as its occupied
 // slots.  Slots are self-contained records {key lo, key hi, occupancy/NULL flags, payload...}.
 // (block-aggregated like table_extract_kernel: one atomic per block reserves the output range)
-__global__ void __launch_bounds__(kExtractThreads) join_export_kernel(const uint4* slots, uint32_t capacity, uint32_t slot_u4, uint4* out,
-                                                                     unsigned long long max_rows, unsigned long long* count) {
+__global__ void __launch_bounds__(kExtractThreads) join_export_kernel(const uint4* slots, const uint8_t* tags, uint32_t capacity, uint32_t slot_u4,
+                                                                     uint4* out, unsigned long long max_rows, unsigned long long* count) {
   __shared__ unsigned long long s_base;
   __shared__ uint32_t s_warp[kExtractThreads / 32];
   const uint64_t seg = ((uint64_t(capacity) + gridDim.x - 1) / gridDim.x + kExtractThreads - 1) / kExtractThreads * kExtractThreads;
   const uint64_t b0 = uint64_t(blockIdx.x) * seg, b1 = b0 + seg < capacity ? b0 + seg : capacity;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  auto occupied = [&](uint64_t i) { return i < b1 && (reinterpret_cast<const uint32_t*>(slots + i * slot_u4)[2] & 1u); };
+  auto occupied = [&](uint64_t i) { return i < b1 && tags[i] != 0; };   // the slot array is never cleared: the tag says whether a slot is live
   uint32_t mine = 0;
   for (uint64_t i = b0 + threadIdx.x; i < b1; i += kExtractThreads) mine += occupied(i);
   mine = __reduce_add_sync(0xffffffffu, mine);
@@ -153,25 +153,39 @@ __global__ void __launch_bounds__(kExtractThreads) join_export_kernel(const uint
   }
 }
 
-// Builds the table from dense build rows (the output of a build-sink pipeline, or the fragments of a
-// broadcast / partitioned exchange): linear probing from the key's home bucket, CAS on the occupancy
-// word, then tag byte + slot.  capacity >= 2 x rows, so an empty slot always exists.
+// Builds the table from dense build rows (the output of a build-sink pipeline, or the fragments of a broadcast /
+// partitioned exchange).  A row claims the first empty tag byte of its home bucket (or of the buckets that follow:
+// linear probing) with a 64-bit CAS on the bucket's tag word, then writes its slot.  Only the tag directory has to
+// start out zeroed and only it sees atomics -- 1 byte per slot, L2 resident -- while the slot array is written
+// exactly once, a whole 16 / 32-byte record per row, and never cleared.  capacity >= 2 x rows, so an empty tag
+// always exists.
 __global__ void join_build_kernel(uint4* slots, uint8_t* tags, uint32_t mask, uint32_t shift, uint32_t slot_u4, const uint4* rows, uint64_t nrows) {
   for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < nrows; r += uint64_t(gridDim.x) * blockDim.x) {
     const uint4 s0 = rows[r * slot_u4];
     const uint64_t hk = join_hash(int64_t((uint64_t(s0.y) << 32) | s0.x));
-    uint32_t i = join_home(hk, shift);
+    const unsigned long long tag = join_tag8(hk, shift);
+    uint32_t base = join_home(hk, shift);
     for (;;) {
-      uint32_t* slot = reinterpret_cast<uint32_t*>(slots + uint64_t(i) * slot_u4);
-      if (atomicCAS(slot + 2, 0u, s0.z) == 0u) {
-        tags[i] = uint8_t(join_tag8(hk, shift));
-        slot[0] = s0.x;
-        slot[1] = s0.y;
-        slot[3] = s0.w;
-        if (slot_u4 == 2) slots[uint64_t(i) * 2 + 1] = rows[r * 2 + 1];
+      unsigned long long* word = reinterpret_cast<unsigned long long*>(tags + base);
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(word);
+      uint32_t pos = kJoinBucket;
+      for (;;) {
+        const uint32_t z0 = ~(((uint32_t(cur) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | uint32_t(cur) | 0x7F7F7F7Fu);          // 0x80 per empty tag
+        const uint32_t z1 = ~(((uint32_t(cur >> 32) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | uint32_t(cur >> 32) | 0x7F7F7F7Fu);
+        if (!(z0 | z1)) break;                                                      // bucket full: go on with the next one
+        pos = z0 ? (uint32_t(__ffs(int(z0))) - 1u) >> 3 : 4u + ((uint32_t(__ffs(int(z1))) - 1u) >> 3);
+        const unsigned long long seen = atomicCAS(word, cur, cur | (tag << (8u * pos)));
+        if (seen == cur) break;                                                     // the tag byte is ours
+        cur = seen;
+        pos = kJoinBucket;
+      }
+      if (pos < kJoinBucket) {
+        const uint64_t i = uint64_t(base) + pos;
+        slots[i * slot_u4] = s0;
+        if (slot_u4 == 2) slots[i * 2 + 1] = rows[r * 2 + 1];
         break;
       }
-      i = (i + 1) & mask;
+      base = (base + kJoinBucket) & mask;
     }
   }
 }
@@ -1461,6 +1475,7 @@ const char* variant_name(const Lowered& L) {
 
 pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
                         uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out) {
+  NvtxRange nvtx_("pgf:pipeline_run");
   std::lock_guard<std::mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   Lowered L;
@@ -1476,6 +1491,10 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     PGF_TRY(scan_sync_descs(ctx, *L.scan));
     L.dev.descs = L.scan->d_descs;
     L.dev.classes = L.scan->d_classes;
+    if (L.scan->h_classes.size() == 1) {
+      L.dev.single_class = 1;
+      L.dev.class0 = L.scan->h_classes[0];
+    }
   }
 
   pgf_result* res = new (std::nothrow) pgf_result();
@@ -1588,7 +1607,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
       if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %u slots", jt.capacity);
       mem.ptrs.push_back(jt.d_slots);
       CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
-      CU(ctx, cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream));
+      CU(ctx, cudaMemsetAsync(reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes, 0, tag_bytes, ctx->compute_stream));
       if (nrows) {
         uint32_t shift = 64;
         for (uint64_t c = cap; c > 1; c >>= 1) shift--;
@@ -1695,6 +1714,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
 constexpr size_t kPartialHeaderOff = kHostArena / 2;
 
 pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, void* dev_state_out, uint64_t state_cap) {
+  NvtxRange nvtx_("pgf:pipeline_partial");
   std::lock_guard<std::mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
@@ -1705,6 +1725,10 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
     PGF_TRY(scan_sync_descs(ctx, *L.scan));
     L.dev.descs = L.scan->d_descs;
     L.dev.classes = L.scan->d_classes;
+    if (L.scan->h_classes.size() == 1) {
+      L.dev.single_class = 1;
+      L.dev.class0 = L.scan->h_classes[0];
+    }
   }
   const uint32_t aw = L.acc_cls == CLS_I128 ? 2 : 1;
   const uint32_t ew = entry_words(plan->nexprs, aw);
@@ -1733,6 +1757,7 @@ pgf_status pipeline_run_partial_async(pgf_ctx* ctx, const pgf_pipeline* plan, vo
 
 pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* dev_states, uint64_t stride,
                           uint32_t nstates, bool bounded, pgf_result** out) {
+  NvtxRange nvtx_("pgf:merge_partials");
   std::lock_guard<std::mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "partial states exist for aggregate sinks only");
@@ -1879,7 +1904,7 @@ pgf_status join_export(pgf_ctx* ctx, const JoinTable& jt, void* dev_rows_out, ui
   unsigned long long* h_cnt = reinterpret_cast<unsigned long long*>(ctx->h_flags + 4);
   CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, ctx->compute_stream));
   const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(jt.capacity) + kExtractThreads - 1) / kExtractThreads, uint64_t(ctx->sm_count) * 8));
-  join_export_kernel<<<grid, kExtractThreads, 0, ctx->compute_stream>>>(jt.d_slots, jt.capacity, jt.slot_u4, static_cast<uint4*>(dev_rows_out),
+  join_export_kernel<<<grid, kExtractThreads, 0, ctx->compute_stream>>>(jt.d_slots, reinterpret_cast<const uint8_t*>(jt.d_slots) + uint64_t(jt.capacity) * jt.slot_u4 * sizeof(uint4), jt.capacity, jt.slot_u4, static_cast<uint4*>(dev_rows_out),
                                                            capacity_rows, d_cnt);
   CU(ctx, cudaGetLastError());
   CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
@@ -1909,7 +1934,7 @@ pgf_status join_from_fragments(pgf_ctx* ctx, const JoinTable& like, const void* 
   const uint64_t slot_bytes = cap * row_bytes, tag_bytes = cap + 16;
   jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
   if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
-  cudaError_t e = cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream);
+  cudaError_t e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes, 0, tag_bytes, ctx->compute_stream);
   uint8_t* tags = reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes;
   for (uint32_t f = 0; f < nfragments && e == cudaSuccess; ++f) {
     if (!counts[f]) continue;
@@ -1962,7 +1987,7 @@ pgf_status table_from_rows(pgf_ctx* ctx, const JoinTable& like, const uint4* row
   const uint64_t slot_bytes = cap * jt.slot_u4 * sizeof(uint4), tag_bytes = cap + 16;
   jt.d_slots = static_cast<uint4*>(ctx->join_alloc(slot_bytes + tag_bytes, &jt.alloc_bytes));
   if (!jt.d_slots) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a join table of %llu slots", (unsigned long long)cap);
-  cudaError_t e = cudaMemsetAsync(jt.d_slots, 0, slot_bytes + tag_bytes, ctx->compute_stream);
+  cudaError_t e = cudaMemsetAsync(reinterpret_cast<uint8_t*>(jt.d_slots) + slot_bytes, 0, tag_bytes, ctx->compute_stream);
   if (e == cudaSuccess && nrows) {
     uint32_t shift = 64;
     for (uint64_t c = cap; c > 1; c >>= 1) shift--;
@@ -1982,6 +2007,7 @@ pgf_status table_from_rows(pgf_ctx* ctx, const JoinTable& like, const uint4* row
 
 // AggregateExec Partial -> all-gather -> Final in one call (the collectives stay behind the C ABI).
 pgf_status pipeline_run_sharded(pgf_ctx* ctx, const pgf_pipeline* plan, uint64_t max_groups, pgf_result** out) {
+  NvtxRange nvtx_("pgf:pipeline_run_sharded");
   if (ctx->comm_world == 1) return pipeline_run(ctx, plan, false, nullptr, 0, nullptr, false, out);
   if (plan->sink != PGF_SINK_AGGREGATE) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "pgf_pipeline_run_sharded runs aggregate sinks");
   uint64_t state_bytes = 0;
@@ -2004,6 +2030,7 @@ pgf_status pipeline_run_sharded(pgf_ctx* ctx, const pgf_pipeline* plan, uint64_t
 
 // Join exchange over NCCL: broadcast (all-gather of every rank's rows) or hash partition (all-to-all).
 pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t* out_handle, uint64_t* nvlink_bytes) {
+  NvtxRange nvtx_("pgf:join_exchange");
   std::lock_guard<std::mutex> g(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   auto it = ctx->joins.find(handle);
@@ -2032,14 +2059,39 @@ pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t*
     if (!exported.alloc(nrows * row_bytes)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: row buffer");
     CU(ctx, cudaMemsetAsync(d_cnt, 0, 8, st));
     const uint32_t grid = uint32_t(std::min<uint64_t>((uint64_t(src.capacity) + kExtractThreads - 1) / kExtractThreads, uint64_t(ctx->sm_count) * 8));
-    join_export_kernel<<<grid, kExtractThreads, 0, st>>>(src.d_slots, src.capacity, src.slot_u4, static_cast<uint4*>(exported.p), nrows, d_cnt);
+    join_export_kernel<<<grid, kExtractThreads, 0, st>>>(src.d_slots, reinterpret_cast<const uint8_t*>(src.d_slots) + uint64_t(src.capacity) * src.slot_u4 * sizeof(uint4), src.capacity,
+                                                         src.slot_u4, static_cast<uint4*>(exported.p), nrows, d_cnt);
     CU(ctx, cudaGetLastError());
     rows = static_cast<const uint4*>(exported.p);
   }
   uint64_t sent = 0;
   Buf recv{ctx};
   uint64_t total = 0;
-  if (world == 1) {
+  const uint32_t emu_world = (mode >> 8) & 0xFFu, emu_rank = (mode >> 16) & 0xFFu;
+  if (world == 1 && partition && emu_world > 1) {
+    // single-process emulation of one rank of an emu_world-way partition (tests on one GPU): the same count /
+    // scatter kernels, then this rank keeps the segment it would have been sent by the only contributor
+    if (emu_world > kMaxRanks || emu_rank >= emu_world) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "bad emulated rank / world");
+    CU(ctx, cudaMemsetAsync(d_cnt, 0, 8 * kMaxRanks, st));
+    const uint32_t grid = uint32_t(std::min<uint64_t>(std::max<uint64_t>((nrows + 255) / 256, 1), uint64_t(ctx->sm_count) * 4));
+    if (nrows) partition_count_kernel<<<grid, 256, 0, st>>>(rows, nrows, src.slot_u4, emu_world, d_cnt);
+    CU(ctx, cudaGetLastError());
+    CU(ctx, cudaMemcpyAsync(h_cnt, d_cnt, 8 * kMaxRanks, cudaMemcpyDeviceToHost, st));
+    CU(ctx, cudaStreamSynchronize(st));
+    std::vector<uint64_t> cnt(emu_world), off(emu_world);
+    uint64_t o = 0;
+    for (uint32_t p = 0; p < emu_world; ++p) { cnt[p] = h_cnt[p]; off[p] = o; o += cnt[p]; }
+    if (o != nrows) return ctx->fail(PGF_ERR_STATE, "partition count lost rows");
+    Buf sendbuf{ctx};
+    if (!sendbuf.alloc(nrows * row_bytes) || !recv.alloc(cnt[emu_rank] * row_bytes)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: partition buffers");
+    for (uint32_t p = 0; p < emu_world; ++p) h_cnt[p] = off[p];
+    CU(ctx, cudaMemcpyAsync(d_cnt, h_cnt, 8 * emu_world, cudaMemcpyHostToDevice, st));
+    if (nrows) partition_scatter_kernel<<<grid, 256, 0, st>>>(rows, nrows, src.slot_u4, emu_world, d_cnt, static_cast<uint4*>(sendbuf.p));
+    CU(ctx, cudaGetLastError());
+    total = cnt[emu_rank];
+    CU(ctx, cudaMemcpyAsync(recv.p, static_cast<uint8_t*>(sendbuf.p) + off[emu_rank] * row_bytes, total * row_bytes, cudaMemcpyDeviceToDevice, st));
+    CU(ctx, cudaStreamSynchronize(st));
+  } else if (world == 1) {
     if (!recv.alloc(nrows * row_bytes)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange: row buffer");
     CU(ctx, cudaMemcpyAsync(recv.p, rows, nrows * row_bytes, cudaMemcpyDeviceToDevice, st));
     total = nrows;

@@ -1258,27 +1258,93 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
           for (uint32_t i = threadIdx.x; i < nrec * rw; i += blockDim.x)
             reinterpret_cast<uint64_t*>(stages)[i] = *reinterpret_cast<volatile uint64_t*>(P.cta_rec + i);
         __syncthreads();
-        // a record leads its group if no earlier record names the same slot; (leader, argument) pairs are
-        // dealt to the threads, each adds the records of its slot in CTA order
-        for (uint32_t r = threadIdx.x / 16u; r < nrec; r += blockDim.x / 16u) {
-          const uint32_t e = threadIdx.x % 16u;
-          const uint64_t tag = recs[uint64_t(r) * rw];
-          if (tag == 0ull || e >= P.nexprs) continue;
-          bool leader = true;
-          for (uint32_t q = 0; q < r; ++q) leader &= recs[uint64_t(q) * rw] != tag;
-          if (!leader) continue;
-          double sum = 0.0;
-          bool first = true;
-          for (uint32_t q = r; q < nrec; ++q) {
-            if (recs[uint64_t(q) * rw] != tag) continue;
-            const double v = __longlong_as_double((long long)recs[uint64_t(q) * rw + 2u + e]);
-            sum = first ? v : __dadd_rn(sum, v);
-            first = false;
+        // Reduction in a FIXED shape (so the bits do not depend on which CTA finished first), in parallel:
+        //  1. the distinct slots named by the records of the first CTAs (normally all there are: 1 without GROUP
+        //     BY, 4 for Q1) form a short list;
+        //  2. one warp per (listed slot, argument): lane l adds the records of CTAs l, l + 32, ... in that order,
+        //     then the lanes are combined by a shuffle tree;
+        //  3. records naming a slot that is not listed (a group no early CTA met) take the generic path below.
+        // What the table already holds came from the rows of the slow path (NULL inputs, more than kRegGroups
+        // groups per CTA); every CTA finished those before it took its ticket.
+        constexpr uint32_t kListMax = 32;
+        uint64_t* lst = reinterpret_cast<uint64_t*>(&sh->red[0][0]);   // kListMax entries: red[] is idle now
+        static_assert(sizeof(sh->red) >= kListMax * sizeof(uint64_t), "slot list lives in the reduction scratch");
+        if (threadIdx.x == 0) {
+          uint32_t n = 0;
+          const uint32_t look = min(nrec, 8u * kRegGroups);
+          for (uint32_t r = 0; r < look && n < kListMax; ++r) {
+            const uint64_t tag = recs[uint64_t(r) * rw];
+            bool known = tag == 0ull;
+            for (uint32_t q = 0; q < n; ++q) known |= lst[q] == tag;
+            if (!known) lst[n++] = tag;
           }
-          // what the table already holds came from the rows of the slow path (NULL inputs, more than
-          // kRegGroups groups per CTA); every CTA finished those before it took its ticket
-          double* dst = reinterpret_cast<double*>(P.table.acc + (tag - 1ull) * P.nexprs + e);
-          *dst = __dadd_rn(*dst, sum);
+          sh->dict_n = n;   // (the dictionary is no longer needed)
+          sh->dict_lock = 0;
+        }
+        __syncthreads();
+        const uint32_t nl = sh->dict_n;
+        const uint32_t nwarps = blockDim.x >> 5;
+        for (uint32_t task = warp; task < nl * P.nexprs; task += nwarps) {
+          const uint32_t e = task % P.nexprs;
+          const uint64_t tag = lst[task / P.nexprs];
+          double part = 0.0;
+          int any = 0;
+          for (uint32_t c = lane; c < gridDim.x; c += 32u) {
+#pragma unroll
+            for (uint32_t g = 0; g < kRegGroups; ++g) {
+              const uint64_t* rec = recs + uint64_t(c * kRegGroups + g) * rw;
+              if (rec[0] == tag) {
+                const double v = __longlong_as_double((long long)rec[2u + e]);
+                part = any ? __dadd_rn(part, v) : v;
+                any = 1;
+              }
+            }
+          }
+#pragma unroll
+          for (int o = 16; o; o >>= 1) {
+            const double pv = __shfl_down_sync(0xffffffffu, part, o);
+            const int pa = __shfl_down_sync(0xffffffffu, any, o);
+            if (int(lane) < o && pa) {
+              part = any ? __dadd_rn(part, pv) : pv;
+              any = 1;
+            }
+          }
+          if (lane == 0 && any) {
+            double* dst = reinterpret_cast<double*>(P.table.acc + (tag - 1ull) * P.nexprs + e);
+            *dst = __dadd_rn(*dst, part);
+          }
+        }
+        // 3. unlisted slots (rare): a record leads its group if no earlier record names the same slot; (leader,
+        // argument) pairs are dealt to the threads, each adds the records of its slot in CTA order
+        bool unlisted = false;
+        for (uint32_t r = threadIdx.x; r < nrec; r += blockDim.x) {
+          const uint64_t tag = recs[uint64_t(r) * rw];
+          bool known = tag == 0ull;
+          for (uint32_t q = 0; q < nl; ++q) known |= lst[q] == tag;
+          unlisted |= !known;
+        }
+        if (unlisted) atomicExch(&sh->dict_lock, 1u);
+        __syncthreads();
+        if (sh->dict_lock) {
+          for (uint32_t r = threadIdx.x / 16u; r < nrec; r += blockDim.x / 16u) {
+            const uint32_t e = threadIdx.x % 16u;
+            const uint64_t tag = recs[uint64_t(r) * rw];
+            if (tag == 0ull || e >= P.nexprs) continue;
+            bool leader = true;
+            for (uint32_t q = 0; q < nl; ++q) leader &= lst[q] != tag;
+            for (uint32_t q = 0; q < r; ++q) leader &= recs[uint64_t(q) * rw] != tag;
+            if (!leader) continue;
+            double sum = 0.0;
+            bool first = true;
+            for (uint32_t q = r; q < nrec; ++q) {
+              if (recs[uint64_t(q) * rw] != tag) continue;
+              const double v = __longlong_as_double((long long)recs[uint64_t(q) * rw + 2u + e]);
+              sum = first ? v : __dadd_rn(sum, v);
+              first = false;
+            }
+            double* dst = reinterpret_cast<double*>(P.table.acc + (tag - 1ull) * P.nexprs + e);
+            *dst = __dadd_rn(*dst, sum);
+          }
         }
       }
     }

@@ -120,3 +120,91 @@ def gpu_q1_d(scan):
     aggs = [(AggFunc.SUM, [Factor.of(0)]), (AggFunc.SUM, [Factor.of(1)]), (AggFunc.SUM, disc_price), (AggFunc.SUM, charge),
             (AggFunc.AVG, [Factor.of(0)]), (AggFunc.AVG, [Factor.of(1)]), (AggFunc.AVG, [Factor.of(2)]), (AggFunc.COUNT_STAR, None)]
     return scan.pipeline().filter(6, Cmp.LE, D_1998_09_02).aggregate([4, 5], aggs)
+
+
+def q3_bloom_params(ncust: int, nord: int, bits_per_key: int = 16):
+    """Runtime filters sized bits_per_key per expected build key (a fifth of the customers, a tenth of the orders)."""
+    from . import BloomParams
+
+    def pow2(n):
+        b = 1
+        while b < n:
+            b <<= 1
+        return b
+    return (BloomParams.new(pow2(bits_per_key * max(1, ncust // 5)), 4, 7), BloomParams.new(pow2(bits_per_key * max(1, nord // 10)), 4, 7))
+
+
+def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment=b"BUILDING", limit=10):
+    """The Q3 shape over page-sharded scans with HASH-PARTITIONED joins, every collective inside
+    the library (pgf_comm_*): the context must carry a communicator.
+
+      customer  -> build rows            -> BROADCAST (small)                     -> T1 on every rank
+      orders    -> probe T1 -> build rows (+ runtime filter over o_orderkey)      -> PARTITION by hash(o_orderkey)
+                                                                                   -> T2 = this rank's share of the orders
+                   runtime filter: OR all-reduce                                  -> the filter knows every build key
+      lineitem  -> date filter -> runtime filter (dense lanes) -> rows {l_orderkey; extendedprice, discount}
+                                                                                   -> PARTITION by hash(l_orderkey)
+      received rows -> probe T2 -> GROUP BY -> top `limit`    (every group lives on the rank that owns its key: no merge)
+      the ranks' top rows -> all-gather (a few hundred bytes) -> the global top `limit`
+
+    Only ~1 % of the lineitem rows cross NVLink: the ones the runtime filter cannot rule out.
+    Returns (rows [(l_orderkey, revenue, o_orderdate, o_shippriority)], stats)."""
+    import struct
+
+    from . import AggFunc, Cmp, ColumnSpec, Factor, TypeTag
+    rank, world = ctx.comm_info()
+    stats = {"nvlink_bytes": 0}
+    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rows_only=True).run()
+    t1, sent = ctx.exchange(r1.join_table, partition=False)
+    stats["nvlink_bytes"] += sent
+    ctx.destroy_join_table(r1.join_table)
+    rf = ctx.runtime_filter(q3_bloom_params(1, nord_total)[1])
+    rf.try_acquire_builder()
+    r2 = orders.pipeline().filter(2, Cmp.LT, Q3_DATE).join(t1, 1).build_join(0, [2, 3], rf, rows_only=True).run()
+    t2, sent = ctx.exchange(r2.join_table, partition=True)
+    stats["nvlink_bytes"] += sent
+    ctx.destroy_join_table(r2.join_table)
+    rf.or_all_reduce()
+    rf.publish_ready()
+    r3 = lineitem.pipeline().bloom_probe(rf, 0).filter(3, Cmp.GT, Q3_DATE).build_join(0, [1, 2], rows_only=True).run()
+    rs3, sent = ctx.exchange(r3.join_table, partition=True, rows_only=True)
+    stats["nvlink_bytes"] += sent
+    ctx.destroy_join_table(r3.join_table)
+    schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Float64), ColumnSpec(TypeTag.Float64)]
+    p4 = (ctx.row_set_pipeline(rs3, schema).join(t2, 0)
+          .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
+                     expected_groups=max(1024, ctx.join_table_info(t2).rows)))
+    if limit:
+        p4.order_by(Q3_ORDER, limit=limit)
+    r4 = p4.run()
+    for h in (t1, t2, rs3):
+        ctx.destroy_join_table(h)
+    stats.update(customer=r1, orders=r2, lineitem=r3, final=r4, rf=rf)
+    rows = [(int(k[0]), float(a[0]), bytes(k[1]), int(k[2])) for k, a in zip(r4.keys, r4.aggs)]
+    if not limit:
+        return rows, stats
+    # the ranks' top rows -> every rank -> the global top `limit`
+    return merge_topk(ctx.comm_all_gather_host(pack_topk(rows, limit)), limit), stats
+
+
+_TOPK_REC = __import__("struct").Struct("<qd12sq")   # l_orderkey, revenue, o_orderdate (<= 12 bytes), o_shippriority
+
+
+def pack_topk(rows, limit: int) -> bytes:
+    """Fixed-size buffer of one rank's top rows: row count, then `limit` records (zero padded)."""
+    import struct
+    body = b"".join(_TOPK_REC.pack(k, v, d, p) for k, v, d, p in rows[:limit])
+    return struct.pack("<q", min(len(rows), limit)) + body.ljust(_TOPK_REC.size * limit, b"\0")
+
+
+def merge_topk(buffers, limit: int):
+    """ORDER BY revenue DESC, o_orderdate LIMIT `limit` over the ranks' buffers (every rank computes the same list)."""
+    import struct
+    merged = []
+    for buf in buffers:
+        n = struct.unpack_from("<q", buf)[0]
+        for i in range(n):
+            k, v, d, p = _TOPK_REC.unpack_from(buf, 8 + i * _TOPK_REC.size)
+            merged.append((k, v, d.rstrip(b"\0"), p))
+    merged.sort(key=lambda r: (-r[1], r[2]))
+    return merged[:limit]

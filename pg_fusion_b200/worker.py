@@ -621,10 +621,22 @@ class Context:
     def comm_all_gather(self, send_ptr: int, recv_ptr: int, nbytes: int) -> None:
         self._check(_lib.lib().pgf_comm_all_gather(self.h, send_ptr, recv_ptr, nbytes))
 
-    def exchange(self, handle: int, partition: bool, rows_only: bool = False) -> Tuple[int, int]:
-        """pgf_join_table_exchange: (new handle, bytes this rank sent over NVLink)."""
+    def comm_all_gather_host(self, payload: bytes) -> List[bytes]:
+        """All-gather of one equally sized host buffer per rank; returns the buffers in rank order."""
+        _, world = self.comm_info()
+        send = (C.c_uint8 * max(1, len(payload))).from_buffer_copy(payload or b"\0")
+        recv = (C.c_uint8 * (max(1, len(payload)) * world))()
+        self._check(_lib.lib().pgf_comm_all_gather_host(self.h, send, recv, len(payload)))
+        raw = bytes(recv)
+        return [raw[i * len(payload):(i + 1) * len(payload)] for i in range(world)]
+
+    def exchange(self, handle: int, partition: bool, rows_only: bool = False, emulate: Optional[Tuple[int, int]] = None) -> Tuple[int, int]:
+        """pgf_join_table_exchange: (new handle, bytes this rank sent over NVLink).  emulate=(world, rank): a context
+        without a communicator plays one rank of a partition of its own rows (single-GPU tests)."""
         out, sent = C.c_uint64(), C.c_uint64()
         mode = (1 if partition else 0) | (4 if rows_only else 0)
+        if emulate is not None:
+            mode |= (emulate[0] & 0xFF) << 8 | (emulate[1] & 0xFF) << 16
         self._check(_lib.lib().pgf_join_table_exchange(self.h, handle, mode, C.byref(out), C.byref(sent)))
         return out.value, sent.value
 

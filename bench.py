@@ -312,6 +312,7 @@ class Shapes:
         self.state = {k: torch.zeros(n, dtype=torch.uint8, device=comm.device) for k, n in (("q6", 4096), ("q1", 8192))}
         self.gathered = {k: torch.zeros(comm.world * v.numel(), dtype=torch.uint8, device=comm.device) for k, v in self.state.items()}
         self.plans = {"q6": T.gpu_q6(self.scans["q6"]), "q1": T.gpu_q1(self.scans["q1"])}
+        self.rf = ctx.runtime_filter(T.q3_bloom_params(1, self.nord)[1]) if comm.world > 1 else None   # one filter slot, recycled every pass
 
     def generate(self):
         G, ctx, c = self.pg.GenTable, self.ctx, self.comm
@@ -335,7 +336,7 @@ class Shapes:
             res, st = self.T.gpu_q3(self.ctx, s["customer"], s["orders"], s["lineitem"], bp, limit=10)
             return [(int(k[0]), float(a[0]), bytes(k[1]), int(k[2])) for k, a in zip(res.keys, res.aggs)], st
         # hash-partitioned joins and GROUP BY; the runtime filter is part of the plan
-        return self.T.gpu_q3_partitioned(self.ctx, s["customer"], s["orders"], s["lineitem"], nord_total=self.nord, limit=10)
+        return self.T.gpu_q3_partitioned(self.ctx, s["customer"], s["orders"], s["lineitem"], nord_total=self.nord, limit=10, rf=self.rf)
 
     def release(self):
         for s in self.scans.values():

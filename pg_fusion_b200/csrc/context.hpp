@@ -110,7 +110,7 @@ struct pgf_ctx {
   void* join_alloc(size_t bytes, size_t* got) {   // caller holds mu or is single threaded per the ABI contract
     size_t best = join_cache.size();
     for (size_t i = 0; i < join_cache.size(); ++i)
-      if (join_cache[i].bytes >= bytes && join_cache[i].bytes <= 2 * bytes + (1u << 20) &&
+      if (join_cache[i].bytes >= bytes && join_cache[i].bytes <= 4 * bytes + (16u << 20) &&
           (best == join_cache.size() || join_cache[i].bytes < join_cache[best].bytes)) best = i;
     if (best != join_cache.size()) {
       void* p = join_cache[best].p;
@@ -130,7 +130,7 @@ struct pgf_ctx {
   }
   void join_free(void* p, size_t bytes) {
     if (!p) return;
-    if (join_cache.size() >= 4) {   // keep the four most recent
+    if (join_cache.size() >= 16) {   // keep the sixteen most recent (a partitioned Q3 pass cycles through ~10 buffers)
       cudaFree(join_cache.front().p);
       join_cache.erase(join_cache.begin());
     }

@@ -193,6 +193,7 @@ struct DevPlan {
   // 1: every page of the scan has layout class 0, whose offsets travel in the plan itself (class0): stage C then
   // reads column offsets from the constant bank instead of chasing descs[page] -> classes[class] through HBM
   uint32_t single_class;
+  uint32_t entry_key_off, pad4;   // single-term specialisation of the compaction pipeline: stage offset of the Int32 entry key
   LayoutClass class0;
   DevBloomProbe bloom[kMaxBlooms];
   DevTerm terms[kMaxTerms];

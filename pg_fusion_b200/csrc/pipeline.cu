@@ -190,6 +190,16 @@ __global__ void join_build_kernel(uint4* slots, uint8_t* tags, uint32_t mask, ui
   }
 }
 
+// RuntimeFilterBuildExec (worker_runtime/src/runtime_filter_plan.rs:227-274,345-363): every build row's key goes into
+// the filter.  Run over the dense build rows after the fused kernel: full lanes, coalesced key reads, and the atomics
+// on the bit array are not tangled with the probe chains of stage C.  (NULL keys never reach the rows.)
+__global__ void bloom_insert_rows_kernel(DevBloom b, const uint4* rows, uint64_t nrows, uint32_t row_u4) {
+  for (uint64_t r = blockIdx.x * uint64_t(blockDim.x) + threadIdx.x; r < nrows; r += uint64_t(gridDim.x) * blockDim.x) {
+    const uint4 s0 = rows[r * row_u4];
+    bloom_insert(b, (uint64_t(s0.y) << 32) | s0.x);
+  }
+}
+
 // ---- hash-partitioned exchange: rows grouped by owner rank = join_partition(key) --------
 // pass 1 counts the rows of every destination, pass 2 scatters them behind per-destination cursors (block-local
 // counts first, one atomic per block and destination).
@@ -350,6 +360,53 @@ __global__ void __launch_bounds__(kTopkThreads) topk_pick_kernel(DevSort S, cons
   if (b == kNoEntry) return;
   if (threadIdx.x == 0) { taken[b] = 1; out[0] = round + 1; }
   for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out[1 + uint64_t(round) * S.ew + w] = entries[uint64_t(b) * S.ew + w];
+}
+
+// Two-launch top-k (k <= PGF_TOPK_DEVICE_MAX): every block selects the k best entries of its own segment (k rounds of
+// a block-wide arg-best over at most a few thousand entries, winners masked by index), then one block selects the k
+// best of the blocks' candidates.  2 launches instead of 2k.
+__global__ void __launch_bounds__(kTopkThreads) topk_local_kernel(DevSort S, const uint64_t* entries, uint32_t n, uint32_t k, uint32_t* cand) {
+  const uint32_t seg = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t b0 = blockIdx.x * seg, b1 = min(n, b0 + seg);
+  __shared__ uint32_t s_taken[PGF_TOPK_DEVICE_MAX];
+  for (uint32_t r = 0; r < k; ++r) {
+    uint32_t mine = kNoEntry;
+    for (uint32_t i = b0 + threadIdx.x; i < b1; i += kTopkThreads) {
+      bool taken = false;
+      for (uint32_t q = 0; q < r; ++q) taken |= s_taken[q] == i;
+      if (!taken) mine = better(S, entries, mine, i);
+    }
+    const uint32_t b = block_best(S, entries, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      s_taken[r] = b;
+      cand[blockIdx.x * k + r] = b;
+    }
+    __syncthreads();
+  }
+}
+__global__ void __launch_bounds__(kTopkThreads) topk_final_kernel(DevSort S, const uint64_t* entries, uint32_t ncand, uint32_t k, const uint32_t* cand,
+                                                                   uint64_t* out) {
+  __shared__ uint32_t s_taken[PGF_TOPK_DEVICE_MAX];
+  uint32_t found = 0;
+  for (uint32_t r = 0; r < k; ++r) {
+    uint32_t mine = kNoEntry;
+    for (uint32_t c = threadIdx.x; c < ncand; c += kTopkThreads) {
+      const uint32_t i = cand[c];
+      if (i == kNoEntry) continue;
+      bool taken = false;
+      for (uint32_t q = 0; q < r; ++q) taken |= s_taken[q] == i;
+      if (!taken) mine = better(S, entries, mine, i);
+    }
+    const uint32_t b = block_best(S, entries, mine);
+    __syncthreads();
+    if (threadIdx.x == 0) s_taken[r] = b;
+    __syncthreads();
+    if (b == kNoEntry) break;
+    for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out[1 + uint64_t(r) * S.ew + w] = entries[uint64_t(b) * S.ew + w];
+    found = r + 1;
+  }
+  if (threadIdx.x == 0) out[0] = found;
 }
 
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
@@ -514,6 +571,7 @@ class Lowering {
     D.njoins = plan_->njoins;
     L_->nj = plan_->njoins;
 
+
     for (uint32_t b = 0; b < plan_->nbloom; ++b) {
       auto bt = ctx_->blooms.find(plan_->bloom[b].bloom);
       if (bt == ctx_->blooms.end()) return ctx_->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown bloom filter %llu", (unsigned long long)plan_->bloom[b].bloom);
@@ -589,11 +647,19 @@ class Lowering {
       D.nitems = s.rows ? 1 : 0;
     } else if (probe_) {
       PGF_TRY(layout_stage_probe(s));
-      if (D.nterms == 1 && D.terms[0].op == TERM_IN_RANGE && D.used_null_mask == 0 && D.terms[0].ref.ld == LD_VIEW) L_->t0 = LD_VIEW;
     } else {
       PGF_TRY(layout_stage(s));
     }
     fix_refs();
+    if (probe_ && !L_->rowscan && (D.njoins || D.bloom_dense) && D.nbloom == D.bloom_dense) {
+      // the specialisation of probe_pipeline_kernel: one plain string range, nothing nullable, Int32 entry key
+      const DevRef& kr = D.njoins ? D.joins[0].key : D.bloom[0].key;
+      if (D.nterms == 1 && D.terms[0].op == TERM_IN_RANGE && D.used_null_mask == 0 && D.terms[0].ref.ld == LD_VIEW &&
+          kr.src == SRC_PAGE && kr.ld == LD_I32) {
+        L_->t0 = LD_VIEW;
+        D.entry_key_off = kr.off;
+      }
+    }
     return PGF_OK;
   }
 
@@ -1279,20 +1345,17 @@ pgf_status lower_sort(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L, 
 // Selects the k first entries under the ORDER BY on the device; h_state receives [k][entries].
 pgf_status device_topk(pgf_ctx* ctx, const DevSort& S, const uint64_t* d_entries, uint64_t n, uint32_t k,
                        std::vector<uint64_t>* h_state, uint32_t* launches) {
-  const uint32_t nblocks = uint32_t(std::min<uint64_t>((n + kTopkThreads - 1) / kTopkThreads, uint64_t(ctx->sm_count) * 4));
-  const size_t o_taken = 0, o_best = align_up(n, 16), o_out = align_up(o_best + nblocks * 4, 16);
+  // segments of ~2048 entries per block keep the k rounds of the local selection short
+  const uint32_t nblocks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((n + 2047) / 2048, uint64_t(ctx->sm_count) * 8)));
+  const size_t o_cand = 0, o_out = align_up(size_t(nblocks) * k * 4, 16);
   const size_t bytes = o_out + (1 + size_t(k) * S.ew) * 8;
   PGF_TRY(grow(ctx, &ctx->d_topk, &ctx->d_topk_cap, bytes, "the top-k scratch"));
-  uint8_t* taken = ctx->d_topk + o_taken;
-  uint32_t* blk_best = reinterpret_cast<uint32_t*>(ctx->d_topk + o_best);
+  uint32_t* cand = reinterpret_cast<uint32_t*>(ctx->d_topk + o_cand);
   uint64_t* out = reinterpret_cast<uint64_t*>(ctx->d_topk + o_out);
-  CU(ctx, cudaMemsetAsync(ctx->d_topk, 0, bytes, ctx->compute_stream));
-  for (uint32_t r = 0; r < k; ++r) {
-    topk_round_kernel<<<nblocks, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, uint32_t(n), taken, blk_best);
-    topk_pick_kernel<<<1, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, nblocks, blk_best, taken, out, r);
-  }
+  topk_local_kernel<<<nblocks, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, uint32_t(n), k, cand);
+  topk_final_kernel<<<1, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, nblocks * k, k, cand, out);
   CU(ctx, cudaGetLastError());
-  *launches += 2 * k;
+  *launches += 2;
   h_state->assign(1 + size_t(k) * S.ew, 0);
   CU(ctx, cudaMemcpyAsync(h_state->data(), out, h_state->size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
@@ -1528,7 +1591,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     size_t bytes = 0;
     ~RowBuf() { if (p) ctx->join_free(p, bytes); }
   } rowbuf{ctx};
-  uint64_t rows_cap = 0;
+  uint64_t rows_cap = 0, bloom_rows = 0;
   if (plan->sink == PGF_SINK_JOIN_BUILD) {
     rows_cap = plan->expected_groups ? plan->expected_groups : std::max<uint64_t>(L.scan->rows, 1);
     rowbuf.p = ctx->join_alloc(rows_cap * L.build_table.slot_u4 * sizeof(uint4), &rowbuf.bytes);
@@ -1589,6 +1652,18 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
       }
       JoinTable& jt = L.build_table;
       jt.rows = nrows;
+      if (L.dev.has_build_bloom && nrows) {
+        CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
+        const uint32_t bgrid = uint32_t(std::min<uint64_t>((nrows + 255) / 256, uint64_t(ctx->sm_count) * 8));
+        bloom_insert_rows_kernel<<<bgrid, 256, 0, ctx->compute_stream>>>(L.dev.build_bloom, static_cast<const uint4*>(rowbuf.p), nrows, jt.slot_u4);
+        CU(ctx, cudaGetLastError());
+        CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
+        CU(ctx, cudaEventSynchronize(ctx->ev_b));
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->ev_a, ctx->ev_b));
+        total_ms += ms;
+        ++launches;
+        bloom_rows = nrows;
+      }
       if (plan->build_flags & PGF_BUILD_ROWS_ONLY) {  // the row set is the result: no hash table
         jt.d_rows = static_cast<uint4*>(rowbuf.p);
         jt.rows_alloc_bytes = rowbuf.bytes;
@@ -1688,7 +1763,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   res->rows_bloom = c.rows_bloom;
   res->rows_filtered = c.rows_filtered;
   res->rows_out = c.rows_out;
-  res->bloom_rows = c.bloom_rows;
+  res->bloom_rows = bloom_rows;
   res->kernel_ms = total_ms;
   ctx->last_kernel_ms = total_ms;
   res->kernel_launches = launches;
@@ -2041,6 +2116,7 @@ pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t*
   const bool partition = (mode & 3u) == PGF_XCHG_PARTITION, rows_only = (mode & PGF_XCHG_ROWS_ONLY) != 0;
   const uint64_t row_bytes = uint64_t(src.slot_u4) * sizeof(uint4);
   cudaStream_t st = ctx->compute_stream;
+  PhaseTrace trace(st);
   struct Buf {
     pgf_ctx* ctx;
     void* p = nullptr;
@@ -2147,6 +2223,7 @@ pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t*
     PGF_TRY(comm_all_to_all_v(ctx, sendbuf.p, soff.data(), sbytes.data(), recv.p, roff.data(), rbytes.data()));
     CU(ctx, cudaStreamSynchronize(st));   // the send buffer goes back to the cache
   }
+  trace.mark(partition ? "exchange: partition + all-to-all" : "exchange: broadcast");
   // 2. the output: a row set, or a hash table over the received rows
   JoinTable outjt = src;
   outjt.d_slots = nullptr;
@@ -2163,6 +2240,7 @@ pgf_status join_exchange(pgf_ctx* ctx, uint64_t handle, uint32_t mode, uint64_t*
     CU(ctx, cudaStreamSynchronize(st));   // recv goes back to the cache
   }
   CU(ctx, cudaStreamSynchronize(st));   // every temporary of the exchange is idle before it returns to the cache
+  trace.mark("exchange: table from rows");
   const uint64_t id = ctx->next_handle++;
   ctx->joins[id] = outjt;
   *out_handle = id;

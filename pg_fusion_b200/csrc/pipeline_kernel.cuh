@@ -29,8 +29,12 @@ constexpr int kMaxConsumerWarps = 16;
 __host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped, bool fast = false) {
   return (sink == SINK_AGG && grouped && !fast) ? 14 : 16;
 }
+// Producer warps: one feeds the ring of most shapes; the fast GROUP BY path (Q1: 80 bytes per row, seven bulk copies per
+// tile) was starved by a single one (ncu r1: 44 % of its stall samples on the `full` barrier), so there two producers
+// alternate tiles.
+__host__ __device__ constexpr int producer_warps(bool fast = false) { return fast ? 2 : 1; }
 __host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped, bool fast = false) {
-  return (consumer_warps(sink, grouped, fast) + 1) * 32;
+  return (consumer_warps(sink, grouped, fast) + producer_warps(fast)) * 32;
 }
 constexpr int kStages = 4;     // ring depth of streaming pipelines
 #ifndef PGF_JOIN_ROWS
@@ -733,6 +737,7 @@ __global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED, is_fast_groupe
 pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr bool kFastGrouped = is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>();
   constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED, kFastGrouped);
+  constexpr uint32_t PW = uint32_t(producer_warps(kFastGrouped));   // warps 0 .. PW-1 produce, the rest consume
   using Ops = AccOps<ACC>;
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
@@ -781,18 +786,19 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
   // shared-memory accumulator slots of the fast GROUP BY path (behind the ring and the queues)
   [[maybe_unused]] unsigned long long* myacc =
       reinterpret_cast<unsigned long long*>(stages + size_t(kNumStages) * P.stage_bytes + size_t(kMaxConsumerWarps) * kQueueBytesPerWarp) +
-      (threadIdx.x >= 32 ? threadIdx.x - 32 : 0);
+      (threadIdx.x >= PW * 32u ? threadIdx.x - PW * 32u : 0);
   if constexpr (kFastGrouped) {
-    if (warp > 0)
+    if (warp >= PW)
       for (uint32_t q = 0; q < G * (SHAPE::Exprs::size + 1); ++q) myacc[q * kAccThreads] = 0ull;  // +0.0 / integer 0
   }
 
-  if (warp == 0) {
-    // ===== producer: TMA bulk copies of the needed column slices of each row tile =====
+  if (warp < PW) {
+    // ===== producer(s): TMA bulk copies of the needed column slices of each row tile =====
     // One warp feeds the whole CTA, so its per-tile path is kept short: pages are walked with a
     // nested page / tile loop (no divisions), each lane keeps its column's plan entry and the
     // offsets of the current layout class in registers, the byte count is one warp reduction.
     uint32_t ps = 0, pphase = 0;  // ring stage and mbarrier phase of the producer
+    [[maybe_unused]] uint32_t tseq = 0;  // tile sequence number inside the CTA
     // lanes 0..15: values slice of staged column `lane`; lanes 16..31: its validity slice
     const uint32_t mycol = lane & 15u;
     const bool is_validity = lane >= 16;
@@ -819,12 +825,14 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
       const bool active = want && (!is_validity || ((null_mask >> sc.page_col) & 1u));
       for (uint32_t tile = 0, r0 = 0; tile < P.tiles_per_page; ++tile, r0 += P.tile_rows) {
         const uint32_t s = ps;
+        const uint32_t wait_parity = pphase ^ 1u;
+        if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
+        if (PW > 1 && ((tseq++) % PW) != warp) continue;   // the producers take the CTA's tiles in turn
         const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
         uint32_t bytes = 0;
         if (active && n) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * width + 15u) & ~15u);
         const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
-        mbar_wait(&sh->empty[s], pphase ^ 1u);
-        if (++ps == kNumStages) { ps = 0; pphase ^= 1u; }
+        mbar_wait(&sh->empty[s], wait_parity);
         if (lane == 0) {
           sh->meta[s].nrows = n;
           sh->meta[s].null_mask = null_mask;
@@ -839,11 +847,11 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
   } else {
     // ===== consumers =====
     [[maybe_unused]] uint64_t* myqueue = reinterpret_cast<uint64_t*>(stages + size_t(kNumStages) * P.stage_bytes) +
-                                         size_t(warp - 1) * (kQueueBytesPerWarp / 8);
+                                         size_t(warp - PW) * (kQueueBytesPerWarp / 8);
     [[maybe_unused]] auto drain_queue = [&]() {
       if constexpr (SINK == SINK_AGG && GROUPED) {
         __syncwarp();
-        const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - 1]), kQueueCap);
+        const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - PW]), kQueueCap);
         for (uint32_t base = 0; base < n; base += 32u) {
           const uint32_t idx = base + lane;
           if (idx < n) {
@@ -858,7 +866,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
           }
         }
         __syncwarp();
-        if (lane == 0) sh->qcount[warp - 1] = 0;
+        if (lane == 0) sh->qcount[warp - PW] = 0;
         __syncwarp();
       }
     };
@@ -881,7 +889,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
       // bound is warp-uniform: the warp votes below are executed by all 32 lanes.
       constexpr uint32_t R = kRows;
       const uint32_t ngroups = (nrows + 32u * R - 1u) / (32u * R);
-      for (uint32_t pr = (warp - 1 + kConsumerWarps - (k * 5u) % kConsumerWarps) % kConsumerWarps; pr < ngroups; pr += kConsumerWarps) {
+      for (uint32_t pr = (warp - PW + kConsumerWarps - (k * 5u) % kConsumerWarps) % kConsumerWarps; pr < ngroups; pr += kConsumerWarps) {
         const uint32_t b0 = pr * (32u * R);
         uint32_t rr[R];
         bool keep[R];
@@ -1141,7 +1149,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
                 // applies its queue to the global table from a converged point
                 bool queued = false;
                 if constexpr (GROUPED) {
-                  const uint32_t pos = atomicAdd(&sh->qcount[warp - 1], 1u);
+                  const uint32_t pos = atomicAdd(&sh->qcount[warp - PW], 1u);
                   if (pos < kQueueCap) {
                     uint64_t* qe = myqueue + pos * kQueueEntryWords;
 #pragma unroll
@@ -1161,7 +1169,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         }
         if constexpr (SINK == SINK_AGG && GROUPED) {
           __syncwarp();
-          if (*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - 1]) >= kQueueDrainAt) drain_queue();
+          if (*reinterpret_cast<volatile uint32_t*>(&sh->qcount[warp - PW]) >= kQueueDrainAt) drain_queue();
         }
       }
       __syncwarp();
@@ -1176,7 +1184,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
     const uint32_t ng = GROUPED ? sh->dict_n : 1u;
     for (uint32_t g = 0; g < ng; ++g) {
       int64_t slot = 0;
-      if (GROUPED && threadIdx.x == 32) {
+      if (GROUPED && threadIdx.x == PW * 32u) {
         uint64_t key[kKeyWords];
 #pragma unroll
         for (uint32_t w = 0; w < kKeyWords; ++w) key[w] = sh->dict_keys[g][w];
@@ -1188,7 +1196,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         uint64_t rows = 0;
         if constexpr (kFastGrouped) {
           constexpr uint32_t NE = SHAPE::Exprs::size;
-          if (warp > 0) {
+          if (warp >= PW) {
             if (e < NE) a = slot_value<ACC>(myacc + (g * (NE + 1) + e) * kAccThreads);
             else if (e == P.nexprs) rows = myacc[(g * (NE + 1) + NE) * kAccThreads];
           }
@@ -1203,18 +1211,18 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
             }
           }
         }
-        if (warp == 0) { a = Ops::zero(); rows = 0; }
+        if (warp < PW) { a = Ops::zero(); rows = 0; }
         if (e < P.nexprs) {
 #pragma unroll
           for (int o = 16; o; o >>= 1) a = Ops::add(a, Ops::shfl_xor(a, o));
-          if (lane == 0 && warp > 0) *reinterpret_cast<AccT*>(&sh->red[warp - 1][0]) = a;
+          if (lane == 0 && warp >= PW) *reinterpret_cast<AccT*>(&sh->red[warp - PW][0]) = a;
         } else {
 #pragma unroll
           for (int o = 16; o; o >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, o);
-          if (lane == 0 && warp > 0) sh->red[warp - 1][0] = rows;
+          if (lane == 0 && warp >= PW) sh->red[warp - PW][0] = rows;
         }
         __syncthreads();
-        if (threadIdx.x == 32 && slot >= 0) {
+        if (threadIdx.x == PW * 32u && slot >= 0) {
           if (e < P.nexprs) {
             AccT t = Ops::zero();
             for (int w = 0; w < kConsumerWarps; ++w) t = Ops::add(t, *reinterpret_cast<AccT*>(&sh->red[w][0]));
@@ -1238,7 +1246,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         __syncthreads();
       }
       if constexpr (ACC == CLS_F64) {
-        if (threadIdx.x == 32) P.cta_rec[(uint64_t(blockIdx.x) * kRegGroups + g) * (2u + P.nexprs)] = uint64_t(slot) + 1ull;  // 0 = no record
+        if (threadIdx.x == PW * 32u) P.cta_rec[(uint64_t(blockIdx.x) * kRegGroups + g) * (2u + P.nexprs)] = uint64_t(slot) + 1ull;  // 0 = no record
       }
     }
     if constexpr (ACC == CLS_F64) {

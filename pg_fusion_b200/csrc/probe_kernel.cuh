@@ -41,7 +41,7 @@ constexpr int kPConsumerWarps = PGF_PROBE_WARPS;
 constexpr int kPThreads = kPConsumerWarps * 32;
 constexpr uint32_t kPMaxDepth = 4;                                   // tiles in flight per warp
 constexpr uint32_t kPQueueEntries = 64;                              // per warp and queue; drained 32 at a time
-constexpr uint32_t kPQueueBytesPerWarp = 2u * kPQueueEntries * 16u;  // survivors + tag hits
+constexpr uint32_t kPQueueBytesPerWarp = 2u * kPQueueEntries * 16u + 32u * 8u;  // survivors + tag hits + the tag windows in flight
 
 struct PStageMeta {
   uint32_t nrows, null_mask, page, r0;
@@ -49,9 +49,13 @@ struct PStageMeta {
 struct PWarpCtl {  // one per warp
   uint64_t full[kPMaxDepth];
   PStageMeta meta[kPMaxDepth];
-  uint8_t pad[128 - kPMaxDepth * (8 + sizeof(PStageMeta))];
+  // counters that are touched once per tile or only by stages B / C: kept here, not in registers of the stage A loop
+  uint32_t n_in, n_out, n_bad, n_groups, n_bloom_rej, pad0;
+  uint64_t dbar;       // completes when the descriptor of the next tile's page has landed in dnext
+  PageDesc dnext;
+  uint8_t pad1[16];
 };
-static_assert(sizeof(PWarpCtl) == 128, "per-warp control block");
+static_assert(sizeof(PWarpCtl) == 160 && offsetof(PWarpCtl, dnext) % 16 == 0, "per-warp control block");
 __host__ __device__ constexpr uint32_t probe_shared_bytes() { return uint32_t(kPConsumerWarps) * uint32_t(sizeof(PWarpCtl)); }
 
 // ---- L2 residency control: the page stream is read once (evict_first), the tag directories and the
@@ -78,6 +82,20 @@ __device__ __forceinline__ uint2 ldg_tags8(const uint8_t* p, bool pred, uint64_t
   asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %3, 0;\n\t@p ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %4;\n\t}"
       : "+r"(v.x), "+r"(v.y)
       : "l"(p), "r"(uint32_t(pred)), "l"(policy));
+  return v;
+}
+// The same window as an asynchronous copy into the lane's shared-memory slot.  A register destination would tie
+// the load to the scoreboard every other global load of the kernel shares, and the compiler waits on that one at
+// the top of the next chunk; the copy is waited for where stage B resolves the batch, a whole batch later.
+__device__ __forceinline__ void tags8_async(uint32_t smem_dst, const uint8_t* p, bool pred, uint64_t policy) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 8, %3;\n\t}"
+               ::"r"(smem_dst), "l"(p), "r"(uint32_t(pred)), "l"(policy) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ uint2 tags8_collect(uint32_t smem_src) {
+  uint2 v;
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_src) : "memory");
   return v;
 }
 
@@ -273,7 +291,10 @@ struct JoinIter {
 // ---- sinks (stage C, dense lanes) -----------------------------------------------------------
 // group_slot() without waiting: -2 when the probe runs into a slot another thread is publishing.  The
 // caller retries from a converged point, so lanes of one warp never spin on each other.
-__device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uint64_t* key, uint32_t nwords, uint32_t knull, uint64_t h) {
+// (*inserted is set when the call created the group: the caller counts new groups per thread and adds them to
+// GroupTable::used once per warp at the end of the kernel -- one same-address atomic per group serialises in L2.)
+__device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uint64_t* key, uint32_t nwords, uint32_t knull, uint64_t h,
+                                                  uint32_t* inserted) {
   uint32_t i = uint32_t(h) & t.mask;
   const uint32_t ready = 2u | (knull << 8);
   for (uint32_t probes = 0; probes <= t.mask; ++probes, i = (i + 1) & t.mask) {
@@ -286,7 +307,7 @@ __device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uin
           if (w < nwords) t.keys[uint64_t(i) * kKeyWords + w] = key[w];
         __threadfence();
         atomicExch(t.state + i, ready);
-        atomicAdd(t.used, 1u);
+        *inserted += 1u;
         return i;
       }
       s = old;
@@ -309,7 +330,7 @@ __device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uin
 // lineitems of an order are neighbours) elect a leader with match.any: one table lookup per group, warp
 // and batch, and no two lanes of a warp ever insert the same key.
 template <uint32_t ACC>
-__device__ __forceinline__ void sink_agg_grouped(const DevPlan& P, const GRow& g, bool found, uint32_t lane, uint32_t& bad) {
+__device__ __forceinline__ void sink_agg_grouped(const DevPlan& P, const GRow& g, bool found, uint32_t lane, uint32_t& bad, uint32_t& new_groups) {
   using Ops = AccOps<ACC>;
   uint64_t key[kKeyWords] = {0, 0, 0, 0};
   uint32_t knull = 0;
@@ -350,7 +371,7 @@ __device__ __forceinline__ void sink_agg_grouped(const DevPlan& P, const GRow& g
   bool todo = own;
   while (__any_sync(0xffffffffu, todo)) {
     if (todo) {
-      const int64_t s = group_slot_try(P.table, key, P.nkeywords, knull, h);
+      const int64_t s = group_slot_try(P.table, key, P.nkeywords, knull, h, &new_groups);
       if (s != -2) { slot = s; todo = false; }
     }
   }
@@ -387,7 +408,8 @@ __device__ __forceinline__ void sink_agg_single(const DevPlan& P, const GRow& g,
 }
 
 // HashJoinExec build side: append {key, occupancy / NULL flags, payload} to the dense row array
-__device__ __forceinline__ void sink_build(const DevPlan& P, const GRow& g, bool found, uint32_t lane, uint32_t& n_bloom_ins) {
+// (RuntimeFilterBuildExec: the filter is populated from the dense rows afterwards, bloom_insert_rows_kernel in pipeline.cu)
+__device__ __forceinline__ void sink_build(const DevPlan& P, const GRow& g, bool found, uint32_t lane) {
   const JoinBuild& jb = P.build;
   const bool valid = found && g_valid(jb.key, g);  // NULL keys never match: not inserted
   const uint32_t m = __ballot_sync(0xffffffffu, valid);
@@ -429,7 +451,6 @@ __device__ __forceinline__ void sink_build(const DevPlan& P, const GRow& g, bool
   } else {
     atomicExch(P.table.overflow, 1u);
   }
-  if (P.has_build_bloom) { bloom_insert(P.build_bloom, uint64_t(key)); ++n_bloom_ins; }
 }
 
 // ---- stage C: n entries on dense lanes: probe chains, second join, sink ---------------------
@@ -438,7 +459,7 @@ __device__ __forceinline__ void sink_build(const DevPlan& P, const GRow& g, bool
 // e: {page, row, key lo, key hi} of a page scan, or {row index lo, hi, key lo, key hi} of a row-set scan (ROWS).
 template <uint32_t ACC, bool ROWS = false>
 __device__ __forceinline__ void stage_c(const DevPlan& P, uint4 e, bool act, uint32_t lane, uint32_t& n_out, uint32_t& n_bad,
-                                        uint32_t& n_bloom_ins) {
+                                        uint32_t& n_groups) {
   GRow g;
   g.pay0 = g.pay1 = g.rec = nullptr;
   g.occ0 = g.occ1 = g.occr = 0;
@@ -503,10 +524,10 @@ __device__ __forceinline__ void stage_c(const DevPlan& P, uint4 e, bool act, uin
     if (!m) break;
     n_out += __popc(m);
     if (P.sink == SINK_AGG) {
-      if (P.nkeys) sink_agg_grouped<ACC>(P, g, found, lane, n_bad);
+      if (P.nkeys) sink_agg_grouped<ACC>(P, g, found, lane, n_bad, n_groups);
       else sink_agg_single<ACC>(P, g, found, lane);
     } else if (P.sink == SINK_JOIN_BUILD) {
-      sink_build(P, g, found, lane, n_bloom_ins);
+      sink_build(P, g, found, lane);
     }
     __syncwarp();
   }
@@ -560,8 +581,9 @@ __device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stag
 }
 
 // ---- the kernel ------------------------------------------------------------------------------
-// T0 >= 0: the predicate is exactly one plain range term of load kind T0 over a NOT NULL column and
-// no staged column is nullable (the Q3 pipelines); T0 < 0: generic.
+// T0 >= 0 (the Q3 pipelines): the predicate is exactly one plain range term of load kind T0 over a NOT NULL
+// column, no staged column is nullable, every runtime filter is probed on dense lanes (stage B) and the entry key
+// (join key or dense filter key) is an Int32 page column staged at P.entry_key_off; T0 < 0: generic.
 template <uint32_t ACC, int T0>
 __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr bool kNoNull = T0 >= 0;
@@ -579,14 +601,17 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
   uint8_t* stages = smem_raw + stages_off;
   uint4* q1 = reinterpret_cast<uint4*>(smem_raw + q_off);
   uint4* q2 = q1 + kPQueueEntries;
+  const uint32_t tagslot = smem_u32(q2 + kPQueueEntries) + lane * 8u;   // this lane's tag window in flight
   if (lane == 0) {
+    ctl->n_in = ctl->n_out = ctl->n_bad = ctl->n_groups = ctl->n_bloom_rej = 0;
+    mbar_init(&ctl->dbar, 1);
     for (uint32_t s = 0; s < kPMaxDepth; ++s) mbar_init(&ctl->full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   __syncwarp();
 
-  uint32_t n_in = 0, n_bloom = 0, n_filt = 0, n_out = 0, n_bad = 0, n_bloom_ins = 0, n_bloom_rej = 0;
+  uint32_t n_bloom = 0, n_filt = 0, n_bad = 0;   // (n_bad: stage A's out-of-line views; the rest of the counters: PWarpCtl)
 
   // ---- this warp's tile stream: tiles wg, wg + nw, wg + 2 nw, ... of the scan (tile = tile_rows rows of a page)
   const uint32_t wg = blockIdx.x * kPConsumerWarps + warp, nw = gridDim.x * kPConsumerWarps;
@@ -608,11 +633,20 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     my_soff = is_validity ? sc.valid_off : sc.smem_off;
     my_pcol = sc.page_col;
   }
-  PageDesc dnext{};  // descriptor of the page of the next tile to issue, loaded one tile ahead
-  if (my_tiles) dnext = P.descs[ipage];
+  // The descriptor of the page of the next tile to issue is fetched one tile ahead by a bulk copy of its own (an
+  // ordinary load would be waited for at the top of the next chunk, see tags8_async): parity of fetch i is i & 1.
+  auto fetch_desc = [&]() {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(&ctl->dbar, uint32_t(sizeof(PageDesc)));
+      tma_load_1d_hint(&ctl->dnext, P.descs + ipage, uint32_t(sizeof(PageDesc)), &ctl->dbar, pol_stream);
+    }
+  };
+  if (my_tiles) fetch_desc();
   auto issue_next = [&]() {
     if (issued >= my_tiles) return;
-    const PageDesc d = dnext;
+    mbar_wait(&ctl->dbar, issued & 1u);
+    const uint2 dw = *reinterpret_cast<const uint2*>(&ctl->dnext);   // {row_count, layout_class | null_mask << 16}
+    struct { uint32_t row_count, layout_class, null_mask; } d{dw.x, dw.y & 0xFFFFu, dw.y >> 16};
     if (d.layout_class != cur_class) {  // rare: pages of one scan share their layout class
       cur_class = d.layout_class;
       const LayoutClass* lc = P.classes + cur_class;
@@ -627,9 +661,10 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
     if (lane == 0) {
       ctl->meta[is] = PStageMeta{n, null_mask, ipage, r0};
+      ctl->n_in += n;
       mbar_arrive_expect_tx(&ctl->full[is], total);
     }
-    __syncwarp();
+    __syncwarp();   // (also: every lane has read dnext before the next fetch overwrites it)
     if (bytes)
       tma_load_1d_hint(stages + size_t(is) * P.stage_bytes + my_soff,
                        P.pages + uint64_t(ipage) * P.page_stride + my_coff + (is_validity ? (r0 >> 3) : r0 * my_width), bytes, &ctl->full[is], pol_stream);
@@ -638,7 +673,7 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     if (itip >= P.tiles_per_page) { itip -= P.tiles_per_page; ++ipage; }
     ++issued;
     if (++is == D) is = 0;
-    if (issued < my_tiles) dnext = P.descs[ipage];  // in flight while the warp works on its next tile
+    if (issued < my_tiles) fetch_desc();  // in flight while the warp works on its next tile
   };
   for (uint32_t i = 0; i < D; ++i) issue_next();
 
@@ -652,7 +687,6 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     // batch whose tag loads are in flight (stage B issued, not yet resolved)
     bool pend = false, pact = false;
     uint4 pe = make_uint4(0, 0, 0, 0);
-    uint2 pw = make_uint2(0, 0);
     uint32_t ptag = 0;
 
     // -- stage C: n tag hits (32, or what is left when draining) on dense lanes
@@ -661,14 +695,18 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       uint4 e = make_uint4(0, 0, 0, 0);
       if (lane < n) e = q2[q2n + lane];
       __syncwarp();
-      stage_c<ACC>(P, e, lane < n, lane, n_out, n_bad, n_bloom_ins);
+      uint32_t c_out = 0, c_bad = 0, c_groups = 0;
+      stage_c<ACC>(P, e, lane < n, lane, c_out, c_bad, c_groups);
+      if (lane == 0) ctl->n_out += c_out;               // warp uniform
+      if (c_bad) atomicAdd(&ctl->n_bad, c_bad);         // per lane, rare
+      if (c_groups) atomicAdd(&ctl->n_groups, c_groups);
     };
     // -- stage B: resolve the tag loads of the pending batch (SIMD-in-register byte compares), compact its hits
     // into q2; then pop n survivors onto dense lanes, hash them and issue their tag loads
     auto run_b = [&](uint32_t n) {
       if (pend) {
         pend = false;
-        const bool hit = pact && window_may_match(pw, ptag);
+        const bool hit = pact && window_may_match(tags8_collect(tagslot), ptag);
         const uint32_t m = __ballot_sync(0xffffffffu, hit);
         if (m) {
           if (hit) q2[q2n + __popc(m & lt)] = pe;
@@ -683,14 +721,15 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
         __syncwarp();
         if (P.bloom_dense) {  // the runtime filter on the entry key, probed on dense lanes
           const bool alive = pact && bloom_contains(P.bloom[0].bloom, (uint64_t(pe.w) << 32) | pe.z);
-          n_bloom_rej += __popc(__ballot_sync(0xffffffffu, pact && !alive));
+          const uint32_t rej = __popc(__ballot_sync(0xffffffffu, pact && !alive));
+          if (lane == 0) ctl->n_bloom_rej += rej;
           pact = alive;
         }
         if (P.njoins) {
           const DevJoin& j = P.joins[0];
           const uint64_t h = join_hash(int64_t((uint64_t(pe.w) << 32) | pe.z));
           ptag = join_tag8(h, j.shift);
-          pw = ldg_tags8(j.tags + join_home(h, j.shift), pact, pol_keep);
+          tags8_async(tagslot, j.tags + join_home(h, j.shift), pact, pol_keep);
           pend = true;
         } else {   // no join: the survivors are the sink's rows
           const uint32_t m = __ballot_sync(0xffffffffu, pact);
@@ -707,7 +746,6 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       const PStageMeta meta = ctl->meta[cs];
       const uint8_t* stage = stages + size_t(cs) * P.stage_bytes;
       if (++cs == D) { cs = 0; cphase ^= 1u; }
-      n_in += meta.nrows;
       for (uint32_t r0 = 0; r0 < meta.nrows; r0 += 32u) {
         // -- stage A: runtime Bloom probes (NULL key => DefinitelyAbsent, shared.rs:367-374), conjuncts,
         // compaction of the survivors
@@ -715,7 +753,7 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
         const bool has = r < meta.nrows;
         const uint32_t rr = has ? r : 0u;  // row 0 of a tile always exists
         bool keep = has;
-        if (P.nbloom > P.bloom_dense) {
+        if (T0 < 0 && P.nbloom > P.bloom_dense) {
           for (uint32_t b = P.bloom_dense; b < P.nbloom; ++b) {
             const DevBloomProbe& bp = P.bloom[b];
             const Row rq{stage, rr, meta.null_mask, nullptr, 0};
@@ -726,8 +764,20 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
           }
           n_bloom += __popc(__ballot_sync(0xffffffffu, keep));
         }
+        // the entry's key (join key, or the key of the dense runtime filter): its load is issued ahead of the
+        // conjuncts', so that one wait covers both
+        int64_t key = 0;
+        bool kvalid = true;
         if constexpr (T0 >= 0) {
-          keep = keep && term_pass1<T0, true>(P.terms[0], stage, rr, 0u, n_bad);
+          key = reinterpret_cast<const int32_t*>(stage + P.entry_key_off)[rr];
+        } else if (P.njoins | P.bloom_dense) {
+          const DevRef& kr = P.njoins ? P.joins[0].key : P.bloom[0].key;
+          const Row rq{stage, rr, meta.null_mask, nullptr, 0};
+          key = load_i64(kr, rq);
+          if constexpr (!kNoNull) kvalid = ref_valid(kr, rq);
+        }
+        if constexpr (T0 >= 0) {
+          keep = keep & term_pass1<T0, true>(P.terms[0], stage, rr, 0u, n_bad);   // (row rr exists on every lane: no branch)
         } else {
           for (uint32_t t = 0; t < P.nterms; ++t) {
             if (!__any_sync(0xffffffffu, keep)) break;
@@ -736,25 +786,14 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
         }
         uint32_t m = __ballot_sync(0xffffffffu, keep);
         n_filt += __popc(m);
-        int64_t key = 0;
-        if (P.njoins) {
-          const DevJoin& j = P.joins[0];
-          const Row rq{stage, rr, meta.null_mask, nullptr, 0};
-          key = load_i64(j.key, rq);
-          if constexpr (!kNoNull) {
-            const bool valid = ref_valid(j.key, rq);  // NULL keys never match: an inner join drops the row
-            if (P.bloom_dense) n_bloom_rej += __popc(__ballot_sync(0xffffffffu, keep && !valid));   // ... and DefinitelyAbsent
-            keep = keep && valid;
-            m = __ballot_sync(0xffffffffu, keep);
-          }
-        } else if (P.bloom_dense) {  // no join: the entry carries the runtime filter's key
-          const DevBloomProbe& bp = P.bloom[0];
-          const Row rq{stage, rr, meta.null_mask, nullptr, 0};
-          key = load_i64(bp.key, rq);
-          if constexpr (!kNoNull) {
-            const bool valid = ref_valid(bp.key, rq);  // NULL key => DefinitelyAbsent (shared.rs:367-374)
-            n_bloom_rej += __popc(__ballot_sync(0xffffffffu, keep && !valid));
-            keep = keep && valid;
+        if constexpr (!kNoNull) {
+          // NULL keys never match (an inner join drops the row) and are DefinitelyAbsent for a filter (shared.rs:367-374)
+          if (P.njoins | P.bloom_dense) {
+            if (P.bloom_dense) {
+              const uint32_t rej = __popc(__ballot_sync(0xffffffffu, keep && !kvalid));
+              if (lane == 0) ctl->n_bloom_rej += rej;
+            }
+            keep = keep && kvalid;
             m = __ballot_sync(0xffffffffu, keep);
           }
         }
@@ -777,28 +816,28 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       if (q2n >= 32u) run_c(32u);
     }
     while (q2n) run_c(min(q2n, 32u));
+    __syncwarp();
+    const uint32_t n_in = ctl->n_in;
     if (P.nbloom == P.bloom_dense) n_bloom = n_in;   // no probe ran in stage A
-    n_bloom -= n_bloom_rej;                          // rows_bloom = rows the runtime filters did not reject
-    n_filt -= n_bloom_rej;                           // rows_filtered = rows past the filters AND the predicate
+    n_bloom -= ctl->n_bloom_rej;                     // rows_bloom = rows the runtime filters did not reject
+    n_filt -= ctl->n_bloom_rej;                      // rows_filtered = rows past the filters AND the predicate
   }
 
   // counters (RuntimeFilter*/Worker* style metrics).  n_in .. n_out are warp-uniform in the consumer
   // warps (ballot popcounts): one lane adds them; n_bad and n_bloom_ins are per lane.
   {
     unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.counters);
+    uint32_t bad = n_bad;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) bad += __shfl_xor_sync(0xffffffffu, bad, o);
     if (lane == 0) {
-      if (n_in) atomicAdd(dst + 0, (unsigned long long)n_in);
+      bad += ctl->n_bad;
+      if (ctl->n_in) atomicAdd(dst + 0, (unsigned long long)ctl->n_in);
       if (n_bloom) atomicAdd(dst + 1, (unsigned long long)n_bloom);
       if (n_filt) atomicAdd(dst + 2, (unsigned long long)n_filt);
-      if (n_out) atomicAdd(dst + 3, (unsigned long long)n_out);
-    }
-    uint32_t vals[2] = {n_bloom_ins, n_bad};
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint32_t v = vals[q];
-#pragma unroll
-      for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0 && v) atomicAdd(dst + 4 + q, (unsigned long long)v);
+      if (ctl->n_out) atomicAdd(dst + 3, (unsigned long long)ctl->n_out);
+      if (bad) atomicAdd(dst + 5, (unsigned long long)bad);
+      if (ctl->n_groups) atomicAdd(P.table.used, ctl->n_groups);   // groups this warp created
     }
   }
 }
@@ -811,7 +850,7 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
 template <uint32_t ACC>
 __global__ void __launch_bounds__(256) rows_pipeline_kernel(const __grid_constant__ DevPlan P) {
   const uint32_t lane = threadIdx.x & 31;
-  uint32_t n_out = 0, n_bad = 0, n_bloom_ins = 0, n_in = 0;
+  uint32_t n_out = 0, n_bad = 0, n_groups = 0, n_in = 0;
   const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5), w0 = uint64_t(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (uint64_t base = w0 * 32u; base < P.row_count; base += nwarps * 32u) {
     const uint64_t i = base + lane;
@@ -823,20 +862,23 @@ __global__ void __launch_bounds__(256) rows_pipeline_kernel(const __grid_constan
       e.w = head.y;
     }
     n_in += __popc(__ballot_sync(0xffffffffu, act));
-    stage_c<ACC, true>(P, e, act, lane, n_out, n_bad, n_bloom_ins);
+    stage_c<ACC, true>(P, e, act, lane, n_out, n_bad, n_groups);
   }
   unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.counters);
   if (lane == 0) {
     if (n_in) { atomicAdd(dst + 0, (unsigned long long)n_in); atomicAdd(dst + 1, (unsigned long long)n_in); atomicAdd(dst + 2, (unsigned long long)n_in); }
     if (n_out) atomicAdd(dst + 3, (unsigned long long)n_out);
   }
-  uint32_t vals[2] = {n_bloom_ins, n_bad};
+  uint32_t vals[2] = {n_groups, n_bad};
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     uint32_t v = vals[q];
 #pragma unroll
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && v) atomicAdd(dst + 4 + q, (unsigned long long)v);
+    if (lane == 0 && v) {
+      if (q == 0) atomicAdd(P.table.used, v);
+      else atomicAdd(dst + 5, (unsigned long long)v);
+    }
   }
 }
 

@@ -39,7 +39,8 @@ def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDIN
         rf1 = ctx.runtime_filter(bloom_params[0])
         rf1.try_acquire_builder()
     # customer(BUILDING) -> join table T1 keyed by c_custkey (+ Bloom for the orders scan)
-    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1).run()
+    hint = lambda scan, frac: int(scan.info().rows * frac) + 4096   # build-row buffer sizing (too small = one more pass)
+    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rf1, expected_rows=hint(customer, 0.25)).run()
     if rf1 is not None:
         rf1.publish_ready()
     # orders: [Bloom probe] -> o_orderdate < date -> probe T1 -> T2 keyed by o_orderkey with payload
@@ -48,7 +49,7 @@ def gpu_q3(ctx, customer, orders, lineitem, bloom_params=None, segment=b"BUILDIN
         p2.bloom_probe(rf1, 1)
         rf2 = ctx.runtime_filter(bloom_params[1])
         rf2.try_acquire_builder()
-    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(r1.join_table, 1).build_join(0, [2, 3], rf2).run()
+    r2 = p2.filter(2, Cmp.LT, Q3_DATE).join(r1.join_table, 1).build_join(0, [2, 3], rf2, expected_rows=hint(orders, 0.125)).run()
     if rf2 is not None:
         rf2.publish_ready()
     # lineitem: [Bloom probe] -> l_shipdate > date -> probe T2 -> GROUP BY l_orderkey, o_orderdate, o_shippriority
@@ -134,7 +135,7 @@ def q3_bloom_params(ncust: int, nord: int, bits_per_key: int = 16):
     return (BloomParams.new(pow2(bits_per_key * max(1, ncust // 5)), 4, 7), BloomParams.new(pow2(bits_per_key * max(1, nord // 10)), 4, 7))
 
 
-def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment=b"BUILDING", limit=10):
+def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment=b"BUILDING", limit=10, rf=None):
     """The Q3 shape over page-sharded scans with HASH-PARTITIONED joins, every collective inside
     the library (pgf_comm_*): the context must carry a communicator.
 
@@ -151,22 +152,29 @@ def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment
     Returns (rows [(l_orderkey, revenue, o_orderdate, o_shippriority)], stats)."""
     import struct
 
-    from . import AggFunc, Cmp, ColumnSpec, Factor, TypeTag
+    from . import AggFunc, Cmp, ColumnSpec, Factor, RuntimeFilterState, TypeTag
     rank, world = ctx.comm_info()
     stats = {"nvlink_bytes": 0}
-    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rows_only=True).run()
+    # build-row buffers are sized from TPC-H's selectivities (a hint that is too small costs one more pass, never a
+    # wrong result): a fifth of the customers, an eighth of the orders, a thirtieth of the lineitems survive
+    hint = lambda scan, frac: int(scan.info().rows * frac) + 4096
+    r1 = customer.pipeline().filter(1, Cmp.EQ, segment).build_join(0, [], rows_only=True, expected_rows=hint(customer, 0.25)).run()
     t1, sent = ctx.exchange(r1.join_table, partition=False)
     stats["nvlink_bytes"] += sent
     ctx.destroy_join_table(r1.join_table)
-    rf = ctx.runtime_filter(q3_bloom_params(1, nord_total)[1])
+    own_rf = rf is None
+    if own_rf:
+        rf = ctx.runtime_filter(q3_bloom_params(1, nord_total)[1])
+    elif rf.snapshot()[1] == RuntimeFilterState.Ready:   # a filter slot recycled from the previous query
+        rf.retire_ready_after_quiescence()
     rf.try_acquire_builder()
-    r2 = orders.pipeline().filter(2, Cmp.LT, Q3_DATE).join(t1, 1).build_join(0, [2, 3], rf, rows_only=True).run()
+    r2 = orders.pipeline().filter(2, Cmp.LT, Q3_DATE).join(t1, 1).build_join(0, [2, 3], rf, rows_only=True, expected_rows=hint(orders, 0.125)).run()
     t2, sent = ctx.exchange(r2.join_table, partition=True)
     stats["nvlink_bytes"] += sent
     ctx.destroy_join_table(r2.join_table)
     rf.or_all_reduce()
     rf.publish_ready()
-    r3 = lineitem.pipeline().bloom_probe(rf, 0).filter(3, Cmp.GT, Q3_DATE).build_join(0, [1, 2], rows_only=True).run()
+    r3 = lineitem.pipeline().bloom_probe(rf, 0).filter(3, Cmp.GT, Q3_DATE).build_join(0, [1, 2], rows_only=True, expected_rows=hint(lineitem, 1 / 30)).run()
     rs3, sent = ctx.exchange(r3.join_table, partition=True, rows_only=True)
     stats["nvlink_bytes"] += sent
     ctx.destroy_join_table(r3.join_table)
@@ -179,7 +187,9 @@ def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment
     r4 = p4.run()
     for h in (t1, t2, rs3):
         ctx.destroy_join_table(h)
-    stats.update(customer=r1, orders=r2, lineitem=r3, final=r4, rf=rf)
+    if own_rf:
+        rf.destroy()
+    stats.update(customer=r1, orders=r2, lineitem=r3, final=r4, rf=None if own_rf else rf)
     rows = [(int(k[0]), float(a[0]), bytes(k[1]), int(k[2])) for k, a in zip(r4.keys, r4.aggs)]
     if not limit:
         return rows, stats

@@ -82,6 +82,13 @@ def test_compaction_pipeline_kernels_use_bulk_copies_mbarriers_and_l2_hints(tmp_
     log = open(os.path.join(BUILD, "pipeline_inst_probe.ptxas.log")).read()
     entries = re.findall(r"Compiling entry function '(\S+)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
                          r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", log)
+    entries = [e for e in entries if e[0].startswith("_ZN3pgf21probe_pipeline_kernel")]
     assert len(entries) == 6
     for name, stack, st, ld, regs in entries:
-        assert int(st) <= 64 and int(ld) <= 64, f"{name[:80]} spills {st}/{ld} bytes"
+        # <ACC, T0>: ACC 2 = Decimal128 sums (four-word accumulators in stage C, which runs for joined rows only)
+        limit = 256 if "kernelILj2E" in name else 16
+        assert int(st) <= limit and int(ld) <= limit, f"{name[:80]} spills {st}/{ld} bytes"
+    for k in kernels:
+        # the tag windows of stage B travel by asynchronous copies into shared memory (no register scoreboard is held
+        # across chunks), and the next page descriptor by a bulk copy of its own
+        assert "LDGSTS" in k and "DEPBAR" in k, k.split("\n")[0]

@@ -169,3 +169,37 @@ def test_redundant_and_saturated_bloom_probes_are_dropped_by_default():
         sat.publish_ready()
         dropped = probe.pipeline().bloom_probe(sat, 0).count().run()
         assert dropped.rows_bloom == dropped.rows_in == dropped.rows_out                # (b) saturated
+
+
+def test_two_join_probes_on_one_stream(ctx):
+    """VERDICT r1 grammar gap: two HashJoinExec probes fused into one scan stream -- lineitem probes the orders
+    table and, with the matched order's o_custkey (a payload of the first join), the customer table.  Checked
+    against the oracle's nested hash joins (multisets: duplicates on both build sides multiply)."""
+    pages, (ct, ot, lt) = U.q3_host_tables(300, 3000, 40_000, seed=21, dup_keys=True, rows_per_page=700)
+    scans = []
+    for pg_, schema in zip(pages, (U.CUSTOMER_SCHEMA, U.ORDERS_SCHEMA, U.LINEITEM_Q3_SCHEMA)):
+        s = ctx.declare_scan(schema)
+        s.push_pages(pg_)
+        s.finish()
+        scans.append(s)
+    cust, orders, li = scans
+    tc = cust.pipeline().filter(1, Cmp.EQ, b"BUILDING").build_join(0, []).run()
+    to = orders.pipeline().filter(2, Cmp.LT, U.Q3_DATE).build_join(0, [1, 3]).run()      # payload: o_custkey, o_shippriority
+    probe = lambda: li.pipeline().filter(3, Cmp.GT, U.Q3_DATE).join(to.join_table, 0).join(tc.join_table, (1, 0))
+    res = probe().aggregate([0], [(AggFunc.COUNT_STAR, None), (AggFunc.SUM, [Factor.of(1)])], expected_groups=4096).run()
+    res_i = probe().aggregate([0], [(AggFunc.SUM, [Factor.of((1, 1))])], expected_groups=4096).run()   # Int64 sums: exact
+    assert res.variant == "compact_1_string_term"
+    # oracle: orders |><| customer first (as a table), then lineitem |><| that
+    cust_f = ct.select(O.filter_rows(ct, E.col(1).eq(E.s(b"BUILDING"))))
+    ord_f = ot.select(O.filter_rows(ot, E.col(2).lt(E.s(U.Q3_DATE))))
+    _, probe_rows = O.hash_join_pairs(cust_f, 0, ord_f, 1)
+    ord_j = ord_f.take(probe_rows)
+    want = O.aggregate(lt, E.col(3).gt(E.s(U.Q3_DATE)), [E.col(0)], [(O.AGG_COUNT_STAR, None), (O.AGG_SUM, E.col(1))], joins=[(ord_j, 0, 0, 0)])
+    want_i = O.aggregate(lt, E.col(3).gt(E.s(U.Q3_DATE)), [E.col(0)], [(O.AGG_SUM, E.col(3, 1))], joins=[(ord_j, 0, 0, 0)])
+    assert res.rows_out == res_i.rows_out == want.rows_joined > 0
+    U.assert_agg_equal(res, want, rel=1e-12)
+    U.assert_agg_equal(res_i, want_i, rel=0)
+    for h in (tc.join_table, to.join_table):
+        ctx.destroy_join_table(h)
+    for s in scans:
+        s.release()

@@ -150,10 +150,16 @@ pgf_status pgf_layout_plan_new(const pgf_column_spec *specs, uint32_t ncols, uin
 /* compute_fixed_row_cap, page/row_estimator/src/lib.rs:353-371 */
 pgf_status pgf_layout_fixed_row_cap(const pgf_column_spec *specs, uint32_t ncols,
                                     uint32_t block_size, uint32_t *cap_out);
-/* BlockRef::open, page/arrow_layout/src/access.rs:36-42 */
+/* BlockRef::open, page/arrow_layout/src/access.rs:36-42.  Strict reference v1: type tags 1..9 only
+ * (TypeTag::from_raw, types.rs:93-112); a block carrying the Decimal128 extension tag is
+ * PGF_ERR_LAYOUT_INVALID_TYPE_TAG here, exactly as in the reference. */
 pgf_status pgf_block_validate(const uint8_t *block, size_t len);
+/* The same check with this library's format extensions switched on explicitly. */
+#define PGF_LAYOUT_EXT_DECIMAL128 1u
+pgf_status pgf_block_validate_ext(const uint8_t *block, size_t len, uint32_t extensions);
 /* ArrowPageDecoder::import_owned checks, page/import/src/lib.rs:117-206 (all of them,
- * host side; the scan ingest path below splits them between host and device) */
+ * host side; the scan ingest path below splits them between host and device).  The Decimal128
+ * extension tag passes only under a schema that names it. */
 pgf_status pgf_block_import_check(uint16_t kind, uint16_t flags, const uint8_t *block, size_t len,
                                   const pgf_column_spec *schema, uint32_t ncols);
 /* init_block, page/arrow_layout/src/access.rs:640-654; then bulk column writes in the

@@ -230,7 +230,8 @@ int orc_layout_plan_new(const orc_column_spec *specs, uint32_t ncols, uint32_t m
 int orc_fixed_row_cap(const orc_column_spec *specs, uint32_t ncols, uint32_t block_size,
                       uint32_t *cap_out);
 int orc_init_block(uint8_t *block, size_t len, const orc_layout_plan *plan); /* access.rs:640-654 */
-int orc_block_validate(const uint8_t *block, size_t len);   /* BlockRef::open, access.rs:36-42 */
+int orc_block_validate(const uint8_t *block, size_t len);   /* BlockRef::open, access.rs:36-42 (+ the Decimal128 extension tag) */
+int orc_block_validate_v1(const uint8_t *block, size_t len); /* the same, reference v1 tags 1..9 only */
 int orc_block_write_fixed(uint8_t *block, size_t len, uint32_t col, uint32_t row,
                           const void *bytes, uint32_t nbytes); /* access.rs:316-319 */
 int orc_block_write_bool(uint8_t *block, size_t len, uint32_t col, uint32_t row, int value);

@@ -194,7 +194,12 @@ static int layout_from_desc(uint32_t max_rows, const orc_column_desc *d, orc_col
 
 /* BlockRef::open = read header, validate_block_prefix, validate_desc_layout_in_block
  * (access.rs:36-42; validate.rs:85-107,141-172) */
-int orc_block_validate(const uint8_t *block, size_t len) {
+static int validate_impl(const uint8_t *block, size_t len, int allow_ext);
+int orc_block_validate(const uint8_t *block, size_t len) { return validate_impl(block, len, 1); }
+/* the reference as it is: TypeTag::from_raw knows 1..9 (types.rs:93-112), so the Decimal128 extension tag is
+ * InvalidTypeTag */
+int orc_block_validate_v1(const uint8_t *block, size_t len) { return validate_impl(block, len, 0); }
+static int validate_impl(const uint8_t *block, size_t len, int allow_ext) {
   if (len < HEADER_SIZE) return ORC_LE_BLOCK_SLICE_TOO_SMALL;
   orc_block_header h;
   read_header(block, &h);
@@ -208,6 +213,7 @@ int orc_block_validate(const uint8_t *block, size_t len) {
     orc_column_desc d;
     orc_column_layout l;
     read_desc(block, c, &d);
+    if (!allow_ext && d.type_tag == ORC_T_DECIMAL128) return ORC_LE_INVALID_TYPE_TAG;
     rc = layout_from_desc(h.max_rows, &d, &l);
     if (rc) return rc;
     if (d.validity_off != cursor) return ORC_LE_COLUMN_DESC_MISMATCH;
@@ -444,7 +450,9 @@ int orc_import_check(uint16_t kind, uint16_t flags, const uint8_t *block, size_t
                      const orc_column_spec *schema, uint32_t ncols) {
   if (kind != ORC_ARROW_LAYOUT_BATCH_KIND) return ORC_IE_WRONG_KIND;
   if (flags != 0) return ORC_IE_UNSUPPORTED_FLAGS;
-  int rc = orc_block_validate(block, len);
+  int ext = 0; /* the Decimal128 extension tag exists only under a schema that names it */
+  for (uint32_t c = 0; c < ncols; ++c) ext |= schema[c].type_tag == ORC_T_DECIMAL128;
+  int rc = validate_impl(block, len, ext);
   if (rc) return rc;
   orc_block_header h;
   read_header(block, &h);

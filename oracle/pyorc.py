@@ -154,6 +154,7 @@ def lib():
         L.orc_fixed_row_cap.argtypes = [P(ColumnSpec), u32, u32, P(u32)]
         L.orc_init_block.argtypes = [vp, C.c_size_t, P(LayoutPlan)]
         L.orc_block_validate.argtypes = [vp, C.c_size_t]
+        L.orc_block_validate_v1.argtypes = [vp, C.c_size_t]
         L.orc_block_write_fixed.argtypes = [vp, C.c_size_t, u32, u32, vp, u32]
         L.orc_block_write_bool.argtypes = [vp, C.c_size_t, u32, u32, C.c_int]
         L.orc_block_write_null.argtypes = [vp, C.c_size_t, u32, u32]
@@ -357,6 +358,11 @@ class Block:
 
 def block_validate(buf: np.ndarray) -> int:
     return lib().orc_block_validate(_ptr(buf), buf.size)
+
+
+def block_validate_v1(buf: np.ndarray) -> int:
+    """BlockRef::open as the reference has it: type tags 1..9 only (no Decimal128 extension)."""
+    return lib().orc_block_validate_v1(_ptr(buf), buf.size)
 
 
 def import_check(kind: int, flags: int, buf: np.ndarray, cols: Sequence[tuple]) -> int:

@@ -152,6 +152,7 @@ _SIGNATURES = {
     "pgf_layout_plan_new": (i32, [P(ColumnSpec), u32, u32, u32, P(LayoutPlanC)]),
     "pgf_layout_fixed_row_cap": (i32, [P(ColumnSpec), u32, u32, P(u32)]),
     "pgf_block_validate": (i32, [vp, C.c_size_t]),
+    "pgf_block_validate_ext": (i32, [vp, C.c_size_t, u32]),
     "pgf_block_import_check": (i32, [u16, u16, vp, C.c_size_t, P(ColumnSpec), u32]),
     "pgf_block_init": (i32, [vp, C.c_size_t, P(LayoutPlanC)]),
     "pgf_block_write_column": (i32, [vp, C.c_size_t, u32, u32, vp, vp]),

@@ -96,9 +96,15 @@ def fixed_row_cap(specs: Sequence[ColumnSpec], block_size: int = DEFAULT_BLOCK_S
     return cap.value
 
 
-def validate_block(block: np.ndarray) -> int:
-    """BlockRef::open: returns the pgf_status (0 = valid)."""
+LAYOUT_EXT_DECIMAL128 = 1
+
+
+def validate_block(block: np.ndarray, extensions: int = 0) -> int:
+    """BlockRef::open: returns the pgf_status (0 = valid).  Strict reference v1 (type tags 1..9) unless
+    `extensions` switches this library's Decimal128 tag on."""
     block = np.ascontiguousarray(block, dtype=np.uint8)
+    if extensions:
+        return _lib.lib().pgf_block_validate_ext(block.ctypes.data_as(C.c_void_p), block.size, extensions)
     return _lib.lib().pgf_block_validate(block.ctypes.data_as(C.c_void_p), block.size)
 
 

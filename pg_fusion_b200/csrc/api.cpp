@@ -253,7 +253,11 @@ pgf_status pgf_layout_fixed_row_cap(const pgf_column_spec* specs, uint32_t ncols
 }
 pgf_status pgf_block_validate(const uint8_t* block, size_t len) {
   if (!block) return PGF_ERR_INVALID_ARGUMENT;
-  return validate_block(block, len);
+  return validate_block(block, len, /*allow_ext=*/false);
+}
+pgf_status pgf_block_validate_ext(const uint8_t* block, size_t len, uint32_t extensions) {
+  if (!block || (extensions & ~uint32_t(PGF_LAYOUT_EXT_DECIMAL128))) return PGF_ERR_INVALID_ARGUMENT;
+  return validate_block(block, len, (extensions & PGF_LAYOUT_EXT_DECIMAL128) != 0);
 }
 pgf_status pgf_block_import_check(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,
                                   const pgf_column_spec* schema, uint32_t ncols) {

@@ -155,7 +155,7 @@ pgf_status fixed_row_cap(const pgf_column_spec* specs, uint32_t ncols, uint32_t 
   return PGF_OK;
 }
 
-pgf_status validate_block(const uint8_t* block, size_t len) {
+pgf_status validate_block(const uint8_t* block, size_t len, bool allow_ext) {
   if (len < sizeof(BlockHeader)) return PGF_ERR_LAYOUT_BLOCK_SLICE_TOO_SMALL;
   const BlockHeader h = load_header(block);
   if (len < h.block_size) return PGF_ERR_LAYOUT_BLOCK_SLICE_TOO_SMALL;          // validate.rs:90-96
@@ -175,7 +175,7 @@ pgf_status validate_block(const uint8_t* block, size_t len) {
   uint64_t cur = h.front_base;
   for (uint32_t c = 0; c < h.col_count; ++c) {
     const ColumnDesc d = load_desc(block, c);
-    if (!known_type(d.type_tag)) return PGF_ERR_LAYOUT_INVALID_TYPE_TAG;
+    if (!known_type(d.type_tag, allow_ext)) return PGF_ERR_LAYOUT_INVALID_TYPE_TAG;
     if (((d.flags & kFlagView) != 0) != is_view(d.type_tag)) return PGF_ERR_LAYOUT_INCONSISTENT_VIEW_FLAG;
     auto vl = round_up(bitmap_len(h.max_rows), kAlign);
     auto dl = reserved_values(d.type_tag, h.max_rows);
@@ -198,7 +198,11 @@ pgf_status check_block_schema(uint16_t kind, uint16_t flags, const uint8_t* bloc
                               const pgf_column_spec* schema, uint32_t ncols) {
   if (kind != PGF_ARROW_LAYOUT_BATCH_KIND) return PGF_ERR_IMPORT_WRONG_KIND;    // import/src/lib.rs:121-126
   if (flags != 0) return PGF_ERR_IMPORT_UNSUPPORTED_FLAGS;                      // :127-131
-  if (pgf_status st = validate_block(block, len)) return st;
+  // the Decimal128 extension tag is structurally valid only under a schema that names it (the caller's opt-in);
+  // under a reference schema it is InvalidTypeTag, as in TypeTag::from_raw
+  bool ext = false;
+  for (uint32_t c = 0; c < ncols; ++c) ext |= schema[c].type_tag == PGF_T_DECIMAL128;
+  if (pgf_status st = validate_block(block, len, ext)) return st;
   const BlockHeader h = load_header(block);
   if (h.col_count != ncols) return PGF_ERR_IMPORT_SCHEMA_COLUMN_COUNT_MISMATCH; // :209-214
   // validate_schema runs over every column before any column is imported (:134-138, :208-234)

@@ -40,7 +40,9 @@ static_assert(sizeof(BlockHeader) == 40 && sizeof(ColumnDesc) == 20 && sizeof(By
               "on-page struct sizes are part of the format (arrow_layout/src/tests.rs:7-17)");
 
 inline bool is_view(int t) { return t == PGF_T_UTF8VIEW || t == PGF_T_BINARYVIEW; }
-inline bool known_type(int t) { return t >= PGF_T_BOOLEAN && t <= PGF_T_DECIMAL128; }
+// Reference v1 pages know the tags 1..9 (TypeTag::from_raw, types.rs:93-112); 10 (Decimal128) is this library's
+// extension and is accepted only where the caller opted in (a schema / layout plan that names it).
+inline bool known_type(int t, bool allow_ext = true) { return t >= PGF_T_BOOLEAN && t <= (allow_ext ? PGF_T_DECIMAL128 : PGF_T_BINARYVIEW); }
 // bytes per row of the values buffer; 0 for the bit-packed Boolean (types.rs:139-147)
 inline uint32_t row_width(int t) {
   switch (t) {
@@ -56,8 +58,9 @@ pgf_status plan_layout(const pgf_column_spec* specs, uint32_t ncols, uint32_t ma
                        uint32_t block_size, pgf_layout_plan* out);
 pgf_status fixed_row_cap(const pgf_column_spec* specs, uint32_t ncols, uint32_t block_size,
                          uint32_t* cap);
-// Structural validation (header + descriptors tile the front region exactly).
-pgf_status validate_block(const uint8_t* block, size_t len);
+// Structural validation (header + descriptors tile the front region exactly).  allow_ext = false is the
+// reference's BlockRef::open: a descriptor with the Decimal128 extension tag is InvalidTypeTag.
+pgf_status validate_block(const uint8_t* block, size_t len, bool allow_ext = true);
 // Structural + schema + null_count bounds: everything that must hold before the device may
 // touch the page.  Row-level checks (bitmap popcount, views) run on the device.
 pgf_status check_block_structure(uint16_t kind, uint16_t flags, const uint8_t* block, size_t len,

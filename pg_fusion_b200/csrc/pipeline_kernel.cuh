@@ -156,6 +156,23 @@ __device__ __forceinline__ I128 i128_mul(I128 a, I128 b) {  // low 128 bits (wra
   return r;
 }
 
+// The same low 128 bits, cheaper when the operands are narrow -- which money columns are: a Decimal128 that is the
+// sign extension of its low 32 (64) bits multiplies as a signed 32 x 32 -> 64 (64 x 64 -> 128) product, and the
+// wrapping product of two sign-extended numbers IS the sign extension of that product.  One IMAD.WIDE against ~24
+// integer instructions for the general case; the branch is taken by whole warps in practice.
+__device__ __forceinline__ I128 i128_mul_narrow(I128 a, I128 b) {
+  const int32_t a0 = int32_t(uint32_t(a.lo)), b0 = int32_t(uint32_t(b.lo));
+  const bool a32 = int64_t(a.lo) == int64_t(a0) && a.hi == uint64_t(int64_t(a0) >> 63);
+  const bool b32 = int64_t(b.lo) == int64_t(b0) && b.hi == uint64_t(int64_t(b0) >> 63);
+  if (a32 && b32) {
+    const int64_t p = int64_t(a0) * int64_t(b0);
+    return I128{uint64_t(p), uint64_t(p >> 63)};
+  }
+  if (a.hi == uint64_t(int64_t(a.lo) >> 63) && b.hi == uint64_t(int64_t(b.lo) >> 63))
+    return I128{a.lo * b.lo, uint64_t(__mul64hi((long long)a.lo, (long long)b.lo))};
+  return i128_mul(a, b);
+}
+
 template <uint32_t ACC>
 struct AccOps;
 template <>
@@ -639,10 +656,10 @@ __device__ __forceinline__ I128 eval_fast_i128(const DevExpr& e, const uint8_t* 
   };
   auto cst = [&](int f) { return I128{uint64_t(e.f[f].ci_lo), uint64_t(e.f[f].ci_hi)}; };
   if constexpr (FORM == int(FORM_X)) return col(0);
-  else if constexpr (FORM == int(FORM_XY)) return i128_mul(col(0), col(1));
-  else if constexpr (FORM == int(FORM_X_CMY)) return i128_mul(col(0), i128_sub(cst(1), col(1)));
-  else if constexpr (FORM == int(FORM_X_CMY_CPZ)) return i128_mul(i128_mul(col(0), i128_sub(cst(1), col(1))), i128_add(cst(2), col(2)));
-  else return i128_mul(prev, i128_add(cst(2), col(2)));  // FORM_PREV_CPZ
+  else if constexpr (FORM == int(FORM_XY)) return i128_mul_narrow(col(0), col(1));
+  else if constexpr (FORM == int(FORM_X_CMY)) return i128_mul_narrow(col(0), i128_sub(cst(1), col(1)));
+  else if constexpr (FORM == int(FORM_X_CMY_CPZ)) return i128_mul_narrow(i128_mul_narrow(col(0), i128_sub(cst(1), col(1))), i128_add(cst(2), col(2)));
+  else return i128_mul_narrow(prev, i128_add(cst(2), col(2)));  // FORM_PREV_CPZ
 }
 
 template <uint32_t ACC, int FORM>

@@ -107,6 +107,23 @@ def test_product_writer_is_byte_identical_to_oracle_writer():
     assert O.import_check(0x4152, 0, block, U.orc_cols(schema)) == 0
 
 
+def test_decimal128_extension_tag_is_rejected_by_the_reference_v1_checks():
+    """TypeTag::from_raw knows 1..9 (page/arrow_layout/src/types.rs:93-112): BlockRef::open on a block carrying this
+    library's Decimal128 tag is InvalidTypeTag, and so is an import under a schema that does not name the tag."""
+    schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Decimal128, True)]
+    vals = np.zeros((3, 16), np.uint8)
+    vals[:, 0] = [1, 2, 3]
+    block = AL.encode_block(schema, [(np.array([1, 2, 3], np.int32), None), (vals, np.array([True, False, True]))], 3, 3, 4096)
+    invalid_tag = 109   # PGF_ERR_LAYOUT_INVALID_TYPE_TAG = LayoutError::InvalidTypeTag
+    assert AL.validate_block(block) == O.block_validate_v1(block) == invalid_tag
+    assert AL.validate_block(block, AL.LAYOUT_EXT_DECIMAL128) == O.block_validate(block) == 0
+    # the caller's schema is the opt-in: it passes under the schema that names the tag ...
+    assert AL.import_check(0x4152, 0, block, schema) == O.import_check(0x4152, 0, block, U.orc_cols(schema)) == 0
+    # ... and is InvalidTypeTag (before any schema comparison) under a reference-only schema
+    ref_schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Uuid, True)]
+    assert AL.import_check(0x4152, 0, block, ref_schema) == O.import_check(0x4152, 0, block, U.orc_cols(ref_schema)) == invalid_tag
+
+
 def test_import_rejections_match_oracle_codes():
     schema, cols, block = _mixed_block_via_product()
     oc = U.orc_cols(schema)

@@ -566,16 +566,20 @@ def run_e2e(args, ctx, pg, comm, sh, numa):
     def push(name):
         host, pages = hosts[name]
         scans[name].reset()
-        scans[name].push_pages_ptr(host.data_ptr(), pages, PAGE)
-        scans[name].finish()
+        scans[name].push_pages_ptr(host.data_ptr(), pages, PAGE)   # returns once the pages are admitted and their DMA is queued
 
     def step():
-        push("q6")
+        # the pages of all five scans are handed over first (their H2D copies queue back to back on the library's copy
+        # stream, the way a worker receives the pages of concurrent scans), then every scan is finished (device import
+        # checks) and its pipeline run in turn: the checks and kernels of one scan overlap the copies of the next
+        for name in ("q6", "q1", "customer", "orders", "lineitem"):
+            push(name)
+        scans["q6"].finish()
         r6 = e2e_sh.agg("q6")
-        push("q1")
+        scans["q1"].finish()
         r1 = e2e_sh.agg("q1")
         for name in ("customer", "orders", "lineitem"):
-            push(name)
+            scans[name].finish()
         r3, st3 = e2e_sh.q3()
         return r6, r1, r3, st3
 

@@ -669,9 +669,44 @@ pgf_status pgf_bloom_or_device_words(pgf_ctx* ctx, uint64_t bloom, const void* d
 pgf_status pgf_bloom_or_all_reduce(pgf_ctx* ctx, uint64_t bloom) {
   BLOOM_OR_FAIL(ctx, bloom, b);
   if (ctx->comm_world == 1) return PGF_OK;
-  // all-gather of the word arrays + OR of every array into the local one (NCCL has no bitwise-OR reduction)
   const uint64_t bytes = b->params.word_count * 8;
   CU(ctx, cudaSetDevice(ctx->device));
+  const uint64_t world = uint64_t(ctx->comm_world), rank = uint64_t(ctx->comm_rank);
+  if (bytes >= (1u << 20) && b->params.word_count % (2 * world) == 0) {
+    // Large filters (the 32 MiB one of SF100's orders): reduce-scatter + all-gather, written with the collectives
+    // NCCL has (it has no bitwise-OR reduction).  Rank r owns words [r, r + 1) * chunk: every rank sends every owner
+    // its copy of the owner's chunk (grouped send / recv), the owner ORs the `world` copies, and an in-place all-gather
+    // hands the finished chunks round.  2 x 7/8 of the array crosses NVLink per rank instead of 7 x the array
+    // (0.51 ms for 32 MiB on 8 GPUs with the plain all-gather).
+    const uint64_t chunk_words = b->params.word_count / world, chunk_bytes = chunk_words * 8;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (ctx->d_xchg_cap < bytes) {
+      CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
+      if (ctx->d_xchg) cudaFree(ctx->d_xchg);
+      ctx->d_xchg = nullptr;
+      ctx->d_xchg_cap = 0;
+      void* p = nullptr;
+      if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "exchange scratch"); }
+      ctx->d_xchg = static_cast<uint8_t*>(p);
+      ctx->d_xchg_cap = bytes;
+    }
+    uint64_t soff[64], sbytes[64], roff[64], rbytes[64];
+    if (world > 64) return ctx->fail(PGF_ERR_INVALID_ARGUMENT, "at most 64 ranks");
+    for (uint64_t p = 0; p < world; ++p) {
+      soff[p] = p * chunk_bytes; sbytes[p] = p == rank ? 0 : chunk_bytes;     // (the own copy is already in place)
+      roff[p] = p * chunk_bytes; rbytes[p] = p == rank ? 0 : chunk_bytes;
+    }
+    PGF_TRY(comm_all_to_all_v(ctx, b->d_words, soff, sbytes, ctx->d_xchg, roff, rbytes));
+    // the copies of MY chunk sit at d_xchg[p * chunk] for p != rank; slot `rank` of the scratch is skipped by pointing
+    // the kernel at two runs of arrays
+    uint64_t* mine = b->d_words + rank * chunk_words;
+    const uint32_t grid = uint32_t(std::min<uint64_t>((chunk_words + 255) / 256, 1184));
+    if (rank) PGF_TRY(bloom_or_strided(ctx, mine, reinterpret_cast<const uint64_t*>(ctx->d_xchg), chunk_words, uint32_t(rank), grid));
+    if (rank + 1 < world)
+      PGF_TRY(bloom_or_strided(ctx, mine, reinterpret_cast<const uint64_t*>(ctx->d_xchg) + (rank + 1) * chunk_words, chunk_words, uint32_t(world - rank - 1), grid));
+    return comm_all_gather(ctx, mine, b->d_words, chunk_bytes);   // in place: my chunk is already where it belongs
+  }
+  // small filters: all-gather of the word arrays + OR of every array into the local one
   if (ctx->d_xchg_cap < bytes * uint64_t(ctx->comm_world)) {
     CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
     if (ctx->d_xchg) cudaFree(ctx->d_xchg);

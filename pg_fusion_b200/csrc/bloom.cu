@@ -545,6 +545,13 @@ pgf_status bloom_count_bits(pgf_ctx* ctx, BloomSlot& b) {
   return PGF_OK;
 }
 
+// dst[i] |= src[a * nwords + i] for a < narrays (the caller holds the device)
+pgf_status bloom_or_strided(pgf_ctx* ctx, uint64_t* dst, const uint64_t* src, uint64_t nwords, uint32_t narrays, uint32_t grid) {
+  bloom_or_kernel<<<grid ? grid : 1, 256, 0, ctx->compute_stream>>>(dst, src, nwords, narrays);
+  CU(ctx, cudaGetLastError());
+  return PGF_OK;
+}
+
 pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, uint64_t nwords, uint32_t narrays) {
   CU(ctx, cudaSetDevice(ctx->device));
   const uint32_t grid = uint32_t((nwords + 255) / 256 < 1184 ? (nwords + 255) / 256 : 1184);

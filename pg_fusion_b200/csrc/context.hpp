@@ -197,6 +197,7 @@ pgf_status bloom_probe_host_keys(pgf_ctx* ctx, BloomSlot& b, bool ready, const v
                                  uint8_t* decisions, pgf_probe_stats* stats);
 pgf_status bloom_probe_scan(pgf_ctx* ctx, BloomSlot& b, bool ready, Scan& s, uint32_t col,
                             uint8_t* decisions, pgf_probe_stats* stats);
+pgf_status bloom_or_strided(pgf_ctx* ctx, uint64_t* dst, const uint64_t* src, uint64_t nwords, uint32_t narrays, uint32_t grid);
 pgf_status bloom_or_device(pgf_ctx* ctx, BloomSlot& b, const void* dev_words, uint64_t nwords,
                            uint32_t narrays);
 pgf_status bloom_count_bits(pgf_ctx* ctx, BloomSlot& b);

@@ -193,7 +193,12 @@ struct DevPlan {
   // 1: every page of the scan has layout class 0, whose offsets travel in the plan itself (class0): stage C then
   // reads column offsets from the constant bank instead of chasing descs[page] -> classes[class] through HBM
   uint32_t single_class;
-  uint32_t entry_key_off, pad4;   // single-term specialisation of the compaction pipeline: stage offset of the Int32 entry key
+  uint32_t entry_key_off;   // single-term specialisation of the compaction pipeline: stage offset of the Int32 entry key
+  // page columns stage C reads straight from HBM (late materialisation): it starts those reads before it walks the
+  // probe chain, so the row's DRAM round trips overlap the chain's instead of following them
+  uint32_t nlate;
+  uint8_t late_pcol[8];
+  uint8_t late_width[8];
   LayoutClass class0;
   DevBloomProbe bloom[kMaxBlooms];
   DevTerm terms[kMaxTerms];

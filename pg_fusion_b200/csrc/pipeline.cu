@@ -33,6 +33,10 @@ struct PhaseTrace {
   explicit PhaseTrace(cudaStream_t s) : stream(s) {
     const char* e = std::getenv("PGF_TRACE");
     on = e && *e && *e != '0';
+    if (const char* only = std::getenv("PGF_TRACE_RANK")) {   // one rank of a torchrun job
+      const char* r = std::getenv("RANK");
+      on = on && r && std::strcmp(r, only) == 0;
+    }
     if (on) { cudaStreamSynchronize(stream); t = std::chrono::steady_clock::now(); }
   }
   void mark(const char* what) {
@@ -322,91 +326,113 @@ __device__ int sort_compare(const DevSort& S, const uint64_t* a, const uint64_t*
 }
 
 constexpr uint32_t kTopkThreads = 256;
+constexpr uint32_t kTopkItems = 8;                              // entries per thread
+constexpr uint32_t kTopkSeg = kTopkThreads * kTopkItems;        // entries per block and level
 constexpr uint32_t kNoEntry = 0xFFFFFFFFu;
 
-__device__ __forceinline__ uint32_t better(const DevSort& S, const uint64_t* entries, uint32_t x, uint32_t y) {
-  if (x == kNoEntry) return y;
-  if (y == kNoEntry) return x;
-  return sort_compare(S, entries + uint64_t(x) * S.ew, entries + uint64_t(y) * S.ew) <= 0 ? x : y;
-}
-
-__device__ uint32_t block_best(const DevSort& S, const uint64_t* entries, uint32_t mine) {
-  __shared__ uint32_t sbest[kTopkThreads];
-  sbest[threadIdx.x] = mine;
-  __syncthreads();
-  for (uint32_t o = kTopkThreads / 2; o; o >>= 1) {
-    if (threadIdx.x < o) sbest[threadIdx.x] = better(S, entries, sbest[threadIdx.x], sbest[threadIdx.x + o]);
-    __syncthreads();
-  }
-  return sbest[0];
-}
-
-// one selection round: every block proposes its best entry that is not taken yet
-__global__ void __launch_bounds__(kTopkThreads) topk_round_kernel(DevSort S, const uint64_t* entries, uint32_t n,
-                                                                 const uint8_t* taken, uint32_t* blk_best) {
-  uint32_t mine = kNoEntry;
-  for (uint32_t i = blockIdx.x * kTopkThreads + threadIdx.x; i < n; i += gridDim.x * kTopkThreads)
-    if (!taken[i]) mine = better(S, entries, mine, i);
-  const uint32_t b = block_best(S, entries, mine);
-  if (threadIdx.x == 0) blk_best[blockIdx.x] = b;
-}
-
-// ... and one block picks the winner of the round, marks it and copies it to the output
-__global__ void __launch_bounds__(kTopkThreads) topk_pick_kernel(DevSort S, const uint64_t* entries, uint32_t nblocks,
-                                                                const uint32_t* blk_best, uint8_t* taken, uint64_t* out, uint32_t round) {
-  uint32_t mine = kNoEntry;
-  for (uint32_t i = threadIdx.x; i < nblocks; i += kTopkThreads) mine = better(S, entries, mine, blk_best[i]);
-  const uint32_t b = block_best(S, entries, mine);
-  if (b == kNoEntry) return;
-  if (threadIdx.x == 0) { taken[b] = 1; out[0] = round + 1; }
-  for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out[1 + uint64_t(round) * S.ew + w] = entries[uint64_t(b) * S.ew + w];
-}
-
-// Two-launch top-k (k <= PGF_TOPK_DEVICE_MAX): every block selects the k best entries of its own segment (k rounds of
-// a block-wide arg-best over at most a few thousand entries, winners masked by index), then one block selects the k
-// best of the blocks' candidates.  2 launches instead of 2k.
-__global__ void __launch_bounds__(kTopkThreads) topk_local_kernel(DevSort S, const uint64_t* entries, uint32_t n, uint32_t k, uint32_t* cand) {
-  const uint32_t seg = (n + gridDim.x - 1) / gridDim.x;
-  const uint32_t b0 = blockIdx.x * seg, b1 = min(n, b0 + seg);
-  __shared__ uint32_t s_taken[PGF_TOPK_DEVICE_MAX];
-  for (uint32_t r = 0; r < k; ++r) {
-    uint32_t mine = kNoEntry;
-    for (uint32_t i = b0 + threadIdx.x; i < b1; i += kTopkThreads) {
-      bool taken = false;
-      for (uint32_t q = 0; q < r; ++q) taken |= s_taken[q] == i;
-      if (!taken) mine = better(S, entries, mine, i);
+// Order-preserving 64-bit summary of an entry under the FIRST ORDER BY term (smaller sorts first):
+//   summary(a) < summary(b)  implies  a sorts before b;
+// equal summaries say nothing and are decided by sort_compare().  One or two loads and a handful of integer
+// instructions per entry, against the generic comparator's loop over terms, kinds and tie-break words.
+__device__ uint64_t sort_summary(const DevSort& S, const uint64_t* e) {
+  const DevSortKey& k = S.k[0];
+  bool null;
+  if (k.kind <= SK_KEY_DEC) null = (e[kKeyWords] >> k.null_bit) & 1;
+  else if (k.kind == SK_COUNT) null = false;
+  else null = e[k.cnt_word] == 0;
+  if (null) return k.nulls_first ? 0ull : ~0ull;
+  constexpr uint64_t kSign = 0x8000000000000000ull;
+  auto sat64 = [&](uint64_t lo, uint64_t hi) -> uint64_t {   // i128 -> i64, saturating: monotone, exact for the values that fit
+    if (hi == uint64_t(int64_t(lo) >> 63)) return lo ^ kSign;
+    return int64_t(hi) < 0 ? 0ull : ~0ull;
+  };
+  auto f64key = [&](double d) -> uint64_t {                  // IEEE totalOrder, as an unsigned key
+    int64_t x = __double_as_longlong(d);
+    x ^= int64_t(uint64_t(x >> 63) >> 1);
+    return uint64_t(x) ^ kSign;
+  };
+  uint64_t v;
+  switch (k.kind) {
+    case SK_KEY_INT: case SK_I64_SUM: v = e[k.word] ^ kSign; break;
+    case SK_KEY_VIEW:   // the first eight bytes of the string, big-endian
+      v = (uint64_t(__byte_perm(uint32_t(e[k.word] >> 32), 0, 0x0123)) << 32) | __byte_perm(uint32_t(e[k.word + 1]), 0, 0x0123);
+      break;
+    case SK_KEY_DEC: case SK_I128_SUM: v = sat64(e[k.word], e[k.word + 1]); break;
+    case SK_F64_SUM: v = f64key(__longlong_as_double(e[k.word])); break;
+    case SK_F64_AVG: v = f64key(__longlong_as_double(e[k.word]) / double(e[k.cnt_word])); break;
+    case SK_I128_AVG: {
+      const __int128 q = (__int128)(((unsigned __int128)e[k.word + 1] << 64) | e[k.word]) * 10000 / (__int128)e[k.cnt_word];
+      v = sat64(uint64_t(q), uint64_t(q >> 64));
+      break;
     }
-    const uint32_t b = block_best(S, entries, mine);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      s_taken[r] = b;
-      cand[blockIdx.x * k + r] = b;
-    }
-    __syncthreads();
+    default: v = e[k.cnt_word]; break;  // COUNT
   }
+  if (k.desc) v = ~v;
+  return v < 1ull ? 1ull : (v > ~0ull - 1ull ? ~0ull - 1ull : v);   // 0 and ~0 belong to the NULLs
 }
-__global__ void __launch_bounds__(kTopkThreads) topk_final_kernel(DevSort S, const uint64_t* entries, uint32_t ncand, uint32_t k, const uint32_t* cand,
-                                                                   uint64_t* out) {
-  __shared__ uint32_t s_taken[PGF_TOPK_DEVICE_MAX];
+
+struct TopkPick {
+  uint64_t p;
+  uint32_t i;
+};
+__device__ __forceinline__ TopkPick topk_better(const DevSort& S, const uint64_t* entries, TopkPick x, TopkPick y) {
+  if (x.i == kNoEntry) return y;
+  if (y.i == kNoEntry) return x;
+  if (x.p != y.p) return x.p < y.p ? x : y;
+  return sort_compare(S, entries + uint64_t(x.i) * S.ew, entries + uint64_t(y.i) * S.ew) <= 0 ? x : y;
+}
+
+// Top-k selection (k <= PGF_TOPK_DEVICE_MAX), one level: every block takes kTopkSeg entries (the table's entries at
+// level 0, the candidates of the level below afterwards), keeps their summaries in registers and runs k rounds of a
+// block-wide arg-best (thread-local scan of 8 registers, shuffle butterfly, 8 warp winners).  A level shrinks its
+// input by kTopkSeg / k >= 32, so 1.1 M groups take three launches of a few microseconds each (the first version --
+// k rounds of the generic comparator over global memory, then ONE block over every block's candidates -- took
+// 0.5 ms at SF10, longer than the lineitem pipeline itself).  out_rows != nullptr: the final level; the winners'
+// entries are written in order, out_rows[0] = how many.
+__global__ void __launch_bounds__(kTopkThreads) topk_select_kernel(DevSort S, const uint64_t* entries, const uint32_t* in_idx, uint32_t n, uint32_t k,
+                                                                    uint32_t* out_idx, uint64_t* out_rows) {
+  __shared__ uint64_t s_p[kTopkThreads / 32];
+  __shared__ uint32_t s_i[kTopkThreads / 32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t b0 = uint64_t(blockIdx.x) * kTopkSeg;
+  TopkPick mine[kTopkItems];
+#pragma unroll
+  for (uint32_t j = 0; j < kTopkItems; ++j) {
+    const uint64_t at = b0 + j * kTopkThreads + threadIdx.x;
+    uint32_t i = kNoEntry;
+    if (at < n) i = in_idx ? in_idx[at] : uint32_t(at);
+    mine[j].i = i;
+    mine[j].p = i != kNoEntry ? sort_summary(S, entries + uint64_t(i) * S.ew) : ~0ull;
+  }
   uint32_t found = 0;
   for (uint32_t r = 0; r < k; ++r) {
-    uint32_t mine = kNoEntry;
-    for (uint32_t c = threadIdx.x; c < ncand; c += kTopkThreads) {
-      const uint32_t i = cand[c];
-      if (i == kNoEntry) continue;
-      bool taken = false;
-      for (uint32_t q = 0; q < r; ++q) taken |= s_taken[q] == i;
-      if (!taken) mine = better(S, entries, mine, i);
+    TopkPick best{~0ull, kNoEntry};
+#pragma unroll
+    for (uint32_t j = 0; j < kTopkItems; ++j) best = topk_better(S, entries, best, mine[j]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const TopkPick other{__shfl_xor_sync(0xffffffffu, best.p, o), __shfl_xor_sync(0xffffffffu, best.i, o)};
+      best = topk_better(S, entries, best, other);   // (a total order: both lanes of a pair keep the same entry)
     }
-    const uint32_t b = block_best(S, entries, mine);
+    if (lane == 0) { s_p[warp] = best.p; s_i[warp] = best.i; }
     __syncthreads();
-    if (threadIdx.x == 0) s_taken[r] = b;
+    best = TopkPick{s_p[0], s_i[0]};
+#pragma unroll
+    for (uint32_t w = 1; w < kTopkThreads / 32; ++w) best = topk_better(S, entries, best, TopkPick{s_p[w], s_i[w]});
     __syncthreads();
-    if (b == kNoEntry) break;
-    for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out[1 + uint64_t(r) * S.ew + w] = entries[uint64_t(b) * S.ew + w];
+    if (threadIdx.x == 0) out_idx[uint64_t(blockIdx.x) * k + r] = best.i;
+    if (best.i == kNoEntry) {   // fewer than k entries in this segment
+      for (uint32_t q = r + 1 + threadIdx.x; q < k; q += kTopkThreads) out_idx[uint64_t(blockIdx.x) * k + q] = kNoEntry;
+      break;
+    }
+    if (out_rows)
+      for (uint32_t w = threadIdx.x; w < S.ew; w += kTopkThreads) out_rows[1 + uint64_t(r) * S.ew + w] = entries[uint64_t(best.i) * S.ew + w];
     found = r + 1;
+#pragma unroll
+    for (uint32_t j = 0; j < kTopkItems; ++j)
+      if (mine[j].i == best.i) mine[j].i = kNoEntry;   // taken
   }
-  if (threadIdx.x == 0) out[0] = found;
+  if (out_rows && threadIdx.x == 0) out_rows[0] = found;
 }
 
 // Final merge of partial states (AggregateExec FinalPartitioned): one launch per state, in
@@ -781,6 +807,12 @@ class Lowering {
         return PGF_OK;
       }
       if (late && probe_) {
+        bool listed = false;
+        for (uint32_t c = 0; c < D.nlate; ++c) listed |= D.late_pcol[c] == uint8_t(r.col);
+        if (!listed && D.nlate < 8) {
+          D.late_pcol[D.nlate] = uint8_t(r.col);
+          D.late_width[D.nlate++] = uint8_t(row_width(type));
+        }
         out->src = SRC_PAGE;
         out->ld = ld_kind(type);
         out->type = uint8_t(type);
@@ -1345,17 +1377,29 @@ pgf_status lower_sort(pgf_ctx* ctx, const pgf_pipeline* plan, const Lowered& L, 
 // Selects the k first entries under the ORDER BY on the device; h_state receives [k][entries].
 pgf_status device_topk(pgf_ctx* ctx, const DevSort& S, const uint64_t* d_entries, uint64_t n, uint32_t k,
                        std::vector<uint64_t>* h_state, uint32_t* launches) {
-  // segments of ~2048 entries per block keep the k rounds of the local selection short
-  const uint32_t nblocks = uint32_t(std::max<uint64_t>(1, std::min<uint64_t>((n + 2047) / 2048, uint64_t(ctx->sm_count) * 8)));
-  const size_t o_cand = 0, o_out = align_up(size_t(nblocks) * k * 4, 16);
+  if (n >= kNoEntry) return ctx->fail(PGF_ERR_NOT_ELIGIBLE, "device top-k over %llu groups", (unsigned long long)n);
+  auto blocks_for = [](uint64_t m) { return (m + kTopkSeg - 1) / kTopkSeg; };
+  // candidate lists of the levels ping-pong between two buffers: level 0 writes blocks(n) * k indices, level 1 far fewer
+  const uint64_t nb0 = blocks_for(n);
+  const size_t o_a = 0, o_b = align_up(size_t(nb0) * k * 4, 16), o_out = o_b + align_up(size_t(blocks_for(nb0 * k)) * k * 4 + 16, 16);
   const size_t bytes = o_out + (1 + size_t(k) * S.ew) * 8;
   PGF_TRY(grow(ctx, &ctx->d_topk, &ctx->d_topk_cap, bytes, "the top-k scratch"));
-  uint32_t* cand = reinterpret_cast<uint32_t*>(ctx->d_topk + o_cand);
+  uint32_t* buf[2] = {reinterpret_cast<uint32_t*>(ctx->d_topk + o_a), reinterpret_cast<uint32_t*>(ctx->d_topk + o_b)};
   uint64_t* out = reinterpret_cast<uint64_t*>(ctx->d_topk + o_out);
-  topk_local_kernel<<<nblocks, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, uint32_t(n), k, cand);
-  topk_final_kernel<<<1, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, nblocks * k, k, cand, out);
+  const uint32_t* in = nullptr;
+  uint64_t m = n;
+  int cur = 0;
+  while (m > kTopkSeg) {
+    const uint64_t nb = blocks_for(m);
+    topk_select_kernel<<<uint32_t(nb), kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, in, uint32_t(m), k, buf[cur], nullptr);
+    in = buf[cur];
+    m = nb * k;
+    cur ^= 1;
+    ++*launches;
+  }
+  topk_select_kernel<<<1, kTopkThreads, 0, ctx->compute_stream>>>(S, d_entries, in, uint32_t(m), k, buf[cur], out);
   CU(ctx, cudaGetLastError());
-  *launches += 2;
+  ++*launches;
   h_state->assign(1 + size_t(k) * S.ew, 0);
   CU(ctx, cudaMemcpyAsync(h_state->data(), out, h_state->size() * 8, cudaMemcpyDeviceToHost, ctx->compute_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));

@@ -92,6 +92,16 @@ __device__ __forceinline__ void tags8_async(uint32_t smem_dst, const uint8_t* p,
                ::"r"(smem_dst), "l"(p), "r"(uint32_t(pred)), "l"(policy) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
+#ifndef PGF_LATE_PREFETCH
+#define PGF_LATE_PREFETCH 1   // 0: off, 1: into L1, 2: into L2
+#endif
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#if PGF_LATE_PREFETCH == 1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif PGF_LATE_PREFETCH == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
 __device__ __forceinline__ uint2 tags8_collect(uint32_t smem_src) {
   uint2 v;
   asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -482,6 +492,13 @@ __device__ __forceinline__ void stage_c(const DevPlan& P, uint4 e, bool act, uin
       g.lc = P.single_class ? &P.class0 : P.classes + d.layout_class;
       g.nulls = d.null_mask & P.used_null_mask;
     }
+    // Build sinks copy every late column of every row that finds its partner, and behind a selective predicate most
+    // entries that reach stage C do: start the reads of the row's late columns now, so that they are in flight while
+    // the chain walk waits for the tag window and the slot (ncu r2: 40 % of the stall samples of the orders pipeline
+    // sat on these loads, one HBM round trip after the other; -6 % on that pipeline).  Not for aggregate sinks: two
+    // thirds of the lineitem side's tag hits are false, and the prefetch cost it 8 % at SF100.
+    if (PGF_LATE_PREFETCH && P.sink == SINK_JOIN_BUILD && act)
+      for (uint32_t c = 0; c < P.nlate; ++c) prefetch_line(g.page + g.lc->values_off[P.late_pcol[c]] + g.r * uint32_t(P.late_width[c]));
   }
   JoinIter it0, it1;
   it0.cand = it1.cand = 0;

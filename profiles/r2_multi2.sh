@@ -1,12 +1,12 @@
 #!/bin/bash
+# Round 2, 2 GPUs: library-communicator parity (incl. the reduce-scatter Bloom OR), the partitioned Q3 breakdown with
+# the library's own phase trace (SF10: latency-dominated, like SF100 on many GPUs), bench at SF10 and SF100.
 N=${1:-2}
 mkdir -p gpurun_out
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-echo "== pytest (top-k, joins, exchange)"; timeout 900 python -m pytest tests/test_gpu_sort.py tests/test_gpu_join.py tests/test_gpu_exchange.py tests/test_gpu_multi_rank.py -m gpu -q 2>&1 | tail -3
-echo "== library comm parity"; timeout 900 $TR --master-port 29541 tests/run_multi_gpu_lib.py 2>&1 | tail -1
-port=29550
-for sf in 10 100; do port=$((port+1)); echo "== breakdown sf$sf"; timeout 600 $TR --master-port $port profiles/q3_partitioned_breakdown.py $sf 2>&1 | grep -v "^\*\|OMP_NUM\|^$\|NCCL version" | tail -14; done
-for sf in 10 100; do port=$((port+1))
-echo "== bench sf$sf N=$N"; timeout 1200 $TR --master-port $port bench.py --gpus $N --sf $sf --steps 5 --warmup 3 --no-extras > gpurun_out/r2_bench_sf${sf}_n$N.json 2> gpurun_out/r2_bench_sf${sf}_n$N.err; tail -3 gpurun_out/r2_bench_sf${sf}_n$N.err | grep -v "^\*\|OMP_NUM\|^$"; python -c "
-import json; d=json.loads([l for l in open('gpurun_out/r2_bench_sf${sf}_n$N.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], {k:v['ms_per_pass'] for k,v in d['shapes'].items()}, d['parity'].get('mismatches'), d['e2e']['value'], d['shapes']['q3'].get('nvlink_bytes_sent_per_pass_rank0'))"
-done
+echo "== library comm parity"; timeout 600 $TR --master-port 29541 tests/run_multi_gpu_lib.py 2>&1 | grep -v "^\*\|OMP_NUM\|^$" | tail -3
+echo "== breakdown sf10"; timeout 600 $TR --master-port 29552 profiles/q3_partitioned_breakdown.py 10 2>&1 | grep -v "^\*\|OMP_NUM\|^$\|NCCL version" | tail -14
+echo "== phase trace sf10 (rank 0; every mark synchronises)"; PGF_TRACE_RANK=0 PGF_TRACE=1 timeout 600 $TR --master-port 29553 profiles/q3_partitioned_breakdown.py 10 2> gpurun_out/r2_trace_n$N.log | tail -1; grep "pgf trace" gpurun_out/r2_trace_n$N.log | tail -60
+echo "== breakdown sf100"; timeout 600 $TR --master-port 29554 profiles/q3_partitioned_breakdown.py 100 2>&1 | grep -v "^\*\|OMP_NUM\|^$\|NCCL version" | tail -14
+echo "== bench sf100 N=$N"; timeout 1200 $TR --master-port 29555 bench.py --gpus $N --steps 5 --warmup 3 --no-extras > gpurun_out/r2_bench_sf100_n$N.json 2> gpurun_out/r2_bench_sf100_n$N.err; echo "rc=$?"; tail -3 gpurun_out/r2_bench_sf100_n$N.err | grep -v "^\*\|OMP_NUM\|^$"; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r2_bench_sf100_n$N.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], {k:(round(v['ms_per_pass'],3), round(v['kernel_ms'],3)) for k,v in d['shapes'].items()}, d['parity'].get('mismatches'), 'e2e', d['e2e']['value'], d['e2e'].get('h2d_GBps_per_gpu'), d['e2e'].get('h2d_link_peak_GBps'), d['shapes']['q3'].get('nvlink_bytes_sent_per_pass_rank0'))"

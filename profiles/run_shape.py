@@ -44,9 +44,13 @@ with pg.Context(0) as ctx:
         bp = None
         if shape == "q3bloom":
             bp = (pg.BloomParams.new(pow2(16 * ncust // 5), 4, 7), pg.BloomParams.new(pow2(16 * nord // 10), 4, 7))
+        import time
         for i in range(iters):
-            res, st = U.gpu_q3(ctx, cust, orders, li, bp)
+            t0 = time.perf_counter()
+            res, st = U.gpu_q3(ctx, cust, orders, li, bp, limit=int(os.environ.get("Q3_LIMIT", "0")))
+            wall = (time.perf_counter() - t0) * 1e3
             t = (st["customer"].kernel_ms, st["orders"].kernel_ms, st["lineitem"].kernel_ms)
+            print(f"  whole pass {wall:.3f} ms (host clock, limit={os.environ.get('Q3_LIMIT', '0')}); ", end="")
             print(f"{shape} iter {i}: kernels {t[0]:.4f} {t[1]:.4f} {t[2]:.4f} ms; lineitem {rows * 36 / t[2] / 1e6:.1f} GB/s; "
                   f"bloom->{st['lineitem'].rows_bloom} filter->{st['lineitem'].rows_filtered} joined {st['lineitem'].rows_out} groups {len(res.keys)}")
     elif shape == "bloom":

@@ -44,19 +44,20 @@ def main():
         shard.release()
         whole.release()
 
-    # ---- Bloom OR all-reduce: every rank inserts its shard of the keys; the merged filter is the filter of all keys
-    p = pg.BloomParams.new(1 << 18, 4, 7)
-    nkeys = 100_000
-    lo, hi = MG.shard_range(nkeys, rank, world)
-    keys = ctx.gen_scan(GenTable.KEYS_I64, hi - lo, seed=7, first_row=lo)
-    allkeys = ctx.gen_scan(GenTable.KEYS_I64, nkeys, seed=7)
-    rf, ref = ctx.runtime_filter(p), ctx.runtime_filter(p)
-    rf.try_acquire_builder(); ref.try_acquire_builder()
-    rf.insert_scan(keys, 0); ref.insert_scan(allkeys, 0)
-    rf.or_all_reduce()
-    rf.publish_ready(); ref.publish_ready()
-    assert (rf.words() == ref.words()).all()
-    keys.release(); allkeys.release()
+    # ---- Bloom OR all-reduce: every rank inserts its shard of the keys; the merged filter is the filter of all keys.
+    # 2^18 bits take the all-gather path, 2^24 bits (2 MiB) the reduce-scatter + all-gather path of large filters.
+    for bits, nkeys in ((1 << 18, 100_000), (1 << 24, 1_000_000)):
+        p = pg.BloomParams.new(bits, 4, 7)
+        lo, hi = MG.shard_range(nkeys, rank, world)
+        keys = ctx.gen_scan(GenTable.KEYS_I64, hi - lo, seed=7, first_row=lo)
+        allkeys = ctx.gen_scan(GenTable.KEYS_I64, nkeys, seed=7)
+        rf, ref = ctx.runtime_filter(p), ctx.runtime_filter(p)
+        rf.try_acquire_builder(); ref.try_acquire_builder()
+        rf.insert_scan(keys, 0); ref.insert_scan(allkeys, 0)
+        rf.or_all_reduce()
+        rf.publish_ready(); ref.publish_ready()
+        assert (rf.words() == ref.words()).all(), f"Bloom OR all-reduce of {bits} bits"
+        keys.release(); allkeys.release()
 
     # ---- join exchanges on a plain key / payload table
     n = 50_000

@@ -295,7 +295,7 @@ pgf_status pgf_bloom_publish_to_pool(pgf_ctx *ctx, uint64_t bloom, void *base, u
 enum { PGF_CMP_LT = 0, PGF_CMP_LE = 1, PGF_CMP_GT = 2, PGF_CMP_GE = 3, PGF_CMP_EQ = 4, PGF_CMP_NE = 5 };
 
 typedef struct {
-  int32_t type_tag;   /* PGF_T_FLOAT64 / PGF_T_INT64 / PGF_T_UTF8VIEW / PGF_T_DECIMAL128 ... */
+  int32_t type_tag;   /* PGF_T_FLOAT64 / PGF_T_INT64 / PGF_T_UTF8VIEW / PGF_T_DECIMAL128 / PGF_T_BOOLEAN (i64 = 0 / 1) ... */
   int32_t slen;       /* string literal length (<= 12) */
   double f64;
   int64_t i64;        /* integer literal, or low 64 bits of a Decimal128 literal */

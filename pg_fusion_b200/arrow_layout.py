@@ -151,6 +151,10 @@ def encode_block(specs: Sequence[ColumnSpec], columns: Sequence[Tuple[np.ndarray
     bp = block.ctypes.data_as(C.c_void_p)
     _check(L.pgf_block_init(bp, block.size, C.byref(plan.c)), "init_block")
     for i, (vals, valid) in enumerate(columns):
+        if int(specs[i].type_tag) == int(TypeTag.Boolean):   # bool array -> LSB-first bit-packed values (types.rs:139-147)
+            vals = np.packbits(np.asarray(vals, dtype=bool), bitorder="little")
+            if vals.size == 0:
+                vals = np.zeros(1, np.uint8)
         vals = np.ascontiguousarray(vals)
         vb = None
         if valid is not None:

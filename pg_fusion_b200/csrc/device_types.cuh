@@ -44,14 +44,15 @@ enum : uint8_t { CLS_F64 = 0, CLS_I64 = 1, CLS_I128 = 2 };
 
 struct DevStageCol {
   uint16_t page_col;     // column index in the page
-  uint16_t width;        // bytes per row
+  uint16_t width;        // bytes per row; 0 = bit-packed (Boolean): the tile holds tile_rows / 8 bytes
   uint32_t smem_off;     // offset of the column tile inside a stage
   uint32_t valid_off;    // offset of the validity-bitmap tile inside a stage (nullable only)
   uint16_t nullable;
   uint16_t type;
 };
 
-enum : uint8_t { LD_I16 = 0, LD_I32 = 1, LD_I64 = 2, LD_F32 = 3, LD_F64 = 4, LD_VIEW = 5, LD_DEC = 6 };
+enum : uint8_t { LD_I16 = 0, LD_I32 = 1, LD_I64 = 2, LD_F32 = 3, LD_F64 = 4, LD_VIEW = 5, LD_DEC = 6,
+                 LD_BOOL = 7 /* bit-packed values buffer (types.rs:139-147): predicates only */ };
 constexpr uint32_t kNoValidity = 0xFFFFFFFFu;
 
 struct DevRef {          // where a value comes from

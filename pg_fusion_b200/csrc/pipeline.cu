@@ -706,7 +706,7 @@ class Lowering {
       if (pt.col.source != 0) return not_eligible("predicates are evaluated on scan columns");
       if (pt.cmp < PGF_CMP_LT || pt.cmp > PGF_CMP_NE) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "bad comparison operator");
       DevRef ref;
-      PGF_TRY(lower_ref(pt.col, plan_->njoins, &ref));
+      PGF_TRY(lower_ref(pt.col, plan_->njoins, &ref, /*late=*/false, /*predicate=*/true));
       int64_t k0 = 0;
       uint64_t k1 = 0;
       PGF_TRY(literal_key(pt.lit, ref.type, &k0, &k1));
@@ -782,6 +782,7 @@ class Lowering {
       case PGF_T_FLOAT32: return LD_F32;
       case PGF_T_FLOAT64: return LD_F64;
       case PGF_T_DECIMAL128: return LD_DEC;
+      case PGF_T_BOOLEAN: return LD_BOOL;
       default: return LD_VIEW;
     }
   }
@@ -790,13 +791,15 @@ class Lowering {
   // temporarily holds the slot; fix_ref() turns it into shared-memory offsets once the
   // stage layout is known.
   static constexpr uint32_t kLateRef = 0xFFFFFFFEu;  // `off` of a page column that is not staged (read from HBM by stage C)
-  pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out, bool late = false) {
+  pgf_status lower_ref(const pgf_colref& r, uint32_t joins_visible, DevRef* out, bool late = false, bool predicate = false) {
     Scan& s = *L_->scan;
     DevPlan& D = L_->dev;
     if (r.source == 0) {
       if (r.col < 0 || size_t(r.col) >= s.schema.size()) return ctx_->fail(PGF_ERR_INVALID_ARGUMENT, "column %d out of range", r.col);
       const int type = s.schema[r.col].type_tag;
-      if (row_width(type) == 0 || type == PGF_T_UUID) return not_eligible("Boolean / Uuid columns are not evaluated on the GPU path");
+      // Boolean columns (bit-packed values) are evaluated in predicates only; Uuid columns nowhere
+      if (type == PGF_T_UUID || (type == PGF_T_BOOLEAN && (!predicate || L_->rowscan)))
+        return not_eligible("Uuid columns, and Boolean columns outside predicates, are not evaluated on the GPU path");
       if (L_->rowscan) {  // a column of the scanned row: word 0..1 = key, 3 + payload word = payload (GRow::rec)
         out->src = kSrcRecord;
         out->ld = ld_kind(type);
@@ -887,6 +890,10 @@ class Lowering {
   pgf_status literal_key(const pgf_literal& lit, int col_type, int64_t* k0, uint64_t* k1) {
     *k1 = 0;
     switch (col_type) {
+      case PGF_T_BOOLEAN:
+        if (lit.type_tag != PGF_T_BOOLEAN || (lit.i64 != 0 && lit.i64 != 1)) return not_eligible("Boolean column compared with a non-Boolean literal");
+        *k0 = lit.i64;   // false < true, as in arrow's comparison kernels
+        return PGF_OK;
       case PGF_T_INT16: case PGF_T_INT32: case PGF_T_INT64:
         if (lit.type_tag != PGF_T_INT64 && lit.type_tag != PGF_T_INT32 && lit.type_tag != PGF_T_INT16)
           return not_eligible("integer column compared with a non-integer literal");
@@ -1095,10 +1102,12 @@ class Lowering {
 
   // Shared-memory stage layout: row tiles of at most ~40 KiB, tile_rows a multiple of 128 so
   // every column slice (and validity slice) starts 16-byte aligned.
+  static uint32_t col_tile_bytes(const DevStageCol& sc, uint32_t tile_rows) { return sc.width ? tile_rows * sc.width : tile_rows / 8u; }
+
   pgf_status layout_stage(Scan& s) {
     DevPlan& D = L_->dev;
     uint32_t row_bytes8 = 0;  // bytes per row x 8 (validity counts 1 bit)
-    for (uint32_t c = 0; c < D.nstage_cols; ++c) row_bytes8 += D.scol[c].width * 8u + (D.scol[c].nullable ? 1u : 0u);
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) row_bytes8 += (D.scol[c].width ? D.scol[c].width * 8u : 1u) + (D.scol[c].nullable ? 1u : 0u);
     const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
     const uint64_t page_bytes = (uint64_t(row_bytes8) * max_rows + 7) / 8;
     // Ring shape.  Streaming pipelines: kStages tiles of ~40 KiB (a fraction of a page).  Behind a
@@ -1114,11 +1123,11 @@ class Lowering {
     // is staged, else 16 rows (2-byte values)
     uint32_t gran = 16;
     for (uint32_t c = 0; c < D.nstage_cols; ++c)
-      if (D.scol[c].nullable) gran = 128;
+      if (D.scol[c].nullable || D.scol[c].width == 0) gran = 128;   // (a Boolean column is a bitmap itself)
     auto shape = [&](uint32_t ntiles, uint32_t* tile_rows_out, uint32_t* stage_bytes_out) {
       const uint32_t tile_rows = ((max_rows + ntiles - 1) / ntiles + gran - 1) / gran * gran;
       uint32_t stage_bytes = 0;
-      for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += tile_rows * D.scol[c].width;
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) stage_bytes += col_tile_bytes(D.scol[c], tile_rows);
       for (uint32_t c = 0; c < D.nstage_cols; ++c)
         if (D.scol[c].nullable) stage_bytes += tile_rows / 8;
       *tile_rows_out = tile_rows;
@@ -1148,7 +1157,7 @@ class Lowering {
       uint32_t off = 0;
       for (uint32_t c = 0; c < D.nstage_cols; ++c) {
         D.scol[c].smem_off = off;
-        off += tile_rows * D.scol[c].width;
+        off += col_tile_bytes(D.scol[c], tile_rows);
       }
       for (uint32_t c = 0; c < D.nstage_cols; ++c) {
         D.scol[c].valid_off = off;
@@ -1177,11 +1186,11 @@ class Lowering {
     DevPlan& D = L_->dev;
     const uint32_t max_rows = s.max_page_rows ? s.max_page_rows : 1;
     const uint32_t budget = ((227u * 1024u - probe_shared_bytes()) / uint32_t(kPConsumerWarps) - kPQueueBytesPerWarp) & ~127u;
-    bool nullable = false;
-    for (uint32_t c = 0; c < D.nstage_cols; ++c) nullable |= D.scol[c].nullable != 0;
+    bool nullable = false;   // some staged buffer is a bitmap (validity, or Boolean values): tiles start on 128-row boundaries
+    for (uint32_t c = 0; c < D.nstage_cols; ++c) nullable |= D.scol[c].nullable != 0 || D.scol[c].width == 0;
     auto stage_bytes_for = [&](uint32_t tile_rows) {
       uint32_t b = 0;
-      for (uint32_t c = 0; c < D.nstage_cols; ++c) b += tile_rows * D.scol[c].width + (D.scol[c].nullable ? tile_rows / 8 : 0u);
+      for (uint32_t c = 0; c < D.nstage_cols; ++c) b += col_tile_bytes(D.scol[c], tile_rows) + (D.scol[c].nullable ? tile_rows / 8 : 0u);
       return std::max(128u, (b + 127u) & ~127u);
     };
     // Tile = the largest multiple of 32 rows (of 128 with a staged validity bitmap: its slices must start 16-byte
@@ -1200,7 +1209,7 @@ class Lowering {
     uint32_t off = 0;
     for (uint32_t c = 0; c < D.nstage_cols; ++c) {
       D.scol[c].smem_off = off;
-      off += tile_rows * D.scol[c].width;
+      off += col_tile_bytes(D.scol[c], tile_rows);
     }
     for (uint32_t c = 0; c < D.nstage_cols; ++c) {
       D.scol[c].valid_off = off;

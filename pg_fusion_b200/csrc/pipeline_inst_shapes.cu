@@ -12,7 +12,7 @@ cudaError_t launch_shape(const DevPlan& plan, uint32_t grid, size_t smem, cudaSt
   auto kernel = pipeline_kernel<SINK, ACC, GROUPED, NJ, MAXE, SHAPE>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
-  kernel<<<grid, pipeline_threads(SINK, GROUPED, is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>()), smem, stream>>>(plan);
+  kernel<<<grid, pipeline_threads(SINK, GROUPED, is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>(), ACC), smem, stream>>>(plan);
   return cudaGetLastError();
 }
 

@@ -26,15 +26,17 @@ namespace pgf {
 // accumulators per thread are live (GROUP BY), which needs the larger register budget (12 warps).
 constexpr int kMaxConsumerWarps = 16;
 // `fast`: the fast GROUP BY path keeps its accumulators in shared memory, so it fits 16 warps too.
-__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped, bool fast = false) {
-  return (sink == SINK_AGG && grouped && !fast) ? 14 : 16;
+// The Decimal128 flavour of the fast path runs 15 + 1 warps: 512 threads may use 128 registers each (ptxas caps a
+// block of 513..640 threads at 96), and its two rows of five 128-bit products spilled under 96.
+__host__ __device__ constexpr int consumer_warps(uint32_t sink, bool grouped, bool fast = false, uint32_t acc = CLS_F64) {
+  return (sink == SINK_AGG && grouped && !fast) ? 14 : ((fast && acc == CLS_I128) ? 15 : 16);
 }
 // Producer warps: one feeds the ring of most shapes; the fast GROUP BY path (Q1: 80 bytes per row, seven bulk copies per
 // tile) was starved by a single one (ncu r1: 44 % of its stall samples on the `full` barrier), so there two producers
 // alternate tiles.
-__host__ __device__ constexpr int producer_warps(bool fast = false) { return fast ? 2 : 1; }
-__host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped, bool fast = false) {
-  return (consumer_warps(sink, grouped, fast) + producer_warps(fast)) * 32;
+__host__ __device__ constexpr int producer_warps(bool fast = false, uint32_t acc = CLS_F64) { return (fast && acc != CLS_I128) ? 2 : 1; }
+__host__ __device__ constexpr int pipeline_threads(uint32_t sink, bool grouped, bool fast = false, uint32_t acc = CLS_F64) {
+  return (consumer_warps(sink, grouped, fast, acc) + producer_warps(fast, acc)) * 32;
 }
 constexpr int kStages = 4;     // ring depth of streaming pipelines
 #ifndef PGF_JOIN_ROWS
@@ -289,8 +291,32 @@ __device__ __forceinline__ bool in_range2(uint64_t khi, uint64_t klo, const DevT
   const unsigned __int128 span = (static_cast<unsigned __int128>(uint64_t(T.hi0)) << 64) | T.hi1;
   return (k - lo) <= span;
 }
-__device__ __forceinline__ bool view_in_range(const uint4 v, const DevTerm& T, uint32_t& bad) {
-  bad += v.x > 12u;  // out-of-line views are not compared by this kernel
+// An out-of-line view (length > 12, page/arrow_layout/src/raw.rs:98-110) keeps bytes 0..3 in the view and the whole
+// value in the page's tail arena at `offset` (buffer index, bounds and prefix were verified by the import checks,
+// ingest.cu).  The order-preserving key of a predicate only needs the first 12 bytes and the length -- literals are
+// at most 12 bytes long, so a longer value that agrees with one on 12 bytes is decided by its length -- hence: fetch
+// bytes 4..11 and go on as if the view were inline.  Rare path: the page is only worked out here -- kStreamItem: `at` is
+// the index of the tile in its CTA's stream of the streaming kernel (tiles arrive page by page, pages blockIdx.x,
+// blockIdx.x + gridDim.x, ...); else `at` is the page itself.
+template <bool kStreamItem = false>
+__device__ __forceinline__ uint4 view_first12(uint4 v, const DevPlan& P, uint32_t at) {
+  if (__builtin_expect(v.x > 12u, 0)) {
+    const uint32_t page = kStreamItem ? blockIdx.x + (at / P.tiles_per_page) * gridDim.x : at;
+    const LayoutClass* lc = P.single_class ? &P.class0 : P.classes + P.descs[page].layout_class;
+    const uint8_t* p = P.pages + uint64_t(page) * P.page_stride + lc->pool_base + v.w + 4u;
+    uint32_t a = 0, b = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+      a |= uint32_t(p[k]) << (8u * k);
+      b |= uint32_t(p[4 + k]) << (8u * k);
+    }
+    v.z = a;
+    v.w = b;
+  }
+  return v;
+}
+__device__ __forceinline__ bool view_in_range(uint4 v, const DevTerm& T, const DevPlan& P, uint32_t item) {
+  v = view_first12<true>(v, P, item);
   return in_range2((uint64_t(bswap32(v.y)) << 32) | bswap32(v.z), (uint64_t(bswap32(v.w)) << 32) | v.x, T);
 }
 
@@ -298,7 +324,7 @@ __device__ __forceinline__ bool view_in_range(const uint4 v, const DevTerm& T, u
 // LD >= 0: the term's load kind is a compile-time constant and the term is a plain range.
 template <int LD, bool NONULL>
 __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stage, uint32_t r0, uint32_t r1,
-                                           uint32_t tile_nulls, uint32_t& bad, bool& p0, bool& p1) {
+                                           uint32_t tile_nulls, const DevPlan& P, uint32_t item, bool& p0, bool& p1) {
   const uint8_t* p = stage + T.ref.off;
   bool a, b;
   const uint32_t ld = LD >= 0 ? uint32_t(LD) : uint32_t(T.ref.ld);
@@ -310,7 +336,7 @@ __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stag
     }
     case LD_VIEW: {
       const uint4 v0 = reinterpret_cast<const uint4*>(p)[r0], v1 = reinterpret_cast<const uint4*>(p)[r1];
-      a = view_in_range(v0, T, bad); b = view_in_range(v1, T, bad);
+      a = view_in_range(v0, T, P, item); b = view_in_range(v1, T, P, item);
       break;
     }
     case LD_I32: {
@@ -331,6 +357,10 @@ __device__ __forceinline__ void term_pass2(const DevTerm& T, const uint8_t* stag
     case LD_F32: {
       const int32_t x0 = reinterpret_cast<const int32_t*>(p)[r0], x1 = reinterpret_cast<const int32_t*>(p)[r1];
       a = in_range1(x0 ^ int32_t(uint32_t(x0 >> 31) >> 1), T); b = in_range1(x1 ^ int32_t(uint32_t(x1 >> 31) >> 1), T);
+      break;
+    }
+    case LD_BOOL: {  // bit-packed, LSB first (bitmap.rs:4-29): the key is the bit
+      a = in_range1(int64_t((p[r0 >> 3] >> (r0 & 7u)) & 1u), T); b = in_range1(int64_t((p[r1 >> 3] >> (r1 & 7u)) & 1u), T);
       break;
     }
     default: {  // LD_DEC
@@ -750,11 +780,11 @@ constexpr bool is_fast_grouped() {
 }
 
 template <uint32_t SINK, uint32_t ACC, bool GROUPED, uint32_t NJ, uint32_t MAXE_T, class SHAPE = GenericShape>
-__global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED, is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>()), 1)
+__global__ void __launch_bounds__(pipeline_threads(SINK, GROUPED, is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>(), ACC), 1)
 pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr bool kFastGrouped = is_fast_grouped<SINK, ACC, GROUPED, NJ, SHAPE>();
-  constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED, kFastGrouped);
-  constexpr uint32_t PW = uint32_t(producer_warps(kFastGrouped));   // warps 0 .. PW-1 produce, the rest consume
+  constexpr int kConsumerWarps = consumer_warps(SINK, GROUPED, kFastGrouped, ACC);
+  constexpr uint32_t PW = uint32_t(producer_warps(kFastGrouped, ACC));   // warps 0 .. PW-1 produce, the rest consume
   using Ops = AccOps<ACC>;
   using AccT = typename Ops::T;
   constexpr uint32_t MAXE = SINK == SINK_AGG ? MAXE_T : 1;
@@ -847,7 +877,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         if (PW > 1 && ((tseq++) % PW) != warp) continue;   // the producers take the CTA's tiles in turn
         const uint32_t n = d.row_count > r0 ? min(d.row_count - r0, P.tile_rows) : 0u;
         uint32_t bytes = 0;
-        if (active && n) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * width + 15u) & ~15u);
+        if (active && n) bytes = width == 0u ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * width + 15u) & ~15u);   // (width 0: a bitmap -- validity, or Boolean values)
         const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
         mbar_wait(&sh->empty[s], wait_parity);
         if (lane == 0) {
@@ -858,7 +888,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
         }
         __syncwarp();
         if (bytes)
-          tma_load_1d(stages + size_t(s) * P.stage_bytes + smem_off, col_base + (is_validity ? (r0 >> 3) : r0 * width), bytes, &sh->full[s]);
+          tma_load_1d(stages + size_t(s) * P.stage_bytes + smem_off, col_base + (width == 0u ? (r0 >> 3) : r0 * width), bytes, &sh->full[s]);
       }
     }
   } else {
@@ -939,7 +969,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
             any_keep = false;
 #pragma unroll
             for (uint32_t q = 0; q < R; q += 2) {
-              term_pass2<-1, false>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, n_bad, keep[q], keep[q + 1]);
+              term_pass2<-1, false>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, P, item, keep[q], keep[q + 1]);
               any_keep |= keep[q] || keep[q + 1];
             }
           }
@@ -950,7 +980,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
               any_keep = false;
 #pragma unroll
               for (uint32_t q = 0; q < R; q += 2) {
-                term_pass2<SHAPE::Terms::template at<t>(), SHAPE::no_nulls>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, n_bad, keep[q], keep[q + 1]);
+                term_pass2<SHAPE::Terms::template at<t>(), SHAPE::no_nulls>(P.terms[t], stage, rr[q], rr[q + 1], tile_nulls, P, item, keep[q], keep[q + 1]);
                 any_keep |= keep[q] || keep[q + 1];
               }
             }

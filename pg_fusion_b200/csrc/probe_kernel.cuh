@@ -553,8 +553,8 @@ __device__ __forceinline__ void stage_c(const DevPlan& P, uint4 e, bool act, uin
 // Inline view in range, the way view_in_range() defines it -- the key is the 128-bit number (big-endian bytes 0..3,
 // 4..7, 8..11, length) and the test is (key - lo) <= span, unsigned -- with explicit 32-bit carry chains: 3 byte
 // permutes + 9 integer instructions, against ~45 for the compiler's generic 128-bit arithmetic.
-__device__ __forceinline__ bool view_in_range_fast(const uint4 v, const DevTerm& T, uint32_t& bad) {
-  bad += v.x > 12u;  // out-of-line views are not compared by this kernel
+__device__ __forceinline__ bool view_in_range_fast(uint4 v, const DevTerm& T, const DevPlan& P, uint32_t page) {
+  v = view_first12(v, P, page);   // out-of-line value: its bytes 4..11 come from the page's tail arena
   const uint32_t w0 = bswap32(v.y), w1 = bswap32(v.z), w2 = bswap32(v.w), w3 = v.x;
   const uint32_t l0 = uint32_t(uint64_t(T.lo0) >> 32), l1 = uint32_t(uint64_t(T.lo0)), l2 = uint32_t(T.lo1 >> 32), l3 = uint32_t(T.lo1);
   const uint32_t s0 = uint32_t(uint64_t(T.hi0) >> 32), s1 = uint32_t(uint64_t(T.hi0)), s2 = uint32_t(T.hi1 >> 32), s3 = uint32_t(T.hi1);
@@ -570,13 +570,13 @@ __device__ __forceinline__ bool view_in_range_fast(const uint4 v, const DevTerm&
 
 // FilterExec conjunct for one row of the staged tile (see term_pass2)
 template <int LD, bool NONULL>
-__device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stage, uint32_t r, uint32_t tile_nulls, uint32_t& bad) {
+__device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stage, uint32_t r, uint32_t tile_nulls, const DevPlan& P, uint32_t page) {
   const uint8_t* p = stage + T.ref.off;
   bool a;
   const uint32_t ld = LD >= 0 ? uint32_t(LD) : uint32_t(T.ref.ld);
   switch (ld) {
     case LD_F64: a = in_range1(f64_key(reinterpret_cast<const int64_t*>(p)[r]), T); break;
-    case LD_VIEW: a = view_in_range_fast(reinterpret_cast<const uint4*>(p)[r], T, bad); break;
+    case LD_VIEW: a = view_in_range_fast(reinterpret_cast<const uint4*>(p)[r], T, P, page); break;
     case LD_I32: a = in_range1(reinterpret_cast<const int32_t*>(p)[r], T); break;
     case LD_I64: a = in_range1(reinterpret_cast<const int64_t*>(p)[r], T); break;
     case LD_I16: a = in_range1(reinterpret_cast<const int16_t*>(p)[r], T); break;
@@ -585,6 +585,7 @@ __device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stag
       a = in_range1(x ^ int32_t(uint32_t(x >> 31) >> 1), T);
       break;
     }
+    case LD_BOOL: a = in_range1(int64_t((p[r >> 3] >> (r & 7u)) & 1u), T); break;   // bit-packed values
     default: {  // LD_DEC
       const uint4 v = reinterpret_cast<const uint4*>(p)[r];
       a = in_range2(((uint64_t(v.w) << 32) | v.z) ^ 0x8000000000000000ull, (uint64_t(v.y) << 32) | v.x, T);
@@ -674,7 +675,7 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     const uint32_t null_mask = d.null_mask & P.used_null_mask;
     const bool active = want && n && (!is_validity || ((null_mask >> my_pcol) & 1u));
     uint32_t bytes = 0;
-    if (active) bytes = is_validity ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * my_width + 15u) & ~15u);
+    if (active) bytes = my_width == 0u ? ((((n + 7u) >> 3) + 15u) & ~15u) : ((n * my_width + 15u) & ~15u);   // (width 0: a bitmap -- validity, or Boolean values)
     const uint32_t total = __reduce_add_sync(0xffffffffu, bytes);
     if (lane == 0) {
       ctl->meta[is] = PStageMeta{n, null_mask, ipage, r0};
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
     __syncwarp();   // (also: every lane has read dnext before the next fetch overwrites it)
     if (bytes)
       tma_load_1d_hint(stages + size_t(is) * P.stage_bytes + my_soff,
-                       P.pages + uint64_t(ipage) * P.page_stride + my_coff + (is_validity ? (r0 >> 3) : r0 * my_width), bytes, &ctl->full[is], pol_stream);
+                       P.pages + uint64_t(ipage) * P.page_stride + my_coff + (my_width == 0u ? (r0 >> 3) : r0 * my_width), bytes, &ctl->full[is], pol_stream);
     ipage += dq;
     itip += dr;
     if (itip >= P.tiles_per_page) { itip -= P.tiles_per_page; ++ipage; }
@@ -794,11 +795,11 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
           if constexpr (!kNoNull) kvalid = ref_valid(kr, rq);
         }
         if constexpr (T0 >= 0) {
-          keep = keep & term_pass1<T0, true>(P.terms[0], stage, rr, 0u, n_bad);   // (row rr exists on every lane: no branch)
+          keep = keep & term_pass1<T0, true>(P.terms[0], stage, rr, 0u, P, meta.page);   // (row rr exists on every lane: no branch)
         } else {
           for (uint32_t t = 0; t < P.nterms; ++t) {
             if (!__any_sync(0xffffffffu, keep)) break;
-            keep = keep && term_pass1<-1, false>(P.terms[t], stage, rr, meta.null_mask, n_bad);
+            keep = keep && term_pass1<-1, false>(P.terms[t], stage, rr, meta.null_mask, P, meta.page);
           }
         }
         uint32_t m = __ballot_sync(0xffffffffu, keep);

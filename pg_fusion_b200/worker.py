@@ -153,9 +153,9 @@ class PipelineResult:
 
 def _literal(v, type_tag: Optional[int] = None) -> _lib.Literal:
     lit = _lib.Literal()
-    if isinstance(v, bool):
-        raise TypeError("boolean literals are not supported")
-    if isinstance(v, float):
+    if isinstance(v, bool):   # (before int: bool is an int in Python)
+        lit.type_tag, lit.i64 = int(TypeTag.Boolean), int(v)
+    elif isinstance(v, float):
         lit.type_tag, lit.f64 = int(TypeTag.Float64), v
     elif isinstance(v, int):
         if type_tag == int(TypeTag.Decimal128) or not (-(2**63) <= v < 2**63):

@@ -1116,8 +1116,11 @@ class Lowering {
     // share of busy warp slots from 46 % to 93 % but do not help -- the kernel is issue bound, and
     // the deeper ring of smaller tiles hides the TMA latency better.)
     uint32_t queue_bytes = (D.sink == SINK_AGG && L_->grouped) ? kMaxConsumerWarps * kQueueBytesPerWarp : 0u;
+    // The fast GROUP BY path sends the rows it cannot keep in its slots straight to the global table: it has no
+    // deferred-sink queues, and their 32 KiB go to the ring instead (Q1: 4 x 416-row tiles instead of 4 x 288 --
+    // fewer tile hand-overs per row and 100 KB instead of 69 KB in flight per SM).
     if (const ShapeEntry* se = pick_shape(*L_))
-      if (se->fast_group_exprs) queue_bytes += fast_group_acc_bytes(se->fast_group_exprs);  // + accumulator slots
+      if (se->fast_group_exprs) queue_bytes = fast_group_acc_bytes(se->fast_group_exprs);  // accumulator slots
     const uint32_t smem_budget = 227u * 1024u - uint32_t((sizeof(BlockShared) + 127) & ~size_t(127)) - queue_bytes;
     // tile starts must be 16-byte aligned in every staged buffer: 128 rows when a validity bitmap
     // is staged, else 16 rows (2-byte values)

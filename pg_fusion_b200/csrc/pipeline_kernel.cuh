@@ -832,7 +832,7 @@ pipeline_kernel(const __grid_constant__ DevPlan P) {
 
   // shared-memory accumulator slots of the fast GROUP BY path (behind the ring and the queues)
   [[maybe_unused]] unsigned long long* myacc =
-      reinterpret_cast<unsigned long long*>(stages + size_t(kNumStages) * P.stage_bytes + size_t(kMaxConsumerWarps) * kQueueBytesPerWarp) +
+      reinterpret_cast<unsigned long long*>(stages + size_t(kNumStages) * P.stage_bytes) +   // (the fast path has no deferred-sink queues)
       (threadIdx.x >= PW * 32u ? threadIdx.x - PW * 32u : 0);
   if constexpr (kFastGrouped) {
     if (warp >= PW)

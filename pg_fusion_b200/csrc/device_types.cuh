@@ -153,6 +153,8 @@ struct GroupTable {
   uint64_t* cnt;         // capacity x (nexprs + 1): per-expr non-null counts, then row count
   uint32_t mask;
   uint32_t acc_words;    // 1 or 2
+  uint32_t nexprs;       // accumulators per slot (the thread that creates a group zeroes its acc / cnt words)
+  uint32_t pad;
   uint32_t* overflow;    // set to 1 when the table is full
   uint32_t* used;        // number of occupied slots
 };

@@ -12,6 +12,7 @@ namespace {
 struct ValidateParams {
   const uint8_t* pages;
   const PageDesc* descs;
+  const LayoutClass* classes;
   uint64_t page_stride;
   uint32_t npages;
   uint32_t ncols;
@@ -49,7 +50,23 @@ __global__ void __launch_bounds__(256) validate_pages_kernel(const ValidateParam
   for (uint32_t page = blockIdx.x; page < p.npages; page += gridDim.x) {
     const uint8_t* block = p.pages + page * p.page_stride + kPageHeaderLen;
     const BlockHeader* h = reinterpret_cast<const BlockHeader*>(block);
-    const uint32_t rows = h->row_count;
+    // Everything that indexes memory below comes from the descriptors the HOST built when it admitted the page
+    // (row count, column offsets, pool base), not from the copy of the header that landed in HBM: the copy is
+    // asynchronous, and a page that changed between admission and DMA must not steer the kernel out of bounds.
+    // A header that no longer agrees with its descriptor is reported and the page skipped.
+    const PageDesc pd = p.descs[page];
+    const LayoutClass& lc = p.classes[pd.layout_class];
+    bool same = h->row_count == pd.row_count && h->pool_base + kPageHeaderLen == lc.pool_base && h->col_count == p.ncols &&
+                uint64_t(h->block_size) + kPageHeaderLen <= p.page_stride && h->tail_cursor >= h->pool_base && h->tail_cursor <= h->block_size;
+    for (uint32_t c = 0; same && c < p.ncols; ++c) {
+      const ColumnDesc* d = reinterpret_cast<const ColumnDesc*>(block + sizeof(BlockHeader) + c * sizeof(ColumnDesc));
+      same = d->values_off + kPageHeaderLen == lc.values_off[c] && d->validity_off + kPageHeaderLen == lc.validity_off[c];
+    }
+    if (!same) {
+      if (threadIdx.x == 0) report(p, page, 0, PGF_ERR_IMPORT_PAGE_HEADER_INVALID);
+      continue;
+    }
+    const uint32_t rows = pd.row_count;
     const uint32_t pool_capacity = h->block_size - h->pool_base;
     const uint32_t tail_start = h->tail_cursor - h->pool_base;
     for (uint32_t c = 0; c < p.ncols; ++c) {
@@ -138,6 +155,7 @@ pgf_status scan_device_validate(pgf_ctx* ctx, Scan& s) {
   ValidateParams p{};
   p.pages = s.d_pages;
   p.descs = s.d_descs;
+  p.classes = s.d_classes;
   p.page_stride = ctx->page_size;
   p.npages = uint32_t(s.npages);
   p.ncols = uint32_t(s.schema.size());

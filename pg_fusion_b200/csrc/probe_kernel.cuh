@@ -312,9 +312,7 @@ __device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uin
     if (s == 0) {
       const uint32_t old = atomicCAS(t.state + i, 0u, 1u);
       if (old == 0) {
-#pragma unroll
-        for (uint32_t w = 0; w < kKeyWords; ++w)
-          if (w < nwords) t.keys[uint64_t(i) * kKeyWords + w] = key[w];
+        group_slot_init(t, i, key, nwords);
         __threadfence();
         atomicExch(t.state + i, ready);
         *inserted += 1u;

@@ -82,12 +82,13 @@ def test_q3_top_k_by_revenue(ctx, limit):
         s.release()
 
 
-@pytest.mark.parametrize("limit", [7, 0])
-def test_order_by_with_null_keys_ties_and_integer_sums(ctx, limit):
+@pytest.mark.parametrize("limit,nkeys", [(7, 300), (0, 300), (7, 4000), (64, 4000)])
+def test_order_by_with_null_keys_ties_and_integer_sums(ctx, limit, nkeys):
+    """(4000 keys x 7 strings = ~28 000 groups: the device selection runs two levels; 300 keys: one.)"""
     r = np.random.default_rng(11)
     n = 120_000
     schema = [ColumnSpec(TypeTag.Int32, True), ColumnSpec(TypeTag.Utf8View, True), ColumnSpec(TypeTag.Int64, True)]
-    k = r.integers(0, 300, n).astype(np.int32)
+    k = r.integers(0, nkeys, n).astype(np.int32)
     s = [bytes([66 + int(x)]) * int(1 + x % 3) for x in r.integers(0, 6, n)]
     v = r.integers(-5, 6, n)          # small values: many tied sums
     valid = [r.random(n) > 0.05, r.random(n) > 0.1, r.random(n) > 0.2]
@@ -102,7 +103,8 @@ def test_order_by_with_null_keys_ties_and_integer_sums(ctx, limit):
     rows = list(zip(full.keys, full.aggs))
     for terms in ([("agg", 0, True), ("key", 1, False), ("key", 0, True)],                  # sum DESC (NULLs first), s ASC (NULLs last), k DESC
                   [("key", 1, False, True), ("agg", 2, False), ("key", 0, False)],          # s ASC NULLS FIRST, count(*) ASC, k ASC
-                  [("agg", 1, True), ("key", 0, False, True), ("key", 1, True, False)]):
+                  [("agg", 1, True), ("key", 0, False, True), ("key", 1, True, False)],
+                  [("key", 0, True, False), ("key", 1, False, True)]):                        # k DESC NULLS LAST: the first term alone leaves ties
         got = plan().order_by(terms, limit=limit).run()
         want = py_order(rows, terms, limit)
         assert list(zip(got.keys, got.aggs)) == want   # integer sums and counts: exact, total order given all keys

@@ -99,6 +99,13 @@ pgf_status scan_admit_page(pgf_ctx* ctx, Scan& s, const uint8_t* page, uint32_t 
   return PGF_OK;
 }
 
+// behind the last copy this call queued for the scan
+pgf_status scan_mark_pushed(pgf_ctx* ctx, Scan& s) {
+  if (!s.ev_pushed) CU(ctx, cudaEventCreateWithFlags(&s.ev_pushed, cudaEventDisableTiming));
+  CU(ctx, cudaEventRecord(s.ev_pushed, ctx->copy_stream));
+  return PGF_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -162,6 +169,7 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (auto& kv : ctx->scans) {
+    if (kv.second->ev_pushed) cudaEventDestroy(kv.second->ev_pushed);
     if (kv.second->d_pages) cudaFree(kv.second->d_pages);
     if (kv.second->d_descs) cudaFree(kv.second->d_descs);
     if (kv.second->d_classes) cudaFree(kv.second->d_classes);
@@ -353,7 +361,7 @@ pgf_status pgf_scan_push_pages(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pa
         CU(ctx, cudaMemcpy2DAsync(dst, ctx->page_size, pages + p0 * stride, stride, len, n, cudaMemcpyHostToDevice, ctx->copy_stream));
     }
     s.pending_async += npages;
-    return PGF_OK;
+    return scan_mark_pushed(ctx, s);
   }
   for (uint64_t p = 0; p < npages; ++p) {
     pgf_status st = scan_admit_page(ctx, s, pages + p * stride, len);
@@ -390,7 +398,7 @@ pgf_status pgf_scan_push_pages(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* pa
                             cudaMemcpyHostToDevice, ctx->copy_stream));
     CU(ctx, cudaEventRecord(ctx->staging_ev[b], ctx->copy_stream));
   }
-  return PGF_OK;
+  return scan_mark_pushed(ctx, s);
 }
 
 pgf_status pgf_scan_push_page(pgf_ctx* ctx, uint64_t scan_id, const uint8_t* page, uint32_t len) {
@@ -413,9 +421,13 @@ pgf_status pgf_scan_finish(pgf_ctx* ctx, uint64_t scan_id) {
   std::lock_guard<std::mutex> gc(ctx->mu);
   CU(ctx, cudaSetDevice(ctx->device));
   PGF_TRY(scan_sync_descs(ctx, s));
-  // compute stream waits for the H2D copies; then the row-level import checks run on device
-  CU(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
-  CU(ctx, cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copy, 0));
+  // compute stream waits for the H2D copies of this scan; then the row-level import checks run on device
+  if (s.ev_pushed) {
+    CU(ctx, cudaStreamWaitEvent(ctx->compute_stream, s.ev_pushed, 0));
+  } else {   // (nothing was pushed through the copy stream)
+    CU(ctx, cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+    CU(ctx, cudaStreamWaitEvent(ctx->compute_stream, ctx->ev_copy, 0));
+  }
   PGF_TRY(scan_device_validate(ctx, s));
   s.pending_async = 0;
   s.finished = true;
@@ -440,7 +452,9 @@ pgf_status pgf_scan_reset(pgf_ctx* ctx, uint64_t scan_id) {
   if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
   std::lock_guard<std::mutex> g(s->mu);
   CU(ctx, cudaSetDevice(ctx->device));
-  CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
+  // the scan's own copies and every kernel that may still read its pages; copies of OTHER scans stay in flight
+  if (s->ev_pushed) CU(ctx, cudaEventSynchronize(s->ev_pushed));
+  else CU(ctx, cudaStreamSynchronize(ctx->copy_stream));
   CU(ctx, cudaStreamSynchronize(ctx->compute_stream));
   s->npages = 0;
   s->rows = 0;
@@ -461,6 +475,7 @@ pgf_status pgf_scan_release(pgf_ctx* ctx, uint64_t scan_id) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->compute_stream);
+  if (it->second->ev_pushed) cudaEventDestroy(it->second->ev_pushed);
   if (it->second->d_pages) cudaFree(it->second->d_pages);
   if (it->second->d_descs) cudaFree(it->second->d_descs);
   if (it->second->d_classes) cudaFree(it->second->d_classes);

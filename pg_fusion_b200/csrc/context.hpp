@@ -47,6 +47,10 @@ struct Scan {
   uint64_t d_classes_cap = 0;
   uint32_t max_page_rows = 0;   // largest row_count of any page
   uint64_t pending_async = 0;   // async copies in flight from caller-owned pinned pages
+  // Recorded on the copy stream behind the last copy of THIS scan: finish and reset wait for it, not for the whole
+  // copy stream -- the pages of several scans may be queued at once, and the first scan to finish must not wait
+  // for the copies of the others.
+  cudaEvent_t ev_pushed = nullptr;
   std::mutex mu;                // serialises producers of this scan
 };
 

@@ -137,9 +137,11 @@ pgf_status scan_sync_descs(pgf_ctx* ctx, Scan& s) {
     CU(ctx, cudaMalloc(&s.d_classes, s.d_classes_cap * sizeof(LayoutClass)));
   }
   if (!s.h_descs.empty()) {
-    CU(ctx, cudaMemcpyAsync(s.d_descs, s.h_descs.data(), s.h_descs.size() * sizeof(PageDesc), cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(ctx, cudaMemcpyAsync(s.d_classes, s.h_classes.data(), s.h_classes.size() * sizeof(LayoutClass), cudaMemcpyHostToDevice, ctx->copy_stream));
-    CU(ctx, cudaStreamSynchronize(ctx->copy_stream));  // h_descs is pageable
+    // (on the compute stream: behind the page copies of every scan on the copy stream this small upload would wait
+    // for all of them)
+    CU(ctx, cudaMemcpyAsync(s.d_descs, s.h_descs.data(), s.h_descs.size() * sizeof(PageDesc), cudaMemcpyHostToDevice, ctx->compute_stream));
+    CU(ctx, cudaMemcpyAsync(s.d_classes, s.h_classes.data(), s.h_classes.size() * sizeof(LayoutClass), cudaMemcpyHostToDevice, ctx->compute_stream));
+    CU(ctx, cudaStreamSynchronize(ctx->compute_stream));  // h_descs is pageable
   }
   s.descs_dirty = false;
   return PGF_OK;

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round 2 evidence, one GPU: parity suite, the bench (both arms), the ncu launch list of the bench command, and one
 # ncu --set full capture per shape.  Outputs in gpurun_out/, summarised locally into profiles/ (read_ncu.py, hot_lines.py).
-TAG=${1:-r2}
+TAG=${1:-r2}   # the committed evidence of round 2 carries the tag r2f (final code)
 mkdir -p gpurun_out
 timeout 2400 python -m pytest tests -m gpu -q --durations=8 > gpurun_out/${TAG}_tests.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_tests.log
 tail -14 gpurun_out/${TAG}_tests.log

@@ -179,9 +179,11 @@ def gpu_q3_partitioned(ctx, customer, orders, lineitem, nord_total: int, segment
     stats["nvlink_bytes"] += sent
     ctx.destroy_join_table(r3.join_table)
     schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Float64), ColumnSpec(TypeTag.Float64)]
+    # every group is an order of this rank's share AND the key of at least one routed row: the smaller count bounds
+    # the groups (a group table sized by the orders alone is 4-8 x larger than it need be and falls out of L2)
     p4 = (ctx.row_set_pipeline(rs3, schema).join(t2, 0)
           .aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
-                     expected_groups=max(1024, ctx.join_table_info(t2).rows)))
+                     expected_groups=max(1024, min(ctx.join_table_info(t2).rows, ctx.join_table_info(rs3).rows))))
     if limit:
         p4.order_by(Q3_ORDER, limit=limit)
     r4 = p4.run()

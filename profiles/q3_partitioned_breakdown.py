@@ -51,7 +51,7 @@ r3 = li.pipeline().bloom_probe(rf, 0).filter(3, Cmp.GT, T.Q3_DATE).build_join(0,
 rs3, sent3 = ctx.exchange(r3.join_table, partition=True, rows_only=True); mark("lineitem rows partition")
 schema = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Float64), ColumnSpec(TypeTag.Float64)]
 r4 = (ctx.row_set_pipeline(rs3, schema).join(t2, 0).aggregate([0, (1, 0), (1, 1)], [(AggFunc.SUM, [Factor.of(1), Factor.const_minus(1.0, 2)])],
-      expected_groups=max(1024, ctx.join_table_info(t2).rows)).order_by(T.Q3_ORDER, limit=10).run()); mark("probe + GROUP BY + top-10")
+      expected_groups=max(1024, min(ctx.join_table_info(t2).rows, ctx.join_table_info(rs3).rows))).order_by(T.Q3_ORDER, limit=10).run()); mark("probe + GROUP BY + top-10")
 if rank == 0:
     print(f"SF{sf}, {world} ranks: partitioned Q3 = {total * 1e3:.3f} ms per pass (pipelined)")
     for name, ms in marks:

@@ -39,7 +39,8 @@ enum {
   PGF_ERR_UNKNOWN_HANDLE = 5,
   PGF_ERR_NOT_ELIGIBLE = 6,    /* plan outside the supported grammar: keep the DataFusion node */
   PGF_ERR_STATE = 7,           /* call not valid in the object's current state */
-  PGF_ERR_UNSUPPORTED_DATA = 8,/* e.g. out-of-line (> 12 byte) view in a predicate/key column */
+  PGF_ERR_UNSUPPORTED_DATA = 8,/* e.g. out-of-line (> 12 byte) view in a GROUP BY key or join payload column
+                                  (predicates compare such values through the page's tail arena) */
   PGF_ERR_COMM = 9,            /* NCCL / communicator error */
   /* BloomParamError / BloomAttachError (runtime_filter/src/bloom.rs:103-137) */
   PGF_ERR_BLOOM_ZERO_BIT_COUNT = 20,
@@ -308,7 +309,11 @@ typedef struct {
 typedef struct { int32_t source; int32_t col; } pgf_colref;
 
 /* One conjunct of the FilterExec predicate: <column> <cmp> <literal>.  The predicate is
- * the AND of all terms; a row passes iff every term is TRUE (NULL => dropped). */
+ * the AND of all terms; a row passes iff every term is TRUE (NULL => dropped).  Columns: the
+ * integer and float types, Decimal128, Utf8View / BinaryView (values of any length -- out-of-line
+ * ones are read from the page's tail arena, page/arrow_layout/src/raw.rs:98-110 -- against
+ * literals of at most 12 bytes) and Boolean (bit-packed values, types.rs:139-147; literal
+ * PGF_T_BOOLEAN: `WHERE flag` is flag = true). */
 typedef struct { pgf_colref col; int32_t cmp; int32_t reserved; pgf_literal lit; } pgf_pred_term;
 
 /* Projection / aggregate argument: a product of up to 3 factors, each `x`, `(c - x)` or

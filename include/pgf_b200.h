@@ -243,6 +243,24 @@ pgf_status pgf_bloom_or_device_words(pgf_ctx *ctx, uint64_t bloom, const void *d
  * decision_for_hash / decision_for_null, shared.rs:350-374): decisions[i] is a
  * PGF_PASS_UNFILTERED / PGF_MAYBE_PRESENT / PGF_DEFINITELY_ABSENT byte per row. */
 typedef struct { uint64_t probe_rows, rejected_rows, pass_unfiltered; } pgf_probe_stats;
+
+/* The runtime-filter counters of the reference's metrics registry (runtime_metrics/src/lib.rs:125-131), accumulated
+ * per context: where worker_runtime and backend_service bump a MetricId, the library bumps the field of the same name.
+ *   allocated        pgf_bloom_begin_build succeeded (runtime_filter_plan.rs:92)
+ *   ready            pgf_bloom_publish_ready succeeded (runtime_filter_plan.rs:283)
+ *   pool_exhausted   the planner hook found no free slot and kept the plain join (runtime_filter_plan.rs:89): the hook
+ *                    reports it with pgf_ctx_note_pool_exhausted
+ *   build_rows       keys inserted (runtime_filter_plan.rs:272): pgf_bloom_insert_*, pgf_pipeline.build_bloom
+ *   probe_rows / probe_rows_rejected / probe_pass_unfiltered
+ *                    rows tested against a filter, rows it rejected, and rows that met a filter the probe could not
+ *                    consult -- not Ready, another generation, or dropped by the lowering as redundant
+ *                    (backend_service/src/source.rs:476-488): pgf_bloom_probe_*, fused probes of pgf_pipeline_run */
+typedef struct {
+  uint64_t allocated_total, ready_total, pool_exhausted_total, build_rows_total;
+  uint64_t probe_rows_total, probe_rows_rejected_total, probe_pass_unfiltered_total;
+} pgf_runtime_filter_metrics;
+pgf_status pgf_ctx_runtime_filter_metrics(pgf_ctx *ctx, pgf_runtime_filter_metrics *out);
+pgf_status pgf_ctx_note_pool_exhausted(pgf_ctx *ctx);
 pgf_status pgf_bloom_probe_keys(pgf_ctx *ctx, uint64_t bloom, uint64_t expected_generation,
                                 const void *keys, int32_t key_width, const uint8_t *validity,
                                 uint64_t n, uint8_t *decisions_out, pgf_probe_stats *stats);

@@ -248,7 +248,10 @@ class DeviceRuntimeFilterPool final : public RuntimeFilterPool {
     for (uint64_t b : blooms_) pgf_bloom_destroy(gpu_.raw(), b);
   }
   std::optional<RuntimeFilterBuildHandle> allocate_build(const RuntimeFilterTarget&) override {
-    if (blooms_.size() >= slots_) return std::nullopt;
+    if (blooms_.size() >= slots_) {   // RuntimeFilterPoolExhaustedTotal (runtime_filter_plan.rs:89): a soft miss
+      pgf_ctx_note_pool_exhausted(gpu_.raw());
+      return std::nullopt;
+    }
     RuntimeFilterBuildHandle h;
     gpu_.check(pgf_bloom_create(gpu_.raw(), &params_, &h.bloom));
     blooms_.push_back(h.bloom);

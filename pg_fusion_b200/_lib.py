@@ -52,6 +52,12 @@ class ProbeStats(C.Structure):
     _fields_ = [("probe_rows", u64), ("rejected_rows", u64), ("pass_unfiltered", u64)]
 
 
+class RuntimeFilterMetrics(C.Structure):
+    """pgf_runtime_filter_metrics: the RuntimeFilter* counters of runtime_metrics/src/lib.rs:125-131."""
+    _fields_ = [("allocated_total", u64), ("ready_total", u64), ("pool_exhausted_total", u64), ("build_rows_total", u64),
+                ("probe_rows_total", u64), ("probe_rows_rejected_total", u64), ("probe_pass_unfiltered_total", u64)]
+
+
 class Literal(C.Structure):
     _fields_ = [("type_tag", i32), ("slen", i32), ("f64", C.c_double), ("i64", i64), ("hi", i64), ("str", u8 * 16)]
 
@@ -151,6 +157,8 @@ _SIGNATURES = {
     "pgf_ctx_last_kernel_ms": (C.c_float, [vp]),
     "pgf_layout_plan_new": (i32, [P(ColumnSpec), u32, u32, u32, P(LayoutPlanC)]),
     "pgf_layout_fixed_row_cap": (i32, [P(ColumnSpec), u32, u32, P(u32)]),
+    "pgf_ctx_runtime_filter_metrics": (i32, [vp, P(RuntimeFilterMetrics)]),
+    "pgf_ctx_note_pool_exhausted": (i32, [vp]),
     "pgf_block_validate": (i32, [vp, C.c_size_t]),
     "pgf_block_validate_ext": (i32, [vp, C.c_size_t, u32]),
     "pgf_block_import_check": (i32, [u16, u16, vp, C.c_size_t, P(ColumnSpec), u32]),

@@ -246,6 +246,19 @@ pgf_status pgf_ctx_synchronize(pgf_ctx* ctx) {
 
 float pgf_ctx_last_kernel_ms(const pgf_ctx* ctx) { return ctx ? ctx->last_kernel_ms : 0.f; }
 
+pgf_status pgf_ctx_runtime_filter_metrics(pgf_ctx* ctx, pgf_runtime_filter_metrics* out) {
+  if (!ctx || !out) return PGF_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  *out = ctx->rf_metrics;
+  return PGF_OK;
+}
+pgf_status pgf_ctx_note_pool_exhausted(pgf_ctx* ctx) {
+  if (!ctx) return PGF_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> g(ctx->mu);
+  ctx->rf_metrics.pool_exhausted_total++;
+  return PGF_OK;
+}
+
 void* pgf_ctx_compute_stream(pgf_ctx* ctx) { return ctx ? (void*)ctx->compute_stream : nullptr; }
 
 /* ---- host-side layout ---- */
@@ -591,6 +604,7 @@ pgf_status pgf_bloom_begin_build(pgf_ctx* ctx, uint64_t bloom, uint64_t* generat
   CU(ctx, cudaMemsetAsync(b->d_words, 0, b->params.word_count * 8, ctx->compute_stream));  // bloom.clear()
   b->lifecycle = ((gen + 1) << 2) | PGF_RF_BUILDING;
   if (generation_out) *generation_out = gen + 1;
+  ctx->rf_metrics.allocated_total++;
   return PGF_OK;
 }
 
@@ -608,7 +622,9 @@ pgf_status pgf_bloom_publish_ready(pgf_ctx* ctx, uint64_t bloom) {
   // all inserts were queued on the compute stream; Ready is observable once they are done
   CU(ctx, cudaSetDevice(ctx->device));
   PGF_TRY(bloom_count_bits(ctx, *b));   // synchronises; the fill decides whether fused probes are worth their cost
-  return bloom_transition(ctx, b, PGF_RF_BUILDING, PGF_RF_READY);
+  PGF_TRY(bloom_transition(ctx, b, PGF_RF_BUILDING, PGF_RF_READY));
+  ctx->rf_metrics.ready_total++;
+  return PGF_OK;
 }
 pgf_status pgf_bloom_disable_build(pgf_ctx* ctx, uint64_t bloom) {
   BLOOM_OR_FAIL(ctx, bloom, b);
@@ -625,7 +641,11 @@ pgf_status pgf_bloom_insert_keys(pgf_ctx* ctx, uint64_t bloom, const void* keys,
   if ((!keys && n) || (key_width != 2 && key_width != 4 && key_width != 8)) return PGF_ERR_INVALID_ARGUMENT;
   if (int(b->lifecycle & 3) != PGF_RF_BUILDING)  // pool.rs:480-494 re-checks Building per key
     return ctx->fail(PGF_ERR_LIFECYCLE_INVALID_TRANSITION, "insert into a filter that is not Building");
-  return bloom_insert_host_keys(ctx, *b, keys, key_width, validity, n, rows_inserted);
+  uint64_t ins = 0;
+  PGF_TRY(bloom_insert_host_keys(ctx, *b, keys, key_width, validity, n, &ins));
+  ctx->rf_metrics.build_rows_total += ins;
+  if (rows_inserted) *rows_inserted = ins;
+  return PGF_OK;
 }
 
 pgf_status pgf_bloom_insert_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t scan_id, uint32_t col, uint64_t* rows_inserted) {
@@ -635,7 +655,11 @@ pgf_status pgf_bloom_insert_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t scan_id,
   Scan* s = find_scan(ctx, scan_id);
   if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
   if (!s->finished) return ctx->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)scan_id);
-  return bloom_insert_scan(ctx, *b, *s, col, rows_inserted);
+  uint64_t ins = 0;
+  PGF_TRY(bloom_insert_scan(ctx, *b, *s, col, &ins));
+  ctx->rf_metrics.build_rows_total += ins;
+  if (rows_inserted) *rows_inserted = ins;
+  return PGF_OK;
 }
 
 pgf_status pgf_bloom_read_words(pgf_ctx* ctx, uint64_t bloom, uint64_t* words_out, uint64_t nwords) {
@@ -736,6 +760,13 @@ pgf_status pgf_bloom_or_all_reduce(pgf_ctx* ctx, uint64_t bloom) {
   return bloom_or_device(ctx, *b, ctx->d_xchg, b->params.word_count, uint32_t(ctx->comm_world));
 }
 
+// RuntimeFilterProbeStats::record (backend_service/src/source.rs:474-493)
+static void note_probe(pgf_ctx* ctx, const pgf_probe_stats& st) {
+  ctx->rf_metrics.probe_rows_total += st.probe_rows;
+  ctx->rf_metrics.probe_rows_rejected_total += st.rejected_rows;
+  ctx->rf_metrics.probe_pass_unfiltered_total += st.pass_unfiltered;
+}
+
 pgf_status pgf_bloom_probe_keys(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_generation, const void* keys,
                                 int32_t key_width, const uint8_t* validity, uint64_t n, uint8_t* decisions_out,
                                 pgf_probe_stats* stats) {
@@ -743,7 +774,11 @@ pgf_status pgf_bloom_probe_keys(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_
   if ((!keys && n) || (!decisions_out && n) || (key_width != 2 && key_width != 4 && key_width != 8)) return PGF_ERR_INVALID_ARGUMENT;
   // decision_for_hash: only a Ready filter of the expected generation may reject (shared.rs:350-361)
   const bool ready = (b->lifecycle >> 2) == expected_generation && int(b->lifecycle & 3) == PGF_RF_READY;
-  return bloom_probe_host_keys(ctx, *b, ready, keys, key_width, validity, n, decisions_out, stats);
+  pgf_probe_stats st{};
+  PGF_TRY(bloom_probe_host_keys(ctx, *b, ready, keys, key_width, validity, n, decisions_out, &st));
+  note_probe(ctx, st);
+  if (stats) *stats = st;
+  return PGF_OK;
 }
 
 pgf_status pgf_bloom_probe_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_generation, uint64_t scan_id,
@@ -753,7 +788,11 @@ pgf_status pgf_bloom_probe_scan(pgf_ctx* ctx, uint64_t bloom, uint64_t expected_
   if (!s) return ctx->fail(PGF_ERR_UNKNOWN_HANDLE, "unknown scan %llu", (unsigned long long)scan_id);
   if (!s->finished) return ctx->fail(PGF_ERR_STATE, "scan %llu is not finished", (unsigned long long)scan_id);
   const bool ready = (b->lifecycle >> 2) == expected_generation && int(b->lifecycle & 3) == PGF_RF_READY;
-  return bloom_probe_scan(ctx, *b, ready, *s, col, decisions_out, stats);
+  pgf_probe_stats st{};
+  PGF_TRY(bloom_probe_scan(ctx, *b, ready, *s, col, decisions_out, &st));
+  note_probe(ctx, st);
+  if (stats) *stats = st;
+  return PGF_OK;
 }
 
 /* ---- pipelines ---- */

@@ -106,6 +106,7 @@ struct pgf_ctx {
   uint8_t* d_topk = nullptr;            // scratch of the device top-k selection
   size_t d_topk_cap = 0;
   uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
+  pgf_runtime_filter_metrics rf_metrics{};   // RuntimeFilter* counters (runtime_metrics/src/lib.rs:125-131)
   bool partial_pending = false;         // an asynchronous partial run awaits its merge
   // Recycled join-table allocations: cudaMalloc / cudaFree of GB-sized tables cost 5-20 ms each
   // (page-table work, implicit synchronisation), more than the join kernels themselves.

@@ -524,6 +524,7 @@ struct Lowered {
   size_t smem = 0;
   bool rowscan = false;     // scans a row set (rows_pipeline_kernel) instead of pages
   Scan row_scan;            // its stand-in scan: schema = [key, payload...], rows = rows of the set
+  uint32_t bloom_dropped = 0;  // fused probes the lowering dropped: filter not Ready / other generation / redundant
   bool probe = false;       // runs the compaction pipeline (probe_kernel.cuh): joins and build sinks
   int t0 = -1;              // its predicate specialisation (LD_* of the single plain range term), -1 = generic
   int32_t key_types[4] = {0, 0, 0, 0};
@@ -624,7 +625,10 @@ class Lowering {
       // Only a Ready filter of the expected generation may reject rows; anything else is
       // PassUnfiltered (runtime_filter/src/shared.rs:350-361), i.e. the probe is dropped.
       const BloomSlot& bs = bt->second;
-      if ((bs.lifecycle >> 2) != plan_->bloom[b].expected_generation || int(bs.lifecycle & 3) != PGF_RF_READY) continue;
+      if ((bs.lifecycle >> 2) != plan_->bloom[b].expected_generation || int(bs.lifecycle & 3) != PGF_RF_READY) {
+        L_->bloom_dropped++;
+        continue;
+      }
       DevBloomProbe& bp = D.bloom[D.nbloom];
       bp.bloom = bs.dev;
       PGF_TRY(lower_ref(plan_->bloom[b].key, 0, &bp.key));
@@ -638,7 +642,10 @@ class Lowering {
         // (b) saturated filter: an absent key passes with probability fill^k; above 0.9 the probe costs more than it rejects
         const double fill = double(bs.set_bits) / double(bs.params.bit_count);
         redundant |= std::pow(fill, double(bs.params.hash_count)) > 0.9;
-        if (redundant) continue;   // PassUnfiltered for every row: the result is the same
+        if (redundant) {   // PassUnfiltered for every row: the result is the same
+          L_->bloom_dropped++;
+          continue;
+        }
       }
       D.nbloom++;
     }
@@ -1617,6 +1624,21 @@ const char* variant_name(const Lowered& L) {
 
 }  // namespace
 
+// RuntimeFilter* counters of a fused run (runtime_metrics/src/lib.rs:128-131; caller holds ctx->mu): rows tested
+// against a filter -- every scanned row for filters probed in stage A, the rows past the predicate for the dense
+// filter of the compaction pipeline --, rows rejected, and rows that met a probe the lowering had dropped.
+static void note_fused_probes(pgf_ctx* ctx, const Lowered& L, const Counters& c, uint64_t build_rows) {
+  pgf_runtime_filter_metrics& m = ctx->rf_metrics;
+  m.build_rows_total += build_rows;
+  const uint64_t rejected = c.rows_in - c.rows_bloom;
+  if (L.dev.nbloom) {
+    const bool dense_only = L.dev.bloom_dense && L.dev.nbloom == 1;
+    m.probe_rows_total += dense_only ? c.rows_filtered + rejected : c.rows_in;
+    m.probe_rows_rejected_total += rejected;
+  }
+  m.probe_pass_unfiltered_total += uint64_t(L.bloom_dropped) * c.rows_in;
+}
+
 pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only, void* dev_state_out,
                         uint64_t state_cap, uint64_t* state_bytes, bool partial, pgf_result** out) {
   NvtxRange nvtx_("pgf:pipeline_run");
@@ -1845,6 +1867,7 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
   res->rows_filtered = c.rows_filtered;
   res->rows_out = c.rows_out;
   res->bloom_rows = bloom_rows;
+  note_fused_probes(ctx, L, c, bloom_rows);
   res->kernel_ms = total_ms;
   ctx->last_kernel_ms = total_ms;
   res->kernel_launches = launches;
@@ -2039,6 +2062,7 @@ pgf_status pipeline_merge(pgf_ctx* ctx, const pgf_pipeline* plan, const void* de
   res->kernel_launches = nstates + 1 + topk_launches;
   if (had_partial) {  // statistics of the asynchronous partial run that fed this merge
     const Counters& c = ph->counters;
+    note_fused_probes(ctx, L, c, 0);
     res->rows_in = c.rows_in;
     res->rows_bloom = c.rows_bloom;
     res->rows_filtered = c.rows_filtered;

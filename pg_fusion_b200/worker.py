@@ -656,6 +656,15 @@ class Context:
     def last_kernel_ms(self) -> float:
         return float(_lib.lib().pgf_ctx_last_kernel_ms(self.h))
 
+    def runtime_filter_metrics(self) -> Dict[str, int]:
+        """The RuntimeFilter* counters of this context (runtime_metrics/src/lib.rs:125-131), by field name."""
+        m = _lib.RuntimeFilterMetrics()
+        self._check(_lib.lib().pgf_ctx_runtime_filter_metrics(self.h, C.byref(m)))
+        return {name: int(getattr(m, name)) for name, _ in m._fields_}
+
+    def note_pool_exhausted(self) -> None:
+        self._check(_lib.lib().pgf_ctx_note_pool_exhausted(self.h))
+
     def compute_stream(self) -> int:
         return _lib.lib().pgf_ctx_compute_stream(self.h)
 

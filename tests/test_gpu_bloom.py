@@ -223,3 +223,49 @@ def test_gpu_built_filter_is_published_into_the_shared_memory_pool(ctx):
     assert lifecycle == (gen.value << 2) | int(RuntimeFilterState.Ready)
     with pytest.raises(pg.PgfError):   # a second publish of the same generation is refused
         rf.publish_to_pool(buf.ctypes.data, size.value, slots, slot.value, gen.value)
+
+
+def test_runtime_filter_metric_counters():
+    """The RuntimeFilter* counters of the reference's registry (runtime_metrics/src/lib.rs:125-131), kept per context:
+    allocated / ready / pool exhausted / build rows (worker_runtime/src/runtime_filter_plan.rs:89-92,272,283) and
+    probe rows / rejected / pass-unfiltered (pg/backend_service/src/source.rs:474-493) -- from the stand-alone Bloom
+    calls and from the probes fused into pgf_pipeline_run."""
+    with pg.Context() as c:
+        assert set(c.runtime_filter_metrics().values()) == {0}
+        r = np.random.default_rng(21)
+        n = 40_000
+        build_keys = np.arange(0, 2000, dtype=np.int64)
+        probe_keys = r.integers(0, 20_000, n).astype(np.int64)
+        vals = r.random(n)
+        p = BloomParams.new(1 << 16, 4, 5)
+        rf = c.runtime_filter(p)
+        rf.try_acquire_builder()
+        assert c.runtime_filter_metrics()["allocated_total"] == 1
+        assert rf.insert_keys(build_keys) == 2000
+        # a probe before Ready passes every row unfiltered (shared.rs:350-361)
+        d, st = rf.probe_keys(probe_keys)
+        assert st.pass_unfiltered == n and st.rejected_rows == 0
+        rf.publish_ready()
+        d, st = rf.probe_keys(probe_keys)
+        m = c.runtime_filter_metrics()
+        assert (m["ready_total"], m["build_rows_total"]) == (1, 2000)
+        assert m["probe_rows_total"] == 2 * n and m["probe_pass_unfiltered_total"] == n and m["probe_rows_rejected_total"] == st.rejected_rows > 0
+        # the same filter fused into a scan pipeline: every scanned row is probed, the rejected ones never reach the predicate
+        schema = [ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Float64)]
+        scan = c.declare_scan(schema)
+        scan.push_pages(AL.encode_pages(schema, [(probe_keys, None), (vals, None)]))
+        scan.finish()
+        res = scan.pipeline().bloom_probe(rf, 0).filter(1, pg.Cmp.GE, 0.0).aggregate([], [(pg.AggFunc.COUNT_STAR, None)]).run()
+        m2 = c.runtime_filter_metrics()
+        assert res.rows_in == n and res.rows_in - res.rows_bloom == st.rejected_rows
+        assert m2["probe_rows_total"] - m["probe_rows_total"] == n
+        assert m2["probe_rows_rejected_total"] - m["probe_rows_rejected_total"] == st.rejected_rows
+        # a retired filter cannot be consulted: the fused probe is dropped and its rows pass unfiltered
+        rf.retire_ready_after_quiescence()
+        res = scan.pipeline().bloom_probe(rf, 0).aggregate([], [(pg.AggFunc.COUNT_STAR, None)]).run()
+        m3 = c.runtime_filter_metrics()
+        assert res.aggs[0][0] == n and m3["probe_pass_unfiltered_total"] - m2["probe_pass_unfiltered_total"] == n
+        assert m3["probe_rows_total"] == m2["probe_rows_total"]
+        c.note_pool_exhausted()     # what the planner hook reports when allocate_build finds no free slot
+        assert c.runtime_filter_metrics()["pool_exhausted_total"] == 1
+        scan.release()

@@ -1,12 +1,4 @@
 #!/bin/bash
-# Round 2 A/B: stage A with one row (variant a1) or two rows (default) per lane and step.
-timeout 900 python -m pytest tests/test_gpu_join.py tests/test_gpu_exchange.py tests/test_gpu_bloom.py -m gpu -q -x 2>&1 | tail -2
-for sz in 59986052 600037902; do
-  for v in a1 default; do
-    echo "== q3 rows=$sz $v"
-    if [ $v = default ]; then unset PGF_B200_LIB; else export PGF_B200_LIB=$PWD/pg_fusion_b200/variants/libpgf_b200_$v.so; fi
-    Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 $sz 4 2>&1 | tail -2
-  done
-done
-unset PGF_B200_LIB
-timeout 600 python -m pytest tests/test_gpu_full_size.py -m gpu -q -x -k "q3" 2>&1 | tail -2
+# Experiment: the Q3 lineitem pipeline with a group table sized by the true group count instead of the orders build side
+for hint in 0 1500000 3000000; do echo "== sf100 groups hint $hint"; Q3_GROUPS_HINT=$hint Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 600037902 4 2>&1 | tail -1 | cut -c1-160; done
+for hint in 0 150000; do echo "== sf10 groups hint $hint"; Q3_GROUPS_HINT=$hint Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 59986052 4 2>&1 | tail -1 | cut -c1-160; done

@@ -308,7 +308,7 @@ __device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uin
   uint32_t i = uint32_t(h) & t.mask;
   const uint32_t ready = 2u | (knull << 8);
   for (uint32_t probes = 0; probes <= t.mask; ++probes, i = (i + 1) & t.mask) {
-    uint32_t s = *reinterpret_cast<volatile uint32_t*>(t.state + i);
+    uint32_t s = ld_acquire_u32(t.state + i);
     if (s == 0) {
       const uint32_t old = atomicCAS(t.state + i, 0u, 1u);
       if (old == 0) {
@@ -318,11 +318,10 @@ __device__ __forceinline__ int64_t group_slot_try(const GroupTable& t, const uin
         *inserted += 1u;
         return i;
       }
-      s = old;
+      s = old == 1u ? old : ld_acquire_u32(t.state + i);   // (the CAS itself is relaxed)
     }
     if ((s & 3u) == 1u) return -2;
     if (s == ready) {
-      __threadfence();
       bool same = true;
 #pragma unroll
       for (uint32_t w = 0; w < kKeyWords; ++w)

@@ -63,6 +63,21 @@ def test_registered_float64_shapes_do_not_spill():
     # the budget the launch bounds allow: 16 consumer warps + producer on one SM need <= 96 registers ... 128 for 14 warps
     worst = max(int(e[4]) for e in entries)
     assert worst <= 128, worst
+    # the Decimal128 GROUP BY shape (Q1 "D": <SINK_AGG, CLS_I128, grouped>) runs 15 + 1 warps so that it may use 128
+    # registers: under the 96 of a 576-thread block its two rows of five 128-bit products spilled 200 bytes
+    q1d = [e for e in entries if re.match(r"_ZN3pgf15pipeline_kernelILj1ELj2ELb1E", e[0])]
+    assert len(q1d) == 1 and (int(q1d[0][2]), int(q1d[0][3])) == (0, 0), q1d
+
+
+def test_topk_selection_kernel_keeps_its_entries_in_registers():
+    """ORDER BY ... LIMIT k: one selection kernel per level (topk_select_kernel), eight order summaries per thread
+    in registers, shuffle reductions -- no per-round pass over global memory."""
+    log = open(os.path.join(BUILD, "pipeline.ptxas.log")).read()
+    m = re.search(r"Compiling entry function '(\S*topk_select_kernel\S*)' for 'sm_100a'\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                  r"(\d+) bytes spill loads\nptxas info\s+: Used (\d+) registers", log)
+    assert m, "topk_select_kernel not found in the ptxas log"
+    assert int(m.group(3)) <= 64 and int(m.group(5)) <= 64, m.groups()
+    assert "topk_local_kernel" not in log and "topk_final_kernel" not in log
 
 
 def test_compaction_pipeline_kernels_use_bulk_copies_mbarriers_and_l2_hints(tmp_path):

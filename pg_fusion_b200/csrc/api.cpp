@@ -195,6 +195,7 @@ void pgf_ctx_destroy(pgf_ctx* ctx) {
   if (ctx->d_arena) cudaFree(ctx->d_arena);
   if (ctx->d_out) cudaFree(ctx->d_out);
   if (ctx->d_topk) cudaFree(ctx->d_topk);
+  if (ctx->d_entries) cudaFree(ctx->d_entries);
   if (ctx->h_arena) cudaFreeHost(ctx->h_arena);
   if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
   if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);

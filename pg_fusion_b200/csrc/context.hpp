@@ -105,6 +105,8 @@ struct pgf_ctx {
   size_t d_out_cap = 0;
   uint8_t* d_topk = nullptr;            // scratch of the device top-k selection
   size_t d_topk_cap = 0;
+  uint8_t* d_entries = nullptr;         // stage-C entries of a split join pipeline (grow-only)
+  size_t d_entries_cap = 0;
   uint8_t* h_arena = nullptr;           // pinned mirror of the header and the first result entries
   pgf_runtime_filter_metrics rf_metrics{};   // RuntimeFilter* counters (runtime_metrics/src/lib.rs:125-131)
   bool partial_pending = false;         // an asynchronous partial run awaits its merge

@@ -222,6 +222,12 @@ struct DevPlan {
   // arrival counter of the fixed-order cross-CTA reduction
   uint64_t* cta_rec;
   uint32_t* cta_done;
+  // Split execution of the compaction pipeline (joins): stages A and B append the rows whose tag window matched to
+  // `entries` ({page, row, key lo, key hi}); a second, latency-oriented kernel runs stage C over them.
+  uint4* entries;
+  uint64_t entries_cap;
+  unsigned long long* entries_count;   // entries appended (may exceed entries_cap: then *entries_overflow is set)
+  uint32_t* entries_overflow;
   // row-set scans (rows_pipeline_kernel): dense rows in build-row format instead of pages
   const uint4* row_src;
   uint64_t row_count;

@@ -20,6 +20,7 @@ cudaError_t launch_pipeline(uint32_t sink, uint32_t acc, bool grouped, uint32_t 
                             const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
 // implemented in pipeline_inst_probe.cu: the compaction pipeline (joins, build sinks)
 cudaError_t launch_probe(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream);
+cudaError_t launch_probe_split(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, uint32_t cgrid, cudaStream_t stream);
 cudaError_t launch_rows(uint32_t acc, const DevPlan& plan, uint32_t grid, cudaStream_t stream);
 
 namespace {
@@ -526,6 +527,8 @@ struct Lowered {
   Scan row_scan;            // its stand-in scan: schema = [key, payload...], rows = rows of the set
   uint32_t bloom_dropped = 0;  // fused probes the lowering dropped: filter not Ready / other generation / redundant
   bool probe = false;       // runs the compaction pipeline (probe_kernel.cuh): joins and build sinks
+  bool split = false;       // ... as two kernels: stages A + B, then stage C over the tag hits (plans with a join)
+  uint32_t split_grid = 0;
   int t0 = -1;              // its predicate specialisation (LD_* of the single plain range term), -1 = generic
   int32_t key_types[4] = {0, 0, 0, 0};
   bool key_not_null[4] = {false, false, false, false};
@@ -1539,7 +1542,9 @@ struct ArenaHeader {
   uint32_t overflow, used;   // group-table (or build-row buffer) overflow flag, occupied slots
   unsigned long long build_rows;  // rows a build sink appended (may exceed the buffer when `overflow` is set)
   uint32_t cta_done;         // CTAs that finished (fixed-order Float64 reduction of the streaming kernel)
-  uint32_t pad[15];
+  uint32_t entries_overflow; // split join pipeline: more tag hits than the entry buffer holds (the run is repeated fused)
+  unsigned long long entries;  // ... tag hits appended
+  uint32_t pad[12];
 };
 static_assert(sizeof(ArenaHeader) == 128, "arena header layout");
 constexpr uint64_t kSmallTable = 1ull << 16;   // tables up to this many slots keep their result entries in the arena
@@ -1611,6 +1616,7 @@ pgf_status extract_table(pgf_ctx* ctx, const GroupTable& t, uint64_t capacity, u
 // streaming instantiation.
 cudaError_t launch_fused(const Lowered& L, uint32_t grid, cudaStream_t stream) {
   if (L.rowscan) return launch_rows(L.acc_cls, L.dev, grid, stream);
+  if (L.probe && L.split) return launch_probe_split(L.acc_cls, L.t0, L.dev, grid, L.smem, L.split_grid, stream);
   if (L.probe) return launch_probe(L.acc_cls, L.t0, L.dev, grid, L.smem, stream);
   if (const ShapeEntry* se = pick_shape(L)) return se->fn(L.dev, grid, L.smem, stream);
   return launch_pipeline(L.dev.sink, L.acc_cls, L.grouped, L.nj, L.maxe, L.dev, grid, L.smem, stream);
@@ -1701,6 +1707,24 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     if (!rowbuf.p) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "cannot allocate a build-row buffer of %llu rows", (unsigned long long)rows_cap);
   }
 
+  // Aggregates behind one join probe run split (stages A + B, then stage C over the tag hits) unless
+  // PGF_PROBE_SPLIT=0.  The entry buffer has room for every scanned row (16 bytes each, grow-only, shared by the
+  // context's plans): a row appends at most one entry.  Should the buffer be unobtainable the plan runs fused; a
+  // smaller buffer that overflows (tests force one) repeats the run fused.  (Build sinks stay fused: nearly all their
+  // entries are true matches that end in one append cursor, and the split was 5 % slower there.)
+  uint64_t entries_cap = 0;
+  if (L.probe && !L.rowscan && L.dev.njoins == 1 && L.dev.sink == SINK_AGG && L.dev.nitems) {
+    const char* e = std::getenv("PGF_PROBE_SPLIT");
+    if (!e || *e != '0') {
+      entries_cap = std::max<uint64_t>(L.scan->rows, 1u << 10);
+      if (const char* c = std::getenv("PGF_PROBE_SPLIT_CAP")) entries_cap = std::max<uint64_t>(32, uint64_t(std::atoll(c)));   // tests: force the fallback
+      if (grow(ctx, &ctx->d_entries, &ctx->d_entries_cap, entries_cap * sizeof(uint4), "the stage-C entry buffer") == PGF_OK) {
+        L.split = true;
+        L.split_grid = uint32_t(ctx->sm_count) * 4u;
+      }   // (else: out of memory for an optional buffer is not an error of the plan -- it runs fused)
+    }
+  }
+
   PhaseTrace trace(ctx->compute_stream);
   for (int attempt = 0; attempt < 6; ++attempt) {
     TableAlloc ta;
@@ -1714,10 +1738,14 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     L.dev.cta_done = &ta.d_header->cta_done;
     L.dev.build.rows = static_cast<uint4*>(rowbuf.p);
     L.dev.build.rows_cap = rows_cap;
+    L.dev.entries = reinterpret_cast<uint4*>(ctx->d_entries);
+    L.dev.entries_cap = entries_cap;
+    L.dev.entries_count = &ta.d_header->entries;
+    L.dev.entries_overflow = &ta.d_header->entries_overflow;
     CU(ctx, cudaEventRecord(ctx->ev_a, ctx->compute_stream));
     if (L.dev.nitems) {
       CU(ctx, launch_fused(L, grid, ctx->compute_stream));
-      ++launches;
+      launches += L.split ? 2 : 1;
     }
     CU(ctx, cudaEventRecord(ctx->ev_b, ctx->compute_stream));
     trace.mark("fused kernel");
@@ -1738,6 +1766,10 @@ pgf_status pipeline_run(pgf_ctx* ctx, const pgf_pipeline* plan, bool check_only,
     if (h_header->counters.bad_rows)
       return ctx->fail(PGF_ERR_UNSUPPORTED_DATA, "%llu rows carry out-of-line (> 12 byte) view values in a predicate or key column",
                        (unsigned long long)h_header->counters.bad_rows);
+    if (L.split && h_header->entries_overflow) {  // more tag hits than the entry buffer holds: one fused kernel instead
+      L.split = false;
+      continue;
+    }
     if (agg && h_header->overflow) {  // group table overflow: grow and re-run
       capacity *= 16;
       if (capacity > (1ull << 30)) return ctx->fail(PGF_ERR_OUT_OF_MEMORY, "group table would exceed 2^30 slots");

@@ -4,12 +4,25 @@
 
 namespace pgf {
 
-template <uint32_t ACC, int T0>
+template <uint32_t ACC, int T0, bool SPLIT = false>
 static cudaError_t launch_one(const DevPlan& plan, uint32_t grid, size_t smem, cudaStream_t stream) {
-  auto kernel = probe_pipeline_kernel<ACC, T0>;
+  auto kernel = probe_pipeline_kernel<ACC, T0, SPLIT>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
   if (e != cudaSuccess) return e;
   kernel<<<grid, kPThreads, smem, stream>>>(plan);
+  return cudaGetLastError();
+}
+
+// Split execution: stages A and B (no accumulators: one instantiation serves every accumulator class), then stage C
+// over the appended entries on `cgrid` CTAs.
+cudaError_t launch_probe_split(uint32_t acc, int t0, const DevPlan& plan, uint32_t grid, size_t smem, uint32_t cgrid, cudaStream_t stream) {
+  cudaError_t e = t0 == int(LD_VIEW) ? launch_one<CLS_F64, LD_VIEW, true>(plan, grid, smem, stream) : launch_one<CLS_F64, -1, true>(plan, grid, smem, stream);
+  if (e != cudaSuccess) return e;
+  switch (acc) {
+    case CLS_F64: entries_pipeline_kernel<CLS_F64><<<cgrid, 256, 0, stream>>>(plan); break;
+    case CLS_I64: entries_pipeline_kernel<CLS_I64><<<cgrid, 256, 0, stream>>>(plan); break;
+    default: entries_pipeline_kernel<CLS_I128><<<cgrid, 256, 0, stream>>>(plan); break;
+  }
   return cudaGetLastError();
 }
 

@@ -263,7 +263,8 @@ struct JoinIter {
   bool ended;
 
   __device__ __forceinline__ void load(const DevJoin& j) {
-    const uint2 w = __ldg(reinterpret_cast<const uint2*>(j.tags + base));
+    // (with the evict_last policy stages A / B give the directory: a plain load here made the lines ordinary again)
+    const uint2 w = ldg_tags8(j.tags + base, true, l2_policy_evict_last());
     const TagWindow tw = scan_tags(w, tag);
     cand = tw.cand;
     ended = tw.ended;
@@ -277,6 +278,19 @@ struct JoinIter {
     cand = 0;
     ended = true;
     if (valid) load(j);  // NULL keys never match
+  }
+  // next slot of the chain whose TAG equals the probe key's (its key is still to be compared), or nullptr
+  __device__ __forceinline__ const uint4* next_candidate(const DevJoin& j) {
+    for (;;) {
+      if (cand) {
+        const uint32_t b = uint32_t(__ffsll((long long)cand)) - 1u;
+        cand &= cand - 1ull;
+        return j.slots + uint64_t(base + (b >> 3)) * j.slot_u4;
+      }
+      if (ended) return nullptr;
+      base = (base + kJoinBucket) & j.mask;
+      load(j);
+    }
   }
   // next slot of the chain whose key equals the probe key, or nullptr
   __device__ __forceinline__ const uint32_t* next(const DevJoin& j, uint32_t* occ) {
@@ -599,7 +613,11 @@ __device__ __forceinline__ bool term_pass1(const DevTerm& T, const uint8_t* stag
 // T0 >= 0 (the Q3 pipelines): the predicate is exactly one plain range term of load kind T0 over a NOT NULL
 // column, no staged column is nullable, every runtime filter is probed on dense lanes (stage B) and the entry key
 // (join key or dense filter key) is an Int32 page column staged at P.entry_key_off; T0 < 0: generic.
-template <uint32_t ACC, int T0>
+// SPLIT: stage C is not part of this kernel -- the tag hits are appended to P.entries and entries_pipeline_kernel
+// below runs stage C over them.  Stage C is rare but slow: a batch walks dependent HBM round trips (slot, late
+// columns, group table) and ~1500 divergent instructions while the warp's tile stream stands still; with it compiled
+// out the same 20 warps scan SF100's lineitem side in 2.6 instead of 4.8 ms, and its 96 registers become 64.
+template <uint32_t ACC, int T0, bool SPLIT = false>
 __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __grid_constant__ DevPlan P) {
   constexpr bool kNoNull = T0 >= 0;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -710,6 +728,16 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       uint4 e = make_uint4(0, 0, 0, 0);
       if (lane < n) e = q2[q2n + lane];
       __syncwarp();
+      if constexpr (SPLIT) {   // hand the batch to the stage-C kernel: one reservation per warp, one coalesced store
+        unsigned long long at = 0;
+        if (lane == 0) at = atomicAdd(P.entries_count, (unsigned long long)n);
+        at = __shfl_sync(0xffffffffu, at, 0) + lane;
+        if (lane < n) {
+          if (at < P.entries_cap) P.entries[at] = e;
+          else atomicExch(P.entries_overflow, 1u);
+        }
+        return;
+      }
       uint32_t c_out = 0, c_bad = 0, c_groups = 0;
       stage_c<ACC>(P, e, lane < n, lane, c_out, c_bad, c_groups);
       if (lane == 0) ctl->n_out += c_out;               // warp uniform
@@ -853,6 +881,117 @@ __global__ void __launch_bounds__(kPThreads, 1) probe_pipeline_kernel(const __gr
       if (ctl->n_out) atomicAdd(dst + 3, (unsigned long long)ctl->n_out);
       if (bad) atomicAdd(dst + 5, (unsigned long long)bad);
       if (ctl->n_groups) atomicAdd(P.table.used, ctl->n_groups);   // groups this warp created
+    }
+  }
+}
+
+// ---- stage C as a kernel of its own (split execution: aggregate sinks behind ONE join) --------------
+// 32 warps per SM.  Two phases per warp, both on dense lanes:
+//   match   32 entries at a time: walk the probe chain (tag window from L2, slot from HBM, key compare) and push
+//           every (row, matched slot) pair -- duplicates on the build side multiply -- into the warp's queue.  Two
+//           thirds of the lineitem side's entries are false hits of the 8-bit tag and end here, ~100 instructions in;
+//   sink    whenever 32 matches are queued: assemble the group key from page and payload columns, elect one leader per
+//           group (match.any), look the group up, evaluate the aggregate arguments and add them.  This is the
+//           expensive half (~900 instructions per batch) and it now always runs with full lanes.
+// Nothing else waits for these chains: the scan kernel (stages A and B) has finished its tiles by then.
+constexpr uint32_t kEntryQueue = 64;
+template <uint32_t ACC>
+__global__ void __launch_bounds__(256, 4) entries_pipeline_kernel(const __grid_constant__ DevPlan P) {
+  __shared__ uint4 s_qe[8][kEntryQueue];             // matched rows {page, row, key lo, key hi}
+  __shared__ const uint32_t* s_qs[8][kEntryQueue];   // ... and the slot each of them matched
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* qe = s_qe[warp];
+  const uint32_t** qs = s_qs[warp];
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t qn = 0, n_out = 0, n_bad = 0, n_groups = 0;
+  const DevJoin& j = P.joins[0];
+  auto sink = [&](uint32_t n) {
+    qn -= n;
+    const bool act = lane < n;
+    uint4 e = make_uint4(0, 0, 0, 0);
+    GRow g;
+    g.pay0 = g.pay1 = g.rec = nullptr;
+    g.occ0 = g.occ1 = g.occr = 0;
+    if (act) {
+      e = qe[qn + lane];
+      g.pay0 = qs[qn + lane];
+      g.occ0 = __ldg(g.pay0 + 2);
+    }
+    __syncwarp();
+    g.page = P.pages + uint64_t(e.x) * P.page_stride;
+    g.r = e.y;
+    if (P.single_class && !P.used_null_mask) {
+      g.lc = &P.class0;
+      g.nulls = 0;
+    } else {
+      PageDesc d{};
+      if (act) d = P.descs[e.x];
+      g.lc = P.single_class ? &P.class0 : P.classes + d.layout_class;
+      g.nulls = d.null_mask & P.used_null_mask;
+    }
+    n_out += n;
+    if (P.nkeys) sink_agg_grouped<ACC>(P, g, act, lane, n_bad, n_groups);
+    else sink_agg_single<ACC>(P, g, act, lane);
+    __syncwarp();
+  };
+  const unsigned long long appended = *P.entries_count;
+  const uint64_t n = appended < P.entries_cap ? appended : P.entries_cap;
+  const uint64_t nwarps = uint64_t(gridDim.x) * (blockDim.x >> 5), w0 = uint64_t(blockIdx.x) * (blockDim.x >> 5) + warp;
+  // two entries per lane and step: the two chains (tag window from L2, then the slot from HBM) are independent, so
+  // their round trips overlap -- the match phase is nothing but latency
+  for (uint64_t base = w0 * 64u; base < n; base += nwarps * 64u) {
+    const uint64_t ia = base + lane, ib = ia + 32u;
+    const bool acta = ia < n, actb = ib < n;
+    uint4 ea = make_uint4(0, 0, 0, 0), eb = make_uint4(0, 0, 0, 0);
+    if (acta) ea = __ldg(P.entries + ia);
+    if (actb) eb = __ldg(P.entries + ib);
+    JoinIter ita, itb;
+    ita.init(j, int64_t((uint64_t(ea.w) << 32) | ea.z), acta);   // (NULL keys never reach the entries)
+    itb.init(j, int64_t((uint64_t(eb.w) << 32) | eb.z), actb);
+    for (;;) {
+      // both chains advance to their next candidate slot, both slots are requested, then both keys are compared
+      const uint4* ca = ita.next_candidate(j);
+      const uint4* cb = itb.next_candidate(j);
+      if (!__any_sync(0xffffffffu, (ca != nullptr) | (cb != nullptr))) break;
+      uint4 sa = make_uint4(0, 0, 0, 0), sb = make_uint4(0, 0, 0, 0);
+      if (ca) sa = __ldg(ca);
+      if (cb) sb = __ldg(cb);
+      const bool fa = ca && sa.x == ita.klo && sa.y == ita.khi, fb = cb && sb.x == itb.klo && sb.y == itb.khi;
+      const uint32_t ma = __ballot_sync(0xffffffffu, fa), mb = __ballot_sync(0xffffffffu, fb);
+      if (ma) {
+        if (fa) {
+          const uint32_t at = qn + __popc(ma & lt);
+          qe[at] = ea;
+          qs[at] = reinterpret_cast<const uint32_t*>(ca);
+        }
+        qn += __popc(ma);
+        __syncwarp();
+        if (qn >= 32u) sink(32u);
+      }
+      if (mb) {
+        if (fb) {
+          const uint32_t at = qn + __popc(mb & lt);
+          qe[at] = eb;
+          qs[at] = reinterpret_cast<const uint32_t*>(cb);
+        }
+        qn += __popc(mb);
+        __syncwarp();
+        if (qn >= 32u) sink(32u);
+      }
+    }
+  }
+  if (qn) sink(qn);
+  unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.counters);
+  if (lane == 0 && n_out) atomicAdd(dst + 3, (unsigned long long)n_out);   // (warp uniform)
+  uint32_t vals[2] = {n_groups, n_bad};
+#pragma unroll
+  for (int q = 0; q < 2; ++q) {
+    uint32_t v = vals[q];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && v) {
+      if (q == 0) atomicAdd(P.table.used, v);
+      else atomicAdd(dst + 5, (unsigned long long)v);
     }
   }
 }

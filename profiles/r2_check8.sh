@@ -1,4 +1,3 @@
 #!/bin/bash
-timeout 1500 python -m pytest tests -m gpu -q -x -k "not sf100 and not acero" 2>&1 | tail -3
-echo "== q3 sf100 / sf10"; Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 600037902 4 2>&1 | tail -1 | cut -c1-170; Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 59986052 4 2>&1 | tail -1 | cut -c1-170
-echo "== q1 generic groups"; timeout 300 python profiles/run_shape.py q1 59986052 3 2>&1 | tail -1
+timeout 900 python -m pytest tests/test_gpu_join.py tests/test_gpu_exchange.py tests/test_gpu_cpp_host.py -m gpu -q -x 2>&1 | grep -E "assert|Error|where|passed|failed" | head -12
+for sz in 59986052 600037902; do echo "== q3 rows=$sz"; Q3_LIMIT=10 timeout 300 python profiles/run_shape.py q3 $sz 4 2>&1 | tail -1 | cut -c1-175; done

@@ -203,3 +203,40 @@ def test_two_join_probes_on_one_stream(ctx):
         ctx.destroy_join_table(h)
     for s in scans:
         s.release()
+
+
+def test_split_execution_and_its_fused_fallback_agree(ctx, monkeypatch):
+    """Aggregates behind one join run as two kernels (stages A + B, then stage C over the tag hits).  The same plan as
+    one fused kernel (PGF_PROBE_SPLIT=0) and with an entry buffer that is far too small (the run is repeated fused)
+    must return the same groups, counts and integer sums; duplicates on the build side multiply in all three."""
+    r = np.random.default_rng(12)
+    nb, npr = 20_000, 300_000
+    bk = r.integers(0, 8000, nb).astype(np.int32)
+    pk = r.integers(-1000, 12_000, npr).astype(np.int32)
+    bpay = r.integers(-10**6, 10**6, nb).astype(np.int64)
+    pval = r.integers(-10**6, 10**6, npr).astype(np.int64)
+    bs = [ColumnSpec(TypeTag.Int32), ColumnSpec(TypeTag.Int64)]
+    build, bt = load(ctx, bs, [(bk, None), (bpay, None)])
+    probe, pt = load(ctx, bs, [(pk, None), (pval, None)])
+    b = build.pipeline().build_join(0, [1]).run()
+
+    def run():
+        return (probe.pipeline().filter(1, Cmp.GE, -500_000).join(b.join_table, 0)
+                .aggregate([0], [(AggFunc.SUM, [Factor.of((1, 0))]), (AggFunc.SUM, [Factor.of(1)]), (AggFunc.COUNT_STAR, None)],
+                           expected_groups=16_000).run())   # (room for every group: no table-overflow re-run blurs the launch counts)
+    split = run()
+    monkeypatch.setenv("PGF_PROBE_SPLIT", "0")
+    fused = run()
+    monkeypatch.delenv("PGF_PROBE_SPLIT")
+    monkeypatch.setenv("PGF_PROBE_SPLIT_CAP", "64")
+    fallback = run()
+    monkeypatch.delenv("PGF_PROBE_SPLIT_CAP")
+    want = O.aggregate(pt, E.col(1).ge(E.i64(-500_000)), [E.col(0)], [(O.AGG_SUM, E.col(1, 1)), (O.AGG_SUM, E.col(1)), (O.AGG_COUNT_STAR, None)],
+                       joins=[(bt, 0, 0, 0)])
+    for res in (split, fused, fallback):
+        assert res.rows_out == split.rows_out
+        U.assert_agg_equal(res, want, rel=0)
+    assert split.kernel_launches == fused.kernel_launches + 1          # scan kernel + stage-C kernel
+    assert fallback.kernel_launches > split.kernel_launches            # the split attempt, then the fused run
+    build.release()
+    probe.release()

@@ -23,6 +23,6 @@ NCU="ncu --set full --clock-control none --import-source on"
 $NCU -k regex:pipeline_kernel -s 1 -c 1 -f -o gpurun_out/prof_q6_$TAG python profiles/run_shape.py q6 600037902 3 > gpurun_out/ncu_q6_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q6_$TAG.log
 $NCU -k regex:pipeline_kernel -s 1 -c 1 -f -o gpurun_out/prof_q1_$TAG python profiles/run_shape.py q1 600037902 3 > gpurun_out/ncu_q1_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q1_$TAG.log
 $NCU -k regex:pipeline_kernel -s 1 -c 1 -f -o gpurun_out/prof_q1d_$TAG python profiles/run_shape.py q1d 59986052 3 > gpurun_out/ncu_q1d_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q1d_$TAG.log
-$NCU -k regex:probe_pipeline -s 3 -c 3 -f -o gpurun_out/prof_q3_sf10_$TAG python profiles/run_shape.py q3 59986052 3 > gpurun_out/ncu_q3_sf10_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q3_sf10_$TAG.log
-$NCU -k regex:probe_pipeline -s 3 -c 3 -f -o gpurun_out/prof_q3_sf100_$TAG python profiles/run_shape.py q3 600037902 3 > gpurun_out/ncu_q3_sf100_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q3_sf100_$TAG.log
+$NCU -k "regex:probe_pipeline|entries_pipeline" -s 4 -c 4 -f -o gpurun_out/prof_q3_sf10_$TAG python profiles/run_shape.py q3 59986052 3 > gpurun_out/ncu_q3_sf10_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q3_sf10_$TAG.log
+$NCU -k "regex:probe_pipeline|entries_pipeline" -s 4 -c 4 -f -o gpurun_out/prof_q3_sf100_$TAG python profiles/run_shape.py q3 600037902 3 > gpurun_out/ncu_q3_sf100_$TAG.log 2>&1; tail -1 gpurun_out/ncu_q3_sf100_$TAG.log
 ls -la gpurun_out | tail -20

@@ -7,7 +7,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
 G, P = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 ROWS = {10: 59_986_052, 100: 600_037_902}
-# report name -> (traffic key, index of the shape's kernel inside the report, scale factor, bytes per row)
+# report name -> (traffic key, index of the shape's kernel inside the report, scale factor, bytes per row).  The Q3 reports
+# hold four launches (customer, orders, lineitem scan = stages A + B, lineitem stage C): traffic and time of the lineitem
+# side are the sums of the last two.
 WHAT = {"q6": ("q6_sf100", 0, 100, 40), "q1": ("q1_sf100", 0, 100, 80), "q1d": ("q1d_sf10", 0, 10, 72),
         "q3_sf10": ("q3_sf10", 2, 10, 36), "q3_sf100": ("q3_sf100", 2, 100, 36)}
 traffic_path = os.path.join(P, "r2_traffic.json")
@@ -25,14 +27,17 @@ for name, (key, idx, sf, bpr) in WHAT.items():
         f.write(txt + "\n# source lines by stall samples (all launches of the report)\n" + hot)
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
-    hdr, units, r = rows[0], rows[1], rows[2 + idx]
+    hdr, units = rows[0], rows[1]
+    parts = [rows[2 + idx]]
+    if name.startswith("q3") and len(rows) > 3 + idx and "entries_pipeline" in rows[3 + idx][hdr.index("Kernel Name")]:
+        parts.append(rows[3 + idx])
+    r = parts[0]
     def val(m):
-        v, u = float(r[hdr.index(m)]), units[hdr.index(m)]
-        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-    dur = float(r[hdr.index("gpu__time_duration.sum")]) * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[units[hdr.index("gpu__time_duration.sum")]]
+        return sum(float(q[hdr.index(m)]) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[hdr.index(m)]] for q in parts)
+    dur = sum(float(q[hdr.index("gpu__time_duration.sum")]) for q in parts) * {"us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}[units[hdr.index("gpu__time_duration.sum")]]
     traffic[key] = {"rows": ROWS[sf], "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
                     "dram_bytes_read": val("dram__bytes_read.sum"), "dram_bytes_write": val("dram__bytes_write.sum"),
-                    "algorithmic_bytes": ROWS[sf] * bpr, "kernel_us_under_ncu": dur, "kernel": r[hdr.index("Kernel Name")][:90],
+                    "algorithmic_bytes": ROWS[sf] * bpr, "kernel_us_under_ncu": dur, "kernel": " + ".join(q[hdr.index("Kernel Name")][:60] for q in parts),
                     "source": f"profiles/{out_name} (ncu --set full --clock-control none, one launch)"}
 json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
 for f in (f"launches_{tag}.csv", f"bench_{tag}.json", f"bench_{tag}_reference_arm.json", f"{tag}_tests.log"):

@@ -485,7 +485,7 @@ def run_ours(args):
                                       "joined": int(st3["final"].rows_out if "final" in st3 else st3["lineitem"].rows_out)}})
         worst = min(("q6", "q1", "q3"), key=lambda n: shapes[n]["frac"])
         kernel_names = {"q6": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, false, 0, 2, Q6Shape>", "q1": "pgf::pipeline_kernel<SINK_AGG, CLS_F64, true, 0, 8, Q1Shape8>",
-                        "q3": "pgf::probe_pipeline_kernel<CLS_F64, LD_VIEW> (lineitem: filter + join probe + GROUP BY)"}
+                        "q3": "pgf::probe_pipeline_kernel<CLS_F64, LD_VIEW, SPLIT> + pgf::entries_pipeline_kernel<CLS_F64> (lineitem side: filter + tag probe, then matches + GROUP BY)"}
         traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:

@@ -80,13 +80,14 @@ struct Schema {
 
 // ------------------------------------------------------------------------------ PhysicalExpr
 struct ScalarValue {
-  enum Kind { Null, Float64, Int64, Utf8, Decimal128 } kind = Null;
+  enum Kind { Null, Float64, Int64, Utf8, Decimal128, Boolean } kind = Null;
   double f64 = 0;
   int64_t lo = 0, hi = 0;  // Int64 in lo; Decimal128 unscaled value in (hi:lo)
   std::string str;
   static ScalarValue float64(double v) { ScalarValue s; s.kind = Float64; s.f64 = v; return s; }
   static ScalarValue int64(int64_t v) { ScalarValue s; s.kind = Int64; s.lo = v; s.hi = v < 0 ? -1 : 0; return s; }
   static ScalarValue utf8(std::string v) { ScalarValue s; s.kind = Utf8; s.str = std::move(v); return s; }
+  static ScalarValue boolean(bool v) { ScalarValue s; s.kind = Boolean; s.lo = v ? 1 : 0; return s; }
   static ScalarValue decimal128(int64_t unscaled) { ScalarValue s; s.kind = Decimal128; s.lo = unscaled; s.hi = unscaled < 0 ? -1 : 0; return s; }
   static ScalarValue decimal128(int64_t hi, uint64_t lo) { ScalarValue s; s.kind = Decimal128; s.lo = int64_t(lo); s.hi = hi; return s; }
   std::string to_string() const {
@@ -97,6 +98,7 @@ struct ScalarValue {
       case Int64: o << lo; break;
       case Utf8: o << '"' << str << '"'; break;
       case Decimal128: o << "Decimal128(" << hi << ":" << uint64_t(lo) << ")"; break;
+      case Boolean: o << (lo ? "true" : "false"); break;
     }
     return o.str();
   }
@@ -154,6 +156,7 @@ class Literal final : public PhysicalExpr {
       case ScalarValue::Int64: return PGF_T_INT64;
       case ScalarValue::Utf8: return PGF_T_UTF8VIEW;
       case ScalarValue::Decimal128: return PGF_T_DECIMAL128;
+      case ScalarValue::Boolean: return PGF_T_BOOLEAN;
       default: return 0;
     }
   }
@@ -191,6 +194,7 @@ inline ExprRef lit(double v) { return std::make_shared<Literal>(ScalarValue::flo
 inline ExprRef lit(int64_t v) { return std::make_shared<Literal>(ScalarValue::int64(v)); }
 inline ExprRef lit(const char* v) { return std::make_shared<Literal>(ScalarValue::utf8(v)); }
 inline ExprRef lit(ScalarValue v) { return std::make_shared<Literal>(std::move(v)); }
+inline ExprRef lit_bool(bool v) { return std::make_shared<Literal>(ScalarValue::boolean(v)); }
 inline ExprRef binary(ExprRef l, Operator op, ExprRef r) { return std::make_shared<BinaryExpr>(std::move(l), op, std::move(r)); }
 inline ExprRef and_(ExprRef l, ExprRef r) { return binary(std::move(l), Operator::And, std::move(r)); }
 
@@ -956,6 +960,10 @@ inline pgf_literal make_literal(const ScalarValue& v, int32_t col_tag) {
       l.slen = int32_t(v.str.size());
       std::memcpy(l.str, v.str.data(), v.str.size());
       break;
+    case ScalarValue::Boolean:
+      l.type_tag = PGF_T_BOOLEAN;
+      l.i64 = v.lo;
+      break;
     case ScalarValue::Null:
       throw NotEligible{"NULL literal"};
   }
@@ -1079,6 +1087,15 @@ class Lowering {
   }
 
   void add_conjuncts(const ExprRef& e) {
+    if (auto flag = e->downcast<BoundColumn>()) {   // WHERE flag: a Boolean column is a predicate by itself (flag = true)
+      if (flag->bound().type_tag != PGF_T_BOOLEAN || flag->bound().ref.source != 0) throw NotEligible{"predicate is not a conjunction of comparisons"};
+      if (pod.nterms >= PGF_MAX_TERMS) throw NotEligible{"too many predicate terms"};
+      pgf_pred_term& t = pod.terms[pod.nterms++];
+      t.col = flag->bound().ref;
+      t.cmp = PGF_CMP_EQ;
+      t.lit = make_literal(ScalarValue::boolean(true), PGF_T_BOOLEAN);
+      return;
+    }
     auto b = e->downcast<BinaryExpr>();
     if (!b) throw NotEligible{"predicate is not a conjunction of comparisons"};
     if (b->op() == Operator::And) {

@@ -68,6 +68,7 @@ int main() {
   dump("q3", install_b200_operators(plans::q3(3, 4, 5), nullptr, &skipped));
   dump("q6_decimal", install_b200_operators(plans::q6_d(6), nullptr, &skipped));
   dump("q1_decimal", install_b200_operators(plans::q1_d(7), nullptr, &skipped));
+  dump("flags_filter", install_b200_operators(plans::flags_filter(8), nullptr, &skipped));
   {
     FakePool pool(64);
     PlanRef with_filters = install_runtime_filters(plans::q3(3, 4, 5), 7, pool);

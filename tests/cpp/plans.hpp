@@ -28,6 +28,10 @@ inline Schema orders_q3() {
 }
 inline Schema customer_q3() { return schema_of({{"c_custkey", PGF_T_INT32}, {"c_mktsegment", PGF_T_UTF8VIEW}}); }
 
+inline Schema flags_table() {
+  return schema_of({{"active", PGF_T_BOOLEAN}, {"k", PGF_T_INT64}, {"deleted", PGF_T_BOOLEAN}, {"v", PGF_T_FLOAT64}});
+}
+
 inline PlanRef scan(uint64_t id, Schema s) { return std::make_shared<WorkerPgScanExec>(id, std::move(s)); }
 inline PlanRef filter(ExprRef pred, PlanRef in) {
   return std::make_shared<CoalesceBatchesExec>(std::make_shared<FilterExec>(std::move(pred), std::move(in)));
@@ -47,6 +51,16 @@ inline PlanRef q6(uint64_t scan_id) {
       std::vector<AggregateFunctionExpr>{sum(binary(col("l_extendedprice", 1), Operator::Multiply, col("l_discount", 2)), "revenue"),
                                          count_star("count(*)")},
       filter(pred, li));
+}
+
+// select k, sum(v), count(*) from flags where active and deleted = false and k < 2500 group by k
+// (a Boolean column as a predicate by itself, and one compared with a Boolean literal)
+inline PlanRef flags_filter(uint64_t scan_id) {
+  PlanRef t = scan(scan_id, flags_table());
+  ExprRef pred = and_(and_(col("active", 0), binary(col("deleted", 2), Operator::Eq, lit_bool(false))), binary(col("k", 1), Operator::Lt, lit(int64_t(2500))));
+  return std::make_shared<AggregateExec>(
+      AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{{col("k", 1), "k"}},
+      std::vector<AggregateFunctionExpr>{sum(col("v", 3), "sum(v)"), count_star("count(*)")}, filter(pred, t));
 }
 
 // q01.sql with the standard eight aggregates.  DataFusion's common-subexpression elimination puts

@@ -12,7 +12,7 @@ from types import SimpleNamespace
 
 import pytest
 
-from pg_fusion_b200 import AggFunc, Cmp, Factor, _lib
+from pg_fusion_b200 import AggFunc, Cmp, ColumnSpec, Factor, TypeTag, _lib
 from pg_fusion_b200.worker import PipelineBuilder
 
 from . import util as U
@@ -92,6 +92,14 @@ def test_q1_plan_with_cse_projection_and_sort_lowers_to_the_builder_pod(dump, na
     # above the aggregate is absorbed; Partial -> Final over one partition collapses to Single
     want = pod_bytes(U.gpu_q1(fake_scan(2, U.Q1_SCHEMA)).order_by([("key", 0, False), ("key", 1, False)]))
     assert dump.pods[name] == {0: want}, diff(dump.pods[name][0], want)
+
+
+def test_boolean_predicates_lower_to_the_builder_pod(dump):
+    # WHERE active AND deleted = false AND k < 2500: a bare Boolean column is the term `active = true`
+    schema = [ColumnSpec(TypeTag.Boolean), ColumnSpec(TypeTag.Int64), ColumnSpec(TypeTag.Boolean), ColumnSpec(TypeTag.Float64)]
+    want = pod_bytes(fake_scan(8, schema).pipeline().filter(0, Cmp.EQ, True).filter(2, Cmp.EQ, False).filter(1, Cmp.LT, 2500)
+                     .aggregate([1], [(AggFunc.SUM, [Factor.of(3)]), (AggFunc.COUNT_STAR, None)]))
+    assert dump.pods["flags_filter"] == {0: want}, diff(dump.pods["flags_filter"][0], want)
 
 
 def q3_builders(rf1=None, rf2=None, limit=10):

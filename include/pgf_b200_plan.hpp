@@ -970,7 +970,7 @@ inline pgf_literal make_literal(const ScalarValue& v, int32_t col_tag) {
   return l;
 }
 
-constexpr uint32_t kMaxFusedJoinProbes = 1;
+constexpr uint32_t kMaxFusedJoinProbes = 2;   // = PGF_MAX_JOINS: the second probe's key may be a payload column of the first
 
 inline uint32_t value_words(int32_t type_tag) {  // 32-bit words of a value in a join-table slot
   switch (type_tag) {
@@ -1022,9 +1022,9 @@ class Lowering {
       if (j->on().size() != 1 || !j->on()[0].first->downcast<Column>() || !j->on()[0].second->downcast<Column>())
         throw NotEligible{"join needs exactly one (column, column) key pair"};
       walk(j->right());
-      // the fused kernel probes one join table per pipeline in this build (libpgf_b200 answers
-      // PGF_ERR_NOT_ELIGIBLE for more): a second probe on the same stream keeps its DataFusion node
-      if (pod.njoins >= kMaxFusedJoinProbes) throw NotEligible{"more than one join probe on one scan stream"};
+      // the fused kernel probes up to two join tables per pipeline (the second one in stage C, for the rows the first
+      // join matched); a third probe on the same stream keeps its DataFusion node
+      if (pod.njoins >= kMaxFusedJoinProbes) throw NotEligible{"more than two join probes on one scan stream"};
       const uint32_t slot = pod.njoins++;
       builds.push_back(BuildSpec{j, {}});
       const Bound key = bind(j->right(), j->on()[0].second->downcast<Column>()->index());

@@ -89,6 +89,7 @@ int main(int argc, char** argv) {
     run("q1_partial_final", gpu, plans::q1(2, true));
     run("q3", gpu, plans::q3(3, 4, 5));
     run("q3_all_groups", gpu, plans::q3(3, 4, 5, /*fetch=*/0));
+    run("q3_two_probes", gpu, plans::q3_right_deep_count(3, 4, 5));
     {
       pgf_bloom_params params;
       gpu.check(pgf_bloom_params_new(1u << 20, 4, 0x7067667573696f6eull, &params));  // GUC defaults, pg/extension/src/guc.rs:41-46

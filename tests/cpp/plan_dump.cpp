@@ -127,7 +127,16 @@ int main() {
                                                   std::vector<AggregateFunctionExpr>{count_star("n")}, outer);
     std::vector<std::string> why;
     PlanRef out = install_b200_operators(agg, nullptr, &why);
-    check("two_probes_on_one_stream_stay_datafusion", out->downcast<AggregateExec>() != nullptr && why.size() == 1);
+    check("two_probes_on_one_stream_are_fused", out->downcast<B200PipelineExec>() != nullptr && why.empty());
+    dump("two_probes", out);
+    // a third probe on the same stream is one too many: the plan keeps its DataFusion nodes
+    PlanRef c2 = plans::scan(6, plans::customer_q3());
+    PlanRef third = std::make_shared<HashJoinExec>(c2, outer, HashJoinExec::JoinOn{{col("c_custkey", 0), col("c_custkey", 0)}});
+    PlanRef agg3 = std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                                   std::vector<AggregateFunctionExpr>{count_star("n")}, third);
+    why.clear();
+    PlanRef out3 = install_b200_operators(agg3, nullptr, &why);
+    check("three_probes_on_one_stream_stay_datafusion", out3->downcast<AggregateExec>() != nullptr && !why.empty());
   }
   {
     // limits of the fused kernels that the grammar mirrors, so that joined pipelines (which the library

@@ -161,4 +161,17 @@ inline PlanRef q3(uint64_t customer_id, uint64_t orders_id, uint64_t lineitem_id
   return std::make_shared<SortExec>(order, proj, fetch);
 }
 
+// The same three-way join planned right-deep: customer |><| (orders |><| lineitem) -- the lineitem stream probes the
+// orders table and, for the rows that matched, the customer table with the matched order's o_custkey.  Two probes fused
+// into one scan stream; the same joined rows as q3().
+inline PlanRef q3_right_deep_count(uint64_t customer_id, uint64_t orders_id, uint64_t lineitem_id, const char* segment = "BUILDING") {
+  PlanRef c = filter(binary(col("c_mktsegment", 1), Operator::Eq, lit(segment)), scan(customer_id, customer_q3()));
+  PlanRef o = filter(binary(col("o_orderdate", 2), Operator::Lt, lit("1995-03-15")), scan(orders_id, orders_q3()));
+  PlanRef l = filter(binary(col("l_shipdate", 3), Operator::Gt, lit("1995-03-15")), scan(lineitem_id, lineitem_q3()));
+  PlanRef inner = std::make_shared<HashJoinExec>(o, l, HashJoinExec::JoinOn{{col("o_orderkey", 0), col("l_orderkey", 0)}});
+  PlanRef outer = std::make_shared<HashJoinExec>(c, inner, HashJoinExec::JoinOn{{col("c_custkey", 0), col("o_custkey", 1)}});
+  return std::make_shared<AggregateExec>(AggregateMode::Single, std::vector<std::pair<ExprRef, std::string>>{},
+                                         std::vector<AggregateFunctionExpr>{count_star("joined_rows")}, outer);
+}
+
 }  // namespace plans

@@ -71,7 +71,7 @@ def test_host_checks_pass(dump):
     assert dump.rc == 0, dump.stderr
     assert dump.checks and all(v == "ok" for v in dump.checks.values()), dump.checks
     for name in ("partition_1_is_a_plan_error", "unabsorbed_node_has_no_cpu_operator", "pool_exhaustion_is_soft",
-                 "or_predicate_not_absorbed", "runtime_filter_targets", "two_probes_on_one_stream_stay_datafusion",
+                 "or_predicate_not_absorbed", "runtime_filter_targets", "two_probes_on_one_stream_are_fused", "three_probes_on_one_stream_stay_datafusion",
                  "result_pages_one_per_step", "nothing_after_the_close_step", "limits_record_their_reasons"):
         assert name in dump.checks
 
@@ -100,6 +100,19 @@ def test_boolean_predicates_lower_to_the_builder_pod(dump):
     want = pod_bytes(fake_scan(8, schema).pipeline().filter(0, Cmp.EQ, True).filter(2, Cmp.EQ, False).filter(1, Cmp.LT, 2500)
                      .aggregate([1], [(AggFunc.SUM, [Factor.of(3)]), (AggFunc.COUNT_STAR, None)]))
     assert dump.pods["flags_filter"] == {0: want}, diff(dump.pods["flags_filter"][0], want)
+
+
+def test_two_join_probes_on_one_stream_lower_to_the_builder_pods(dump):
+    # right-deep chain customer |><| (orders |><| lineitem): lineitem probes the orders table with l_orderkey and, for
+    # the rows that matched, the customer table with the matched order's o_custkey (payload 0 of the first join)
+    customer, orders, lineitem = fake_scan(3, U.CUSTOMER_SCHEMA), fake_scan(4, U.ORDERS_SCHEMA), fake_scan(5, U.LINEITEM_Q3_SCHEMA)
+    want = [pod_bytes(orders.pipeline().build_join(0, [1])),          # inner join's build side first: o_orderkey; o_custkey
+            pod_bytes(customer.pipeline().build_join(0, [])),
+            pod_bytes(lineitem.pipeline().join(0, 0).join(0, (1, 0)).aggregate([], [(AggFunc.COUNT_STAR, None)]))]   # (table handles are filled in at execute time)
+    got = dump.pods["two_probes"]
+    assert sorted(got) == [0, 1, 2]
+    for i in range(3):
+        assert got[i] == want[i], f"pipeline {i}: " + diff(got[i], want[i])
 
 
 def q3_builders(rf1=None, rf2=None, limit=10):

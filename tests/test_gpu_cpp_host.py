@@ -106,6 +106,16 @@ def test_q3_plan_top10(runs, ctx, name):
         assert orders["rows_bloom"] == orders["rows_in"] and cust["bloom_rows"] == 0
 
 
+def test_two_join_probes_fused_by_the_cpp_planner(runs, ctx):
+    """The right-deep plan of the same join -- customer |><| (orders |><| lineitem) -- fuses two probes into the lineitem
+    stream (the second with a payload column of the first as its key): the same joined rows as the left-deep Q3."""
+    want, _ = q3_oracle(ctx)
+    got = runs["q3_two_probes"]
+    assert got["rows"] == [[want.rows_joined]]
+    orders, cust, lineitem = got["pipelines"]               # build sides in probe order: the inner join's first
+    assert lineitem["rows_out"] == want.rows_joined and lineitem["variant"] == "compact_1_string_term"
+
+
 def test_q3_plan_all_groups(runs, ctx):
     want, _ = q3_oracle(ctx)
     got = runs["q3_all_groups"]

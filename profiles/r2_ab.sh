@@ -1,6 +1,5 @@
 #!/bin/bash
-# A/B: stage C after the scan (PGF_PROBE_CONCURRENT=0) or concurrently with it on a second stream (default)
-timeout 300 python -m pytest tests/test_gpu_join.py tests/test_gpu_sort.py -m gpu -q -x 2>&1 | tail -3
+# Experiment: join tables at 2 (default), 3 (same as 4 after rounding to 2^k in most cases) and 4 slots per build row
 for sz in 59986052 600037902; do
-  for conc in 0 1; do echo "== q3 rows=$sz concurrent=$conc"; PGF_PROBE_CONCURRENT=$conc Q3_LIMIT=10 timeout 120 python profiles/run_shape.py q3 $sz 4 2>&1 | tail -1 | cut -c1-175; done
+  for f in 2 4; do echo "== q3 rows=$sz capacity factor $f"; PGF_JOIN_CAPACITY_FACTOR=$f Q3_LIMIT=10 timeout 120 python profiles/run_shape.py q3 $sz 4 2>&1 | tail -1 | cut -c1-175; done
 done

@@ -1,2 +1,3 @@
 #!/bin/bash
-timeout 600 python -m pytest tests/test_gpu_cpp_host.py -m gpu -q -x 2>&1 | tail -8
+timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -3
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1

@@ -204,6 +204,47 @@ def cpu_three_shapes(nthreads, rows_q6, rows_q1, rows_q3, passes=1, seed=42):
     return value, out, sample, check
 
 
+def acero_baseline(rows=6_000_000, seed=42):
+    """An independent production CPU engine beside the port (SURVEY 8d baseline iii): pyarrow / Acero (Arrow C++, its
+    default thread pool) over the same TPC-H-shaped columns, held as Arrow arrays in memory -- no page decoding, dates
+    as day numbers (Int32), flags as one-byte strings.  Q6 = filter + sum(price * disc); Q1 = filter + group_by with
+    the eight aggregates.  It is NOT DataFusion; it shows what a vectorised multi-threaded CPU engine does here."""
+    try:
+        import numpy as np
+        import pyarrow as pa
+        import pyarrow.compute as pc
+    except Exception as e:   # (the benchmark does not depend on it)
+        return {"unavailable": str(e)}
+    from oracle import pages_np as PN
+    li = PN.lineitem_columns(rows, seed)
+    t = pa.table({"qty": li["qty"], "price": li["price"], "disc": li["disc"], "tax": li["tax"], "ship": li["ship"].astype(np.int32),
+                  "rf": pa.array(li["rf"].view("S1").astype("U1")), "ls": pa.array(li["ls"].view("S1").astype("U1"))})
+    lo, hi = 731, 1096   # 1994-01-01 <= shipdate < 1995-01-01 as day numbers from 1992-01-01 (oracle/pages_np.py)
+
+    def q6():
+        m = pc.and_(pc.and_(pc.and_(pc.greater_equal(t["ship"], lo), pc.less(t["ship"], hi)),
+                            pc.and_(pc.greater_equal(t["disc"], 0.05), pc.less_equal(t["disc"], 0.07))), pc.less(t["qty"], 24.0))
+        f = t.filter(m)
+        return pc.sum(pc.multiply(f["price"], f["disc"])).as_py()
+
+    def q1():
+        f = t.filter(pc.less_equal(t["ship"], 2436))   # shipdate <= 1998-09-02
+        dp = pc.multiply(f["price"], pc.subtract(1.0, f["disc"]))
+        f = f.append_column("disc_price", dp).append_column("charge", pc.multiply(dp, pc.add(1.0, f["tax"])))
+        return f.group_by(["rf", "ls"]).aggregate([("qty", "sum"), ("price", "sum"), ("disc_price", "sum"), ("charge", "sum"),
+                                                   ("qty", "mean"), ("price", "mean"), ("disc", "mean"), ("qty", "count")]).num_rows
+    out = {"engine": f"pyarrow {pa.__version__} / Acero", "threads": pa.cpu_count(), "rows": rows,
+           "note": "in-memory Arrow columns (no page decoding), dates as Int32 day numbers; an independent CPU engine, not DataFusion"}
+    for name, fn in (("q6", q6), ("q1", q1)):
+        fn()
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            fn()
+        out[name + "_rows_per_s"] = rows * reps / (time.perf_counter() - t0)
+    return out
+
+
 def run_reference(args):
     """Reference arm.  The reference itself (Rust + DataFusion 44) cannot be built in this image (no rustc / cargo, no
     wheel), so the arm times the oracle's port of its semantics on all host cores.  This process imports only
@@ -502,6 +543,8 @@ def run_ours(args):
             cpu = {"value": v1, "unit": "rows/s", "cores": 1, "kind": "port", "per_shape_rows_per_s": s1,
                    "sample": sample1 + "; 1 thread mirrors the reference's single-partition execution (worker_runtime/src/runtime.rs:748-758)",
                    "all_cores": {"value": vn, "cores": cores, "per_shape_rows_per_s": sn, "sample": samplen}}
+            if not args.no_extras:
+                cpu["acero"] = acero_baseline()
         out = {
             "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",

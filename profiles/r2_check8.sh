@@ -1,3 +1,3 @@
 #!/bin/bash
-timeout 2400 python -m pytest tests -m gpu -q 2>&1 | tail -3
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -1
+timeout 600 python bench.py --sf 10 --steps 3 --warmup 3 > gpurun_out/r2d_bench_sf10.json 2> gpurun_out/r2d_bench_sf10.err; echo "rc=$?"; tail -2 gpurun_out/r2d_bench_sf10.err; python -c "
+import json; d=json.loads([l for l in open('gpurun_out/r2d_bench_sf10.json') if l.startswith('{')][-1]); print(d['value'], d['ms_per_step'], {k:(round(v['ms_per_pass'],3), round(v['frac'],3)) for k,v in d['shapes'].items()}, 'e2e', d['e2e']['value'], d['cpu_baseline']['acero'], list(d['other_workloads'])[:3], d['parity'])"
